@@ -1,0 +1,190 @@
+"""Generate golden vectors by running the UNMODIFIED reference files.
+
+Run in the build container only (it needs /root/reference, which does not exist on
+the GPU box):
+
+    python tests/golden/make_golden.py
+
+What it does
+  1. puts /root/reference and oracle/refshims (stand-ins for compressai / torchac /
+     easydict, see oracle/refshims/README.md) on sys.path and imports the reference's
+     own `graphs.models.LLICTI_nets.LLICTI`;
+  2. loads the deterministic synthetic weights (oracle.synthetic_state_dict -- the
+     shipped checkpoint is absent) into the reference model;
+  3. for each case runs the reference's colour transform, lazyDWT, get_params,
+     get_cdfs, compress and decompres, checks the reference round-trips, and checks
+     that oracle/llicti_oracle.py reproduces every stage bit-exactly on this host;
+  4. writes tests/golden/<case>.npz: the small integer artefacts verbatim (image,
+     planes, header, all byte streams), strided subsamples of the big float/int
+     tables, and sha256 digests of the full arrays.
+
+The coder under the reference's `torchac.*` calls is oracle/torchac_port.c (real
+torchac is not installable here): byte streams are "reference model code + restated
+coder" -- see the parity note in that file.
+"""
+import hashlib
+import json
+import os
+import sys
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "refshims"))
+sys.path.insert(0, REF)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from oracle import llicti_oracle as O  # noqa: E402
+from easydict import EasyDict  # noqa: E402  (shim)
+from graphs.models.LLICTI_nets import LLICTI  # noqa: E402  (the reference)
+
+
+def digest(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def ref_config(name):
+    with open(os.path.join(REF, "configs", name)) as f:
+        return EasyDict(json.load(f))
+
+
+def make_image(kind, H, W, idx):
+    if kind == "photo":
+        return O.synthetic_image(H, W, idx)
+    if kind == "const":
+        img = np.empty((3, H, W), dtype=np.uint8)
+        img[0], img[1], img[2] = 200, 31, 97
+        return img
+    if kind == "noise":
+        return np.random.default_rng(idx).integers(0, 256, size=(3, H, W), dtype=np.uint8)
+    if kind == "checker":
+        yy, xx = np.mgrid[0:H, 0:W]
+        v = (((yy + xx) & 1) * 255).astype(np.uint8)
+        return np.stack([v, 255 - v, v])
+    raise ValueError(kind)
+
+
+CASES = [
+    # name, config, kind, H, W
+    ("a_photo_33x47", "llicti_A.json", "photo", 33, 47),
+    ("a_photo_53x77", "llicti_A.json", "photo", 53, 77),
+    ("a_photo_64x96", "llicti_A.json", "photo", 64, 96),
+    ("a_const_40x72", "llicti_A.json", "const", 40, 72),
+    ("a_noise_32x64", "llicti_A.json", "noise", 32, 64),
+    ("a_checker_35x32", "llicti_A.json", "checker", 35, 32),
+    ("b_photo_64x96", "llicti_B.json", "photo", 64, 96),
+    ("b_photo_37x53", "llicti_B.json", "photo", 37, 53),
+]
+
+SUB = 7    # stride of the position subsample stored for the float parameter arrays
+TSUB = 37  # stride of the row subsample stored for the integer CDF tables
+
+
+def run_case(name, cfg_name, kind, H, W, idx):
+    cfg = ref_config(cfg_name)
+    ocfg = O.OracleConfig.from_dict(cfg)
+    sd = O.synthetic_state_dict(ocfg, seed=1337)
+    torch.manual_seed(0)
+    model = LLICTI(cfg).eval()
+    missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not unexpected and all("conditional_prob_model" in k for k in missing), (missing, unexpected)
+
+    rgb = make_image(kind, H, W, idx)
+    x = torch.from_numpy(rgb.astype(np.float32) / np.float32(255.0))[None]  # what ToTensor() yields
+    out = {"rgb": rgb, "config": np.array(cfg_name)}
+    S, M = len(cfg.dwtlevels), cfg.num_mixtures
+
+    with torch.no_grad():
+        # --- stage dumps through the reference's own functions -------------------
+        ycc = model.get_YCoCg_R_from_RGB__intOps(x.clone())
+        minmax = [0, ycc[:, 1].min().item(), ycc[:, 2].min().item(), 255, ycc[:, 1].max().item(), ycc[:, 2].max().item()]
+        xc = ycc.clone()
+        xc[:, 0] = xc[:, 0] - 127
+        xf = xc / 255
+        y_list, flags, pad_int = model.lazyDWT(xf, levels=model.list_scales, clrchs=3, clrjnt=2, pad=True)
+        out["ycocg"] = ycc[0].numpy()
+        out["minmax"] = np.array(minmax, dtype=np.int16)
+        out["pad_int"] = np.array(pad_int)
+        out["pad_flags"] = np.array(flags, dtype=np.uint8)
+        for s in range(S):
+            out[f"planes_{s}"] = torch.round(y_list[s][0] * 255).to(torch.int16).numpy()
+
+        # oracle, same stages
+        dump = O.StageDump()
+        codec = O.OracleCodec(ocfg, sd)
+        o_bsl = codec.compress(rgb, dump)
+        assert np.array_equal(dump.ycocg, out["ycocg"]), "ycocg"
+        assert dump.minmax == minmax and dump.pad_int == pad_int and dump.pad_flags == [list(map(bool, f)) for f in flags]
+        for s in range(S):
+            assert np.array_equal(dump.planes[s], out[f"planes_{s}"]), f"planes {s}"
+
+        shifts = [127, -minmax[1], -minmax[2]]
+        for s in range(S - 1, -1, -1):
+            yl = y_list[s]
+            for b in range(3):
+                mdl = model.entropymodel.entmdls_scale_band[0][b]
+                params = mdl.get_params(yl[:, 0:3 * (b + 1)])
+                p_np = params[0].numpy().copy()
+                assert np.array_equal(p_np, dump.params[(s, b)]), f"params {s},{b}"
+                out[f"params_{s}_{b}_digest"] = np.array(digest(p_np))
+                out[f"params_{s}_{b}_sub"] = p_np.reshape(12 * M, -1)[:, ::SUB].copy()
+                aw, bw, dw = params[:, 9 * M:10 * M], params[:, 10 * M:11 * M], params[:, 11 * M:12 * M]
+                padH, padW = flags[s]
+                for clr in range(3):
+                    sig = params[:, clr * M:(clr + 1) * M]
+                    mu = params[:, (3 + clr) * M:(4 + clr) * M]
+                    wt = params[:, (6 + clr) * M:(7 + clr) * M]
+                    if clr == 1:
+                        mu += aw * yl[:, 3 * (b + 1):3 * (b + 1) + 1]
+                    elif clr == 2:
+                        mu += bw * yl[:, 3 * (b + 1):3 * (b + 1) + 1] + dw * yl[:, 3 * (b + 1) + 1:3 * (b + 1) + 2]
+                    lo = -127 if clr == 0 else minmax[clr]
+                    hi = 128 if clr == 0 else minmax[3 + clr]
+                    tab = mdl.get_cdfs(sig, mu, wt, clrch=clr, int_cdf=True, minVal=lo, maxVal=hi)[0, 0].numpy()
+                    ch, cw = O.crop_shape(b, yl.shape[2], yl.shape[3], padH, padW)
+                    t = np.ascontiguousarray(tab[:ch, :cw]).reshape(ch * cw, -1)
+                    assert np.array_equal(t, dump.tables[(s, b, clr)]), f"table {s},{b},{clr}"
+                    out[f"table_{s}_{b}_{clr}_digest"] = np.array(digest(t))
+                    out[f"table_{s}_{b}_{clr}_sub"] = t[::TSUB].copy()
+
+        # --- the reference's own compress / decompres ----------------------------------
+        bsl, _ = model.compress(x.clone())
+        rec = model.decompres(bsl, torch.device("cpu"))
+        err = ((x - rec) * 255).abs().max().item()
+        assert err < 0.5, f"reference did not round-trip: {err}"
+        assert len(bsl) == 1 + S and all(len(r) == 9 for r in bsl)
+        for i, row in enumerate(bsl):
+            for j, blob in enumerate(row):
+                out[f"stream_{i}_{j}"] = np.frombuffer(blob, dtype=np.uint8).copy()
+                assert blob == o_bsl[i][j], f"stream {i},{j} differs between reference and oracle"
+        assert np.array_equal(codec.decompress(bsl), rgb)
+        total = sum(len(b_) for r in bsl for b_ in r)
+        out["total_bytes"] = np.array(total)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {H}x{W} {cfg_name} bytes={total} bpsp={total * 8 / rgb.size:.3f} pad_int={pad_int} "
+          f"minmax={minmax} -> OK (reference == oracle, lossless)")
+
+
+def canary():
+    """Bit patterns of the two host-dependent float primitives (vector erfc, reduction
+    order); tests skip the bit-exact float checks when the running host disagrees."""
+    x = torch.linspace(-6, 6, 4001, dtype=torch.float32)
+    e = torch.erfc(x)
+    w = torch.from_numpy(np.random.default_rng(5).random((1, 37, 53, 1, 5), dtype=np.float32))
+    wp = w.permute(0, 4, 1, 2, 3).contiguous().permute(0, 2, 3, 4, 1)   # layout of the reference's weights
+    s = torch.sum(wp, dim=4)
+    np.savez_compressed(os.path.join(HERE, "canary.npz"), erfc_digest=np.array(digest(e.numpy())),
+                        sum_digest=np.array(digest(s.numpy())))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    canary()
+    for i, c in enumerate(CASES):
+        run_case(*c, idx=i)
+    sz = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
+    print("fixtures total bytes:", sz)
