@@ -1,0 +1,200 @@
+/*
+ * include/llicti.h -- C ABI of libllicti_b200.so (sm_100a).
+ *
+ * The reference (kamisli-icpl/LLICTI) is pure Python/PyTorch and has no FFI seam of
+ * its own; the seam fixed here is the one its hot path would bind through ctypes:
+ * every entry point replaces a stretch of graphs/models/LLICTI_nets.py or
+ * graphs/layers/entropy_layer_nets.py (file:line given per function, paths relative
+ * to the reference root).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross the boundary;
+ *   - every function returns 0 on success or a negative LLICTI_E_* code; the text
+ *     of the last error on the calling thread is llicti_last_error();
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - "dev" pointers are device pointers owned by the caller; stage-level calls
+ *     neither allocate nor synchronise.  Full-path calls use the context's
+ *     workspace (llicti_reserve) and synchronise only in their *_host variants;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Layouts
+ *   rgb      uint8  [n][3][H][W]                       planar (what ToTensor()*255 holds)
+ *   planes_s int16  [n][12][Hs][Ws]  per scale s       phase order x00,x11,x01,x10; 3 colour
+ *                                                      channels each: Y-127, Co, Cg
+ *   params   float  [n][12*M][Hs*Ws]                   channel order of the reference's conv
+ *                                                      output (sigma | mu | w | a b d)
+ *   bounds   uint32 per coded symbol                   c_low | (c_high-1) << 16
+ *   tables   int16  [P][Lp]                            the reference's integer CDF rows
+ */
+#ifndef LLICTI_H
+#define LLICTI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LLICTI_API __attribute__((visibility("default")))
+#else
+#define LLICTI_API
+#endif
+
+#define LLICTI_ABI_VERSION 1
+#define LLICTI_MAX_SCALES 8
+
+enum {
+    LLICTI_OK = 0,
+    LLICTI_E_ARG = -1,      /* bad argument / unsupported configuration   */
+    LLICTI_E_CUDA = -2,     /* a CUDA runtime call failed                 */
+    LLICTI_E_NOMEM = -3,    /* workspace / output capacity too small      */
+    LLICTI_E_STREAM = -4,   /* malformed bitstream                        */
+    LLICTI_E_NODEVICE = -5  /* no usable CUDA device (no CPU fallback)    */
+};
+
+/* Floating-point conventions of the GMM-CDF stage (see DESIGN.md "numerics profile"). */
+enum {
+    LLICTI_NUM_TORCH_CUDA = 0, /* x/255 as x*(1/255), reductions in ATen's 4-accumulator order */
+    LLICTI_NUM_TORCH_CPU = 1   /* x/255 as IEEE division, reductions left to right              */
+};
+
+enum { LLICTI_CNN_FP32 = 0, LLICTI_CNN_TCGEN05 = 1 };
+
+typedef struct llicti_ctx llicti_ctx;
+
+/* The subset of configs/llicti_*.json the eval_model path reads
+ * (LLICTI_nets.py:19-26, 260-278, 590-603). */
+typedef struct {
+    int32_t num_scales;   /* len(dwtlevels); levels must be 0..num_scales-1        */
+    int32_t chs;          /* config.chs[0]: hidden width of each of the 4 sub-nets  */
+    int32_t num_mixtures; /* 5                                                     */
+    int32_t sub_len;      /* 0: one torchac-compatible stream per (scale,band,channel);
+                             >0: interleaved substreams of about sub_len symbols    */
+    int32_t numerics;     /* LLICTI_NUM_*                                          */
+    int32_t cnn_impl;     /* LLICTI_CNN_*                                          */
+    int32_t device;       /* CUDA device ordinal                                   */
+    int32_t reserved;
+} llicti_config;
+
+/* fp32 host pointers in PyTorch's own layouts (state_dict keys in SURVEY.md 8b).
+ * Branch order of l0_*: 00_11 | 00_01, 11_01 | 00_10, 11_10, 01_10. */
+typedef struct {
+    const float *l0_w[6]; /* (4*chs, 3, kh, kw)                      */
+    const float *l0_b[6]; /* (4*chs)                                 */
+    const float *l1_w[3]; /* per band (4*chs, chs)   groups=4 1x1    */
+    const float *l1_b[3]; /* (4*chs)                                 */
+    const float *l2_w[3]; /* per band (12*M, chs)    groups=4 1x1    */
+    const float *l2_b[3]; /* (12*M)                                  */
+} llicti_weights;
+
+/* Geometry of one image size under a configuration (pure host arithmetic;
+ * restates lazyDWT's shape logic LLICTI_nets.py:218-241 and the crop rules :396-397). */
+typedef struct {
+    int32_t H, W, num_scales;
+    int32_t Hs[LLICTI_MAX_SCALES], Ws[LLICTI_MAX_SCALES];     /* x00 size per scale          */
+    int32_t padH[LLICTI_MAX_SCALES], padW[LLICTI_MAX_SCALES]; /* replicate-pad flags         */
+    int32_t pad_int;                                          /* header word (:230)          */
+    int32_t crop_h[LLICTI_MAX_SCALES][3], crop_w[LLICTI_MAX_SCALES][3]; /* coded region per band */
+    int32_t num_sub[LLICTI_MAX_SCALES][3];                    /* substreams per stream       */
+    int64_t positions;                                        /* sum Hs*Ws                   */
+    int64_t symbols;                                          /* coded symbols per image     */
+    int64_t substreams;                                       /* substreams per image (all 9*S streams) */
+    int64_t max_stream_bytes;                                 /* worst-case bytes of all streams of one image */
+} llicti_geom;
+
+LLICTI_API int llicti_abi_version(void);
+LLICTI_API const char *llicti_last_error(void);
+
+/* Number of CUDA devices visible to the library (0 if none; never fails). */
+LLICTI_API int llicti_device_count(void);
+
+LLICTI_API int llicti_geometry(const llicti_config *cfg, int H, int W, llicti_geom *out);
+
+/* Replaces LLICTI(config).to(device) + load_state_dict (LLICTI_nets.py:93-99, agents/base.py:51-81):
+ * packs the weights into the kernels' layouts on the device. */
+LLICTI_API int llicti_create(const llicti_config *cfg, const llicti_weights *w, llicti_ctx **out);
+LLICTI_API void llicti_destroy(llicti_ctx *ctx);
+
+/* Size the context's device workspace for batches of up to max_images images of H x W. */
+LLICTI_API int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W);
+
+/* ---- stage-level entry points (device pointers, asynchronous) ------------------------ */
+
+/* get_YCoCg_R_from_RGB__intOps + min/max + Y-127 + lazyDWT(pad=True)
+ * (LLICTI_nets.py:62-74, 137-139, 143, 218-241).  planes_dev[s] -> int16 [n][12][Hs][Ws];
+ * minmax_dev int32 [n][4] = minCo, minCg, maxCo, maxCg. */
+LLICTI_API int llicti_color_split(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W,
+                       int16_t *const *planes_dev, int32_t *minmax_dev, void *stream);
+
+/* Inverse lazy DWT of the finest scale + Y+127 + get_RGB_from_YCoCg_R__intOps
+ * (LLICTI_nets.py:501-509, 174-175, 77-88): planes0_dev int16 [n][12][Hs0][Ws0] -> rgb. */
+LLICTI_API int llicti_merge_color(llicti_ctx *ctx, const int16_t *planes0_dev, int n, int H, int W,
+                       uint8_t *rgb_dev, void *stream);
+
+/* LLICTIEntropyModel4.get_params (LLICTI_nets.py:822-825, 721-753, 695-712) for band 0..2:
+ * planes_dev int16 [n][12][Hs][Ws] (phases 0..band read) -> params_dev float [n][12*M][Hs*Ws]. */
+LLICTI_API int llicti_cnn_params(llicti_ctx *ctx, int band, const int16_t *planes_dev, int n, int Hs, int Ws,
+                      float *params_dev, void *stream);
+
+/* Mean coupling + get_cdfs(int_cdf=True) (LLICTI_nets.py:389-392, 938-952, 955-983;
+ * entropy_layer_nets.py:185-204) as a dense table, for parity checks only:
+ * params_dev float [12*M][P], yband_dev int16 [3][P] (centred values of the band being
+ * coded) -> table_dev int16 [P][Lp], Lp = max_val - min_val + 2. */
+LLICTI_API int llicti_cdf_table(llicti_ctx *ctx, const float *params_dev, const int16_t *yband_dev, int clr,
+                     int min_val, int max_val, int P, int16_t *table_dev, void *stream);
+
+/* Same stage, table-free: only the two entries the coder needs per symbol.
+ * sym = yband + shift (LLICTI_nets.py:544-557); bounds_dev[i] = c_low | (c_high-1)<<16. */
+LLICTI_API int llicti_cdf_bounds(llicti_ctx *ctx, const float *params_dev, const int16_t *yband_dev, int clr,
+                      int min_val, int max_val, int P, uint32_t *bounds_dev, void *stream);
+
+/* torchac.encode_int16_normalized_cdf (call site LLICTI_nets.py:406-407) over S interleaved
+ * substreams (S = 1: the torchac bitstream).  Substream j codes symbols j, j+S, ...  into
+ * out_dev + j*slot_bytes; lens_dev[j] receives its byte count. */
+LLICTI_API int llicti_ac_encode_bounds(llicti_ctx *ctx, const uint32_t *bounds_dev, int n_sym, int S,
+                            uint8_t *out_dev, int slot_bytes, uint32_t *lens_dev, void *stream);
+
+/* torchac.decode_int16_normalized_cdf (call site LLICTI_nets.py:492-493) from a dense table:
+ * table_dev int16 [n_sym][Lp]; substream j is in_dev[offs_dev[j] .. offs_dev[j+1]). */
+LLICTI_API int llicti_ac_decode_table(llicti_ctx *ctx, const int16_t *table_dev, int n_sym, int Lp, int S,
+                           const uint8_t *in_dev, const uint32_t *offs_dev, int16_t *sym_dev,
+                           void *stream);
+
+/* ---- full path ---------------------------------------------------------------------- */
+
+/* LLICTI.compress for a batch (LLICTI_nets.py:125-159, 344-413).
+ *   rgb          uint8 [n][3][H][W], host (pinned or pageable) or device memory
+ *   out          receives the 9*num_scales stream blobs of every image, image-major, in
+ *                bytestream_list order (scale S-1..0, index 3*band+clr)
+ *   stream_off   uint64 [n*9*S + 1] byte offsets into out (last = total)
+ *   minmax       int16 [n][6] header words (0,minCo,minCg,255,maxCo,maxCg)   (:139, :348)
+ * The header's remaining pieces (dims, pad word, raw x00) are functions of the input and
+ * the geometry and are assembled by the host wrapper.  *_host copies in and out on
+ * `stream` and returns after the stream is idle; *_dev takes device pointers and is
+ * asynchronous (stream_off / minmax then are device pointers too). */
+LLICTI_API int llicti_encode_host(llicti_ctx *ctx, const uint8_t *rgb, int n, int H, int W, uint8_t *out,
+                       size_t out_cap, uint64_t *stream_off, int16_t *minmax, void *stream);
+LLICTI_API int llicti_encode_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, uint8_t *out_dev,
+                      size_t out_cap, uint64_t *stream_off_dev, int16_t *minmax_dev, void *stream);
+
+/* LLICTI.decompres for a batch (LLICTI_nets.py:161-179, 415-509).
+ *   blob / stream_off  as produced by encode
+ *   minmax             int16 [n][6]
+ *   x00_rgb            uint8 [n][3][h_last][w_last] raw coarsest band (:350, :429)
+ *   rgb_out            uint8 [n][3][H][W] */
+LLICTI_API int llicti_decode_host(llicti_ctx *ctx, const uint8_t *blob, const uint64_t *stream_off,
+                       const int16_t *minmax, const uint8_t *x00_rgb, int n, int H, int W,
+                       uint8_t *rgb_out, void *stream);
+LLICTI_API int llicti_decode_dev(llicti_ctx *ctx, const uint8_t *blob_dev, const uint64_t *stream_off_dev,
+                      const int16_t *minmax_dev, const uint8_t *x00_rgb_dev, int n, int H, int W,
+                      uint8_t *rgb_out_dev, void *stream);
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+LLICTI_API int64_t llicti_launch_count(const llicti_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLICTI_H */

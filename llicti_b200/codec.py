@@ -1,0 +1,268 @@
+"""Host-side handle on one libllicti_b200 context (one per process / GPU).
+
+`Codec` owns the C context, turns a reference-format state_dict into the C weight struct,
+assembles / parses the reference's `bytestream_list` around the batch entry points, and
+exposes the stage-level calls used by the parity tests.  torch is used for device memory and
+streams only; every computation happens inside the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import container
+
+PREFIX = "entropymodel.entmdls_scale_band.0."
+# branch order of llicti_weights.l0_* (include/llicti.h)
+L0_NAMES = [(0, "layer0_00_11"), (1, "layer0_00_01"), (1, "layer0_11_01"),
+            (2, "layer0_00_10"), (2, "layer0_11_10"), (2, "layer0_01_10")]
+L0_SHAPES = {"layer0_00_11": (4, 4), "layer0_00_01": (3, 4), "layer0_11_01": (4, 3),
+             "layer0_00_10": (4, 3), "layer0_11_10": (3, 4), "layer0_01_10": (4, 4)}
+
+
+@dataclass
+class CodecConfig:
+    """What the eval_model path reads from configs/llicti_*.json plus this repo's knobs."""
+    num_scales: int = 5
+    chs: int = 88
+    num_mixtures: int = 5
+    sub_len: int = 0                 # 0 = torchac-compatible streams; >0 = interleaved substreams
+    numerics: int = L.NUM_TORCH_CUDA
+    cnn_impl: int = L.CNN_FP32
+    device: int = 0
+
+    @staticmethod
+    def from_json_dict(cfg, **over) -> "CodecConfig":
+        """Validate the model hyper-parameters exactly as far as the CUDA path supports them
+        (the shipped llicti_A / llicti_B settings; everything else is a dead branch in the
+        reference)."""
+        def need(cond, what):
+            if not cond:
+                raise ValueError(f"unsupported configuration for the B200 path: {what}")
+        need(cfg["clrchs"] == 3 and cfg["clr_joint_mode"] == 2, "clrchs=3, clr_joint_mode=2 required")
+        need(bool(cfg["ycocg"]) and not cfg["mwsa_joint"], "ycocg=true, mwsa_joint=false required")
+        need(cfg["conv_layers"] == 3 and not cfg["combine_layers1toL"], "conv_layers=3, combine_layers1toL=false")
+        need(not cfg["subtract_mean"] and cfg["activfun"] == "ReLU", "subtract_mean=false, activfun=ReLU")
+        need(cfg["distribution"] == "normal" and cfg["num_mixtures"] == 5, "5-component normal mixture")
+        need(cfg["lif_prec_bits"] == 8 and cfg["ent_mdl_num"] == 4, "lif_prec_bits=8, ent_mdl_num=4")
+        lv = list(cfg["dwtlevels"])
+        need(lv == list(range(len(lv))) and 1 <= len(lv) <= L.MAX_SCALES, "dwtlevels must be 0..S-1")
+        need(all(cfg["useprevlevNN"][1:len(lv)]), "one shared model set over scales (useprevlevNN)")
+        need(all(e == 4 for e in cfg["Evens"][:len(lv)]) and all(o == 3 for o in cfg["Odds"][:len(lv)]), "Evens=4, Odds=3")
+        need(int(cfg["chs"][0]) in (88, 60), "chs[0] must be 88 or 60")
+        return CodecConfig(num_scales=len(lv), chs=int(cfg["chs"][0]), **over)
+
+
+def _as_f32(v) -> np.ndarray:
+    if isinstance(v, torch.Tensor):
+        v = v.detach().cpu().numpy()
+    return np.ascontiguousarray(v, dtype=np.float32)
+
+
+class Codec:
+    def __init__(self, cfg: CodecConfig, state_dict: Dict[str, "np.ndarray | torch.Tensor"]):
+        self.lib = L.load()
+        if not torch.cuda.is_available() or self.lib.llicti_device_count() <= 0:
+            raise RuntimeError("llicti_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device("cuda", cfg.device)
+        g = cfg.chs
+        keep = []            # keep the numpy buffers alive during llicti_create
+        w = L.Weights()
+        for i, (band, name) in enumerate(L0_NAMES):
+            kh, kw = L0_SHAPES[name]
+            a = _as_f32(state_dict[f"{PREFIX}{band}.{name}.weight"])
+            b = _as_f32(state_dict[f"{PREFIX}{band}.{name}.bias"])
+            if a.shape != (4 * g, 3, kh, kw) or b.shape != (4 * g,):
+                raise ValueError(f"{name}: unexpected shape {a.shape}")
+            keep += [a, b]
+            w.l0_w[i], w.l0_b[i] = a.ctypes.data, b.ctypes.data
+        for band in range(3):
+            a1 = _as_f32(state_dict[f"{PREFIX}{band}.layers1toL.0.weight"]).reshape(4 * g, g)
+            b1 = _as_f32(state_dict[f"{PREFIX}{band}.layers1toL.0.bias"])
+            a2 = _as_f32(state_dict[f"{PREFIX}{band}.layers1toL.2.weight"]).reshape(12 * cfg.num_mixtures, g)
+            b2 = _as_f32(state_dict[f"{PREFIX}{band}.layers1toL.2.bias"])
+            keep += [a1, b1, a2, b2]
+            w.l1_w[band], w.l1_b[band] = a1.ctypes.data, b1.ctypes.data
+            w.l2_w[band], w.l2_b[band] = a2.ctypes.data, b2.ctypes.data
+        self._ccfg = L.Config(cfg.num_scales, cfg.chs, cfg.num_mixtures, cfg.sub_len, cfg.numerics, cfg.cnn_impl,
+                              cfg.device, 0)
+        self._ctx = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.llicti_create(C.byref(self._ccfg), C.byref(w), C.byref(self._ctx)))
+        self._reserved = (0, 0, 0)
+        del keep
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.lib.llicti_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- geometry / workspace -------------------------------------------------------------
+    def geometry(self, H: int, W: int) -> L.Geom:
+        g = L.Geom()
+        L.check(self.lib.llicti_geometry(C.byref(self._ccfg), H, W, C.byref(g)))
+        return g
+
+    def reserve(self, n: int, H: int, W: int):
+        cur_n, cur_h, cur_w = self._reserved
+        if (H, W) != (cur_h, cur_w) or n > cur_n:
+            L.check(self.lib.llicti_reserve(self._ctx, n, H, W))
+            self._reserved = (n, H, W)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.llicti_launch_count(self._ctx))
+
+    # -- full path, host buffers (the timed end-to-end call) -------------------------------
+    def encode_host(self, rgb: np.ndarray, out: Optional[np.ndarray] = None):
+        """rgb uint8 [n,3,H,W] host array (pinned or pageable).  Returns (blob view, stream_off
+        uint64 [n*9S+1], minmax int16 [n,6])."""
+        assert rgb.dtype == np.uint8 and rgb.ndim == 4 and rgb.shape[1] == 3 and rgb.flags.c_contiguous
+        n, _, H, W = rgb.shape
+        self.reserve(n, H, W)
+        g = self.geometry(H, W)
+        ns = 9 * self.cfg.num_scales
+        cap = n * int(g.max_stream_bytes)
+        if out is None or out.nbytes < cap:
+            out = np.empty(cap, dtype=np.uint8)
+        off = np.empty(n * ns + 1, dtype=np.uint64)
+        mm = np.empty((n, 6), dtype=np.int16)
+        L.check(self.lib.llicti_encode_host(self._ctx, rgb.ctypes.data, n, H, W, out.ctypes.data, out.nbytes,
+                                            off.ctypes.data, mm.ctypes.data, self._stream()))
+        return out[:int(off[-1])], off, mm
+
+    def decode_host(self, blob: np.ndarray, off: np.ndarray, mm: np.ndarray, x00: np.ndarray, n: int, H: int, W: int,
+                    out: Optional[np.ndarray] = None) -> np.ndarray:
+        self.reserve(n, H, W)
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        mm = np.ascontiguousarray(mm, dtype=np.int16)
+        x00 = np.ascontiguousarray(x00, dtype=np.uint8)
+        if out is None:
+            out = np.empty((n, 3, H, W), dtype=np.uint8)
+        L.check(self.lib.llicti_decode_host(self._ctx, blob.ctypes.data, off.ctypes.data, mm.ctypes.data,
+                                            x00.ctypes.data, n, H, W, out.ctypes.data, self._stream()))
+        return out
+
+    # -- full path, device buffers (asynchronous) --------------------------------------------
+    def encode_dev(self, rgb: torch.Tensor):
+        """rgb uint8 [n,3,H,W] CUDA tensor.  Returns CUDA tensors (blob, stream_off, minmax)."""
+        assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
+        n, _, H, W = rgb.shape
+        self.reserve(n, H, W)
+        g = self.geometry(H, W)
+        ns = 9 * self.cfg.num_scales
+        blob = torch.empty(n * int(g.max_stream_bytes), dtype=torch.uint8, device=self.device)
+        off = torch.empty(n * ns + 1, dtype=torch.int64, device=self.device)
+        mm = torch.empty((n, 6), dtype=torch.int16, device=self.device)
+        L.check(self.lib.llicti_encode_dev(self._ctx, rgb.data_ptr(), n, H, W, blob.data_ptr(), blob.numel(),
+                                           off.data_ptr(), mm.data_ptr(), self._stream()))
+        return blob, off, mm
+
+    def decode_dev(self, blob: torch.Tensor, off: torch.Tensor, mm: torch.Tensor, x00: torch.Tensor, n: int, H: int,
+                   W: int) -> torch.Tensor:
+        self.reserve(n, H, W)
+        out = torch.empty((n, 3, H, W), dtype=torch.uint8, device=self.device)
+        L.check(self.lib.llicti_decode_dev(self._ctx, blob.data_ptr(), off.data_ptr(), mm.data_ptr(), x00.data_ptr(),
+                                           n, H, W, out.data_ptr(), self._stream()))
+        return out
+
+    # -- bytestream_list assembly (LLICTI_nets.py:346-354, 409-411) ----------------------------
+    def to_bytestream_lists(self, rgb: np.ndarray, blob: np.ndarray, off: np.ndarray, mm: np.ndarray):
+        S = self.cfg.num_scales
+        g = self.geometry(rgb.shape[2], rgb.shape[3])
+        return container.assemble(S, self.cfg.sub_len, g.Hs[S - 1], g.Ws[S - 1], g.pad_int, rgb, blob, off, mm)
+
+    def from_bytestream_lists(self, bsls: Sequence):
+        """Parse headers; returns (blob, off, minmax, x00, n, H, W)."""
+        return container.parse(self.cfg.num_scales, self.cfg.sub_len, bsls)
+
+    def compress_images(self, rgb: np.ndarray):
+        """uint8 [n,3,H,W] -> list of n bytestream_lists."""
+        blob, off, mm = self.encode_host(rgb)
+        return self.to_bytestream_lists(rgb, blob, off, mm)
+
+    def decompress_images(self, bsls: Sequence) -> np.ndarray:
+        blob, off, mm, x00, n, H, W = self.from_bytestream_lists(bsls)
+        return self.decode_host(blob, off, mm, x00, n, H, W)
+
+    # -- stage-level calls (parity tests) --------------------------------------------------------
+    def color_split(self, rgb: torch.Tensor):
+        n, _, H, W = rgb.shape
+        g = self.geometry(H, W)
+        S = self.cfg.num_scales
+        planes = [torch.empty((n, 12, g.Hs[s], g.Ws[s]), dtype=torch.int16, device=self.device) for s in range(S)]
+        mm = torch.empty((n, 4), dtype=torch.int32, device=self.device)
+        ptrs = (C.c_void_p * S)(*[p.data_ptr() for p in planes])
+        L.check(self.lib.llicti_color_split(self._ctx, rgb.data_ptr(), n, H, W, ptrs, mm.data_ptr(), self._stream()))
+        return planes, mm
+
+    def merge_color(self, planes0: torch.Tensor, H: int, W: int) -> torch.Tensor:
+        n = planes0.shape[0]
+        out = torch.empty((n, 3, H, W), dtype=torch.uint8, device=self.device)
+        L.check(self.lib.llicti_merge_color(self._ctx, planes0.data_ptr(), n, H, W, out.data_ptr(), self._stream()))
+        return out
+
+    def cnn_params(self, band: int, planes: torch.Tensor) -> torch.Tensor:
+        assert planes.dtype == torch.int16 and planes.is_cuda and planes.is_contiguous() and planes.shape[1] == 12
+        n, _, Hs, Ws = planes.shape
+        out = torch.empty((n, 12 * self.cfg.num_mixtures, Hs, Ws), dtype=torch.float32, device=self.device)
+        L.check(self.lib.llicti_cnn_params(self._ctx, band, planes.data_ptr(), n, Hs, Ws, out.data_ptr(), self._stream()))
+        return out
+
+    def cdf_table(self, params: torch.Tensor, yband: torch.Tensor, clr: int, min_val: int, max_val: int) -> torch.Tensor:
+        """params float [60,P], yband int16 [3,P] -> int16 [P, Lp]."""
+        P = params.shape[1]
+        Lp = max_val - min_val + 2
+        out = torch.empty((P, Lp), dtype=torch.int16, device=self.device)
+        L.check(self.lib.llicti_cdf_table(self._ctx, params.data_ptr(), yband.data_ptr(), clr, min_val, max_val, P,
+                                          out.data_ptr(), self._stream()))
+        return out
+
+    def cdf_bounds(self, params: torch.Tensor, yband: torch.Tensor, clr: int, min_val: int, max_val: int) -> torch.Tensor:
+        P = params.shape[1]
+        out = torch.empty(P, dtype=torch.int32, device=self.device)
+        L.check(self.lib.llicti_cdf_bounds(self._ctx, params.data_ptr(), yband.data_ptr(), clr, min_val, max_val, P,
+                                           out.data_ptr(), self._stream()))
+        return out
+
+    def ac_encode_bounds(self, bounds: torch.Tensor, S: int = 1) -> List[bytes]:
+        """bounds int32/uint32 [n_sym] on device -> list of S substream payloads."""
+        n_sym = bounds.numel()
+        per = -(-n_sym // S)
+        slot = (2 * per + per // 64 + 16 + 15) // 16 * 16
+        out = torch.empty(S * slot, dtype=torch.uint8, device=self.device)
+        lens = torch.empty(S, dtype=torch.int32, device=self.device)
+        L.check(self.lib.llicti_ac_encode_bounds(self._ctx, bounds.data_ptr(), n_sym, S, out.data_ptr(), slot,
+                                                 lens.data_ptr(), self._stream()))
+        out_h, lens_h = out.cpu().numpy(), lens.cpu().numpy()
+        return [out_h[j * slot:j * slot + int(lens_h[j])].tobytes() for j in range(S)]
+
+    def ac_decode_table(self, table: torch.Tensor, parts: List[bytes]) -> torch.Tensor:
+        """table int16 [n_sym, Lp] on device, parts = S substream payloads -> int16 [n_sym]."""
+        n_sym, Lp = table.shape
+        S = len(parts)
+        offs = np.zeros(S + 1, dtype=np.uint32)
+        offs[1:] = np.cumsum([len(p) for p in parts])
+        blob = np.frombuffer(b"".join(parts) + b"\0", dtype=np.uint8)
+        d_blob = torch.from_numpy(blob.copy()).to(self.device)
+        d_offs = torch.from_numpy(offs.astype(np.int32)).to(self.device)
+        sym = torch.empty(n_sym, dtype=torch.int16, device=self.device)
+        L.check(self.lib.llicti_ac_decode_table(self._ctx, table.data_ptr(), n_sym, Lp, S, d_blob.data_ptr(),
+                                                d_offs.data_ptr(), sym.data_ptr(), self._stream()))
+        return sym

@@ -1,0 +1,96 @@
+"""Pure host logic around the reference's `bytestream_list` (no GPU needed):
+header assembly / parsing (LLICTI_nets.py:346-354, 420-431, 533-542) and the flat
+(blob, offsets) form the C ABI works on."""
+from typing import Sequence
+
+import numpy as np
+
+
+def mode_tag(sub_len: int) -> bytes:
+    """Header slot 4 (b'' in the reference): b'' = torchac-compatible streams, otherwise
+    [1, sub_len as u32 LE] = interleaved-substream container."""
+    if sub_len <= 0:
+        return b""
+    return bytes([1]) + int(sub_len).to_bytes(4, "little")
+
+
+def parse_mode_tag(tag: bytes) -> int:
+    if len(tag) == 0:
+        return 0
+    if len(tag) != 5 or tag[0] != 1:
+        raise ValueError("unknown container tag in header slot 4")
+    return int.from_bytes(tag[1:5], "little")
+
+
+def image_size_from_header(num_scales: int, h_last: int, w_last: int, pad_int: int):
+    """Undo the pyramid's size bookkeeping: H_{s-1} = 2*H_s - padH_s (pad word has level 0 in
+    its most significant bit pair, LLICTI_nets.py:230)."""
+    h, w = h_last, w_last
+    for s in range(num_scales - 1, -1, -1):
+        bits = (pad_int >> (2 * (num_scales - 1 - s))) & 3
+        h, w = 2 * h - (bits >> 1), 2 * w - (bits & 1)
+    return h, w
+
+
+def assemble(num_scales: int, sub_len: int, h_last: int, w_last: int, pad_int: int, rgb: np.ndarray,
+             blob, off: np.ndarray, minmax: np.ndarray):
+    """(blob, off, minmax) of a batch -> list of bytestream_lists
+    [[hdr(3B), minmax(12B), pad(2B), x00 raw RGB, tag, b'' x4], 9 streams per scale S-1..0]."""
+    n = rgb.shape[0]
+    S = num_scales
+    st = 2 ** S
+    blob_b = blob.tobytes() if isinstance(blob, np.ndarray) else bytes(blob)
+    out = []
+    for i in range(n):
+        hdr = [bytes([S, h_last, w_last]),
+               np.asarray(minmax[i], dtype=np.int16).tobytes(),
+               np.array([pad_int & 0xFFFF], dtype=np.uint16).tobytes(),
+               np.ascontiguousarray(rgb[i, :, 0::st, 0::st]).tobytes(),
+               mode_tag(sub_len), b"", b"", b"", b""]
+        rows = [hdr]
+        for r in range(S):
+            base = i * 9 * S + r * 9
+            rows.append([blob_b[int(off[base + j]):int(off[base + j + 1])] for j in range(9)])
+        out.append(rows)
+    return out
+
+
+def parse(num_scales: int, sub_len: int, bsls: Sequence):
+    """list of bytestream_lists -> (blob u8, off u64 [n*9S+1], minmax i16 [n,6], x00 u8
+    [n,3,h,w], n, H, W).  Raises ValueError on inconsistent headers."""
+    S = num_scales
+    n = len(bsls)
+    if n == 0:
+        raise ValueError("empty batch")
+    dims = None
+    mm = np.empty((n, 6), dtype=np.int16)
+    x00s, parts, offs, pos = [], [], [0], 0
+    for i, bsl in enumerate(bsls):
+        hdr = bsl[0]
+        ns, h_last, w_last = (int(v) for v in np.frombuffer(hdr[0], dtype=np.uint8))
+        if ns != S or len(bsl) != S + 1:
+            raise ValueError(f"stream has {ns} scales, model has {S}")               # LLICTI_nets.py:424
+        got = parse_mode_tag(hdr[4] if len(hdr) > 4 else b"")
+        if got != sub_len:
+            raise ValueError(f"stream coded with sub_len={got}, codec configured with {sub_len}")
+        mm[i] = np.frombuffer(hdr[1], dtype=np.int16)
+        pad_int = int(np.frombuffer(hdr[2], dtype=np.uint16)[0])
+        hw = image_size_from_header(S, h_last, w_last, pad_int)
+        if dims is None:
+            dims = hw
+        elif dims != hw:
+            raise ValueError("all images of a batch must have the same size")
+        if len(hdr[3]) != 3 * h_last * w_last:
+            raise ValueError("raw coarsest band has the wrong length")
+        x00s.append(np.frombuffer(hdr[3], dtype=np.uint8).reshape(3, h_last, w_last))
+        for r in range(1, S + 1):
+            if len(bsl[r]) != 9:
+                raise ValueError("expected 9 streams per scale")
+            for j in range(9):
+                parts.append(bsl[r][j])
+                pos += len(bsl[r][j])
+                offs.append(pos)
+    blob = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    if blob.size == 0:
+        blob = np.zeros(1, dtype=np.uint8)
+    return blob, np.array(offs, dtype=np.uint64), mm, np.stack(x00s), n, dims[0], dims[1]

@@ -1,0 +1,426 @@
+// C ABI of libllicti_b200.so: context, geometry, weight packing, workspace and the host-side
+// sequencing of the kernels for the full compress / decompress path.  See include/llicti.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace llicti {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_substreams(int64_t n, int sub_len) {
+    if (sub_len <= 0) return 1;
+    int64_t s = std::max<int64_t>(1, (n + sub_len - 1) / sub_len);
+    if (s > 32) s = (s + 31) / 32 * 32;
+    return (int)std::min<int64_t>(s, 65535);
+}
+
+int make_plan(const llicti_config &cfg, int H, int W, Plan *out) {
+    LLICTI_REQUIRE(cfg.num_scales >= 1 && cfg.num_scales <= LLICTI_MAX_SCALES, "num_scales %d out of range", cfg.num_scales);
+    LLICTI_REQUIRE(cfg.num_mixtures == kM, "num_mixtures must be %d", kM);
+    LLICTI_REQUIRE(cfg.sub_len >= 0 && cfg.sub_len <= 16384, "sub_len %d out of range [0, 16384]", cfg.sub_len);
+    Plan &p = *out;
+    memset(&p, 0, sizeof(p));
+    llicti_geom &g = p.g;
+    g.H = H; g.W = W; g.num_scales = cfg.num_scales;
+    int hin = H, win = W;
+    for (int s = 0; s < cfg.num_scales; ++s) {
+        LLICTI_REQUIRE(hin >= 2 && win >= 2, "image %dx%d too small for %d scales", H, W, cfg.num_scales);
+        g.Hs[s] = (hin + 1) / 2; g.Ws[s] = (win + 1) / 2;
+        g.padH[s] = g.Hs[s] > hin / 2; g.padW[s] = g.Ws[s] > win / 2;
+        g.pad_int = 4 * g.pad_int + 2 * g.padH[s] + g.padW[s];
+        for (int b = 0; b < 3; ++b) {
+            g.crop_h[s][b] = (b == 0 || b == 2) ? g.Hs[s] - g.padH[s] : g.Hs[s];
+            g.crop_w[s][b] = (b == 0 || b == 1) ? g.Ws[s] - g.padW[s] : g.Ws[s];
+            g.num_sub[s][b] = num_substreams((int64_t)g.crop_h[s][b] * g.crop_w[s][b], cfg.sub_len);
+        }
+        g.positions += (int64_t)g.Hs[s] * g.Ws[s];
+        p.plane_elems[s] = 12ll * g.Hs[s] * g.Ws[s];
+        hin = g.Hs[s]; win = g.Ws[s];
+    }
+    // the reference stores the coarsest size in two uint8 (LLICTI_nets.py:347)
+    LLICTI_REQUIRE(g.Hs[cfg.num_scales - 1] <= 255 && g.Ws[cfg.num_scales - 1] <= 255,
+                   "coarsest band %dx%d does not fit the header's uint8 fields", g.Hs[cfg.num_scales - 1],
+                   g.Ws[cfg.num_scales - 1]);
+    p.n_streams = 9 * cfg.num_scales;
+    int64_t sym = 0, slot = 0;
+    int sub = 0;
+    int k = 0;
+    for (int s = cfg.num_scales - 1; s >= 0; --s)
+        for (int b = 0; b < 3; ++b)
+            for (int c = 0; c < 3; ++c, ++k) {
+                StreamDesc &d = p.sd[k];
+                d.scale = s; d.band = b; d.clr = c;
+                d.Hs = g.Hs[s]; d.Ws = g.Ws[s];
+                d.crop_h = g.crop_h[s][b]; d.crop_w = g.crop_w[s][b];
+                d.n_sym = d.crop_h * d.crop_w;
+                d.S = g.num_sub[s][b];
+                d.sub_first = sub;
+                const int per = (d.n_sym + d.S - 1) / d.S;
+                d.slot_bytes = (2 * per + per / 64 + 16 + 15) / 16 * 16;
+                d.sym_off = sym;
+                d.slot_off = slot;
+                sym += d.n_sym;
+                sub += d.S;
+                slot += (int64_t)d.S * d.slot_bytes;
+                g.max_stream_bytes += (cfg.sub_len > 0 ? 2 + 2 * d.S : 0) + (int64_t)d.S * d.slot_bytes;
+            }
+    g.symbols = sym;
+    g.substreams = sub;
+    p.scratch_bytes = slot;
+    return LLICTI_OK;
+}
+
+// Layer-0 branches in the order of llicti_weights.l0_*: source phase, kernel size, left/top pad.
+struct BranchDef { int band, phase, kh, kw, padl, padt; };
+static const BranchDef kBranches[6] = {
+    {0, 0, 4, 4, 1, 1},   // layer0_00_11  LLICTI_nets.py:651-652
+    {1, 0, 3, 4, 1, 1},   // layer0_00_01  :659-660
+    {1, 1, 4, 3, 1, 2},   // layer0_11_01  :661-662
+    {2, 0, 4, 3, 1, 1},   // layer0_00_10  :670-671
+    {2, 1, 3, 4, 2, 1},   // layer0_11_10  :672-673
+    {2, 2, 4, 4, 2, 1},   // layer0_01_10  :674-675
+};
+
+static int upload(const std::vector<float> &h, float **d) {
+    LLICTI_CUDA(cudaMalloc((void **)d, h.size() * sizeof(float)));
+    LLICTI_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return LLICTI_OK;
+}
+
+static int pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
+    const int G = ctx->cfg.chs, Ch = 4 * G, GP = G + 8;
+    for (int band = 0; band < 3; ++band) {
+        TapTable &t = ctx->taps[band];
+        memset(&t, 0, sizeof(t));
+        int K0 = 0;
+        for (int br = 0; br < 6; ++br)
+            if (kBranches[br].band == band) K0 += 3 * kBranches[br].kh * kBranches[br].kw;
+        LLICTI_REQUIRE(K0 <= 128, "layer-0 depth %d too large", K0);
+        t.K0 = K0;
+        std::vector<float> w0((size_t)4 * K0 * GP, 0.f), b0(Ch, 0.f);
+        int k = 0;
+        for (int br = 0; br < 6; ++br) {
+            const BranchDef &bd = kBranches[br];
+            if (bd.band != band) continue;
+            LLICTI_REQUIRE(w.l0_w[br] && w.l0_b[br], "missing layer-0 weights of branch %d", br);
+            for (int c = 0; c < 3; ++c)
+                for (int dy = 0; dy < bd.kh; ++dy)
+                    for (int dx = 0; dx < bd.kw; ++dx, ++k) {
+                        t.phase[k] = (int8_t)bd.phase; t.chan[k] = (int8_t)c;
+                        t.dy[k] = (int8_t)(dy - bd.padt); t.dx[k] = (int8_t)(dx - bd.padl);
+                        for (int ch = 0; ch < Ch; ++ch)
+                            w0[((size_t)(ch / G) * K0 + k) * GP + ch % G] =
+                                w.l0_w[br][(((size_t)ch * 3 + c) * bd.kh + dy) * bd.kw + dx];
+                    }
+            for (int ch = 0; ch < Ch; ++ch) b0[ch] += w.l0_b[br][ch];
+        }
+        LLICTI_REQUIRE(w.l1_w[band] && w.l1_b[band] && w.l2_w[band] && w.l2_b[band], "missing 1x1 weights of band %d", band);
+        std::vector<float> w1((size_t)4 * G * GP, 0.f), b1(w.l1_b[band], w.l1_b[band] + Ch);
+        for (int g = 0; g < 4; ++g)
+            for (int o = 0; o < G; ++o)
+                for (int i = 0; i < G; ++i) w1[((size_t)g * G + i) * GP + o] = w.l1_w[band][(size_t)(g * G + o) * G + i];
+        std::vector<float> w2((size_t)4 * G * 16, 0.f), b2(w.l2_b[band], w.l2_b[band] + kParamCh);
+        for (int g = 0; g < 4; ++g)
+            for (int o = 0; o < 15; ++o)
+                for (int i = 0; i < G; ++i) w2[((size_t)g * G + i) * 16 + o] = w.l2_w[band][(size_t)(g * 15 + o) * G + i];
+        BandWeightsF32 &bw = ctx->wf32[band];
+        bw.K0 = K0;
+        int rc;
+        if ((rc = upload(w0, &bw.w0)) || (rc = upload(b0, &bw.b0)) || (rc = upload(w1, &bw.w1)) ||
+            (rc = upload(b1, &bw.b1)) || (rc = upload(w2, &bw.w2)) || (rc = upload(b2, &bw.b2)))
+            return rc;
+    }
+    return LLICTI_OK;
+}
+
+static void free_workspace(llicti_ctx *ctx) {
+    cudaFree(ctx->d_sd); ctx->d_sd = nullptr;
+    cudaFree(ctx->d_rgb); ctx->d_rgb = nullptr;
+    for (auto &p : ctx->d_planes) { cudaFree(p); p = nullptr; }
+    cudaFree(ctx->d_minmax); ctx->d_minmax = nullptr;
+    cudaFree(ctx->d_minmax16); ctx->d_minmax16 = nullptr;
+    cudaFree(ctx->d_params); ctx->d_params = nullptr;
+    cudaFree(ctx->d_bounds); ctx->d_bounds = nullptr;
+    cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr;
+    cudaFree(ctx->d_sublen); ctx->d_sublen = nullptr;
+    cudaFree(ctx->d_suboff); ctx->d_suboff = nullptr;
+    cudaFree(ctx->d_stream_bytes); ctx->d_stream_bytes = nullptr;
+    cudaFree(ctx->d_stream_off); ctx->d_stream_off = nullptr;
+    cudaFree(ctx->d_blob); ctx->d_blob = nullptr;
+    cudaFree(ctx->d_x00); ctx->d_x00 = nullptr;
+    ctx->ws_images = 0;
+}
+
+static int check_batch(llicti_ctx *ctx, int n, int H, int W) {
+    LLICTI_REQUIRE(ctx, "null context");
+    LLICTI_REQUIRE(ctx->ws_images > 0, "llicti_reserve has not been called");
+    LLICTI_REQUIRE(n >= 1 && n <= ctx->ws_images && H == ctx->ws_H && W == ctx->ws_W,
+                   "batch %d x %dx%d does not fit the reserved workspace %d x %dx%d", n, H, W, ctx->ws_images,
+                   ctx->ws_H, ctx->ws_W);
+    return LLICTI_OK;
+}
+
+static int read_status(llicti_ctx *ctx, cudaStream_t st) {
+    int32_t s = 0;
+    LLICTI_CUDA(cudaMemcpyAsync(&s, ctx->d_status, sizeof(s), cudaMemcpyDeviceToHost, st));
+    LLICTI_CUDA(cudaStreamSynchronize(st));
+    if (s != 0) {
+        int32_t zero = 0;
+        cudaMemcpyAsync(ctx->d_status, &zero, sizeof(zero), cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+        set_error(s == LLICTI_E_NOMEM ? "device-side capacity overflow while coding" : "malformed bitstream container");
+    }
+    return s;
+}
+
+static int cnn(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params, cudaStream_t st) {
+    if (ctx->cfg.cnn_impl == LLICTI_CNN_FP32) return launch_cnn_fp32(ctx, band, planes, n, Hs, Ws, params, st);
+    set_error("cnn_impl %d is not built into this library", ctx->cfg.cnn_impl);
+    return LLICTI_E_ARG;
+}
+
+}  // namespace llicti
+
+using namespace llicti;
+
+extern "C" {
+
+int llicti_abi_version(void) { return LLICTI_ABI_VERSION; }
+const char *llicti_last_error(void) { return g_err; }
+
+int llicti_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int llicti_geometry(const llicti_config *cfg, int H, int W, llicti_geom *out) {
+    LLICTI_REQUIRE(cfg && out, "null argument");
+    Plan p;
+    const int rc = make_plan(*cfg, H, W, &p);
+    if (rc) return rc;
+    *out = p.g;
+    return LLICTI_OK;
+}
+
+int llicti_create(const llicti_config *cfg, const llicti_weights *w, llicti_ctx **out) {
+    LLICTI_REQUIRE(cfg && w && out, "null argument");
+    LLICTI_REQUIRE(cfg->chs == 88 || cfg->chs == 60, "chs must be 88 or 60 (got %d)", cfg->chs);
+    LLICTI_REQUIRE(cfg->num_mixtures == kM, "num_mixtures must be %d", kM);
+    LLICTI_REQUIRE(cfg->num_scales >= 1 && cfg->num_scales <= LLICTI_MAX_SCALES, "num_scales out of range");
+    LLICTI_REQUIRE(cfg->numerics == LLICTI_NUM_TORCH_CUDA || cfg->numerics == LLICTI_NUM_TORCH_CPU, "bad numerics profile");
+    if (llicti_device_count() <= 0) {
+        set_error("no CUDA device: libllicti_b200 has no CPU fallback");
+        return LLICTI_E_NODEVICE;
+    }
+    LLICTI_CUDA(cudaSetDevice(cfg->device));
+    llicti_ctx *ctx = new llicti_ctx();
+    ctx->cfg = *cfg;
+    ctx->num.div255_recip = cfg->numerics == LLICTI_NUM_TORCH_CUDA;
+    ctx->num.sum_ilp4 = cfg->numerics == LLICTI_NUM_TORCH_CUDA;
+    memset(ctx->wf32, 0, sizeof(ctx->wf32));
+    int rc = pack_weights(ctx, *w);
+    if (rc == LLICTI_OK) {
+        cudaError_t e = cudaMalloc((void **)&ctx->d_status, sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(int32_t));
+        if (e != cudaSuccess) { set_error("cudaMalloc(status): %s", cudaGetErrorString(e)); rc = LLICTI_E_CUDA; }
+    }
+    if (rc != LLICTI_OK) { llicti_destroy(ctx); return rc; }
+    *out = ctx;
+    return LLICTI_OK;
+}
+
+void llicti_destroy(llicti_ctx *ctx) {
+    if (!ctx) return;
+    free_workspace(ctx);
+    for (auto &b : ctx->wf32) { cudaFree(b.w0); cudaFree(b.b0); cudaFree(b.w1); cudaFree(b.b1); cudaFree(b.w2); cudaFree(b.b2); }
+    cudaFree(ctx->tc_weights);
+    cudaFree(ctx->d_status);
+    delete ctx;
+}
+
+int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
+    LLICTI_REQUIRE(ctx && max_images >= 1, "bad argument");
+    Plan p;
+    int rc = make_plan(ctx->cfg, H, W, &p);
+    if (rc) return rc;
+    free_workspace(ctx);
+    ctx->plan = p;
+    const llicti_geom &g = p.g;
+    const size_t n = (size_t)max_images;
+    const int S = g.num_scales;
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_sd, sizeof(StreamDesc) * kMaxStreams));
+    LLICTI_CUDA(cudaMemcpy(ctx->d_sd, p.sd, sizeof(StreamDesc) * kMaxStreams, cudaMemcpyHostToDevice));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_rgb, n * 3 * H * W));
+    for (int s = 0; s < S; ++s) LLICTI_CUDA(cudaMalloc((void **)&ctx->d_planes[s], n * p.plane_elems[s] * sizeof(int16_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_minmax, n * 4 * sizeof(int32_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_minmax16, n * 6 * sizeof(int16_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_params, n * kParamCh * (size_t)g.Hs[0] * g.Ws[0] * sizeof(float)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_bounds, n * (size_t)g.symbols * sizeof(uint32_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_scratch, n * (size_t)p.scratch_bytes));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_sublen, n * (size_t)g.substreams * sizeof(uint32_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_suboff, n * (size_t)g.substreams * sizeof(uint64_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_stream_bytes, (n * p.n_streams + 1) * sizeof(uint64_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_stream_off, (n * p.n_streams + 1) * sizeof(uint64_t)));
+    ctx->blob_cap = n * (size_t)g.max_stream_bytes;
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_blob, ctx->blob_cap));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_x00, n * 3 * (size_t)g.Hs[S - 1] * g.Ws[S - 1]));
+    ctx->ws_images = max_images; ctx->ws_H = H; ctx->ws_W = W;
+    return LLICTI_OK;
+}
+
+int64_t llicti_launch_count(const llicti_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- stage-level ------------------------------------------------------------------------
+int llicti_color_split(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, int16_t *const *planes_dev,
+                       int32_t *minmax_dev, void *stream) {
+    LLICTI_REQUIRE(ctx && rgb_dev && planes_dev && minmax_dev && n >= 1, "bad argument");
+    Plan p;
+    int rc = make_plan(ctx->cfg, H, W, &p);
+    if (rc) return rc;
+    return launch_color_split(ctx, p, rgb_dev, n, planes_dev, minmax_dev, (cudaStream_t)stream);
+}
+
+int llicti_merge_color(llicti_ctx *ctx, const int16_t *planes0_dev, int n, int H, int W, uint8_t *rgb_dev, void *stream) {
+    LLICTI_REQUIRE(ctx && planes0_dev && rgb_dev && n >= 1, "bad argument");
+    Plan p;
+    int rc = make_plan(ctx->cfg, H, W, &p);
+    if (rc) return rc;
+    return launch_merge_color(ctx, p, planes0_dev, n, rgb_dev, (cudaStream_t)stream);
+}
+
+int llicti_cnn_params(llicti_ctx *ctx, int band, const int16_t *planes_dev, int n, int Hs, int Ws, float *params_dev,
+                      void *stream) {
+    LLICTI_REQUIRE(ctx && planes_dev && params_dev && band >= 0 && band < 3 && n >= 1 && Hs >= 1 && Ws >= 1, "bad argument");
+    return cnn(ctx, band, planes_dev, n, Hs, Ws, params_dev, (cudaStream_t)stream);
+}
+
+int llicti_cdf_table(llicti_ctx *ctx, const float *params_dev, const int16_t *yband_dev, int clr, int min_val, int max_val,
+                     int P, int16_t *table_dev, void *stream) {
+    LLICTI_REQUIRE(ctx && params_dev && yband_dev && table_dev && clr >= 0 && clr < 3 && max_val >= min_val && P >= 1, "bad argument");
+    return launch_cdf_table(ctx, params_dev, yband_dev, clr, min_val, max_val, P, table_dev, (cudaStream_t)stream);
+}
+
+int llicti_cdf_bounds(llicti_ctx *ctx, const float *params_dev, const int16_t *yband_dev, int clr, int min_val, int max_val,
+                      int P, uint32_t *bounds_dev, void *stream) {
+    LLICTI_REQUIRE(ctx && params_dev && yband_dev && bounds_dev && clr >= 0 && clr < 3 && max_val >= min_val && P >= 1, "bad argument");
+    return launch_cdf_bounds_flat(ctx, params_dev, yband_dev, clr, min_val, max_val, P, bounds_dev, (cudaStream_t)stream);
+}
+
+int llicti_ac_encode_bounds(llicti_ctx *ctx, const uint32_t *bounds_dev, int n_sym, int S, uint8_t *out_dev, int slot_bytes,
+                            uint32_t *lens_dev, void *stream) {
+    LLICTI_REQUIRE(ctx && bounds_dev && out_dev && lens_dev && n_sym >= 1 && S >= 1 && slot_bytes >= 16 && slot_bytes % 4 == 0,
+                   "bad argument (slot_bytes must be a multiple of 4, >= 16)");
+    return launch_encode_flat(ctx, bounds_dev, n_sym, S, out_dev, slot_bytes, lens_dev, (cudaStream_t)stream);
+}
+
+int llicti_ac_decode_table(llicti_ctx *ctx, const int16_t *table_dev, int n_sym, int Lp, int S, const uint8_t *in_dev,
+                           const uint32_t *offs_dev, int16_t *sym_dev, void *stream) {
+    LLICTI_REQUIRE(ctx && table_dev && in_dev && offs_dev && sym_dev && n_sym >= 1 && Lp >= 2 && S >= 1, "bad argument");
+    return launch_decode_table(ctx, table_dev, n_sym, Lp, S, in_dev, offs_dev, sym_dev, (cudaStream_t)stream);
+}
+
+// ---- full path ----------------------------------------------------------------------------
+int llicti_encode_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, uint8_t *out_dev, size_t out_cap,
+                      uint64_t *stream_off_dev, int16_t *minmax_dev, void *stream) {
+    int rc = check_batch(ctx, n, H, W);
+    if (rc) return rc;
+    LLICTI_REQUIRE(rgb_dev && out_dev && stream_off_dev && minmax_dev, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Plan &p = ctx->plan;
+    const llicti_geom &g = p.g;
+    if ((rc = launch_color_split(ctx, p, rgb_dev, n, ctx->d_planes, ctx->d_minmax, st))) return rc;
+    for (int s = g.num_scales - 1; s >= 0; --s)
+        for (int b = 0; b < 3; ++b) {
+            if ((rc = cnn(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st))) return rc;
+            if ((rc = launch_band_bounds(ctx, p, s, b, ctx->d_params, ctx->d_planes[s], ctx->d_minmax, n, ctx->d_bounds,
+                                         g.symbols, st)))
+                return rc;
+        }
+    if ((rc = launch_encode_all(ctx, p, ctx->d_bounds, g.symbols, n, ctx->d_scratch, p.scratch_bytes, ctx->d_sublen, st))) return rc;
+    if ((rc = launch_compact(ctx, p, n, ctx->d_scratch, p.scratch_bytes, ctx->d_sublen, ctx->d_stream_bytes, stream_off_dev,
+                             out_dev, out_cap, st)))
+        return rc;
+    return launch_minmax16(ctx, ctx->d_minmax, minmax_dev, n, st);
+}
+
+int llicti_encode_host(llicti_ctx *ctx, const uint8_t *rgb, int n, int H, int W, uint8_t *out, size_t out_cap,
+                       uint64_t *stream_off, int16_t *minmax, void *stream) {
+    int rc = check_batch(ctx, n, H, W);
+    if (rc) return rc;
+    LLICTI_REQUIRE(rgb && out && stream_off && minmax, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ns = ctx->plan.n_streams;
+    LLICTI_CUDA(cudaMemcpyAsync(ctx->d_rgb, rgb, (size_t)n * 3 * H * W, cudaMemcpyHostToDevice, st));
+    if ((rc = llicti_encode_dev(ctx, ctx->d_rgb, n, H, W, ctx->d_blob, ctx->blob_cap, ctx->d_stream_off, ctx->d_minmax16, st)))
+        return rc;
+    LLICTI_CUDA(cudaMemcpyAsync(stream_off, ctx->d_stream_off, ((size_t)n * ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    LLICTI_CUDA(cudaMemcpyAsync(minmax, ctx->d_minmax16, (size_t)n * 6 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if ((rc = read_status(ctx, st))) return rc;
+    const uint64_t total = stream_off[(size_t)n * ns];
+    if (total > out_cap) {
+        set_error("output needs %llu bytes, capacity is %llu", (unsigned long long)total, (unsigned long long)out_cap);
+        return LLICTI_E_NOMEM;
+    }
+    LLICTI_CUDA(cudaMemcpyAsync(out, ctx->d_blob, total, cudaMemcpyDeviceToHost, st));
+    LLICTI_CUDA(cudaStreamSynchronize(st));
+    return LLICTI_OK;
+}
+
+int llicti_decode_dev(llicti_ctx *ctx, const uint8_t *blob_dev, const uint64_t *stream_off_dev, const int16_t *minmax_dev,
+                      const uint8_t *x00_rgb_dev, int n, int H, int W, uint8_t *rgb_out_dev, void *stream) {
+    int rc = check_batch(ctx, n, H, W);
+    if (rc) return rc;
+    LLICTI_REQUIRE(blob_dev && stream_off_dev && minmax_dev && x00_rgb_dev && rgb_out_dev, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Plan &p = ctx->plan;
+    const llicti_geom &g = p.g;
+    const int S = g.num_scales;
+    if ((rc = launch_minmax32(ctx, minmax_dev, ctx->d_minmax, n, st))) return rc;
+    if ((rc = launch_index_streams(ctx, p, n, blob_dev, stream_off_dev, ctx->d_suboff, ctx->d_sublen, st))) return rc;
+    if ((rc = launch_x00_from_header(ctx, p, x00_rgb_dev, n, ctx->d_planes[S - 1], st))) return rc;
+    for (int s = S - 1; s >= 0; --s) {
+        for (int b = 0; b < 3; ++b) {
+            if ((rc = cnn(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st))) return rc;
+            if ((rc = launch_decode_band(ctx, p, s, b, ctx->d_params, ctx->d_planes[s], ctx->d_minmax, n, blob_dev,
+                                         ctx->d_suboff, ctx->d_sublen, st)))
+                return rc;
+        }
+        if (s > 0 && (rc = launch_interleave(ctx, p, s, ctx->d_planes[s], ctx->d_planes[s - 1], n, st))) return rc;
+    }
+    return launch_merge_color(ctx, p, ctx->d_planes[0], n, rgb_out_dev, st);
+}
+
+int llicti_decode_host(llicti_ctx *ctx, const uint8_t *blob, const uint64_t *stream_off, const int16_t *minmax,
+                       const uint8_t *x00_rgb, int n, int H, int W, uint8_t *rgb_out, void *stream) {
+    int rc = check_batch(ctx, n, H, W);
+    if (rc) return rc;
+    LLICTI_REQUIRE(blob && stream_off && minmax && x00_rgb && rgb_out, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Plan &p = ctx->plan;
+    const int ns = p.n_streams, S = p.g.num_scales;
+    const uint64_t total = stream_off[(size_t)n * ns];
+    LLICTI_REQUIRE(total <= ctx->blob_cap, "bitstream of %llu bytes exceeds the reserved %llu", (unsigned long long)total,
+                   (unsigned long long)ctx->blob_cap);
+    LLICTI_CUDA(cudaMemcpyAsync(ctx->d_blob, blob, total, cudaMemcpyHostToDevice, st));
+    LLICTI_CUDA(cudaMemcpyAsync(ctx->d_stream_off, stream_off, ((size_t)n * ns + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    LLICTI_CUDA(cudaMemcpyAsync(ctx->d_minmax16, minmax, (size_t)n * 6 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    LLICTI_CUDA(cudaMemcpyAsync(ctx->d_x00, x00_rgb, (size_t)n * 3 * p.g.Hs[S - 1] * p.g.Ws[S - 1], cudaMemcpyHostToDevice, st));
+    if ((rc = llicti_decode_dev(ctx, ctx->d_blob, ctx->d_stream_off, ctx->d_minmax16, ctx->d_x00, n, H, W, ctx->d_rgb, st)))
+        return rc;
+    LLICTI_CUDA(cudaMemcpyAsync(rgb_out, ctx->d_rgb, (size_t)n * 3 * H * W, cudaMemcpyDeviceToHost, st));
+    return read_status(ctx, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// Shared declarations of libllicti_b200.so (sm_100a).  Internal; the public surface is
+// include/llicti.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/llicti.h"
+
+namespace llicti {
+
+constexpr int kM = 5;            // mixtures per colour channel (config.num_mixtures)
+constexpr int kParamCh = 12 * kM;  // 60 output channels of the interpolator CNN
+constexpr int kMaxStreams = 9 * LLICTI_MAX_SCALES;
+
+void set_error(const char *fmt, ...);
+
+#define LLICTI_CUDA(call)                                                                    \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            ::llicti::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,               \
+                                cudaGetErrorString(e__));                                    \
+            return LLICTI_E_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define LLICTI_REQUIRE(cond, ...)                \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::llicti::set_error(__VA_ARGS__);    \
+            return LLICTI_E_ARG;                 \
+        }                                        \
+    } while (0)
+
+// One coded stream = (scale, band, colour channel) of one image.  Same for every image of a
+// batch (uniform H x W), so it lives in a small device table indexed by stream order k.
+struct StreamDesc {
+    int32_t scale, band, clr;
+    int32_t Hs, Ws;            // plane size of the scale
+    int32_t crop_h, crop_w;    // coded region
+    int32_t n_sym;             // crop_h * crop_w
+    int32_t S;                 // interleaved substreams
+    int32_t sub_first;         // index of substream 0 among the image's substreams
+    int32_t slot_bytes;        // encoder scratch bytes per substream
+    int32_t pad_;
+    int64_t sym_off;           // first symbol among the image's symbols
+    int64_t slot_off;          // first scratch byte among the image's scratch
+};
+
+struct Plan {
+    llicti_geom g;
+    int n_streams;                 // 9 * num_scales
+    StreamDesc sd[kMaxStreams];
+    int64_t plane_elems[LLICTI_MAX_SCALES];  // 12 * Hs * Ws
+    int64_t scratch_bytes;         // encoder scratch per image
+    int hdr_per_stream(int k) const { return 0; }
+};
+
+int make_plan(const llicti_config &cfg, int H, int W, Plan *out);
+int num_substreams(int64_t n, int sub_len);
+
+// Packed weights of one band on the device (fp32 path).
+struct BandWeightsF32 {
+    float *w0;   // [K0][Ch]   K0 = 3 * taps, k = ((branch, c, dy, dx))
+    float *b0;   // [Ch]       sum of the branch biases
+    float *w1;   // [4][g][g]  [group][in][out]
+    float *b1;   // [Ch]
+    float *w2;   // [4][g][15] [group][in][out]
+    float *b2;   // [60]
+    int K0;
+};
+
+// Tap table of layer 0: source phase, colour channel and offset of every k.
+struct TapTable {
+    int K0;
+    int8_t phase[128], chan[128], dy[128], dx[128];
+};
+
+struct NumericsProfile {
+    int div255_recip;   // 1: x/255 evaluated as x * (1/255f)  (ATen CUDA); 0: IEEE division
+    int sum_ilp4;       // 1: (((t0+t4)+t1)+t2)+t3 (ATen 4-accumulator); 0: left to right
+};
+
+}  // namespace llicti
+
+struct llicti_ctx {
+    llicti_config cfg;
+    llicti::NumericsProfile num;
+    llicti::BandWeightsF32 wf32[3];
+    llicti::TapTable taps[3];
+    void *tc_weights = nullptr;       // tcgen05 path (packed bf16 operands), see cnn_tc.cu
+    int64_t launches = 0;
+
+    // workspace (llicti_reserve)
+    int ws_images = 0, ws_H = 0, ws_W = 0;
+    llicti::Plan plan;
+    llicti::StreamDesc *d_sd = nullptr;
+    uint8_t *d_rgb = nullptr;
+    int16_t *d_planes[LLICTI_MAX_SCALES] = {};
+    int32_t *d_minmax = nullptr;       // [n][4]
+    int16_t *d_minmax16 = nullptr;     // [n][6] header words
+    float *d_params = nullptr;         // [n][60][P0]
+    uint32_t *d_bounds = nullptr;      // [n][symbols]
+    uint8_t *d_scratch = nullptr;      // [n][scratch_bytes]
+    uint32_t *d_sublen = nullptr;      // [n][substreams]
+    uint64_t *d_suboff = nullptr;      // [n][substreams] (decode)
+    uint64_t *d_stream_bytes = nullptr;  // [n*streams + 1]
+    uint64_t *d_stream_off = nullptr;    // [n*streams + 1]
+    uint8_t *d_blob = nullptr;         // compacted output / decode input
+    size_t blob_cap = 0;
+    uint8_t *d_x00 = nullptr;          // [n][3][h_last][w_last]
+    int32_t *d_status = nullptr;       // device-side error flag
+};
+
+namespace llicti {
+
+// kernels_color.cu
+int launch_color_split(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n, int16_t *const *planes,
+                       int32_t *minmax, cudaStream_t st);
+int launch_merge_color(llicti_ctx *ctx, const Plan &p, const int16_t *planes0, int n, uint8_t *rgb,
+                       cudaStream_t st);
+int launch_x00_from_header(llicti_ctx *ctx, const Plan &p, const uint8_t *x00_rgb, int n, int16_t *planes_last,
+                           cudaStream_t st);
+int launch_interleave(llicti_ctx *ctx, const Plan &p, int scale_from, const int16_t *planes_from,
+                      int16_t *planes_to, int n, cudaStream_t st);
+int launch_minmax16(llicti_ctx *ctx, const int32_t *minmax, int16_t *minmax16, int n, cudaStream_t st);
+int launch_minmax32(llicti_ctx *ctx, const int16_t *minmax16, int32_t *minmax, int n, cudaStream_t st);
+
+// kernels_cnn_fp32.cu
+int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
+                    cudaStream_t st);
+
+// kernels_coder.cu
+int launch_cdf_table(llicti_ctx *ctx, const float *params, const int16_t *yband, int clr, int min_val,
+                     int max_val, int P, int16_t *table, cudaStream_t st);
+int launch_cdf_bounds_flat(llicti_ctx *ctx, const float *params, const int16_t *yband, int clr, int min_val,
+                           int max_val, int P, uint32_t *bounds, cudaStream_t st);
+int launch_band_bounds(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params,
+                       const int16_t *planes, const int32_t *minmax, int n, uint32_t *bounds, int64_t sym_stride,
+                       cudaStream_t st);
+int launch_encode_all(llicti_ctx *ctx, const Plan &p, const uint32_t *bounds, int64_t sym_stride, int n,
+                      uint8_t *scratch, int64_t scratch_stride, uint32_t *sublen, cudaStream_t st);
+int launch_encode_flat(llicti_ctx *ctx, const uint32_t *bounds, int n_sym, int S, uint8_t *out, int slot_bytes,
+                       uint32_t *lens, cudaStream_t st);
+int launch_compact(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *scratch, int64_t scratch_stride,
+                   const uint32_t *sublen, uint64_t *stream_bytes, uint64_t *stream_off, uint8_t *out,
+                   size_t out_cap, cudaStream_t st);
+int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *blob, const uint64_t *stream_off,
+                         uint64_t *suboff, uint32_t *sublen, cudaStream_t st);
+int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params, int16_t *planes,
+                       const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
+                       const uint32_t *sublen, cudaStream_t st);
+int launch_decode_table(llicti_ctx *ctx, const int16_t *table, int n_sym, int Lp, int S, const uint8_t *in,
+                        const uint32_t *offs, int16_t *sym, cudaStream_t st);
+
+}  // namespace llicti

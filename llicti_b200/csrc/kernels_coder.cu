@@ -1,0 +1,519 @@
+// GMM-CDF bounds, arithmetic coding / decoding over interleaved substreams, and the stream
+// container (compaction on encode, indexing on decode).
+//
+// Reference path replaced: LLICTIEntropyLayer.compress / decompress inner loops
+// (graphs/models/LLICTI_nets.py:378-411 and :463-498): per (scale, band, colour channel)
+// mean coupling -> get_cdfs -> torchac.  The reference materialises H x W x Lp int16 tables
+// and ships them to a single CPU thread; here nothing but 4 bytes per symbol (encode) or
+// the 60 network outputs per position (decode) ever leave the chip's caches.
+#include "common.cuh"
+#include "gmm.cuh"
+#include "rangecoder.cuh"
+
+namespace llicti {
+
+// ------------------------------------------------------------------------------------------
+// Dense table / flat bounds for one stream (parity entry points llicti_cdf_table / _bounds)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cdf_table_kernel(const float *__restrict__ params, const int16_t *__restrict__ yband, int clr, int min_val,
+                 int max_val, int P, NumericsProfile np, int16_t *__restrict__ table) {
+    // one warp per position: lanes stride over the Lp table entries
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= P) return;
+    GmmChannel c;
+    load_channel(params, (size_t)P, (size_t)warp, clr, yband[warp], yband[(size_t)P + warp], np, c);
+    const CdfGrid g = make_grid(min_val, max_val);
+    int16_t *row = table + (size_t)warp * g.Lp;
+    for (int k = lane; k < g.Lp; k += 32) row[k] = (int16_t)cdf_q(c, g, k, np);
+}
+
+__device__ __forceinline__ uint32_t symbol_bounds(const GmmChannel &c, const CdfGrid &g, int sym,
+                                                  const NumericsProfile &np) {
+    const uint32_t c_low = cdf_q(c, g, sym, np);
+    const uint32_t c_high = (sym == g.Lp - 2) ? 0x10000u : cdf_q(c, g, sym + 1, np);
+    return c_low | ((c_high - 1u) << 16);
+}
+
+__global__ void __launch_bounds__(128)
+cdf_bounds_flat_kernel(const float *__restrict__ params, const int16_t *__restrict__ yband, int clr, int min_val,
+                       int max_val, int P, NumericsProfile np, uint32_t *__restrict__ bounds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    GmmChannel c;
+    load_channel(params, (size_t)P, (size_t)i, clr, yband[i], yband[(size_t)P + i], np, c);
+    const CdfGrid g = make_grid(min_val, max_val);
+    const int sym = (int)yband[(size_t)clr * P + i] - min_val;
+    bounds[i] = symbol_bounds(c, g, sym, np);
+}
+
+// ------------------------------------------------------------------------------------------
+// Encode side: bounds of a whole band (all images, 3 colour channels per thread)
+// ------------------------------------------------------------------------------------------
+struct BandGeom {
+    int Hs, Ws, crop_h, crop_w, band;
+    int64_t sym_off[3];    // first symbol of the Y / Co / Cg stream among the image's symbols
+};
+
+__global__ void __launch_bounds__(128)
+band_bounds_kernel(const float *__restrict__ params, const int16_t *__restrict__ planes,
+                   const int32_t *__restrict__ minmax, BandGeom bg, NumericsProfile np,
+                   uint32_t *__restrict__ bounds, int64_t sym_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // index in the cropped raster
+    const int img = blockIdx.y;
+    const int n_sym = bg.crop_h * bg.crop_w;
+    if (i >= n_sym) return;
+    const int r = i / bg.crop_w, c = i - r * bg.crop_w;
+    const size_t P = (size_t)bg.Hs * bg.Ws;
+    const size_t pidx = (size_t)r * bg.Ws + c;
+    const float *pp = params + (size_t)img * kParamCh * P;
+    const int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (bg.band + 1)) * P + pidx;
+    const int y0 = yb[0], y1 = yb[P], y2 = yb[2 * P];
+    const int32_t *mm = minmax + img * 4;
+    const int lo[3] = {-127, mm[0], mm[1]};
+    const int hi[3] = {128, mm[2], mm[3]};
+    const int yv[3] = {y0, y1, y2};
+    uint32_t *out = bounds + (size_t)img * sym_stride + i;
+#pragma unroll
+    for (int clr = 0; clr < 3; ++clr) {
+        GmmChannel ch;
+        load_channel(pp, P, pidx, clr, y0, y1, np, ch);
+        const CdfGrid g = make_grid(lo[clr], hi[clr]);
+        out[bg.sym_off[clr]] = symbol_bounds(ch, g, yv[clr] - lo[clr], np);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Encode side: one thread per (image, stream, substream)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_stream(const StreamDesc *sd, int n_streams, int item) {
+    int k = 0;
+    while (k + 1 < n_streams && sd[k + 1].sub_first <= item) ++k;
+    return k;
+}
+
+__global__ void __launch_bounds__(128)
+encode_all_kernel(const StreamDesc *__restrict__ sd_g, int n_streams, int total_sub,
+                  const uint32_t *__restrict__ bounds, int64_t sym_stride, uint8_t *__restrict__ scratch,
+                  int64_t scratch_stride, uint32_t *__restrict__ sublen, int32_t *__restrict__ status) {
+    __shared__ StreamDesc sd[kMaxStreams];
+    for (int e = threadIdx.x; e < n_streams; e += blockDim.x) sd[e] = sd_g[e];
+    __syncthreads();
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    if (item >= total_sub) return;
+    const int k = find_stream(sd, n_streams, item);
+    const StreamDesc &d = sd[k];
+    const int j = item - d.sub_first;
+    const uint32_t *b = bounds + (size_t)img * sym_stride + d.sym_off;
+    AcEncoder enc;
+    enc.init(scratch + (size_t)img * scratch_stride + d.slot_off + (size_t)j * d.slot_bytes, (uint32_t)d.slot_bytes);
+    for (int i = j; i < d.n_sym; i += d.S) {
+        const uint32_t v = b[i];
+        enc.encode(v & 0xFFFFu, (v >> 16) + 1u);
+    }
+    const uint32_t nb = enc.finish();
+    sublen[(size_t)img * total_sub + item] = nb;
+    if (enc.bw.overflow) atomicExch(status, LLICTI_E_NOMEM);
+}
+
+__global__ void __launch_bounds__(128)
+encode_flat_kernel(const uint32_t *__restrict__ bounds, int n_sym, int S, uint8_t *__restrict__ out, int slot_bytes,
+                   uint32_t *__restrict__ lens, int32_t *__restrict__ status) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S) return;
+    AcEncoder enc;
+    enc.init(out + (size_t)j * slot_bytes, (uint32_t)slot_bytes);
+    for (int i = j; i < n_sym; i += S) {
+        const uint32_t v = bounds[i];
+        enc.encode(v & 0xFFFFu, (v >> 16) + 1u);
+    }
+    lens[j] = enc.finish();
+    if (enc.bw.overflow) atomicExch(status, LLICTI_E_NOMEM);
+}
+
+// ------------------------------------------------------------------------------------------
+// Container: [u16 S][u16 len x S][payloads] per stream when sub_len > 0, raw torchac bytes else
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+stream_sizes_kernel(const StreamDesc *__restrict__ sd, int n_streams, int total_sub, int sub_mode,
+                    const uint32_t *__restrict__ sublen, uint64_t *__restrict__ stream_bytes) {
+    const int k = blockIdx.x, img = blockIdx.y;
+    const StreamDesc d = sd[k];
+    const uint32_t *l = sublen + (size_t)img * total_sub + d.sub_first;
+    uint32_t s = 0;
+    for (int j = threadIdx.x; j < d.S; j += blockDim.x) s += l[j];
+    __shared__ uint32_t red[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        stream_bytes[(size_t)img * n_streams + k] = (uint64_t)(red[0] + red[1] + red[2] + red[3]) + (sub_mode ? 2 + 2 * d.S : 0);
+}
+
+// Exclusive scan of `count` uint64 values by one CTA (count = images * streams, a few 10^4 at most).
+__global__ void __launch_bounds__(1024)
+scan_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int count) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < count; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint64_t v = i < count ? in[i] : 0;
+        uint64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t t = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        const uint64_t prefix = carry + (wid ? warp_tot[wid - 1] : 0) + x - v;
+        if (i < count) out[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[count] = carry;
+}
+
+// One CTA per (stream, image): write the container header and copy the substream payloads.
+__global__ void __launch_bounds__(256)
+gather_kernel(const StreamDesc *__restrict__ sd, int n_streams, int total_sub, int sub_mode,
+              const uint8_t *__restrict__ scratch, int64_t scratch_stride, const uint32_t *__restrict__ sublen,
+              const uint64_t *__restrict__ stream_off, uint8_t *__restrict__ out, uint64_t out_cap,
+              int32_t *__restrict__ status) {
+    const int k = blockIdx.x, img = blockIdx.y;
+    const StreamDesc d = sd[k];
+    const uint32_t *l = sublen + (size_t)img * total_sub + d.sub_first;
+    const uint64_t o0 = stream_off[(size_t)img * n_streams + k];
+    const uint64_t o1 = stream_off[(size_t)img * n_streams + k + 1];
+    if (o1 > out_cap) {
+        if (threadIdx.x == 0) atomicExch(status, LLICTI_E_NOMEM);
+        return;
+    }
+    uint8_t *dst = out + o0;
+    const uint8_t *src = scratch + (size_t)img * scratch_stride + d.slot_off;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t hdr = 0;
+    if (sub_mode) {
+        hdr = 2 + 2 * d.S;
+        if (threadIdx.x == 0) { dst[0] = (uint8_t)(d.S & 0xFF); dst[1] = (uint8_t)(d.S >> 8); }
+        for (int j = threadIdx.x; j < d.S; j += blockDim.x) {
+            const uint32_t v = l[j];
+            if (v > 0xFFFFu) atomicExch(status, LLICTI_E_NOMEM);
+            dst[2 + 2 * j] = (uint8_t)(v & 0xFF);
+            dst[3 + 2 * j] = (uint8_t)(v >> 8);
+        }
+    }
+    // each warp walks the substreams in order, keeping a running payload offset
+    __shared__ uint32_t chunk_off[256];
+    uint32_t running = hdr;
+    for (int base = 0; base < d.S; base += 256) {
+        const int j = base + threadIdx.x;
+        const uint32_t v = j < d.S ? l[j] : 0;
+        // block exclusive scan of 256 values
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        __shared__ uint32_t wt[8];
+        if (lane == 31) wt[wid] = x;
+        __syncthreads();
+        uint32_t wp = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < wid) wp += wt[w];
+            tot += wt[w];
+        }
+        chunk_off[threadIdx.x] = running + wp + x - v;
+        __syncthreads();
+        const int cnt = min(256, d.S - base);
+        for (int jj = wid; jj < cnt; jj += 8) {
+            const uint32_t len = l[base + jj];
+            const uint8_t *s = src + (size_t)(base + jj) * d.slot_bytes;
+            uint8_t *t = dst + chunk_off[jj];
+            for (uint32_t b = lane; b < len; b += 32) t[b] = s[b];
+        }
+        running += tot;
+        __syncthreads();
+    }
+}
+
+// Decode side: parse the per-stream containers into absolute substream offsets / lengths.
+__global__ void __launch_bounds__(256)
+index_streams_kernel(const StreamDesc *__restrict__ sd, int n_streams, int total_sub, int sub_mode,
+                     const uint8_t *__restrict__ blob, const uint64_t *__restrict__ stream_off,
+                     uint64_t *__restrict__ suboff, uint32_t *__restrict__ sublen, int32_t *__restrict__ status) {
+    const int k = blockIdx.x, img = blockIdx.y;
+    const StreamDesc d = sd[k];
+    const uint64_t o0 = stream_off[(size_t)img * n_streams + k];
+    const uint64_t o1 = stream_off[(size_t)img * n_streams + k + 1];
+    uint64_t *so = suboff + (size_t)img * total_sub + d.sub_first;
+    uint32_t *sl = sublen + (size_t)img * total_sub + d.sub_first;
+    if (!sub_mode) {
+        if (threadIdx.x == 0) { so[0] = o0; sl[0] = (uint32_t)(o1 - o0); }
+        return;
+    }
+    const uint8_t *src = blob + o0;
+    const uint64_t size = o1 - o0;
+    const uint32_t hdr = 2 + 2 * d.S;
+    if (size < hdr || (int)(src[0] | (src[1] << 8)) != d.S) {
+        if (threadIdx.x == 0) atomicExch(status, LLICTI_E_STREAM);
+        for (int j = threadIdx.x; j < d.S; j += blockDim.x) { so[j] = o0; sl[j] = 0; }
+        return;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ uint32_t wt[8];
+    uint64_t running = hdr;
+    for (int base = 0; base < d.S; base += 256) {
+        const int j = base + threadIdx.x;
+        const uint32_t v = j < d.S ? (uint32_t)(src[2 + 2 * j] | (src[3 + 2 * j] << 8)) : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wt[wid] = x;
+        __syncthreads();
+        uint32_t wp = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < wid) wp += wt[w];
+            tot += wt[w];
+        }
+        if (j < d.S) {
+            const uint64_t off = running + wp + x - v;
+            so[j] = o0 + off;
+            sl[j] = (off + v <= size) ? v : 0;
+            if (off + v > size) atomicExch(status, LLICTI_E_STREAM);
+        }
+        running += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && running != size) atomicExch(status, LLICTI_E_STREAM);
+}
+
+// ------------------------------------------------------------------------------------------
+// Decode side: one thread per (image, substream) of a band; Y, Co, Cg coders advance together
+// ------------------------------------------------------------------------------------------
+// Largest m in [0, Lp-2] with q(m) <= target (torchac's binsearch); returns the symbol and its
+// bounds.  q is evaluated analytically, about log2(Lp) times.
+__device__ __forceinline__ int search_symbol(const GmmChannel &c, const CdfGrid &g, uint32_t target,
+                                             const NumericsProfile &np, uint32_t &c_low, uint32_t &c_high) {
+    int lo = 0, hi = g.Lp - 1;
+    uint32_t qlo = 0xFFFFFFFFu, qhi = 0x10000u;
+    while (lo + 1 < hi) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t q = cdf_q(c, g, mid, np);
+        if (q <= target) { lo = mid; qlo = q; }
+        else { hi = mid; qhi = q; }
+    }
+    if (qlo == 0xFFFFFFFFu) qlo = cdf_q(c, g, lo, np);
+    c_low = qlo;
+    c_high = qhi;
+    return lo;
+}
+
+struct DecodeGeom {
+    int Hs, Ws, crop_h, crop_w, band, padH, padW;
+    int S;            // substreams per stream of this band
+    int sub_first[3]; // first substream of the Y / Co / Cg stream among the image's substreams
+};
+
+__global__ void __launch_bounds__(128)
+decode_band_kernel(const float *__restrict__ params, int16_t *__restrict__ planes, const int32_t *__restrict__ minmax,
+                   DecodeGeom dg, NumericsProfile np, const uint8_t *__restrict__ blob,
+                   const uint64_t *__restrict__ suboff, const uint32_t *__restrict__ sublen, int total_sub) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    if (j >= dg.S) return;
+    const size_t P = (size_t)dg.Hs * dg.Ws;
+    const float *pp = params + (size_t)img * kParamCh * P;
+    int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1)) * P;
+    const int32_t *mm = minmax + img * 4;
+    const int lo[3] = {-127, mm[0], mm[1]};
+    const int hi[3] = {128, mm[2], mm[3]};
+    AcDecoder dec[3];
+    CdfGrid grid[3];
+#pragma unroll
+    for (int clr = 0; clr < 3; ++clr) {
+        const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
+        dec[clr].init(blob + suboff[e], sublen[e]);
+        grid[clr] = make_grid(lo[clr], hi[clr]);
+    }
+    const int n_sym = dg.crop_h * dg.crop_w;
+    const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
+    const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
+    for (int i = j; i < n_sym; i += dg.S) {
+        const int r = i / dg.crop_w, c = i - r * dg.crop_w;
+        const size_t pidx = (size_t)r * dg.Ws + c;
+        int yv[3] = {0, 0, 0};
+#pragma unroll
+        for (int clr = 0; clr < 3; ++clr) {
+            GmmChannel ch;
+            load_channel(pp, P, pidx, clr, yv[0], yv[1], np, ch);
+            uint32_t c_low, c_high;
+            const int sym = search_symbol(ch, grid[clr], dec[clr].target(), np, c_low, c_high);
+            if (i + dg.S < n_sym) dec[clr].consume(c_low, c_high);   // torchac skips the update after the last symbol
+            yv[clr] = sym + lo[clr];
+            const int16_t v = (int16_t)yv[clr];
+            int16_t *dst = yb + (size_t)clr * P + pidx;
+            dst[0] = v;
+            // replicate padding of the short phases (LLICTI_nets.py:512-530)
+            const bool last_c = rep_w && c == dg.crop_w - 1, last_r = rep_h && r == dg.crop_h - 1;
+            if (last_c) dst[1] = v;
+            if (last_r) dst[dg.Ws] = v;
+            if (last_c && last_r) dst[dg.Ws + 1] = v;
+        }
+    }
+}
+
+// torchac.decode_int16_normalized_cdf from a dense table (parity entry point).
+__global__ void __launch_bounds__(128)
+decode_table_kernel(const int16_t *__restrict__ table, int n_sym, int Lp, int S, const uint8_t *__restrict__ in,
+                    const uint32_t *__restrict__ offs, int16_t *__restrict__ sym) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S) return;
+    AcDecoder dec;
+    dec.init(in + offs[j], offs[j + 1] - offs[j]);
+    for (int i = j; i < n_sym; i += S) {
+        const uint16_t *row = reinterpret_cast<const uint16_t *>(table) + (size_t)i * Lp;
+        const uint32_t target = dec.target();
+        int lo = 0, hi = Lp - 1;
+        while (lo + 1 < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (row[mid] <= target) lo = mid; else hi = mid;
+        }
+        sym[i] = (int16_t)lo;
+        if (i + S < n_sym) dec.consume(row[lo], lo == Lp - 2 ? 0x10000u : (uint32_t)row[lo + 1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------------
+int launch_cdf_table(llicti_ctx *ctx, const float *params, const int16_t *yband, int clr, int min_val, int max_val,
+                     int P, int16_t *table, cudaStream_t st) {
+    const int warps_per_block = 4;
+    cdf_table_kernel<<<(P + warps_per_block - 1) / warps_per_block, 128, 0, st>>>(params, yband, clr, min_val, max_val,
+                                                                                 P, ctx->num, table);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_cdf_bounds_flat(llicti_ctx *ctx, const float *params, const int16_t *yband, int clr, int min_val,
+                           int max_val, int P, uint32_t *bounds, cudaStream_t st) {
+    cdf_bounds_flat_kernel<<<(P + 127) / 128, 128, 0, st>>>(params, yband, clr, min_val, max_val, P, ctx->num, bounds);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+static int stream_index(const Plan &p, int scale, int band, int clr) {
+    return (p.g.num_scales - 1 - scale) * 9 + 3 * band + clr;
+}
+
+int launch_band_bounds(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params,
+                       const int16_t *planes, const int32_t *minmax, int n, uint32_t *bounds, int64_t sym_stride,
+                       cudaStream_t st) {
+    BandGeom bg;
+    const StreamDesc &d0 = p.sd[stream_index(p, scale, band, 0)];
+    bg.Hs = d0.Hs; bg.Ws = d0.Ws; bg.crop_h = d0.crop_h; bg.crop_w = d0.crop_w; bg.band = band;
+    for (int c = 0; c < 3; ++c) bg.sym_off[c] = p.sd[stream_index(p, scale, band, c)].sym_off;
+    dim3 grid((d0.n_sym + 127) / 128, n);
+    band_bounds_kernel<<<grid, 128, 0, st>>>(params, planes, minmax, bg, ctx->num, bounds, sym_stride);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_encode_all(llicti_ctx *ctx, const Plan &p, const uint32_t *bounds, int64_t sym_stride, int n,
+                      uint8_t *scratch, int64_t scratch_stride, uint32_t *sublen, cudaStream_t st) {
+    const int total_sub = (int)p.g.substreams;
+    dim3 grid((total_sub + 127) / 128, n);
+    encode_all_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
+                                            scratch_stride, sublen, ctx->d_status);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_encode_flat(llicti_ctx *ctx, const uint32_t *bounds, int n_sym, int S, uint8_t *out, int slot_bytes,
+                       uint32_t *lens, cudaStream_t st) {
+    encode_flat_kernel<<<(S + 127) / 128, 128, 0, st>>>(bounds, n_sym, S, out, slot_bytes, lens, ctx->d_status);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_compact(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *scratch, int64_t scratch_stride,
+                   const uint32_t *sublen, uint64_t *stream_bytes, uint64_t *stream_off, uint8_t *out, size_t out_cap,
+                   cudaStream_t st) {
+    const int total_sub = (int)p.g.substreams;
+    const int sub_mode = ctx->cfg.sub_len > 0;
+    dim3 grid(p.n_streams, n);
+    stream_sizes_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, sub_mode, sublen, stream_bytes);
+    scan_kernel<<<1, 1024, 0, st>>>(stream_bytes, stream_off, n * p.n_streams);
+    gather_kernel<<<grid, 256, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, sub_mode, scratch, scratch_stride, sublen,
+                                        stream_off, out, (uint64_t)out_cap, ctx->d_status);
+    ctx->launches += 3;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *blob, const uint64_t *stream_off,
+                         uint64_t *suboff, uint32_t *sublen, cudaStream_t st) {
+    const int total_sub = (int)p.g.substreams;
+    dim3 grid(p.n_streams, n);
+    index_streams_kernel<<<grid, 256, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, ctx->cfg.sub_len > 0, blob,
+                                               stream_off, suboff, sublen, ctx->d_status);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params, int16_t *planes,
+                       const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
+                       const uint32_t *sublen, cudaStream_t st) {
+    DecodeGeom dg;
+    const StreamDesc &d0 = p.sd[stream_index(p, scale, band, 0)];
+    dg.Hs = d0.Hs; dg.Ws = d0.Ws; dg.crop_h = d0.crop_h; dg.crop_w = d0.crop_w; dg.band = band;
+    dg.padH = p.g.padH[scale]; dg.padW = p.g.padW[scale];
+    dg.S = d0.S;
+    for (int c = 0; c < 3; ++c) dg.sub_first[c] = p.sd[stream_index(p, scale, band, c)].sub_first;
+    dim3 grid((dg.S + 127) / 128, n);
+    decode_band_kernel<<<grid, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen,
+                                             (int)p.g.substreams);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_decode_table(llicti_ctx *ctx, const int16_t *table, int n_sym, int Lp, int S, const uint8_t *in,
+                        const uint32_t *offs, int16_t *sym, cudaStream_t st) {
+    decode_table_kernel<<<(S + 127) / 128, 128, 0, st>>>(table, n_sym, Lp, S, in, offs, sym);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+}  // namespace llicti

@@ -1,0 +1,233 @@
+// Integer YCoCg-R lifting, min/max scan and the scale pyramid (forward and inverse).
+// Reference: graphs/models/LLICTI_nets.py:62-88 (lifting), :137-139 (min/max), :143 (Y-127),
+// :218-241 (lazyDWT with replicate padding), :446-454 / :501-509 (inverse), :571-582.
+// All arithmetic is exact integer work; the kernels are HBM-bound (3 B/px in, 6 B/px out for
+// the finest scale).
+#include "common.cuh"
+
+namespace llicti {
+
+__device__ __forceinline__ void rgb_to_ycocg(int r, int g, int b, int &y, int &co, int &cg) {
+    co = r - b;
+    int t = b + (co >> 1);   // arithmetic shift == floor division by 2
+    cg = g - t;
+    y = t + (cg >> 1);
+}
+
+__device__ __forceinline__ void ycocg_to_rgb(int y, int co, int cg, int &r, int &g, int &b) {
+    int t = y - (cg >> 1);
+    g = cg + t;
+    b = t - (co >> 1);
+    r = b + co;
+}
+
+// One thread per position (r, c) of the scale-0 grid: reads the 2x2 pixel block (with the
+// replicate rule for the short phases) and writes 12 int16 planes.
+__global__ void __launch_bounds__(256)
+split_rgb_kernel(const uint8_t *__restrict__ rgb, int H, int W, int Hs, int Ws, int H11, int W11,
+                 int16_t *__restrict__ planes, int32_t *__restrict__ minmax) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;
+    int mnCo = 1 << 20, mnCg = 1 << 20, mxCo = -(1 << 20), mxCg = -(1 << 20);
+    if (c < Ws) {
+        const uint8_t *base = rgb + (size_t)img * 3 * H * W;
+        int16_t *out = planes + (size_t)img * 12 * Hs * Ws + (size_t)r * Ws + c;
+        const size_t ps = (size_t)Hs * Ws;
+        const int r1 = 2 * min(r, H11 - 1) + 1, c1 = 2 * min(c, W11 - 1) + 1;
+        const int rr[4] = {2 * r, r1, 2 * r, r1};   // x00, x11, x01, x10
+        const int cc[4] = {2 * c, c1, c1, 2 * c};
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            const size_t o = (size_t)rr[ph] * W + cc[ph];
+            const int R = base[o], G = base[o + (size_t)H * W], B = base[o + 2 * (size_t)H * W];
+            int y, co, cg;
+            rgb_to_ycocg(R, G, B, y, co, cg);
+            out[(ph * 3 + 0) * ps] = (int16_t)(y - 127);
+            out[(ph * 3 + 1) * ps] = (int16_t)co;
+            out[(ph * 3 + 2) * ps] = (int16_t)cg;
+            mnCo = min(mnCo, co); mxCo = max(mxCo, co);
+            mnCg = min(mnCg, cg); mxCg = max(mxCg, cg);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnCo = min(mnCo, __shfl_xor_sync(0xffffffffu, mnCo, o));
+        mnCg = min(mnCg, __shfl_xor_sync(0xffffffffu, mnCg, o));
+        mxCo = max(mxCo, __shfl_xor_sync(0xffffffffu, mxCo, o));
+        mxCg = max(mxCg, __shfl_xor_sync(0xffffffffu, mxCg, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mnCo <= mxCo) {
+        atomicMin(minmax + img * 4 + 0, mnCo);
+        atomicMin(minmax + img * 4 + 1, mnCg);
+        atomicMax(minmax + img * 4 + 2, mxCo);
+        atomicMax(minmax + img * 4 + 3, mxCg);
+    }
+}
+
+// Scale s+1 from the x00 planes of scale s (both int16).
+__global__ void __launch_bounds__(256)
+split_x00_kernel(const int16_t *__restrict__ prev, int Hp, int Wp, int Hs, int Ws, int H11, int W11,
+                 int16_t *__restrict__ planes) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;
+    if (c >= Ws) return;
+    const int16_t *base = prev + (size_t)img * 12 * Hp * Wp;   // channels 0..2 = x00 of the finer scale
+    int16_t *out = planes + (size_t)img * 12 * Hs * Ws + (size_t)r * Ws + c;
+    const size_t ps = (size_t)Hs * Ws, pp = (size_t)Hp * Wp;
+    const int r1 = 2 * min(r, H11 - 1) + 1, c1 = 2 * min(c, W11 - 1) + 1;
+    const int rr[4] = {2 * r, r1, 2 * r, r1};
+    const int cc[4] = {2 * c, c1, c1, 2 * c};
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        const size_t o = (size_t)rr[ph] * Wp + cc[ph];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) out[(ph * 3 + ch) * ps] = base[o + ch * pp];
+    }
+}
+
+__global__ void init_minmax_kernel(int32_t *minmax, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        minmax[i * 4 + 0] = 1 << 20;
+        minmax[i * 4 + 1] = 1 << 20;
+        minmax[i * 4 + 2] = -(1 << 20);
+        minmax[i * 4 + 3] = -(1 << 20);
+    }
+}
+
+__global__ void minmax16_kernel(const int32_t *__restrict__ mm, int16_t *__restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {   // header words [minY, minCo, minCg, maxY, maxCo, maxCg], LLICTI_nets.py:137-139
+        out[i * 6 + 0] = 0;
+        out[i * 6 + 1] = (int16_t)mm[i * 4 + 0];
+        out[i * 6 + 2] = (int16_t)mm[i * 4 + 1];
+        out[i * 6 + 3] = 255;
+        out[i * 6 + 4] = (int16_t)mm[i * 4 + 2];
+        out[i * 6 + 5] = (int16_t)mm[i * 4 + 3];
+    }
+}
+
+__global__ void minmax32_kernel(const int16_t *__restrict__ mm16, int32_t *__restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out[i * 4 + 0] = mm16[i * 6 + 1];
+        out[i * 4 + 1] = mm16[i * 6 + 2];
+        out[i * 4 + 2] = mm16[i * 6 + 4];
+        out[i * 4 + 3] = mm16[i * 6 + 5];
+    }
+}
+
+// Coarsest x00 from the header's raw RGB (LLICTI_nets.py:429-430, :444).
+__global__ void x00_header_kernel(const uint8_t *__restrict__ x00, int h, int w, int16_t *__restrict__ planes, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    if (i >= h * w) return;
+    const uint8_t *base = x00 + (size_t)img * 3 * h * w;
+    int y, co, cg;
+    rgb_to_ycocg(base[i], base[i + h * w], base[i + 2 * h * w], y, co, cg);
+    int16_t *out = planes + (size_t)img * 12 * h * w + i;
+    out[0] = (int16_t)(y - 127);
+    out[(size_t)h * w] = (int16_t)co;
+    out[2 * (size_t)h * w] = (int16_t)cg;
+}
+
+// Inverse lazy DWT of scale s into the x00 planes of scale s-1 (cropped to Ht x Wt).
+__global__ void __launch_bounds__(256)
+interleave_kernel(const int16_t *__restrict__ from, int Hs, int Ws, int16_t *__restrict__ to, int Ht, int Wt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;
+    if (c >= Wt) return;
+    const int ph = (r & 1) ? ((c & 1) ? 1 : 3) : ((c & 1) ? 2 : 0);
+    const size_t ps = (size_t)Hs * Ws, pt = (size_t)Ht * Wt;
+    const int16_t *src = from + (size_t)img * 12 * ps + (size_t)(ph * 3) * ps + (size_t)(r >> 1) * Ws + (c >> 1);
+    int16_t *dst = to + (size_t)img * 12 * pt + (size_t)r * Wt + c;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) dst[ch * pt] = src[ch * ps];
+}
+
+// Final inverse lazy DWT + Y+127 + inverse lifting -> planar RGB uint8.
+__global__ void __launch_bounds__(256)
+merge_rgb_kernel(const int16_t *__restrict__ from, int Hs, int Ws, uint8_t *__restrict__ rgb, int H, int W) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;
+    if (c >= W) return;
+    const int ph = (r & 1) ? ((c & 1) ? 1 : 3) : ((c & 1) ? 2 : 0);
+    const size_t ps = (size_t)Hs * Ws;
+    const int16_t *src = from + (size_t)img * 12 * ps + (size_t)(ph * 3) * ps + (size_t)(r >> 1) * Ws + (c >> 1);
+    int R, G, B;
+    ycocg_to_rgb(src[0] + 127, src[ps], src[2 * ps], R, G, B);
+    uint8_t *dst = rgb + (size_t)img * 3 * H * W + (size_t)r * W + c;
+    dst[0] = (uint8_t)R;
+    dst[(size_t)H * W] = (uint8_t)G;
+    dst[2 * (size_t)H * W] = (uint8_t)B;
+}
+
+int launch_color_split(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n, int16_t *const *planes,
+                       int32_t *minmax, cudaStream_t st) {
+    const llicti_geom &g = p.g;
+    init_minmax_kernel<<<(n + 127) / 128, 128, 0, st>>>(minmax, n);
+    {
+        dim3 grid((g.Ws[0] + 255) / 256, g.Hs[0], n);
+        split_rgb_kernel<<<grid, 256, 0, st>>>(rgb, g.H, g.W, g.Hs[0], g.Ws[0], g.H / 2, g.W / 2, planes[0], minmax);
+    }
+    ctx->launches += 2;
+    for (int s = 1; s < g.num_scales; ++s) {
+        dim3 grid((g.Ws[s] + 255) / 256, g.Hs[s], n);
+        split_x00_kernel<<<grid, 256, 0, st>>>(planes[s - 1], g.Hs[s - 1], g.Ws[s - 1], g.Hs[s], g.Ws[s],
+                                                g.Hs[s - 1] / 2, g.Ws[s - 1] / 2, planes[s]);
+        ctx->launches += 1;
+    }
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_merge_color(llicti_ctx *ctx, const Plan &p, const int16_t *planes0, int n, uint8_t *rgb, cudaStream_t st) {
+    const llicti_geom &g = p.g;
+    dim3 grid((g.W + 255) / 256, g.H, n);
+    merge_rgb_kernel<<<grid, 256, 0, st>>>(planes0, g.Hs[0], g.Ws[0], rgb, g.H, g.W);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_x00_from_header(llicti_ctx *ctx, const Plan &p, const uint8_t *x00_rgb, int n, int16_t *planes_last,
+                           cudaStream_t st) {
+    const llicti_geom &g = p.g;
+    const int s = g.num_scales - 1;
+    dim3 grid((g.Hs[s] * g.Ws[s] + 127) / 128, n);
+    x00_header_kernel<<<grid, 128, 0, st>>>(x00_rgb, g.Hs[s], g.Ws[s], planes_last, n);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_interleave(llicti_ctx *ctx, const Plan &p, int scale_from, const int16_t *planes_from, int16_t *planes_to,
+                      int n, cudaStream_t st) {
+    const llicti_geom &g = p.g;
+    const int s = scale_from, t = scale_from - 1;
+    dim3 grid((g.Ws[t] + 255) / 256, g.Hs[t], n);
+    interleave_kernel<<<grid, 256, 0, st>>>(planes_from, g.Hs[s], g.Ws[s], planes_to, g.Hs[t], g.Ws[t]);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_minmax16(llicti_ctx *ctx, const int32_t *minmax, int16_t *minmax16, int n, cudaStream_t st) {
+    minmax16_kernel<<<(n + 127) / 128, 128, 0, st>>>(minmax, minmax16, n);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+int launch_minmax32(llicti_ctx *ctx, const int16_t *minmax16, int32_t *minmax, int n, cudaStream_t st) {
+    minmax32_kernel<<<(n + 127) / 128, 128, 0, st>>>(minmax16, minmax, n);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+}  // namespace llicti

@@ -1,0 +1,175 @@
+"""CPU-side checks of the C ABI and the host logic (no compute calls: no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import llicti_oracle as O
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from llicti_b200 import _lib as L
+    hdr = open(os.path.join(ROOT, "include", "llicti.h")).read()
+    declared = set(re.findall(r"LLICTI_API[^;(]*?\b(llicti_\w+)\s*\(", hdr))
+    assert len(declared) >= 19
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert built_lib.llicti_abi_version() == 1
+
+
+def test_struct_layouts_match_header(built_lib):
+    from llicti_b200 import _lib as L
+    assert C.sizeof(L.Config) == 32
+    assert C.sizeof(L.Weights) == 8 * 24
+    # int32 x (3 + 4*8 + 1 + 3*24) = 108 -> 432 bytes, then 4 x int64
+    assert C.sizeof(L.Geom) == 432 + 32
+
+
+@pytest.mark.parametrize("H,W,S", [(512, 768, 5), (1356, 2040, 5), (2160, 3840, 5), (512, 512, 5), (33, 47, 5),
+                                   (53, 77, 5), (35, 32, 5), (17, 17, 5), (64, 96, 2), (37, 53, 2), (255, 257, 3)])
+def test_geometry_matches_oracle_pyramid(built_lib, H, W, S):
+    from llicti_b200 import _lib as L
+    cfg = L.Config(S, 88, 5, 0, 0, 0, 0, 0)
+    g = L.Geom()
+    assert built_lib.llicti_geometry(C.byref(cfg), H, W, C.byref(g)) == 0
+    planes, flags, pad_int = O.pyramid_split(np.zeros((3, H, W), dtype=np.int16), tuple(range(S)))
+    assert g.pad_int == pad_int
+    sym = 0
+    for s in range(S):
+        assert (g.Hs[s], g.Ws[s]) == planes[s].shape[1:]
+        assert [bool(g.padH[s]), bool(g.padW[s])] == flags[s]
+        for b in range(3):
+            ch, cw = O.crop_shape(b, g.Hs[s], g.Ws[s], *flags[s])
+            assert (g.crop_h[s][b], g.crop_w[s][b]) == (ch, cw)
+            sym += 3 * ch * cw
+    assert g.symbols == sym
+    assert g.positions == sum(p.shape[1] * p.shape[2] for p in planes)
+
+
+def test_survey_geometry_table(built_lib):
+    from llicti_b200 import _lib as L
+    cfg = L.Config(5, 88, 5, 0, 0, 0, 0, 0)
+    g = L.Geom()
+    for (H, W), (pos, sym, pad) in {(512, 768): (130944, 1178496, 0), (1356, 2040): (921432, 8290464, 38),
+                                    (2160, 3840): (2762160, 24858720, 2), (512, 512): (87296, 785664, 0)}.items():
+        assert built_lib.llicti_geometry(C.byref(cfg), H, W, C.byref(g)) == 0
+        assert (g.positions, g.symbols, g.pad_int) == (pos, sym, pad)
+
+
+@pytest.mark.parametrize("sub_len", [64, 2048])
+def test_substream_counts_match_oracle(built_lib, sub_len):
+    from llicti_b200 import _lib as L
+    cfg = L.Config(5, 88, 5, sub_len, 0, 0, 0, 0)
+    g = L.Geom()
+    assert built_lib.llicti_geometry(C.byref(cfg), 512, 768, C.byref(g)) == 0
+    tot = 0
+    for s in range(5):
+        for b in range(3):
+            n = g.crop_h[s][b] * g.crop_w[s][b]
+            assert g.num_sub[s][b] == O.num_substreams(n, sub_len)
+            tot += 3 * g.num_sub[s][b]
+    assert g.substreams == tot
+
+
+def test_error_behaviour_without_device(built_lib):
+    from llicti_b200 import _lib as L
+    g = L.Geom()
+    bad = L.Config(5, 88, 5, 0, 0, 0, 0, 0)
+    assert built_lib.llicti_geometry(C.byref(bad), 8, 8, C.byref(g)) == L.E_ARG          # too small for 5 scales
+    assert b"too small" in built_lib.llicti_last_error()
+    assert built_lib.llicti_geometry(C.byref(bad), 512, 8161 * 2, C.byref(g)) == L.E_ARG  # coarsest > 255 (uint8 header)
+    bad = L.Config(5, 88, 4, 0, 0, 0, 0, 0)
+    assert built_lib.llicti_geometry(C.byref(bad), 64, 64, C.byref(g)) == L.E_ARG
+    if built_lib.llicti_device_count() == 0:
+        ctx = C.c_void_p()
+        w = L.Weights()
+        ok = L.Config(5, 88, 5, 0, 0, 0, 0, 0)
+        assert built_lib.llicti_create(C.byref(ok), C.byref(w), C.byref(ctx)) == L.E_NODEVICE
+        assert b"no CPU fallback" in built_lib.llicti_last_error()
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from llicti_b200 import Codec, CodecConfig
+    cfg = O.OracleConfig()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Codec(CodecConfig(), O.synthetic_state_dict(cfg))
+
+
+def test_container_assemble_parse_round_trip():
+    from llicti_b200 import container
+    rng = np.random.default_rng(0)
+    S, n, H, W = 2, 3, 37, 53
+    planes, flags, pad_int = O.pyramid_split(np.zeros((3, H, W), dtype=np.int16), (0, 1))
+    h_last, w_last = planes[-1].shape[1:]
+    rgb = rng.integers(0, 256, size=(n, 3, H, W), dtype=np.uint8)
+    lens = rng.integers(0, 50, size=n * 9 * S)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    blob = rng.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    mm = rng.integers(-255, 256, size=(n, 6)).astype(np.int16)
+    for sub_len in (0, 512):
+        bsls = container.assemble(S, sub_len, h_last, w_last, pad_int, rgb, blob, off, mm)
+        assert len(bsls) == n and all(len(b) == S + 1 and all(len(r) == 9 for r in b) for b in bsls)
+        assert bsls[0][0][0] == bytes([S, h_last, w_last])
+        assert bsls[0][0][3] == np.ascontiguousarray(rgb[0, :, ::4, ::4]).tobytes()
+        blob2, off2, mm2, x00, n2, H2, W2 = container.parse(S, sub_len, bsls)
+        assert (n2, H2, W2) == (n, H, W)
+        assert np.array_equal(blob2, blob) and np.array_equal(off2, off) and np.array_equal(mm2, mm)
+        assert np.array_equal(x00, rgb[:, :, ::4, ::4])
+        with pytest.raises(ValueError):
+            container.parse(S, sub_len + 1, bsls)
+    with pytest.raises(ValueError):
+        container.parse(3, 0, container.assemble(S, 0, h_last, w_last, pad_int, rgb, blob, off, mm))
+
+
+def test_header_matches_oracle_header():
+    from llicti_b200 import container
+    cfg = O.OracleConfig()
+    img = O.synthetic_image(53, 77, 2)
+    o = O.OracleCodec(cfg, O.synthetic_state_dict(cfg), sub_len=128)
+    d = O.StageDump()
+    bsl = o.compress(img, d)
+    mm = np.array([d.minmax], dtype=np.int16)
+    h_last, w_last = d.planes[-1].shape[1:]
+    off = np.zeros(46, dtype=np.uint64)
+    mine = container.assemble(5, 128, h_last, w_last, d.pad_int, img[None], np.zeros(1, np.uint8), off, mm)[0]
+    assert mine[0] == bsl[0]
+    assert container.image_size_from_header(5, h_last, w_last, d.pad_int) == (53, 77)
+
+
+def test_config_validation():
+    import json
+    from llicti_b200 import CodecConfig
+    for name, chs, S in (("llicti_A.json", 88, 5), ("llicti_B.json", 60, 2)):
+        cfg = json.load(open(os.path.join(ROOT, "configs", name)))
+        cc = CodecConfig.from_json_dict(cfg)
+        assert (cc.chs, cc.num_scales) == (chs, S)
+        assert cfg["mode"] == "eval_model" and cfg["agent"] == "LLICTIAgent"
+        bad = dict(cfg, clr_joint_mode=0)
+        with pytest.raises(ValueError):
+            CodecConfig.from_json_dict(bad)
+
+
+def test_model_state_dict_names_match_reference_layout():
+    import json
+    import torch
+    from llicti_b200 import LLICTI
+    cfg = json.load(open(os.path.join(ROOT, "configs", "llicti_A.json")))
+    m = LLICTI(cfg)
+    names = dict(m.named_parameters())
+    assert len(names) == 24
+    assert sum(p.numel() for p in names.values()) == 196596
+    ocfg = O.OracleConfig()
+    sd = {k: torch.from_numpy(v) for k, v in O.synthetic_state_dict(ocfg).items()}
+    assert set(sd) == set(names)
+    # compressai's extra buffers in a reference checkpoint must not break loading
+    sd["entropymodel.entmdls_scale_band.0.0.conditional_prob_model._offset"] = torch.zeros(0, dtype=torch.int32)
+    m.load_state_dict(sd)
+    assert torch.equal(m.state_dict()["entropymodel.entmdls_scale_band.0.1.layer0_11_01.weight"],
+                       sd["entropymodel.entmdls_scale_band.0.1.layer0_11_01.weight"])
