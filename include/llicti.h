@@ -194,6 +194,15 @@ LLICTI_API int llicti_decode_dev(llicti_ctx *ctx, const uint8_t *blob_dev, const
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 LLICTI_API int64_t llicti_launch_count(const llicti_ctx *ctx);
 
+/* Per-kernel-class device time, measured with CUDA events recorded on the launching stream
+ * around every launch while profiling is enabled.  Classes: 0 colour+pyramid split, 1 CNN,
+ * 2 CDF bounds, 3 range encode, 4 container compaction, 5 container indexing, 6 range decode
+ * (+ CDF search), 7 inverse pyramid / colour merge.  llicti_profile_read waits for the
+ * recorded events, returns summed milliseconds and launch-group counts, and clears them. */
+#define LLICTI_KERNEL_CLASSES 8
+LLICTI_API int llicti_profile(llicti_ctx *ctx, int enable);
+LLICTI_API int llicti_profile_read(llicti_ctx *ctx, double *ms, int64_t *count);
+
 #ifdef __cplusplus
 }
 #endif

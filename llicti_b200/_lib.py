@@ -13,6 +13,7 @@ MAX_SCALES = 8
 OK, E_ARG, E_CUDA, E_NOMEM, E_STREAM, E_NODEVICE = 0, -1, -2, -3, -4, -5
 NUM_TORCH_CUDA, NUM_TORCH_CPU = 0, 1
 CNN_FP32, CNN_TCGEN05 = 0, 1
+KERNEL_CLASSES = ("split", "cnn", "bounds", "encode", "compact", "index", "decode", "merge")
 
 
 class Config(C.Structure):
@@ -75,6 +76,8 @@ _PROTOS = {
     "llicti_decode_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_void_p, C.c_void_p]),
     "llicti_launch_count": (C.c_int64, [C.c_void_p]),
+    "llicti_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "llicti_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 
 EXPORTS = tuple(_PROTOS)

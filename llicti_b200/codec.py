@@ -128,6 +128,16 @@ class Codec:
     def launches(self) -> int:
         return int(self.lib.llicti_launch_count(self._ctx))
 
+    def profile(self, enable: bool):
+        L.check(self.lib.llicti_profile(self._ctx, int(enable)))
+
+    def profile_read(self):
+        """{class: (milliseconds, launch groups)} since profiling was enabled / last read."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        L.check(self.lib.llicti_profile_read(self._ctx, ms, cnt))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(L.KERNEL_CLASSES)}
+
     # -- full path, host buffers (the timed end-to-end call) -------------------------------
     def encode_host(self, rgb: np.ndarray, out: Optional[np.ndarray] = None):
         """rgb uint8 [n,3,H,W] host array (pinned or pageable).  Returns (blob view, stream_off

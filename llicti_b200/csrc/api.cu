@@ -282,6 +282,31 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
 
 int64_t llicti_launch_count(const llicti_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int llicti_profile(llicti_ctx *ctx, int enable) {
+    LLICTI_REQUIRE(ctx, "null context");
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    ctx->prof_ev.clear();
+    ctx->prof_cls.clear();
+    ctx->prof_on = enable != 0;
+    return LLICTI_OK;
+}
+
+int llicti_profile_read(llicti_ctx *ctx, double *ms, int64_t *count) {
+    LLICTI_REQUIRE(ctx && ms && count, "null argument");
+    for (int i = 0; i < LLICTI_KERNEL_CLASSES; ++i) { ms[i] = 0; count[i] = 0; }
+    for (size_t i = 0; i < ctx->prof_cls.size(); ++i) {
+        LLICTI_CUDA(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+        float t = 0.f;
+        LLICTI_CUDA(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        ms[ctx->prof_cls[i]] += t;
+        count[ctx->prof_cls[i]] += 1;
+    }
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    ctx->prof_ev.clear();
+    ctx->prof_cls.clear();
+    return LLICTI_OK;
+}
+
 // ---- stage-level ------------------------------------------------------------------------
 int llicti_color_split(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, int16_t *const *planes_dev,
                        int32_t *minmax_dev, void *stream) {

@@ -95,6 +95,11 @@ struct llicti_ctx {
     void *tc_weights = nullptr;       // tcgen05 path (packed bf16 operands), see cnn_tc.cu
     int64_t launches = 0;
 
+    // optional per-kernel-class timing with CUDA events on the launching stream (llicti_profile)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;   // pairs (begin, end)
+    std::vector<int> prof_cls;
+
     // workspace (llicti_reserve)
     int ws_images = 0, ws_H = 0, ws_W = 0;
     llicti::Plan plan;
@@ -117,6 +122,29 @@ struct llicti_ctx {
 };
 
 namespace llicti {
+
+enum KernelClass { KC_SPLIT = 0, KC_CNN = 1, KC_BOUNDS = 2, KC_ENCODE = 3, KC_COMPACT = 4, KC_INDEX = 5,
+                   KC_DECODE = 6, KC_MERGE = 7, KC_COUNT = 8 };
+
+// Brackets the kernels launched in its lifetime with two events when profiling is on.
+struct ProfScope {
+    llicti_ctx *ctx;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr, e = nullptr;
+    ProfScope(llicti_ctx *c, int cls, cudaStream_t s) : ctx(c), st(s) {
+        if (!ctx->prof_on) return;
+        cudaEventCreate(&b);
+        cudaEventCreate(&e);
+        cudaEventRecord(b, st);
+        ctx->prof_cls.push_back(cls);
+    }
+    ~ProfScope() {
+        if (!b) return;
+        cudaEventRecord(e, st);
+        ctx->prof_ev.push_back(b);
+        ctx->prof_ev.push_back(e);
+    }
+};
 
 // kernels_color.cu
 int launch_color_split(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n, int16_t *const *planes,

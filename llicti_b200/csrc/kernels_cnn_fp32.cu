@@ -148,6 +148,7 @@ cnn_fp32_kernel(const int16_t *__restrict__ planes, int Hs, int Ws, int K0, TapT
 
 int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
                     cudaStream_t st) {
+    ProfScope prof_(ctx, KC_CNN, st);
     const int G = ctx->cfg.chs;
     const int P = Hs * Ws;
     const TapTable &t = ctx->taps[band];

@@ -435,6 +435,7 @@ static int stream_index(const Plan &p, int scale, int band, int clr) {
 int launch_band_bounds(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params,
                        const int16_t *planes, const int32_t *minmax, int n, uint32_t *bounds, int64_t sym_stride,
                        cudaStream_t st) {
+    ProfScope prof_(ctx, KC_BOUNDS, st);
     BandGeom bg;
     const StreamDesc &d0 = p.sd[stream_index(p, scale, band, 0)];
     bg.Hs = d0.Hs; bg.Ws = d0.Ws; bg.crop_h = d0.crop_h; bg.crop_w = d0.crop_w; bg.band = band;
@@ -448,6 +449,7 @@ int launch_band_bounds(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
 
 int launch_encode_all(llicti_ctx *ctx, const Plan &p, const uint32_t *bounds, int64_t sym_stride, int n,
                       uint8_t *scratch, int64_t scratch_stride, uint32_t *sublen, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_ENCODE, st);
     const int total_sub = (int)p.g.substreams;
     dim3 grid((total_sub + 127) / 128, n);
     encode_all_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
@@ -468,6 +470,7 @@ int launch_encode_flat(llicti_ctx *ctx, const uint32_t *bounds, int n_sym, int S
 int launch_compact(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *scratch, int64_t scratch_stride,
                    const uint32_t *sublen, uint64_t *stream_bytes, uint64_t *stream_off, uint8_t *out, size_t out_cap,
                    cudaStream_t st) {
+    ProfScope prof_(ctx, KC_COMPACT, st);
     const int total_sub = (int)p.g.substreams;
     const int sub_mode = ctx->cfg.sub_len > 0;
     dim3 grid(p.n_streams, n);
@@ -482,6 +485,7 @@ int launch_compact(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *scratch
 
 int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *blob, const uint64_t *stream_off,
                          uint64_t *suboff, uint32_t *sublen, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_INDEX, st);
     const int total_sub = (int)p.g.substreams;
     dim3 grid(p.n_streams, n);
     index_streams_kernel<<<grid, 256, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, ctx->cfg.sub_len > 0, blob,
@@ -494,6 +498,7 @@ int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *b
 int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params, int16_t *planes,
                        const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
                        const uint32_t *sublen, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_DECODE, st);
     DecodeGeom dg;
     const StreamDesc &d0 = p.sd[stream_index(p, scale, band, 0)];
     dg.Hs = d0.Hs; dg.Ws = d0.Ws; dg.crop_h = d0.crop_h; dg.crop_w = d0.crop_w; dg.band = band;

@@ -168,6 +168,7 @@ merge_rgb_kernel(const int16_t *__restrict__ from, int Hs, int Ws, uint8_t *__re
 
 int launch_color_split(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n, int16_t *const *planes,
                        int32_t *minmax, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_SPLIT, st);
     const llicti_geom &g = p.g;
     init_minmax_kernel<<<(n + 127) / 128, 128, 0, st>>>(minmax, n);
     {
@@ -186,6 +187,7 @@ int launch_color_split(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n
 }
 
 int launch_merge_color(llicti_ctx *ctx, const Plan &p, const int16_t *planes0, int n, uint8_t *rgb, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_MERGE, st);
     const llicti_geom &g = p.g;
     dim3 grid((g.W + 255) / 256, g.H, n);
     merge_rgb_kernel<<<grid, 256, 0, st>>>(planes0, g.Hs[0], g.Ws[0], rgb, g.H, g.W);
@@ -196,6 +198,7 @@ int launch_merge_color(llicti_ctx *ctx, const Plan &p, const int16_t *planes0, i
 
 int launch_x00_from_header(llicti_ctx *ctx, const Plan &p, const uint8_t *x00_rgb, int n, int16_t *planes_last,
                            cudaStream_t st) {
+    ProfScope prof_(ctx, KC_MERGE, st);
     const llicti_geom &g = p.g;
     const int s = g.num_scales - 1;
     dim3 grid((g.Hs[s] * g.Ws[s] + 127) / 128, n);
@@ -207,6 +210,7 @@ int launch_x00_from_header(llicti_ctx *ctx, const Plan &p, const uint8_t *x00_rg
 
 int launch_interleave(llicti_ctx *ctx, const Plan &p, int scale_from, const int16_t *planes_from, int16_t *planes_to,
                       int n, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_MERGE, st);
     const llicti_geom &g = p.g;
     const int s = scale_from, t = scale_from - 1;
     dim3 grid((g.Ws[t] + 255) / 256, g.Hs[t], n);
@@ -217,6 +221,7 @@ int launch_interleave(llicti_ctx *ctx, const Plan &p, int scale_from, const int1
 }
 
 int launch_minmax16(llicti_ctx *ctx, const int32_t *minmax, int16_t *minmax16, int n, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_MERGE, st);
     minmax16_kernel<<<(n + 127) / 128, 128, 0, st>>>(minmax, minmax16, n);
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
@@ -224,6 +229,7 @@ int launch_minmax16(llicti_ctx *ctx, const int32_t *minmax, int16_t *minmax16, i
 }
 
 int launch_minmax32(llicti_ctx *ctx, const int16_t *minmax16, int32_t *minmax, int n, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_MERGE, st);
     minmax32_kernel<<<(n + 127) / 128, 128, 0, st>>>(minmax16, minmax, n);
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
