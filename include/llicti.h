@@ -75,7 +75,7 @@ typedef struct {
     int32_t numerics;     /* LLICTI_NUM_*                                          */
     int32_t cnn_impl;     /* LLICTI_CNN_*                                          */
     int32_t device;       /* CUDA device ordinal                                   */
-    int32_t reserved;
+    int32_t decode_impl;  /* 0: one warp per substream (default); 1: one thread per substream */
 } llicti_config;
 
 /* fp32 host pointers in PyTorch's own layouts (state_dict keys in SURVEY.md 8b).

@@ -19,7 +19,7 @@ KERNEL_CLASSES = ("split", "cnn", "bounds", "encode", "compact", "index", "decod
 class Config(C.Structure):
     _fields_ = [("num_scales", C.c_int32), ("chs", C.c_int32), ("num_mixtures", C.c_int32),
                 ("sub_len", C.c_int32), ("numerics", C.c_int32), ("cnn_impl", C.c_int32),
-                ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("device", C.c_int32), ("decode_impl", C.c_int32)]
 
 
 class Weights(C.Structure):

@@ -35,6 +35,7 @@ class CodecConfig:
     numerics: int = L.NUM_TORCH_CUDA
     cnn_impl: int = L.CNN_FP32
     device: int = 0
+    decode_impl: int = 0             # 0 = one warp per substream, 1 = one thread per substream
 
     @staticmethod
     def from_json_dict(cfg, **over) -> "CodecConfig":
@@ -91,7 +92,7 @@ class Codec:
             w.l1_w[band], w.l1_b[band] = a1.ctypes.data, b1.ctypes.data
             w.l2_w[band], w.l2_b[band] = a2.ctypes.data, b2.ctypes.data
         self._ccfg = L.Config(cfg.num_scales, cfg.chs, cfg.num_mixtures, cfg.sub_len, cfg.numerics, cfg.cnn_impl,
-                              cfg.device, 0)
+                              cfg.device, cfg.decode_impl)
         self._ctx = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(self.lib.llicti_create(C.byref(self._ccfg), C.byref(w), C.byref(self._ctx)))

@@ -186,7 +186,8 @@ static int read_status(llicti_ctx *ctx, cudaStream_t st) {
 
 static int cnn(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params, cudaStream_t st) {
     if (ctx->cfg.cnn_impl == LLICTI_CNN_FP32) return launch_cnn_fp32(ctx, band, planes, n, Hs, Ws, params, st);
-    set_error("cnn_impl %d is not built into this library", ctx->cfg.cnn_impl);
+    if (ctx->cfg.cnn_impl == LLICTI_CNN_TCGEN05) return launch_cnn_tc(ctx, band, planes, n, Hs, Ws, params, st);
+    set_error("unknown cnn_impl %d", ctx->cfg.cnn_impl);
     return LLICTI_E_ARG;
 }
 
@@ -231,6 +232,7 @@ int llicti_create(const llicti_config *cfg, const llicti_weights *w, llicti_ctx 
     ctx->num.sum_ilp4 = cfg->numerics == LLICTI_NUM_TORCH_CUDA;
     memset(ctx->wf32, 0, sizeof(ctx->wf32));
     int rc = pack_weights(ctx, *w);
+    if (rc == LLICTI_OK) rc = tc_pack_weights(ctx, *w);
     if (rc == LLICTI_OK) {
         cudaError_t e = cudaMalloc((void **)&ctx->d_status, sizeof(int32_t));
         if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(int32_t));
@@ -245,7 +247,7 @@ void llicti_destroy(llicti_ctx *ctx) {
     if (!ctx) return;
     free_workspace(ctx);
     for (auto &b : ctx->wf32) { cudaFree(b.w0); cudaFree(b.b0); cudaFree(b.w1); cudaFree(b.b1); cudaFree(b.w2); cudaFree(b.b2); }
-    cudaFree(ctx->tc_weights);
+    tc_free_weights(ctx);
     cudaFree(ctx->d_status);
     delete ctx;
 }

@@ -162,6 +162,12 @@ int launch_minmax32(llicti_ctx *ctx, const int16_t *minmax16, int32_t *minmax, i
 int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
                     cudaStream_t st);
 
+// cnn_tc.cu
+int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w);
+void tc_free_weights(llicti_ctx *ctx);
+int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
+                  cudaStream_t st);
+
 // kernels_coder.cu
 int launch_cdf_table(llicti_ctx *ctx, const float *params, const int16_t *yband, int clr, int min_val,
                      int max_val, int P, int16_t *table, cudaStream_t st);

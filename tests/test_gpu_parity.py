@@ -25,10 +25,11 @@ def L(built_lib):
     return _lib
 
 
-def make_codec(L, ocfg, sd, sub_len=0, numerics=None):
+def make_codec(L, ocfg, sd, sub_len=0, numerics=None, cnn_impl=0, decode_impl=0):
     from llicti_b200 import Codec, CodecConfig
     return Codec(CodecConfig(num_scales=len(ocfg.dwtlevels), chs=ocfg.chs, sub_len=sub_len,
-                             numerics=L.NUM_TORCH_CUDA if numerics is None else numerics), sd)
+                             numerics=L.NUM_TORCH_CUDA if numerics is None else numerics, cnn_impl=cnn_impl,
+                             decode_impl=decode_impl), sd)
 
 
 EDGE_IMAGES = {
@@ -87,11 +88,42 @@ def test_cnn_params_close_to_oracle(L, cfgname):
             np.testing.assert_allclose(got, ref, rtol=CNN_RTOL, atol=CNN_ATOL, err_msg=f"scale {s} band {b}")
 
 
-def test_cnn_is_batch_and_position_invariant(L):
+# tcgen05 path: bf16 operands (integer inputs exact, weights and hidden activations rounded to
+# bf16), fp32 accumulation in TMEM.  Stated tolerance against the fp32 oracle:
+TC_ATOL = 6e-3    # absolute, on outputs of magnitude <= ~1.3 (sigma/mu in value/255 units, weights, coupling)
+TC_RTOL = 2e-2
+
+
+@pytest.mark.parametrize("cfgname", ["A", "B"])
+def test_cnn_tcgen05_close_to_oracle(L, cfgname):
+    ocfg = O.OracleConfig() if cfgname == "A" else O.OracleConfig(dwtlevels=(0, 1), chs=60)
+    sd = O.synthetic_state_dict(ocfg)
+    codec = make_codec(L, ocfg, sd, cnn_impl=L.CNN_TCGEN05)
+    fp32 = make_codec(L, ocfg, sd, cnn_impl=L.CNN_FP32)
+    net = O.OracleNet(ocfg, sd)
+    img = O.synthetic_image(70, 91, 7)
+    cen = O.rgb_to_ycocg_r(img)
+    cen[0] -= 127
+    planes, _, _ = O.pyramid_split(cen, ocfg.dwtlevels)
+    worst = 0.0
+    for s in (0, len(planes) - 1):
+        d_pl = torch.from_numpy(planes[s][None]).cuda()
+        for b in range(3):
+            ref = net.params(b, planes[s])
+            got = codec.cnn_params(b, d_pl)[0].cpu().numpy()
+            worst = max(worst, float(np.abs(got - ref).max()))
+            np.testing.assert_allclose(got, ref, rtol=TC_RTOL, atol=TC_ATOL, err_msg=f"scale {s} band {b}")
+            ref32 = fp32.cnn_params(b, d_pl)[0].cpu().numpy()
+            np.testing.assert_allclose(got, ref32, rtol=TC_RTOL, atol=TC_ATOL)
+    print(f"tcgen05 CNN max abs error vs oracle ({cfgname}): {worst:.3e}")
+
+
+@pytest.mark.parametrize("cnn_impl", [0, 1])
+def test_cnn_is_batch_and_position_invariant(L, cnn_impl):
     """The decoder recomputes the network band by band on other launch shapes; a position's
     outputs must not depend on its neighbours in the batch or on the tile it falls into."""
     ocfg = O.OracleConfig()
-    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg))
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), cnn_impl=cnn_impl)
     rng = np.random.default_rng(0)
     pl = torch.from_numpy(rng.integers(-128, 128, size=(3, 12, 37, 45)).astype(np.int16)).cuda()
     for b in range(3):
@@ -239,11 +271,12 @@ def test_decoder_reads_reference_golden_streams(L, name):
 
 
 # ---------------------------------------------------------------------------- full path (a)
+@pytest.mark.parametrize("impl", [(0, 0), (1, 0), (0, 1)], ids=["fp32-warp", "tcgen05-warp", "fp32-scalar"])
 @pytest.mark.parametrize("sub_len", [0, 64, 2048])
 @pytest.mark.parametrize("name", list(EDGE_IMAGES))
-def test_round_trip_lossless(L, name, sub_len):
+def test_round_trip_lossless(L, name, sub_len, impl):
     ocfg = O.OracleConfig()
-    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=sub_len)
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=sub_len, cnn_impl=impl[0], decode_impl=impl[1])
     img = EDGE_IMAGES[name]()
     bsl = codec.compress_images(img[None])[0]
     assert len(bsl) == 6 and all(len(r) == 9 for r in bsl)
@@ -251,9 +284,23 @@ def test_round_trip_lossless(L, name, sub_len):
     assert np.array_equal(rec, img)
 
 
-def test_round_trip_config_b_batch(L):
+def test_scalar_and_warp_decoders_agree(L):
+    """Both decode kernels read the same streams (they find the symbol torchac's search finds)."""
+    ocfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(ocfg)
+    img = O.synthetic_image(95, 161, 3)
+    for sub_len in (0, 256):
+        enc = make_codec(L, ocfg, sd, sub_len=sub_len)
+        bsl = enc.compress_images(img[None])
+        for decode_impl in (0, 1):
+            dec = make_codec(L, ocfg, sd, sub_len=sub_len, decode_impl=decode_impl)
+            assert np.array_equal(dec.decompress_images(bsl)[0], img)
+
+
+@pytest.mark.parametrize("cnn_impl", [0, 1])
+def test_round_trip_config_b_batch(L, cnn_impl):
     ocfg = O.OracleConfig(dwtlevels=(0, 1), chs=60)
-    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=0)
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=0, cnn_impl=cnn_impl)
     imgs = np.stack([O.synthetic_image(96, 128, i) for i in range(5)])
     bsls = codec.compress_images(imgs)
     assert np.array_equal(codec.decompress_images(bsls), imgs)
@@ -285,7 +332,7 @@ def test_kodak_shape_round_trip_and_rate(L):
     imgs = np.stack([O.synthetic_image(512, 768, i) for i in range(2)])
     sizes = {}
     for sub_len in (0, 4096):
-        codec = make_codec(L, ocfg, sd, sub_len=sub_len)
+        codec = make_codec(L, ocfg, sd, sub_len=sub_len, cnn_impl=L.CNN_TCGEN05)
         bsls = codec.compress_images(imgs)
         assert np.array_equal(codec.decompress_images(bsls), imgs)
         sizes[sub_len] = sum(len(b) for bsl in bsls for r in bsl for b in r)
