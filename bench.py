@@ -152,7 +152,7 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def algorithmic_work(geom, chs, n, blob_bytes):
+def algorithmic_work(geom, chs, n, blob_bytes, decode_impl=0):
     """Per-step algorithmic bytes / flops of each kernel class for n images."""
     S = geom.num_scales
     pos = [geom.Hs[s] * geom.Ws[s] for s in range(S)]
@@ -165,7 +165,9 @@ def algorithmic_work(geom, chs, n, blob_bytes):
         "cnn": n * sum(pos[s] * (2 * 3 * (b + 1) + 240) for s in range(S) for b in range(3)),
         "bounds": n * coded_pos * (240 + 6 + 12),                               # 258 B per (position, band)
         "encode": n * geom.symbols * 4 + blob_bytes,                            # 4 B bounds in + bytes out
-        "decode": n * coded_pos * (240 + 6) + blob_bytes,                       # params in, symbols out, bytes in
+        "window": n * coded_pos * (240 + 6 + 3 * 64),                           # params + samples in, 3 window rows out
+        "decode": (n * coded_pos * (3 * 64 + 6) + blob_bytes) if decode_impl == 0   # window rows + bytes in, symbols out
+        else (n * coded_pos * (240 + 6) + blob_bytes),                          # legacy: params in, symbols out, bytes in
         "merge": n * (2 * 12 * sum(pos) + 3 * geom.H * geom.W),
     }
 
@@ -183,7 +185,7 @@ def run_b200(args, rank, world, local_rank):
     ocfg = O.OracleConfig.from_dict(cfg)
     sd = O.synthetic_state_dict(ocfg)
     codec = Codec(CodecConfig.from_json_dict(cfg, sub_len=sub_len, numerics=L.NUM_TORCH_CUDA, cnn_impl=args.cnn,
-                                             device=local_rank), sd)
+                                             device=local_rank, decode_impl=args.decode_impl), sd)
     geom = codec.geometry(H, W)
     S = geom.num_scales
     st = 2 ** S
@@ -244,6 +246,7 @@ def run_b200(args, rank, world, local_rank):
     clocks.start()
     launches0 = codec.launches
     codec.profile(True)
+    codec.decode_stats()
     t_enc = t_dec = 0.0
     for _ in range(args.steps):
         a, b, *_ = dev_step(True)
@@ -252,6 +255,7 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     prof = codec.profile_read()
     codec.profile(False)
+    dstats = codec.decode_stats()
     launches = codec.launches - launches0
     clk = clocks.stop()
 
@@ -289,7 +293,7 @@ def run_b200(args, rank, world, local_rank):
         pk = json.load(open(pk_path))
         peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops_sustained": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
                  "src": "measured"}
-    work_step = algorithmic_work(geom, ocfg.chs, n_img, blob_bytes)
+    work_step = algorithmic_work(geom, ocfg.chs, n_img, blob_bytes, args.decode_impl)
     kernel_ms = {k: v[0] / K for k, v in prof.items()}
     dom = max(kernel_ms, key=kernel_ms.get)
     if dom == "cnn" and args.cnn == 1:
@@ -320,6 +324,7 @@ def run_b200(args, rank, world, local_rank):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "model_config": cfg_name, "images_per_gpu": n_img, "height": H, "width": W,
                    "sub_len": sub_len, "cnn_impl": "tcgen05" if args.cnn == 1 else "fp32-cuda-core",
+                   "decode_impl": "windows+chains" if args.decode_impl == 0 else "legacy-warp",
                    "weights": "oracle.synthetic_state_dict(seed=1337) (shipped checkpoint absent)",
                    "l2": "256 MiB buffer written before every timed encode and decode (L2 flushed)",
                    "parallelism": f"images sharded over {world} GPU(s), no data-path collective"},
@@ -331,6 +336,7 @@ def run_b200(args, rank, world, local_rank):
                 "encode_mpps": mp * K / (h_enc / 1e3), "decode_mpps": mp * K / (h_dec / 1e3),
                 "api": "llicti_encode_host + llicti_decode_host, pinned host buffers"},
         "gpu_launches": int(launches_total), "clocks": clk,
+        "decode_stats_per_step": {k: v / K for k, v in dstats.items()},
     }
     print(json.dumps(line), flush=True)
 
@@ -343,7 +349,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--images", type=int, default=0, help="override images per GPU")
-    ap.add_argument("--cnn", type=int, default=int(os.environ.get("LLICTI_CNN", "0")), help="0 fp32, 1 tcgen05")
+    ap.add_argument("--cnn", type=int, default=int(os.environ.get("LLICTI_CNN", "1")), help="0 fp32 CUDA cores, 1 tcgen05")
+    ap.add_argument("--decode-impl", type=int, default=0, help="0 windows + serial chains, 1 legacy one-warp-per-chain")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -75,7 +75,7 @@ typedef struct {
     int32_t numerics;     /* LLICTI_NUM_*                                          */
     int32_t cnn_impl;     /* LLICTI_CNN_*                                          */
     int32_t device;       /* CUDA device ordinal                                   */
-    int32_t decode_impl;  /* 0: one warp per substream (default); 1: one thread per substream */
+    int32_t decode_impl;  /* 0: CDF windows + serial coder chains (default); 1: legacy, one warp per chain does both */
 } llicti_config;
 
 /* fp32 host pointers in PyTorch's own layouts (state_dict keys in SURVEY.md 8b).
@@ -197,11 +197,17 @@ LLICTI_API int64_t llicti_launch_count(const llicti_ctx *ctx);
 /* Per-kernel-class device time, measured with CUDA events recorded on the launching stream
  * around every launch while profiling is enabled.  Classes: 0 colour+pyramid split, 1 CNN,
  * 2 CDF bounds, 3 range encode, 4 container compaction, 5 container indexing, 6 range decode
- * (+ CDF search), 7 inverse pyramid / colour merge.  llicti_profile_read waits for the
+ * (serial coder chains), 7 inverse pyramid / colour merge, 8 decode-side CDF windows.  llicti_profile_read waits for the
  * recorded events, returns summed milliseconds and launch-group counts, and clears them. */
-#define LLICTI_KERNEL_CLASSES 8
+#define LLICTI_KERNEL_CLASSES 9
 LLICTI_API int llicti_profile(llicti_ctx *ctx, int enable);
 LLICTI_API int llicti_profile_read(llicti_ctx *ctx, double *ms, int64_t *count);
+
+/* Decode-side counters since the last reset (synchronises the device): out8[0] symbols that
+ * fell outside their pre-computed CDF window and took the full analytic search, out8[1] polls
+ * of consumer warps waiting for windows, out8[2] polls of producer warps waiting for decoded
+ * samples (piped schedule).  Diagnostics for bench.py; not on the data path. */
+LLICTI_API int llicti_decode_stats(llicti_ctx *ctx, uint64_t *out8, int reset);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ MAX_SCALES = 8
 OK, E_ARG, E_CUDA, E_NOMEM, E_STREAM, E_NODEVICE = 0, -1, -2, -3, -4, -5
 NUM_TORCH_CUDA, NUM_TORCH_CPU = 0, 1
 CNN_FP32, CNN_TCGEN05 = 0, 1
-KERNEL_CLASSES = ("split", "cnn", "bounds", "encode", "compact", "index", "decode", "merge")
+KERNEL_CLASSES = ("split", "cnn", "bounds", "encode", "compact", "index", "decode", "merge", "window")
 
 
 class Config(C.Structure):
@@ -78,6 +78,7 @@ _PROTOS = {
     "llicti_launch_count": (C.c_int64, [C.c_void_p]),
     "llicti_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "llicti_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "llicti_decode_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
 }
 
 EXPORTS = tuple(_PROTOS)

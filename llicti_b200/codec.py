@@ -35,7 +35,7 @@ class CodecConfig:
     numerics: int = L.NUM_TORCH_CUDA
     cnn_impl: int = L.CNN_FP32
     device: int = 0
-    decode_impl: int = 0             # 0 = one warp per substream, 1 = one thread per substream
+    decode_impl: int = 0             # 0 = CDF windows + serial chains, 1 = legacy one-warp-per-chain
 
     @staticmethod
     def from_json_dict(cfg, **over) -> "CodecConfig":
@@ -134,10 +134,16 @@ class Codec:
 
     def profile_read(self):
         """{class: (milliseconds, launch groups)} since profiling was enabled / last read."""
-        ms = (C.c_double * 8)()
-        cnt = (C.c_int64 * 8)()
+        ms = (C.c_double * len(L.KERNEL_CLASSES))()
+        cnt = (C.c_int64 * len(L.KERNEL_CLASSES))()
         L.check(self.lib.llicti_profile_read(self._ctx, ms, cnt))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(L.KERNEL_CLASSES)}
+
+    def decode_stats(self, reset: bool = True):
+        """Decode-side diagnostics: window misses and pipeline waits since the last reset."""
+        out = (C.c_uint64 * 8)()
+        L.check(self.lib.llicti_decode_stats(self._ctx, out, int(reset)))
+        return {"slow_path_symbols": int(out[0]), "consumer_polls": int(out[1]), "producer_polls": int(out[2])}
 
     # -- full path, host buffers (the timed end-to-end call) -------------------------------
     def encode_host(self, rgb: np.ndarray, out: Optional[np.ndarray] = None):

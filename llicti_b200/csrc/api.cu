@@ -159,6 +159,9 @@ static void free_workspace(llicti_ctx *ctx) {
     cudaFree(ctx->d_stream_off); ctx->d_stream_off = nullptr;
     cudaFree(ctx->d_blob); ctx->d_blob = nullptr;
     cudaFree(ctx->d_x00); ctx->d_x00 = nullptr;
+    cudaFree(ctx->d_items); ctx->d_items = nullptr; ctx->items_cap = 0;
+    cudaFree(ctx->d_item_flags); ctx->d_item_flags = nullptr;
+    cudaFree(ctx->d_syms); ctx->d_syms = nullptr; ctx->sym_cap = 0;
     ctx->ws_images = 0;
 }
 
@@ -278,6 +281,11 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
     ctx->blob_cap = n * (size_t)g.max_stream_bytes;
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_blob, ctx->blob_cap));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_x00, n * 3 * (size_t)g.Hs[S - 1] * g.Ws[S - 1]));
+    ctx->items_cap = (int64_t)n * decode_items_per_image(p);
+    LLICTI_CUDA(cudaMalloc(&ctx->d_items, (size_t)ctx->items_cap * 2048));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)ctx->items_cap * sizeof(uint32_t)));
+    ctx->sym_cap = ((int64_t)g.Hs[0] * g.Ws[0] + 63) / 64 * 64;
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_syms, n * 3 * (size_t)ctx->sym_cap * sizeof(int16_t)));
     ctx->ws_images = max_images; ctx->ws_H = H; ctx->ws_W = W;
     return LLICTI_OK;
 }
@@ -307,6 +315,12 @@ int llicti_profile_read(llicti_ctx *ctx, double *ms, int64_t *count) {
     ctx->prof_ev.clear();
     ctx->prof_cls.clear();
     return LLICTI_OK;
+}
+
+int llicti_decode_stats(llicti_ctx *ctx, uint64_t *out8, int reset) {
+    LLICTI_REQUIRE(ctx && out8, "null argument");
+    LLICTI_CUDA(cudaDeviceSynchronize());
+    return read_decode_stats(out8, reset);
 }
 
 // ---- stage-level ------------------------------------------------------------------------

@@ -118,13 +118,18 @@ struct llicti_ctx {
     uint8_t *d_blob = nullptr;         // compacted output / decode input
     size_t blob_cap = 0;
     uint8_t *d_x00 = nullptr;          // [n][3][h_last][w_last]
+    void *d_items = nullptr;           // decode windows: 2 KB items of 32 steps of one chain (kernels_decode.cu)
+    int64_t items_cap = 0;             // in items
+    int16_t *d_syms = nullptr;         // [n][3][sym_cap] compact decoded symbols of the band in flight
+    int64_t sym_cap = 0;
+    uint32_t *d_item_flags = nullptr;  // [items_cap] readiness flags of the piped decode schedule
     int32_t *d_status = nullptr;       // device-side error flag
 };
 
 namespace llicti {
 
 enum KernelClass { KC_SPLIT = 0, KC_CNN = 1, KC_BOUNDS = 2, KC_ENCODE = 3, KC_COMPACT = 4, KC_INDEX = 5,
-                   KC_DECODE = 6, KC_MERGE = 7, KC_COUNT = 8 };
+                   KC_DECODE = 6, KC_MERGE = 7, KC_WINDOW = 8, KC_COUNT = 9 };
 
 // Brackets the kernels launched in its lifetime with two events when profiling is on.
 struct ProfScope {
@@ -188,6 +193,8 @@ int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *b
 int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params, int16_t *planes,
                        const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
                        const uint32_t *sublen, cudaStream_t st);
+int64_t decode_items_per_image(const Plan &p);
+int read_decode_stats(uint64_t *out, int reset);
 int launch_decode_table(llicti_ctx *ctx, const int16_t *table, int n_sym, int Lp, int S, const uint8_t *in,
                         const uint32_t *offs, int16_t *sym, cudaStream_t st);
 

@@ -322,236 +322,6 @@ index_streams_kernel(const StreamDesc *__restrict__ sd, int n_streams, int total
     if (threadIdx.x == 0 && running != size) atomicExch(status, LLICTI_E_STREAM);
 }
 
-// ------------------------------------------------------------------------------------------
-// Decode side: one thread per (image, substream) of a band; Y, Co, Cg coders advance together
-// ------------------------------------------------------------------------------------------
-// Largest m in [0, Lp-2] with q(m) <= target (torchac's binsearch); returns the symbol and its
-// bounds.  q is evaluated analytically, about log2(Lp) times.
-__device__ __forceinline__ int search_symbol(const GmmChannel &c, const CdfGrid &g, uint32_t target,
-                                             const NumericsProfile &np, uint32_t &c_low, uint32_t &c_high) {
-    int lo = 0, hi = g.Lp - 1;
-    uint32_t qlo = 0xFFFFFFFFu, qhi = 0x10000u;
-    while (lo + 1 < hi) {
-        const int mid = (lo + hi) >> 1;
-        const uint32_t q = cdf_q(c, g, mid, np);
-        if (q <= target) { lo = mid; qlo = q; }
-        else { hi = mid; qhi = q; }
-    }
-    if (qlo == 0xFFFFFFFFu) qlo = cdf_q(c, g, lo, np);
-    c_low = qlo;
-    c_high = qhi;
-    return lo;
-}
-
-struct DecodeGeom {
-    int Hs, Ws, crop_h, crop_w, band, padH, padW;
-    int S;            // substreams per stream of this band
-    int sub_first[3]; // first substream of the Y / Co / Cg stream among the image's substreams
-};
-
-__global__ void __launch_bounds__(128)
-decode_band_kernel(const float *__restrict__ params, int16_t *__restrict__ planes, const int32_t *__restrict__ minmax,
-                   DecodeGeom dg, NumericsProfile np, const uint8_t *__restrict__ blob,
-                   const uint64_t *__restrict__ suboff, const uint32_t *__restrict__ sublen, int total_sub) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int img = blockIdx.y;
-    if (j >= dg.S) return;
-    const size_t P = (size_t)dg.Hs * dg.Ws;
-    const float *pp = params + (size_t)img * kParamCh * P;
-    int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1)) * P;
-    const int32_t *mm = minmax + img * 4;
-    const int lo[3] = {-127, mm[0], mm[1]};
-    const int hi[3] = {128, mm[2], mm[3]};
-    AcDecoder dec[3];
-    CdfGrid grid[3];
-#pragma unroll
-    for (int clr = 0; clr < 3; ++clr) {
-        const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
-        dec[clr].init(blob + suboff[e], sublen[e]);
-        grid[clr] = make_grid(lo[clr], hi[clr]);
-    }
-    const int n_sym = dg.crop_h * dg.crop_w;
-    const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
-    const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
-    for (int i = j; i < n_sym; i += dg.S) {
-        const int r = i / dg.crop_w, c = i - r * dg.crop_w;
-        const size_t pidx = (size_t)r * dg.Ws + c;
-        int yv[3] = {0, 0, 0};
-#pragma unroll
-        for (int clr = 0; clr < 3; ++clr) {
-            GmmChannel ch;
-            load_channel(pp, P, pidx, clr, yv[0], yv[1], np, ch);
-            uint32_t c_low, c_high;
-            const int sym = search_symbol(ch, grid[clr], dec[clr].target(), np, c_low, c_high);
-            if (i + dg.S < n_sym) dec[clr].consume(c_low, c_high);   // torchac skips the update after the last symbol
-            yv[clr] = sym + lo[clr];
-            const int16_t v = (int16_t)yv[clr];
-            int16_t *dst = yb + (size_t)clr * P + pidx;
-            dst[0] = v;
-            // replicate padding of the short phases (LLICTI_nets.py:512-530)
-            const bool last_c = rep_w && c == dg.crop_w - 1, last_r = rep_h && r == dg.crop_h - 1;
-            if (last_c) dst[1] = v;
-            if (last_r) dst[dg.Ws] = v;
-            if (last_c && last_r) dst[dg.Ws + 1] = v;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Decode side, warp-cooperative: one WARP per (image, substream).  The coder state is kept
-// replicated (uniform) in all 32 lanes; the lanes evaluate 32 candidate table entries at once,
-// so a symbol usually costs one q evaluation of latency instead of log2(Lp) serial ones.
-// The symbol found is the one torchac's binary search finds (q is strictly increasing).
-// ------------------------------------------------------------------------------------------
-constexpr unsigned kFull = 0xffffffffu;
-
-// 16-bit cumulative count from the coder state; floor((value-low+1)*2^16 - 1) / span) in fp64
-// is exact here: num < 2^49, span <= 2^32, and a non-integer quotient is at least 2^-32 away
-// from an integer while the fp64 quotient is within 2^-36 of the true one.
-__device__ __forceinline__ uint32_t target_fp64(uint32_t low, uint32_t high, uint32_t value) {
-    const double span = (double)(high - low) + 1.0;
-    const double num = ((double)(value - low) + 1.0) * 65536.0 - 1.0;
-    return __double2uint_rd(num / span) & 0xFFFFu;
-}
-
-struct WarpParams {   // the 60 network outputs of one position, two per lane
-    float p0, p1;
-    __device__ __forceinline__ void load(const float *__restrict__ pp, size_t P, size_t pidx, int lane) {
-        p0 = pp[(size_t)lane * P + pidx];
-        p1 = lane < kParamCh - 32 ? pp[(size_t)(lane + 32) * P + pidx] : 0.f;
-    }
-    __device__ __forceinline__ float get(int ch) const {
-        return ch < 32 ? __shfl_sync(kFull, p0, ch) : __shfl_sync(kFull, p1, ch - 32);
-    }
-};
-
-__device__ __forceinline__ void warp_channel(const WarpParams &wp, int clr, int y0, int y1, const NumericsProfile &np,
-                                             GmmChannel &c) {
-#pragma unroll
-    for (int m = 0; m < kM; ++m) {
-        c.sigma[m] = wp.get(clr * kM + m);
-        c.mu[m] = wp.get((3 + clr) * kM + m);
-        c.w[m] = wp.get((6 + clr) * kM + m);
-    }
-    if (clr == 1) {
-        const float f0 = div255((float)y0, np);
-#pragma unroll
-        for (int m = 0; m < kM; ++m) c.mu[m] = __fadd_rn(c.mu[m], __fmul_rn(wp.get(9 * kM + m), f0));
-    } else if (clr == 2) {
-        const float f0 = div255((float)y0, np), f1 = div255((float)y1, np);
-#pragma unroll
-        for (int m = 0; m < kM; ++m) {
-            const float u = __fadd_rn(__fmul_rn(wp.get(10 * kM + m), f0), __fmul_rn(wp.get(11 * kM + m), f1));
-            c.mu[m] = __fadd_rn(c.mu[m], u);
-        }
-    }
-    gmm_prepare(c, np);
-}
-
-// Largest m in [0, Lp-2] with q(m) <= target, found by rounds of 32 parallel probes: first a
-// unit-stride window around the predicted value, then (rarely) a coarse round over what is left
-// of [0, Lp-1] and a final unit-stride round.  Entry Lp-1 acts as the 0x10000 sentinel.
-__device__ __forceinline__ int warp_search(const GmmChannel &c, const CdfGrid &g, uint32_t target,
-                                           const NumericsProfile &np, int lane, uint32_t &c_low, uint32_t &c_high) {
-    const int last = g.Lp - 1;
-    float mean = 0.f;
-#pragma unroll
-    for (int m = 0; m < kM; ++m) mean = fmaf(c.w[m], c.mu[m], mean);
-    const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
-    int lo = 0, hi = last;
-    int base = min(max(kc - 15, 0), max(last - 31, 0));
-    int stride = 1;
-    for (;;) {
-        const int k = base + lane * stride;
-        const uint32_t qv = k < last ? cdf_q(c, g, k, np) : 0x10000u;
-        const unsigned le = __ballot_sync(kFull, qv <= target);
-        const int cnt = __popc(le);
-        if (cnt == 0) {
-            if (base == 0 && stride == 1) {      // target below q(0): torchac's search returns 0
-                c_low = __shfl_sync(kFull, qv, 0);
-                c_high = __shfl_sync(kFull, qv, 1);
-                return 0;
-            }
-            hi = base == 0 ? stride : base;
-        } else if (cnt == 32) {
-            lo = base + 31 * stride;
-        } else {
-            lo = base + (cnt - 1) * stride;
-            hi = min(base + cnt * stride, last);
-            if (stride == 1) {
-                c_low = __shfl_sync(kFull, qv, cnt - 1);
-                c_high = __shfl_sync(kFull, qv, cnt);
-                return lo;
-            }
-        }
-        stride = max((hi - lo + 30) / 31, 1);
-        base = lo;
-    }
-}
-
-__global__ void __launch_bounds__(128)
-decode_band_warp_kernel(const float *__restrict__ params, int16_t *__restrict__ planes,
-                        const int32_t *__restrict__ minmax, DecodeGeom dg, NumericsProfile np,
-                        const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
-                        const uint32_t *__restrict__ sublen, int total_sub) {
-    const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // substream = warp
-    const int img = blockIdx.y;
-    if (j >= dg.S) return;
-    const size_t P = (size_t)dg.Hs * dg.Ws;
-    const float *pp = params + (size_t)img * kParamCh * P;
-    int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1)) * P;
-    const int32_t *mm = minmax + img * 4;
-    const int lo[3] = {-127, mm[0], mm[1]};
-    const int hi[3] = {128, mm[2], mm[3]};
-    AcDecoder dec[3];
-    CdfGrid grid[3];
-#pragma unroll
-    for (int clr = 0; clr < 3; ++clr) {
-        const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
-        dec[clr].init(blob + suboff[e], sublen[e]);
-        grid[clr] = make_grid(lo[clr], hi[clr]);
-    }
-    const int n_sym = dg.crop_h * dg.crop_w;
-    const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
-    const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
-    WarpParams cur, nxt;
-    if (j < n_sym) {
-        const int r = j / dg.crop_w, c = j - r * dg.crop_w;
-        cur.load(pp, P, (size_t)r * dg.Ws + c, lane);
-    }
-    for (int i = j; i < n_sym; i += dg.S) {
-        const int r = i / dg.crop_w, c = i - r * dg.crop_w;
-        const size_t pidx = (size_t)r * dg.Ws + c;
-        const int in = i + dg.S;
-        if (in < n_sym) {          // prefetch the next position's network outputs
-            const int rn = in / dg.crop_w, cn = in - rn * dg.crop_w;
-            nxt.load(pp, P, (size_t)rn * dg.Ws + cn, lane);
-        }
-        int yv[3] = {0, 0, 0};
-#pragma unroll
-        for (int clr = 0; clr < 3; ++clr) {
-            GmmChannel ch;
-            warp_channel(cur, clr, yv[0], yv[1], np, ch);
-            uint32_t c_low, c_high;
-            const uint32_t target = target_fp64(dec[clr].low, dec[clr].high, dec[clr].value);
-            const int sym = warp_search(ch, grid[clr], target, np, lane, c_low, c_high);
-            if (in < n_sym) dec[clr].consume(c_low, c_high);
-            yv[clr] = sym + lo[clr];
-        }
-        if (lane < 3) {
-            const int16_t v = (int16_t)(lane == 0 ? yv[0] : lane == 1 ? yv[1] : yv[2]);
-            int16_t *dst = yb + (size_t)lane * P + pidx;
-            dst[0] = v;
-            const bool last_c = rep_w && c == dg.crop_w - 1, last_r = rep_h && r == dg.crop_h - 1;
-            if (last_c) dst[1] = v;
-            if (last_r) dst[dg.Ws] = v;
-            if (last_c && last_r) dst[dg.Ws + 1] = v;
-        }
-        cur = nxt;
-    }
-}
-
 // torchac.decode_int16_normalized_cdf from a dense table (parity entry point).
 __global__ void __launch_bounds__(128)
 decode_table_kernel(const int16_t *__restrict__ table, int n_sym, int Lp, int S, const uint8_t *__restrict__ in,
@@ -656,30 +426,6 @@ int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *b
     dim3 grid(p.n_streams, n);
     index_streams_kernel<<<grid, 256, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, ctx->cfg.sub_len > 0, blob,
                                                stream_off, suboff, sublen, ctx->d_status);
-    ctx->launches += 1;
-    LLICTI_CUDA(cudaGetLastError());
-    return LLICTI_OK;
-}
-
-int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params, int16_t *planes,
-                       const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
-                       const uint32_t *sublen, cudaStream_t st) {
-    ProfScope prof_(ctx, KC_DECODE, st);
-    DecodeGeom dg;
-    const StreamDesc &d0 = p.sd[stream_index(p, scale, band, 0)];
-    dg.Hs = d0.Hs; dg.Ws = d0.Ws; dg.crop_h = d0.crop_h; dg.crop_w = d0.crop_w; dg.band = band;
-    dg.padH = p.g.padH[scale]; dg.padW = p.g.padW[scale];
-    dg.S = d0.S;
-    for (int c = 0; c < 3; ++c) dg.sub_first[c] = p.sd[stream_index(p, scale, band, c)].sub_first;
-    if (ctx->cfg.decode_impl == 1) {    // scalar variant: one thread per substream (kept for A/B measurements)
-        dim3 grid((dg.S + 127) / 128, n);
-        decode_band_kernel<<<grid, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen,
-                                                 (int)p.g.substreams);
-    } else {                         // one warp per substream
-        dim3 grid((dg.S + 3) / 4, n);
-        decode_band_warp_kernel<<<grid, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen,
-                                                      (int)p.g.substreams);
-    }
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;

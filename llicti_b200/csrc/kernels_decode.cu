@@ -1,0 +1,680 @@
+// Decode side of the entropy layer: mean coupling -> integer GMM CDF -> arithmetic decoding
+// (LLICTIEntropyLayer.decompress inner loop, graphs/models/LLICTI_nets.py:463-498, with
+// torchac.decode_int16_normalized_cdf at :492-493).
+//
+// The reference builds the dense H x W x Lp table for every stream and lets one CPU thread
+// binary-search it symbol by symbol.  Here the work is split by what depends on the coder state:
+//
+//   producers  (any number of warps, no coder state): for every symbol, the 31 exact table
+//              entries q(base .. base+30) around the predicted value -- a "window" -- packed
+//              with `base` into one 64-byte row.  32 symbols of one chain form a 2 KB item.
+//   consumers  (one warp per coded chain, the serial part): per symbol one 64-bit multiply and
+//              compare per lane, a ballot, two shuffles and the interval update.  No erfc, no
+//              division, no table search on the critical path.  A symbol outside its window
+//              (rare) takes the slow path: the full analytic search of `warp_search`.
+//
+// Two schedules use the same two device functions:
+//   split   six launches per band (window Y, consume Y, window Co, ...): any number of
+//           substreams; the Y -> Co -> Cg coupling is ordered by the launches.
+//   piped   one launch per band when every stream is a single torchac chain (sub_len = 0):
+//           three consumer warps per image (Y, Co, Cg) run concurrently with the producers in
+//           one grid of one-warp CTAs that are all co-resident.  Consumers publish decoded samples
+//           by writing them over a sentinel in the planes (data = flag, no fence on the serial
+//           path); producers publish items through per-item flags.  The serial chain per band is
+//           n_sym steps instead of 3 * n_sym.
+#include "common.cuh"
+#include "gmm.cuh"
+#include "rangecoder.cuh"
+#include "warp_gmm.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace llicti {
+
+__device__ unsigned long long g_decode_stats[8];   // 0 slow-path symbols, 1 consumer flag polls, 2 producer sample polls
+
+constexpr int kWin = 31;                 // table entries per window (lane 31 carries `base`)
+constexpr int16_t kSentinel = (int16_t)0x8080;   // memset(0x80): never a sample value (|v| <= 255)
+
+// Lane 31 of every window row: base | nq << 9, nq = number of real table entries in the window.
+__device__ __forceinline__ uint32_t window_info(int base, int last) { return (uint32_t)base | ((uint32_t)min(kWin, max(last - base, 0)) << 9); }
+
+struct DecodeGeom {
+    int Hs, Ws, crop_h, crop_w, band, padH, padW;
+    int n_sym;            // crop_h * crop_w
+    int S;                // substreams (chains) per stream of this band
+    int max_steps;        // ceil(n_sym / S)
+    int items_per_chain;  // ceil(max_steps / 32)
+    int sub_first[3];     // first substream of the Y / Co / Cg stream among the image's substreams
+};
+
+// ---- strong (L2-coherent) accesses for data exchanged between CTAs of one running grid --------
+__device__ __forceinline__ int ld_relaxed_s16(const int16_t *p) {
+    short v;
+    asm volatile("ld.relaxed.gpu.global.s16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+    return (int)v;
+}
+__device__ __forceinline__ void st_relaxed_s16(int16_t *p, int v) {
+    asm volatile("st.relaxed.gpu.global.b16 [%0], %1;" ::"l"(p), "h"((short)v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Decoded symbol of coding-order index i of one (image, channel); in the piped schedule the
+// array starts as sentinels and the consumer's store is the publication (data = flag).
+template <bool kPipe>
+__device__ __forceinline__ int read_symbol(const int16_t *p) {
+    if (!kPipe) return (int)*p;
+    int v = ld_relaxed_s16(p);
+    while (v == (int)kSentinel) {       // not decoded yet
+        __nanosleep(200);
+        v = ld_relaxed_s16(p);
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Producer: the windows of 32 consecutive steps of one chain.  Item layout: uint4 [4][32 lanes],
+// lane l holds its own entries q(base_s + l) of steps s = 8 v + e in element e of its v-th uint4.
+// `syms` = compact symbol arrays of this image's band, [3][sym_cap] in coding order.
+// ------------------------------------------------------------------------------------------
+template <bool kPipe>
+__device__ __forceinline__ void produce_item(const float *__restrict__ pp, const int16_t *syms, size_t sym_cap, size_t P,
+                                             const DecodeGeom &dg, int clr, const int (&lo)[3], const CdfGrid &g, int j,
+                                             int tb, const NumericsProfile &np, uint4 *__restrict__ item, uint16_t *stage,
+                                             int lane) {
+    const int last = g.Lp - 1;
+    const int t = tb * 32 + lane;
+    const long long i = (long long)j + (long long)t * dg.S;
+    GmmChannel ch;
+#pragma unroll
+    for (int m = 0; m < kM; ++m) { ch.sigma[m] = 1.f; ch.mu[m] = 0.f; ch.w[m] = 0.2f; }
+    int base = 0;
+    if (i < dg.n_sym) {
+        const int r = (int)(i / dg.crop_w), c = (int)(i - (long long)r * dg.crop_w);
+        const size_t pidx = (size_t)r * dg.Ws + c;
+        int y0 = 0, y1 = 0;
+        if (clr >= 1) y0 = read_symbol<kPipe>(syms + i) + lo[0];
+        if (clr == 2) y1 = read_symbol<kPipe>(syms + sym_cap + i) + lo[1];
+        load_channel(pp, P, pidx, clr, y0, y1, np, ch);
+        float mean = 0.f;
+#pragma unroll
+        for (int m = 0; m < kM; ++m) mean = fmaf(ch.w[m], ch.mu[m], mean);
+        const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
+        base = min(max(kc - kWin / 2, 0), max(last - (kWin - 1), 0));
+    }
+    const int nv = min(32, (dg.n_sym - j + dg.S - 1) / dg.S - tb * 32);   // valid steps of this item (warp-uniform)
+    uint16_t *my = stage + lane * 34;     // 17-word pitch: conflict-free writes and reads
+#pragma unroll 1
+    for (int s = 0; s < nv; ++s) {
+        GmmChannel b;
+#pragma unroll
+        for (int m = 0; m < kM; ++m) {
+            b.sigma[m] = __shfl_sync(kFull, ch.sigma[m], s);
+            b.mu[m] = __shfl_sync(kFull, ch.mu[m], s);
+            b.w[m] = __shfl_sync(kFull, ch.w[m], s);
+        }
+        const int bs = __shfl_sync(kFull, base, s);
+        const int k = bs + lane;
+        uint32_t q = window_info(bs, last);
+        if (lane < kWin) q = k < last ? cdf_q(b, g, k, np) : 0u;
+        my[s] = (uint16_t)q;
+    }
+    __syncwarp();
+    const uint32_t *mw = reinterpret_cast<const uint32_t *>(my);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        uint4 o;
+        o.x = mw[4 * v + 0]; o.y = mw[4 * v + 1]; o.z = mw[4 * v + 2]; o.w = mw[4 * v + 3];
+        if (kPipe) __stcg(item + v * 32 + lane, o); else item[v * 32 + lane] = o;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// Consumer: the serial arithmetic decoder of one chain over pre-computed windows.
+// ------------------------------------------------------------------------------------------
+// Slow path: the symbol is outside the window.  Full analytic search (identical result to
+// torchac's binary search over the dense row).
+// Returns c_low | (c_high - 1) << 16 | symbol << 32.
+__device__ __noinline__ uint64_t slow_symbol(const float *__restrict__ pp, const int16_t *syms, size_t sym_cap, size_t P,
+                                             int crop_w, int Ws, long long i, int clr, int lo0, int lo1, CdfGrid g,
+                                             NumericsProfile np, uint32_t low, uint32_t high, uint32_t value, int lane,
+                                             int pipe) {
+    if (lane == 0) atomicAdd(&g_decode_stats[0], 1ull);
+    const int r = (int)(i / crop_w), c = (int)(i - (long long)r * crop_w);
+    const size_t pidx = (size_t)r * Ws + c;
+    int y0 = 0, y1 = 0;
+    if (clr >= 1) y0 = (pipe ? ld_relaxed_s16(syms + i) : (int)syms[i]) + lo0;
+    if (clr == 2) y1 = (pipe ? ld_relaxed_s16(syms + sym_cap + i) : (int)syms[sym_cap + i]) + lo1;
+    WarpParams wp;
+    wp.load(pp, P, pidx, lane);
+    GmmChannel ch;
+    warp_channel(wp, clr, y0, y1, np, ch);
+    const uint64_t span = (uint64_t)high - (uint64_t)low + 1ull;
+    const uint64_t num = (((uint64_t)value - (uint64_t)low + 1ull) << 16) - 1ull;
+    const uint32_t target = (uint32_t)(num / span) & 0xFFFFu;
+    uint32_t c_low, c_high;
+    const int sym = warp_search(ch, g, target, np, lane, c_low, c_high);
+    return (uint64_t)c_low | ((uint64_t)(c_high - 1u) << 16) | ((uint64_t)(uint32_t)sym << 32);
+}
+
+// Serial coder state of one chain: torchac's (low, high, value) registers over a bit window that
+// always holds at least 32 upcoming bits, refilled from two look-ahead words AFTER each step, so
+// neither a memory access nor a refill sits between two symbols.
+struct ChainCoder {
+    uint32_t low, high, value;
+    const uint32_t *w;           // 4-byte aligned base (<= stream start)
+    uint32_t lo_byte, hi_byte;   // valid bytes [lo, hi) relative to w
+    uint32_t idx, a0, a1;        // next word index, the two upcoming words
+    uint32_t bhi, blo;           // upcoming bits, left aligned in bhi:blo
+    int avail;
+
+    __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
+        const uint32_t b0 = i * 4u;
+        uint32_t v = 0u;
+        if (b0 < hi_byte) {
+            v = __byte_perm(__ldg(w + i), 0, 0x0123);   // first stream byte in the most significant position
+            if (b0 < lo_byte) v &= 0xFFFFFFFFu >> (8u * (lo_byte - b0));
+            if (b0 + 4u > hi_byte) v &= 0xFFFFFFFFu << (8u * (b0 + 4u - hi_byte));   // torchac reads zeros past the end
+        }
+        return v;
+    }
+    __device__ __forceinline__ void skip(int sh) {      // 0 <= sh <= 32; keeps >= 32 bits in the window
+        const uint64_t b = (((uint64_t)bhi << 32) | blo) << sh;
+        bhi = (uint32_t)(b >> 32);
+        blo = (uint32_t)b;
+        avail -= sh;
+        if (avail < 32) {
+            const uint64_t ins = (uint64_t)a0 << (32 - avail);
+            bhi |= (uint32_t)(ins >> 32);
+            blo |= (uint32_t)ins;
+            avail += 32;
+            a0 = a1;
+            a1 = fetch(idx++);
+        }
+    }
+    __device__ __forceinline__ void init(const uint8_t *ptr, uint32_t n) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
+        w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        lo_byte = (uint32_t)(a & 3);
+        hi_byte = lo_byte + n;
+        const uint64_t b = (uint64_t)fetch(0) << (32 + 8 * lo_byte);
+        bhi = (uint32_t)(b >> 32);
+        blo = (uint32_t)b;
+        avail = 32 - 8 * (int)lo_byte;
+        a0 = fetch(1);
+        a1 = fetch(2);
+        idx = 3;
+        skip(0);
+        low = 0; high = 0xFFFFFFFFu;
+        value = bhi;
+        skip(32);
+    }
+};
+
+// torchac's interval update and renormalisation for the symbol with bounds (c_low, c_high), as a
+// pure function of the coder registers.  The bit-serial E1/E2/E3 loop shifts out
+//   n = clz(nl ^ nh)                          equal leading bits (E1/E2 run), then
+//   k = the run of (1, 0) bit pairs after the first differing pair  (E3 / underflow run).
+// With d = nl ^ nh and m = nl & ~nh (ones at the (1, 0) pairs; the run occupies n+1 .. n+k),
+// d & ~(m << 1) has its first one exactly at n + k, so ONE clz gives the total shift sh = n + k.
+// After the shift the top pair is (0, 1) whether or not an underflow happened; it happened iff
+// the top bit of nl << sh is set, which is also the bit torchac flips in `value`.
+struct NextState { uint32_t low, high, value; int sh; uint32_t nl; };
+__device__ __forceinline__ NextState next_state(uint32_t low, uint32_t high, uint32_t value, uint32_t next_bits,
+                                                uint32_t c_low, uint32_t c_high) {
+    const uint32_t sm1 = high - low;                                    // span - 1; span * c = sm1 * c + c
+    NextState o;
+    o.nl = low + (uint32_t)(((uint64_t)sm1 * c_low + c_low) >> 16);
+    const uint32_t nh = (low - 1u) + (uint32_t)(((uint64_t)sm1 * c_high + c_high) >> 16);
+    o.sh = __clz((o.nl ^ nh) & ~((o.nl & ~nh) << 1));                   // <= 31 whenever nl < nh
+    const uint32_t ls = o.nl << o.sh;
+    o.low = ls & 0x7FFFFFFFu;
+    o.high = (nh << o.sh) | ~(0xFFFFFFFFu << o.sh) | 0x80000000u;
+    o.value = __funnelshift_l(next_bits, value, o.sh) ^ (ls & 0x80000000u);
+    return o;
+}
+
+template <bool kPipe>
+__device__ __forceinline__ uint4 load_chunk(const uint4 *p) { return kPipe ? __ldcg(p) : *p; }
+
+__device__ __forceinline__ uint32_t chunk_entry(const uint4 &q, int e) {
+    const uint32_t w = (e >> 1) == 0 ? q.x : (e >> 1) == 1 ? q.y : (e >> 1) == 2 ? q.z : q.w;
+    return (e & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+struct ChainCtx {       // what the (rare) slow path needs
+    const float *pp;
+    const int16_t *syms;
+    size_t sym_cap, P;
+    int crop_w, Ws, clr, lo0, lo1, S;
+};
+
+// One symbol.  Lane l holds table entry q(base + l) of this symbol's window and evaluates, for the
+// candidate "symbol = base + l", the complete next coder state; which candidate is right is
+//   low + ((span * q(s)) >> 16) <= value          (<=> q(s) <= floor(((value-low+1) 2^16 - 1) / span),
+// torchac's search key), so a ballot picks the lane and four shuffles fetch its state.  The only
+// work after the ballot is the selection.
+template <bool kPipe>
+__device__ __forceinline__ int decode_step(ChainCoder &cc, uint32_t raw, int last, long long i, const ChainCtx &cx,
+                                           const CdfGrid &g, const NumericsProfile &np, int lane) {
+    // window geometry and the upper bound of each candidate: data only, off the serial chain
+    const uint32_t info = __shfl_sync(kFull, raw, 31);
+    const int base = (int)(info & 511u), nq = (int)(info >> 9);
+    const uint32_t up = __shfl_down_sync(kFull, raw, 1);
+    const uint32_t c_high = lane + 1 < nq ? up : 0x10000u;
+    const uint32_t vmask = (1u << nq) - 1u;
+    const uint32_t zmask = base == 0 ? 1u : 0u;          // target below q(0): torchac's search returns symbol 0
+    const uint32_t lim = base + nq < last ? (uint32_t)(nq - 1) : 31u;   // li >= lim: beyond the window
+    const NextState ns = next_state(cc.low, cc.high, cc.value, cc.bhi, raw, c_high);
+    const uint32_t li = (uint32_t)__popc((__ballot_sync(kFull, cc.value >= ns.nl) & vmask) | zmask) - 1u;
+    int sym, sh;
+    if (li >= lim) {                                      // includes li = -1: below a window that does not start at 0
+        const uint64_t pk = slow_symbol(cx.pp, cx.syms, cx.sym_cap, cx.P, cx.crop_w, cx.Ws, i, cx.clr, cx.lo0, cx.lo1, g, np,
+                                        cc.low, cc.high, cc.value, lane, kPipe ? 1 : 0);
+        const NextState s2 = next_state(cc.low, cc.high, cc.value, cc.bhi, (uint32_t)pk & 0xFFFFu,
+                                        (((uint32_t)pk >> 16) & 0xFFFFu) + 1u);
+        cc.low = s2.low; cc.high = s2.high; cc.value = s2.value; sh = s2.sh;
+        sym = (int)(pk >> 32);
+    } else {
+        cc.low = __shfl_sync(kFull, ns.low, li);
+        cc.high = __shfl_sync(kFull, ns.high, li);
+        cc.value = __shfl_sync(kFull, ns.value, li);
+        sh = __shfl_sync(kFull, ns.sh, li);
+        sym = base + (int)li;
+    }
+    cc.skip(sh);     // (torchac does not update after the last symbol; the state is dead by then)
+    return sym;
+}
+
+// `out` = compact symbol array of this (image, channel) in coding order; chain j writes j, j+S, ...
+template <bool kPipe>
+__device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, const CdfGrid &g, int j,
+                                              const NumericsProfile &np, int16_t *out, const uint4 *__restrict__ items,
+                                              uint32_t *flags, const uint8_t *__restrict__ stream, uint32_t stream_len,
+                                              int lane) {
+    const int S = cx.S;
+    const int n_steps = (n_sym - j + S - 1) / S;
+    if (n_steps <= 0) return;
+    const int n_items = (n_steps + 31) >> 5;      // an item = 4 chunks of 8 steps (one uint4 per lane each)
+    const int n_full = n_steps >> 3, tail = n_steps & 7;
+    const int last = g.Lp - 1;
+    unsigned long long polls = 0;
+
+    ChainCoder cc;
+    cc.init(stream, stream_len);
+    long long i = j;
+    int16_t *dst = out + j;
+
+    if (kPipe)
+        while (ld_relaxed_u32(flags) == 0u) { ++polls; __nanosleep(100); }
+    const uint4 *src = items + lane;
+    uint4 q0 = load_chunk<kPipe>(src), q1 = load_chunk<kPipe>(src + 32), q2 = load_chunk<kPipe>(src + 64),
+          q3 = load_chunk<kPipe>(src + 96);
+    uint4 n0 = q0, n1 = q1, n2 = q2, n3 = q3;
+    uint32_t f_next = kPipe && n_items > 1 ? ld_relaxed_u32(flags + 1) : 1u;   // readiness of item 1, looked at one item later
+
+    for (int it = 0; it < n_items; ++it) {
+        // the next item is fetched while this one is decoded (32 steps of distance)
+        bool have_next = it + 1 >= n_items;
+        uint32_t f_next2 = 1u;
+        if (it + 1 < n_items) {
+            if (!kPipe || f_next != 0u) {
+                const uint4 *nx = src + (size_t)(it + 1) * 128;
+                n0 = load_chunk<kPipe>(nx); n1 = load_chunk<kPipe>(nx + 32); n2 = load_chunk<kPipe>(nx + 64); n3 = load_chunk<kPipe>(nx + 96);
+                have_next = true;
+            }
+            if (kPipe && it + 2 < n_items) f_next2 = ld_relaxed_u32(flags + it + 2);
+        }
+        const int full_here = min(4, n_full - it * 4);
+#pragma unroll 1
+        for (int v = 0; v < full_here; ++v) {
+            const uint4 q = v == 0 ? q0 : v == 1 ? q1 : v == 2 ? q2 : q3;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int sym = decode_step<kPipe>(cc, chunk_entry(q, e), last, i, cx, g, np, lane);
+                if (lane == 0) {
+                    if (kPipe) st_relaxed_s16(dst, sym); else *dst = (int16_t)sym;
+                }
+                i += S;
+                dst += S;
+            }
+        }
+        if (it == n_items - 1 && tail) {
+            const int v = max(full_here, 0);
+            const uint4 q = v == 0 ? q0 : v == 1 ? q1 : v == 2 ? q2 : q3;
+#pragma unroll 1
+            for (int e = 0; e < tail; ++e) {
+                const uint32_t w = (e >> 1) == 0 ? q.x : (e >> 1) == 1 ? q.y : (e >> 1) == 2 ? q.z : q.w;
+                const int sym = decode_step<kPipe>(cc, (e & 1) ? (w >> 16) : (w & 0xFFFFu), last, i, cx, g, np, lane);
+                if (lane == 0) {
+                    if (kPipe) st_relaxed_s16(dst, sym); else *dst = (int16_t)sym;
+                }
+                i += S;
+                dst += S;
+            }
+        }
+        if (!have_next) {
+            while (ld_relaxed_u32(flags + it + 1) == 0u) { ++polls; __nanosleep(100); }
+            const uint4 *nx = src + (size_t)(it + 1) * 128;
+            n0 = load_chunk<kPipe>(nx); n1 = load_chunk<kPipe>(nx + 32); n2 = load_chunk<kPipe>(nx + 64); n3 = load_chunk<kPipe>(nx + 96);
+        }
+        q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+        f_next = f_next2;
+    }
+    if (kPipe && lane == 0 && polls) atomicAdd(&g_decode_stats[1], polls);
+}
+
+// Compact symbols of a decoded band -> centred samples in the planes, with the replicate padding
+// of the short phases (_pad_decoded_tensor, LLICTI_nets.py:512-530).
+__global__ void __launch_bounds__(256)
+scatter_band_kernel(const int16_t *__restrict__ syms, size_t sym_cap, int16_t *__restrict__ planes,
+                    const int32_t *__restrict__ minmax, DecodeGeom dg, int n) {
+    const int img = blockIdx.y / 3, clr = blockIdx.y - 3 * img;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dg.n_sym) return;
+    const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
+    const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
+    const size_t P = (size_t)dg.Hs * dg.Ws;
+    const int32_t *mm = minmax + img * 4;
+    const int lo = clr == 0 ? -127 : clr == 1 ? mm[0] : mm[1];
+    const int r = i / dg.crop_w, c = i - r * dg.crop_w;
+    const int16_t v = (int16_t)((int)syms[((size_t)img * 3 + clr) * sym_cap + i] + lo);
+    int16_t *dst = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1) + clr) * P + (size_t)r * dg.Ws + c;
+    dst[0] = v;
+    const bool last_c = rep_w && c == dg.crop_w - 1, last_r = rep_h && r == dg.crop_h - 1;
+    if (last_c) dst[1] = v;
+    if (last_r) dst[dg.Ws] = v;
+    if (last_c && last_r) dst[dg.Ws + 1] = v;
+}
+
+static __device__ __forceinline__ void band_grids(const int32_t *mm, int (&lo)[3], CdfGrid (&g)[3]) {
+    lo[0] = -127; lo[1] = mm[0]; lo[2] = mm[1];
+    g[0] = make_grid(-127, 128); g[1] = make_grid(mm[0], mm[2]); g[2] = make_grid(mm[1], mm[3]);
+}
+
+// ---- split schedule ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+window_kernel(const float *__restrict__ params, const int16_t *__restrict__ syms, size_t sym_cap,
+              const int32_t *__restrict__ minmax, DecodeGeom dg, int clr, NumericsProfile np, uint4 *__restrict__ items,
+              int n) {
+    __shared__ __align__(16) uint16_t stage[4][32 * 34];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long per_img = (long long)dg.S * dg.items_per_chain;
+    const long long total = per_img * n;
+    for (long long w = (long long)blockIdx.x * 4 + wib; w < total; w += (long long)gridDim.x * 4) {
+        const int img = (int)(w / per_img);
+        const long long rem = w - (long long)img * per_img;
+        // chain-minor order: neighbouring warps work on neighbouring chains of the same step block,
+        // so their (strided) parameter reads share sectors
+        const int tb = (int)(rem / dg.S), j = (int)(rem - (long long)tb * dg.S);
+        if ((long long)j + (long long)tb * 32 * dg.S >= dg.n_sym) continue;
+        const size_t P = (size_t)dg.Hs * dg.Ws;
+        int lo[3];
+        CdfGrid g[3];
+        band_grids(minmax + img * 4, lo, g);
+        uint4 *item = items + ((((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain + tb) * 128;
+        produce_item<false>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
+                            g[clr], j, tb, np, item, stage[wib], lane);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+consume_kernel(const float *__restrict__ params, int16_t *__restrict__ syms, size_t sym_cap,
+               const int32_t *__restrict__ minmax, DecodeGeom dg, int clr, NumericsProfile np,
+               const uint4 *__restrict__ items, const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
+               const uint32_t *__restrict__ sublen, int total_sub, int n) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (long long)n * dg.S) return;
+    const int img = (int)(w / dg.S), j = (int)(w - (long long)img * dg.S);
+    const size_t P = (size_t)dg.Hs * dg.Ws;
+    int lo[3];
+    CdfGrid g[3];
+    band_grids(minmax + img * 4, lo, g);
+    int16_t *isyms = syms + (size_t)img * 3 * sym_cap;
+    const ChainCtx cx = {params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], dg.S};
+    const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
+    const uint4 *chain_items = items + (((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain * 128;
+    consume_chain<false>(cx, dg.n_sym, g[clr], j, np, isyms + (size_t)clr * sym_cap, chain_items, nullptr, blob + suboff[e],
+                         sublen[e], lane);
+}
+
+// ---- piped schedule (S == 1): grid of one-warp CTAs, consumers first --------------------------
+__global__ void __launch_bounds__(32)
+decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t sym_cap, const int32_t *__restrict__ minmax,
+                        DecodeGeom dg, NumericsProfile np, uint4 *items, uint32_t *flags,
+                        const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
+                        const uint32_t *__restrict__ sublen, int total_sub, int n) {
+    __shared__ __align__(16) uint16_t stage[32 * 34];
+    const int lane = threadIdx.x;
+    const size_t P = (size_t)dg.Hs * dg.Ws;
+    const int n_cons = 3 * n;
+    int lo[3];
+    CdfGrid g[3];
+    if ((int)blockIdx.x < n_cons) {
+        const int img = blockIdx.x / 3, clr = blockIdx.x - 3 * img;
+        band_grids(minmax + img * 4, lo, g);
+        int16_t *isyms = syms + (size_t)img * 3 * sym_cap;
+        const ChainCtx cx = {params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], 1};
+        const size_t e = (size_t)img * total_sub + dg.sub_first[clr];
+        const size_t chain = (size_t)img * 3 + clr;
+        consume_chain<true>(cx, dg.n_sym, g[clr], 0, np, isyms + (size_t)clr * sym_cap, items + chain * dg.items_per_chain * 128,
+                            flags + chain * dg.items_per_chain, blob + suboff[e], sublen[e], lane);
+        return;
+    }
+    // Producers are split into three groups, one per colour channel, each walking its channel's
+    // items in (step block, image) order.  Y items wait for nothing; a Co (Cg) item waits for the
+    // Y (and Co) symbols of its 32 positions, i.e. for consumers that only depend on items earlier
+    // in the same orders -- the earliest unfinished item of every group can always run.
+    const int np_total = (int)gridDim.x - n_cons;
+    const int p = (int)blockIdx.x - n_cons;
+    const int gy = max(np_total / 5, 1), gco = max((np_total - gy) / 2, 1);
+    int clr, gp, gsize;
+    if (p < gy) { clr = 0; gp = p; gsize = gy; }
+    else if (p < gy + gco) { clr = 1; gp = p - gy; gsize = gco; }
+    else { clr = 2; gp = p - gy - gco; gsize = np_total - gy - gco; }
+    const long long total = (long long)dg.items_per_chain * n;
+    for (long long w = gp; w < total; w += gsize) {
+        const int tb = (int)(w / n);
+        const int img = (int)(w - (long long)tb * n);
+        const int chain = img * 3 + clr;
+        band_grids(minmax + img * 4, lo, g);
+        uint4 *item = items + ((size_t)chain * dg.items_per_chain + tb) * 128;
+        produce_item<true>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
+                           g[clr], 0, tb, np, item, stage, lane);
+        // every lane's stores happen before the flag store: warp barrier, then a cumulative fence
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            st_release_u32(flags + (size_t)chain * dg.items_per_chain + tb, 1u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Legacy schedule (decode_impl = 1): one warp per chain does everything, Y, Co, Cg in turn.
+// Kept for A/B measurements against the windowed schedules.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+decode_band_warp_kernel(const float *__restrict__ params, int16_t *__restrict__ planes,
+                        const int32_t *__restrict__ minmax, DecodeGeom dg, NumericsProfile np,
+                        const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
+                        const uint32_t *__restrict__ sublen, int total_sub) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // substream = warp
+    const int img = blockIdx.y;
+    if (j >= dg.S) return;
+    const size_t P = (size_t)dg.Hs * dg.Ws;
+    const float *pp = params + (size_t)img * kParamCh * P;
+    int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1)) * P;
+    const int32_t *mm = minmax + img * 4;
+    const int lo[3] = {-127, mm[0], mm[1]};
+    const int hi[3] = {128, mm[2], mm[3]};
+    AcDecoder dec[3];
+    CdfGrid grid[3];
+#pragma unroll
+    for (int clr = 0; clr < 3; ++clr) {
+        const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
+        dec[clr].init(blob + suboff[e], sublen[e]);
+        grid[clr] = make_grid(lo[clr], hi[clr]);
+    }
+    const int n_sym = dg.n_sym;
+    const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
+    const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
+    WarpParams cur, nxt;
+    if (j < n_sym) {
+        const int r = j / dg.crop_w, c = j - r * dg.crop_w;
+        cur.load(pp, P, (size_t)r * dg.Ws + c, lane);
+    }
+    for (int i = j; i < n_sym; i += dg.S) {
+        const int r = i / dg.crop_w, c = i - r * dg.crop_w;
+        const size_t pidx = (size_t)r * dg.Ws + c;
+        const int in = i + dg.S;
+        if (in < n_sym) {          // prefetch the next position's network outputs
+            const int rn = in / dg.crop_w, cn = in - rn * dg.crop_w;
+            nxt.load(pp, P, (size_t)rn * dg.Ws + cn, lane);
+        }
+        int yv[3] = {0, 0, 0};
+#pragma unroll
+        for (int clr = 0; clr < 3; ++clr) {
+            GmmChannel ch;
+            warp_channel(cur, clr, yv[0], yv[1], np, ch);
+            uint32_t c_low, c_high;
+            const uint32_t target = target_fp64(dec[clr].low, dec[clr].high, dec[clr].value);
+            const int sym = warp_search(ch, grid[clr], target, np, lane, c_low, c_high);
+            if (in < n_sym) dec[clr].consume(c_low, c_high);
+            yv[clr] = sym + lo[clr];
+        }
+        if (lane < 3) {
+            const int16_t v = (int16_t)(lane == 0 ? yv[0] : lane == 1 ? yv[1] : yv[2]);
+            int16_t *dst = yb + (size_t)lane * P + pidx;
+            dst[0] = v;
+            const bool last_c = rep_w && c == dg.crop_w - 1, last_r = rep_h && r == dg.crop_h - 1;
+            if (last_c) dst[1] = v;
+            if (last_r) dst[dg.Ws] = v;
+            if (last_c && last_r) dst[dg.Ws + 1] = v;
+        }
+        cur = nxt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Launcher
+// ------------------------------------------------------------------------------------------
+static int stream_index(const Plan &p, int scale, int band, int clr) {
+    return (p.g.num_scales - 1 - scale) * 9 + 3 * band + clr;
+}
+
+static DecodeGeom make_decode_geom(const Plan &p, int scale, int band) {
+    DecodeGeom dg;
+    const StreamDesc &d0 = p.sd[stream_index(p, scale, band, 0)];
+    dg.Hs = d0.Hs; dg.Ws = d0.Ws; dg.crop_h = d0.crop_h; dg.crop_w = d0.crop_w; dg.band = band;
+    dg.padH = p.g.padH[scale]; dg.padW = p.g.padW[scale];
+    dg.n_sym = d0.n_sym;
+    dg.S = d0.S;
+    dg.max_steps = (d0.n_sym + d0.S - 1) / d0.S;
+    dg.items_per_chain = (dg.max_steps + 31) / 32;
+    for (int c = 0; c < 3; ++c) dg.sub_first[c] = p.sd[stream_index(p, scale, band, c)].sub_first;
+    return dg;
+}
+
+// Window items (2 KB each) one image needs for its largest band.
+int64_t decode_items_per_image(const Plan &p) {
+    int64_t m = 0;
+    for (int s = 0; s < p.g.num_scales; ++s)
+        for (int b = 0; b < 3; ++b) {
+            const DecodeGeom dg = make_decode_geom(p, s, b);
+            m = std::max<int64_t>(m, 3ll * dg.S * dg.items_per_chain);
+        }
+    return m;
+}
+
+int read_decode_stats(uint64_t *out, int reset) {
+    unsigned long long h[8];
+    LLICTI_CUDA(cudaMemcpyFromSymbol(h, g_decode_stats, sizeof(h)));
+    for (int i = 0; i < 8; ++i) out[i] = h[i];
+    if (reset) {
+        unsigned long long z[8] = {};
+        LLICTI_CUDA(cudaMemcpyToSymbol(g_decode_stats, z, sizeof(z)));
+    }
+    return LLICTI_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params, int16_t *planes,
+                       const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
+                       const uint32_t *sublen, cudaStream_t st) {
+    const DecodeGeom dg = make_decode_geom(p, scale, band);
+    const int total_sub = (int)p.g.substreams;
+    if (ctx->cfg.decode_impl == 1) {
+        ProfScope prof_(ctx, KC_DECODE, st);
+        dim3 grid((dg.S + 3) / 4, n);
+        decode_band_warp_kernel<<<grid, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub);
+        ctx->launches += 1;
+        LLICTI_CUDA(cudaGetLastError());
+        return LLICTI_OK;
+    }
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        LLICTI_CUDA(cudaGetDevice(&dev));
+        LLICTI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    uint4 *items = reinterpret_cast<uint4 *>(ctx->d_items);
+    int16_t *syms = ctx->d_syms;
+    const size_t sym_cap = (size_t)ctx->sym_cap;
+    const long long items_band = 3ll * n * dg.S * dg.items_per_chain;
+    LLICTI_REQUIRE(items && syms && items_band <= ctx->items_cap && (size_t)dg.n_sym <= sym_cap, "decode workspace too small");
+    // one-warp CTAs: 32 resident per SM at most; keep well below so the whole grid is co-resident
+    const int resident = sm_count * 24;
+    const int producers = (int)std::min<long long>(items_band, (long long)sm_count * env_int("LLICTI_PIPE_PRODUCERS_PER_SM", 4));
+    const bool piped = dg.S == 1 && producers >= 5 && 3 * n + producers <= resident && !env_int("LLICTI_NO_PIPE", 0);
+    if (piped) {
+        ProfScope prof_(ctx, KC_DECODE, st);
+        // sentinels over the symbol arrays (data = flag), zeros over the item flags
+        LLICTI_CUDA(cudaMemsetAsync(syms, 0x80, (size_t)n * 3 * sym_cap * sizeof(int16_t), st));
+        LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, (size_t)items_band * sizeof(uint32_t), st));
+        decode_band_pipe_kernel<<<3 * n + producers, 32, 0, st>>>(params, syms, sym_cap, minmax, dg, ctx->num, items,
+                                                                 ctx->d_item_flags, blob, suboff, sublen, total_sub, n);
+        ctx->launches += 1;
+    } else {
+        const long long win_warps = (long long)n * dg.S * dg.items_per_chain;
+        const int win_blocks = (int)std::min<long long>((win_warps + 3) / 4, (long long)sm_count * 16);
+        const long long chains = (long long)n * dg.S;
+        const int con_blocks = (int)((chains + 3) / 4);
+        for (int clr = 0; clr < 3; ++clr) {
+            {
+                ProfScope prof_(ctx, KC_WINDOW, st);
+                window_kernel<<<win_blocks, 128, 0, st>>>(params, syms, sym_cap, minmax, dg, clr, ctx->num, items, n);
+            }
+            {
+                ProfScope prof_(ctx, KC_DECODE, st);
+                consume_kernel<<<con_blocks, 128, 0, st>>>(params, syms, sym_cap, minmax, dg, clr, ctx->num, items, blob,
+                                                           suboff, sublen, total_sub, n);
+            }
+            ctx->launches += 2;
+        }
+    }
+    {
+        ProfScope prof_(ctx, KC_MERGE, st);
+        scatter_band_kernel<<<dim3((dg.n_sym + 255) / 256, 3 * n), 256, 0, st>>>(syms, sym_cap, planes, minmax, dg, n);
+        ctx->launches += 1;
+    }
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+}  // namespace llicti

@@ -152,4 +152,79 @@ struct AcDecoder {
     }
 };
 
+// MSB-first bit source reading aligned 32-bit words two words ahead of the coder, so no memory
+// latency sits on the serial decode chain.  Bytes outside [ptr, ptr + n) read as zero (torchac
+// reads zeros past the end of the stream).
+struct BitReaderW {
+    const uint32_t *w;        // 4-byte aligned base (<= ptr)
+    uint32_t lo_byte, hi_byte;   // valid bytes [lo, hi) relative to w
+    uint32_t idx;             // next word to fetch
+    uint32_t a0, a1;          // the two upcoming words
+    uint64_t buf;             // upcoming bits, left aligned
+    int avail;
+
+    __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
+        const uint32_t b0 = i * 4u;
+        if (b0 >= hi_byte) return 0u;
+        uint32_t v = __byte_perm(__ldg(w + i), 0, 0x0123);   // first byte in the most significant position
+        if (b0 < lo_byte) v &= 0xFFFFFFFFu >> (8u * (lo_byte - b0));
+        if (b0 + 4u > hi_byte) v &= 0xFFFFFFFFu << (8u * (b0 + 4u - hi_byte));
+        return v;
+    }
+    __device__ __forceinline__ void init(const uint8_t *ptr, uint32_t n) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
+        w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        lo_byte = (uint32_t)(a & 3);
+        hi_byte = lo_byte + n;
+        const uint32_t w0 = fetch(0);
+        buf = (uint64_t)w0 << (32 + 8 * lo_byte);
+        avail = 32 - 8 * (int)lo_byte;
+        a0 = fetch(1);
+        a1 = fetch(2);
+        idx = 3;
+    }
+    __device__ __forceinline__ uint32_t take(int n) {   // 1 <= n <= 32
+        if (avail < n) {
+            buf |= (uint64_t)a0 << (32 - avail);
+            avail += 32;
+            a0 = a1;
+            a1 = fetch(idx++);
+        }
+        const uint32_t v = (uint32_t)(buf >> (64 - n));
+        buf <<= n;
+        avail -= n;
+        return v;
+    }
+};
+
+// Same arithmetic as AcDecoder over the look-ahead bit source.
+struct AcDecoderW {
+    uint32_t low, high, value;
+    BitReaderW br;
+
+    __device__ __forceinline__ void init(const uint8_t *ptr, uint32_t n) {
+        low = 0; high = 0xFFFFFFFFu;
+        br.init(ptr, n);
+        value = br.take(32);
+    }
+    __device__ __forceinline__ void consume(uint32_t c_low, uint32_t c_high) {
+        const uint64_t span = (uint64_t)high - (uint64_t)low + 1ull;
+        high = (low - 1u) + (uint32_t)((span * c_high) >> 16);
+        low = low + (uint32_t)((span * c_low) >> 16);
+        const int n = __clz(low ^ high);
+        if (n > 0) {
+            low <<= n;
+            high = (high << n) | ((1u << n) - 1u);
+            value = (value << n) | br.take(n);
+        }
+        const uint32_t y = (low << 1) & ~(high << 1);
+        const int k = __clz(~y);
+        if (k > 0) {
+            low = (low << k) & 0x7FFFFFFFu;
+            high = (high << k) | 0x80000000u | ((1u << k) - 1u);
+            value = ((value << k) | br.take(k)) ^ 0x80000000u;
+        }
+    }
+};
+
 }  // namespace llicti

@@ -105,7 +105,7 @@ class LLICTI(nn.Module):
         over = {}
         over["sub_len"] = int(cfgd.get("b200_sub_len", 0) if sub_len is None else sub_len)
         over["numerics"] = int(cfgd.get("b200_numerics", L.NUM_TORCH_CUDA) if numerics is None else numerics)
-        over["cnn_impl"] = int(cfgd.get("b200_cnn_impl", L.CNN_FP32) if cnn_impl is None else cnn_impl)
+        over["cnn_impl"] = int(cfgd.get("b200_cnn_impl", L.CNN_TCGEN05) if cnn_impl is None else cnn_impl)
         self.codec_config = CodecConfig.from_json_dict(cfgd, **over)
         self.list_scales = list(cfgd["dwtlevels"])
         self.num_scales = len(self.list_scales)
