@@ -12,6 +12,8 @@
 
 namespace llicti {
 
+constexpr long long kWarpChainLimit = 148 * 16;   // chains up to which the coder runs one warp per chain
+
 // ------------------------------------------------------------------------------------------
 // Dense table / flat bounds for one stream (parity entry points llicti_cdf_table / _bounds)
 // ------------------------------------------------------------------------------------------
@@ -107,6 +109,67 @@ __device__ __forceinline__ void encode_strided(AcEncoder &enc, const uint32_t *_
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (i + u * S < n_sym) enc.encode(v[u] & 0xFFFFu, (v[u] >> 16) + 1u);
+    }
+}
+
+// Warp-per-chain variant for when chains are few and long (torchac-compatible streams): the
+// lanes fetch 32 bounds with one coalesced load a block ahead and all mirror the (uniform) coder
+// state, so there is neither divergence between chains nor memory latency on the serial chain.
+__device__ __forceinline__ void encode_strided_warp(AcEncoder &enc, const uint32_t *__restrict__ b, int j, int n_sym, int S,
+                                                    int lane) {
+    const int n_steps = (n_sym - j + S - 1) / S;
+    uint32_t cur = lane < n_steps ? b[(size_t)j + (size_t)lane * S] : 0u;
+    for (int t0 = 0; t0 < n_steps; t0 += 32) {
+        const int t1 = t0 + 32 + lane;
+        const uint32_t nxt = t1 < n_steps ? b[(size_t)j + (size_t)t1 * S] : 0u;
+        const int m = min(32, n_steps - t0);
+#pragma unroll 4
+        for (int s = 0; s < m; ++s) {
+            const uint32_t v = __shfl_sync(0xffffffffu, cur, s);
+            enc.encode(v & 0xFFFFu, (v >> 16) + 1u);
+        }
+        cur = nxt;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+encode_all_warp_kernel(const StreamDesc *__restrict__ sd_g, int n_streams, int total_sub,
+                       const uint32_t *__restrict__ bounds, int64_t sym_stride, uint8_t *__restrict__ scratch,
+                       int64_t scratch_stride, uint32_t *__restrict__ sublen, int32_t *__restrict__ status) {
+    __shared__ StreamDesc sd[kMaxStreams];
+    for (int e = threadIdx.x; e < n_streams; e += blockDim.x) sd[e] = sd_g[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int img = blockIdx.y;
+    if (item >= total_sub) return;
+    const int k = find_stream(sd, n_streams, item);
+    const StreamDesc &d = sd[k];
+    const int j = item - d.sub_first;
+    const uint32_t *b = bounds + (size_t)img * sym_stride + d.sym_off;
+    AcEncoder enc;
+    enc.init(scratch + (size_t)img * scratch_stride + d.slot_off + (size_t)j * d.slot_bytes, (uint32_t)d.slot_bytes, lane == 0);
+    encode_strided_warp(enc, b, j, d.n_sym, d.S, lane);
+    const uint32_t nb = enc.finish();
+    if (lane == 0) {
+        sublen[(size_t)img * total_sub + item] = nb;
+        if (enc.bw.overflow) atomicExch(status, LLICTI_E_NOMEM);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+encode_flat_warp_kernel(const uint32_t *__restrict__ bounds, int n_sym, int S, uint8_t *__restrict__ out, int slot_bytes,
+                        uint32_t *__restrict__ lens, int32_t *__restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= S) return;
+    AcEncoder enc;
+    enc.init(out + (size_t)j * slot_bytes, (uint32_t)slot_bytes, lane == 0);
+    encode_strided_warp(enc, bounds, j, n_sym, S, lane);
+    const uint32_t nb = enc.finish();
+    if (lane == 0) {
+        lens[j] = nb;
+        if (enc.bw.overflow) atomicExch(status, LLICTI_E_NOMEM);
     }
 }
 
@@ -387,9 +450,15 @@ int launch_encode_all(llicti_ctx *ctx, const Plan &p, const uint32_t *bounds, in
                       uint8_t *scratch, int64_t scratch_stride, uint32_t *sublen, cudaStream_t st) {
     ProfScope prof_(ctx, KC_ENCODE, st);
     const int total_sub = (int)p.g.substreams;
-    dim3 grid((total_sub + 127) / 128, n);
-    encode_all_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
-                                            scratch_stride, sublen, ctx->d_status);
+    if ((long long)total_sub * n <= kWarpChainLimit) {      // few, long chains: one warp each
+        dim3 grid((total_sub + 3) / 4, n);
+        encode_all_warp_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
+                                                     scratch_stride, sublen, ctx->d_status);
+    } else {
+        dim3 grid((total_sub + 127) / 128, n);
+        encode_all_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
+                                                scratch_stride, sublen, ctx->d_status);
+    }
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;
@@ -397,7 +466,10 @@ int launch_encode_all(llicti_ctx *ctx, const Plan &p, const uint32_t *bounds, in
 
 int launch_encode_flat(llicti_ctx *ctx, const uint32_t *bounds, int n_sym, int S, uint8_t *out, int slot_bytes,
                        uint32_t *lens, cudaStream_t st) {
-    encode_flat_kernel<<<(S + 127) / 128, 128, 0, st>>>(bounds, n_sym, S, out, slot_bytes, lens, ctx->d_status);
+    if (S <= kWarpChainLimit)
+        encode_flat_warp_kernel<<<(S + 3) / 4, 128, 0, st>>>(bounds, n_sym, S, out, slot_bytes, lens, ctx->d_status);
+    else
+        encode_flat_kernel<<<(S + 127) / 128, 128, 0, st>>>(bounds, n_sym, S, out, slot_bytes, lens, ctx->d_status);
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;

@@ -192,7 +192,7 @@ struct ChainCoder {
         bhi = (uint32_t)(b >> 32);
         blo = (uint32_t)b;
         avail -= sh;
-        if (avail < 32) {
+        if (__builtin_expect(avail < 32, 0)) {
             const uint64_t ins = (uint64_t)a0 << (32 - avail);
             bhi |= (uint32_t)(ins >> 32);
             blo |= (uint32_t)ins;
@@ -277,7 +277,7 @@ __device__ __forceinline__ int decode_step(ChainCoder &cc, uint32_t raw, int las
     const NextState ns = next_state(cc.low, cc.high, cc.value, cc.bhi, raw, c_high);
     const uint32_t li = (uint32_t)__popc((__ballot_sync(kFull, cc.value >= ns.nl) & vmask) | zmask) - 1u;
     int sym, sh;
-    if (li >= lim) {                                      // includes li = -1: below a window that does not start at 0
+    if (__builtin_expect(li >= lim, 0)) {                 // includes li = -1: below a window that does not start at 0
         const uint64_t pk = slow_symbol(cx.pp, cx.syms, cx.sym_cap, cx.P, cx.crop_w, cx.Ws, i, cx.clr, cx.lo0, cx.lo1, g, np,
                                         cc.low, cc.high, cc.value, lane, kPipe ? 1 : 0);
         const NextState s2 = next_state(cc.low, cc.high, cc.value, cc.bhi, (uint32_t)pk & 0xFFFFu,

@@ -21,16 +21,17 @@ struct BitWriter {
     uint64_t acc;      // pending bits, right aligned
     int nbits;         // number of pending bits (< 32 between calls)
     int overflow;
+    bool writer;       // false in the lanes of a warp-per-chain encoder that only mirror the state
 
-    __device__ __forceinline__ void init(uint8_t *b, uint32_t c) {
-        base = b; cap = c; nbytes = 0; acc = 0; nbits = 0; overflow = 0;
+    __device__ __forceinline__ void init(uint8_t *b, uint32_t c, bool wr = true) {
+        base = b; cap = c; nbytes = 0; acc = 0; nbits = 0; overflow = 0; writer = wr;
     }
     __device__ __forceinline__ void put(uint32_t bits, int count) {   // 0 <= count <= 32
         acc = (acc << count) | bits;
         nbits += count;
         if (nbits >= 32) {
             const uint32_t word = (uint32_t)(acc >> (nbits - 32));
-            if (nbytes + 4 <= cap) *reinterpret_cast<uint32_t *>(base + nbytes) = __byte_perm(word, 0, 0x0123);
+            if (nbytes + 4 <= cap) { if (writer) *reinterpret_cast<uint32_t *>(base + nbytes) = __byte_perm(word, 0, 0x0123); }
             else overflow = 1;
             nbytes += 4;
             nbits -= 32;
@@ -46,7 +47,7 @@ struct BitWriter {
         const int nb = (nbits + 7) >> 3;
         const uint32_t word = nbits ? (uint32_t)(acc << (32 - nbits)) : 0u;
         for (int i = 0; i < nb; ++i) {
-            if (nbytes + i < cap) base[nbytes + i] = (uint8_t)(word >> (24 - 8 * i));
+            if (nbytes + i < cap) { if (writer) base[nbytes + i] = (uint8_t)(word >> (24 - 8 * i)); }
             else overflow = 1;
         }
         nbytes += nb;
@@ -59,30 +60,33 @@ struct AcEncoder {
     uint32_t low, high, pending;
     BitWriter bw;
 
-    __device__ __forceinline__ void init(uint8_t *slot, uint32_t cap) {
+    __device__ __forceinline__ void init(uint8_t *slot, uint32_t cap, bool writer = true) {
         low = 0; high = 0xFFFFFFFFu; pending = 0;
-        bw.init(slot, cap);
+        bw.init(slot, cap, writer);
     }
+    // Interval update + renormalisation.  n = equal leading bits (emitted), k = underflow run
+    // (counted in `pending`); d & ~(m << 1) has its first one at n + k (see next_state() in
+    // kernels_decode.cu), so the registers are shifted once, branch-free; only the bit output
+    // of a step that resolves pending underflow bits takes a branch.
     __device__ __forceinline__ void encode(uint32_t c_low, uint32_t c_high) {
-        const uint64_t span = (uint64_t)high - (uint64_t)low + 1ull;
-        high = (low - 1u) + (uint32_t)((span * c_high) >> 16);
-        low = low + (uint32_t)((span * c_low) >> 16);
-        const int n = __clz(low ^ high);
-        if (n > 0) {
-            const uint32_t b = low >> 31;
+        const uint32_t sm1 = high - low;                               // span - 1; span * c = sm1 * c + c
+        const uint32_t nl = low + (uint32_t)(((uint64_t)sm1 * c_low + c_low) >> 16);
+        const uint32_t nh = (low - 1u) + (uint32_t)(((uint64_t)sm1 * c_high + c_high) >> 16);
+        const uint32_t d = nl ^ nh;
+        const int n = __clz(d);
+        const int sh = __clz(d & ~((nl & ~nh) << 1));
+        if (__builtin_expect(pending != 0u && n > 0, 0)) {
+            const uint32_t b = nl >> 31;
             bw.put(b, 1);
-            if (pending) { bw.put_run(b ^ 1u, pending); pending = 0; }
-            if (n > 1) bw.put((low << 1) >> (33 - n), n - 1);
-            low <<= n;
-            high = (high << n) | ((1u << n) - 1u);
+            bw.put_run(b ^ 1u, pending);
+            pending = 0;
+            if (n > 1) bw.put((nl << 1) >> (33 - n), n - 1);
+        } else {
+            bw.put(__funnelshift_l(nl, 0u, n), n);                     // the n leading bits of nl (n = 0: nothing)
         }
-        const uint32_t y = (low << 1) & ~(high << 1);
-        const int k = __clz(~y);
-        if (k > 0) {
-            pending += k;
-            low = (low << k) & 0x7FFFFFFFu;
-            high = (high << k) | 0x80000000u | ((1u << k) - 1u);
-        }
+        pending += (uint32_t)(sh - n);
+        low = (nl << sh) & 0x7FFFFFFFu;
+        high = (nh << sh) | ~(0xFFFFFFFFu << sh) | 0x80000000u;
     }
     __device__ __forceinline__ uint32_t finish() {
         pending += 1;
