@@ -329,6 +329,7 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "256 MiB buffer written before every timed encode and decode (L2 flushed)",
                    "parallelism": f"images sharded over {world} GPU(s), no data-path collective"},
         "encode_mpps": mp * K / (t_enc / 1e3), "decode_mpps": mp * K / (t_dec / 1e3),
+        "encode_ms_per_step": t_enc / K, "decode_ms_per_step": t_dec / K,
         "bpsp": bytes_total * 8 / (px_total * 3), "compressed_bytes_per_step": bytes_total,
         "roofline": roof, "kernel_ms_per_step": kernel_ms, "cnn_tflops": cnn_tflops,
         "cpu_baseline": cpu,

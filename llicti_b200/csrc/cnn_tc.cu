@@ -1,50 +1,90 @@
 // tcgen05 (5th-gen tensor core) version of the per-band interpolator CNN
 // (LLICTI_nets.py:721-753 layer 0, :695-712 grouped 1x1 layers, :822-825 get_params).
 //
-// The network is four independent 3-layer MLPs (sigma, mu, weights, coupling) sharing one
-// im2col tile.  One CTA owns ONE sub-network of one band: its bf16 weights (<= 46 KB) are
-// fetched once with a TMA bulk copy and stay in shared memory while the CTA walks over
-// 128-position tiles:
+// The network is four independent 3-layer MLPs (sigma, mu, weights, coupling) over one shared
+// im2col tile.  A persistent CTA (one per SM) owns TWO of the four sub-networks of a band: their
+// bf16 weights (<= 92 KB) arrive once by a TMA bulk copy and stay in shared memory while the CTA
+// walks over 128-position tiles.  Nine warps, three roles:
 //
-//   im2col (integers, exact in bf16) -> smem A0
-//   tcgen05.mma  D0[128 x NP] = A0[128 x K0p] * W0^T     (accumulator in TMEM)
-//   epilogue     H = bf16(relu(D0 + b0))                  -> smem (K-major operand of layer 1)
-//   tcgen05.mma  D1 = H * W1^T ; epilogue H = bf16(relu(D1 + b1))
-//   tcgen05.mma  D2[128 x 16] = H * W2^T ; epilogue params = D2 + b2 -> global (fp32)
+//   warps 4-7  im2col producers: row t of the A tile = the receptive field of position t, gathered
+//              from the int16 planes with replicate padding (integers, exact in bf16), two stages;
+//   warp  8    one elected lane issues every tcgen05.mma:
+//                L0  D0[128 x 2NP]  = A[128 x K0p] * W0^T          (both sub-networks at once)
+//                L1  D1_g[128 x NP] = H0_g * W1_g^T                (into D0_g's TMEM columns)
+//                L2  D2_g[128 x 16] = H1_g * W2_g^T
+//              L0 of tile t+1 is issued before L1/L2 of tile t, so the tensor pipe works on the
+//              next tile while the epilogue warps turn D0/D1 of this one into operands;
+//   warps 0-3  epilogue: TMEM -> registers -> ReLU -> bf16 -> shared (K-major operand of the next
+//              layer); layer 2 -> fp32 params in global memory.
 //
-// The 4*chs-wide activations never touch HBM.  Two CTAs are resident per SM (104 KB smem,
-// 256 TMEM columns each), so one CTA's epilogue overlaps the other's MMAs.
+// Two tiles are in flight in TMEM (2 x (2NP + 32) <= 448 columns).  Biases ride in two spare K
+// slots as a bf16 hi + lo pair against constant-one activation columns (which the previous
+// layer's weights regenerate), so the epilogues are pure ReLU + pack.  The 4*chs-wide
+// activations never touch HBM.
 //
-// Operands use the un-swizzled K-major canonical layout ("interleave"): 16-byte chunks of 8
-// bf16 along K, element (row, k) at (k/8)*LBO + (row/8)*SBO + (row%8)*16 + (k%8)*2 with
-// SBO = 128 B and LBO = rows*16 B, i.e. [k-chunk][row][16 B].  Epilogue thread t owns row t,
-// so its 16-byte stores are contiguous across a warp (bank-conflict free) and need no swizzle.
+// Operands use the un-swizzled K-major canonical layout: 16-byte chunks of 8 bf16 along K,
+// element (row, k) at (k/8)*LBO + (row/8)*128 + (row%8)*16 + (k%8)*2, i.e. [k-chunk][row][16 B];
+// thread t owns row t, so its 16-byte stores are contiguous across a warp (conflict-free).
 //
-// A position's outputs depend only on its own receptive field and the fixed instruction
-// sequence (no split-K, no atomics), so compress and decompres compute identical parameters.
+// A position's outputs depend only on its own receptive field and a fixed instruction sequence
+// (no split-K, no atomics), so compress and decompres compute bit-identical parameters whatever
+// the batch size, tile position or launch.
 #include <cuda_bf16.h>
 #include <string.h>
 
 #include <algorithm>
+#include <utility>
 
 #include "common.cuh"
 
 namespace llicti {
 
-constexpr int TC_M = 128;        // positions per tile = UMMA_M
-constexpr int TC_THREADS = 128;  // one thread per tile row / TMEM lane
-constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_M = 128;            // positions per tile = UMMA_M
+constexpr int TC_THREADS = 288;      // 4 epilogue warps, 4 im2col warps, 1 MMA warp
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_SLOT_COLS = 256;    // TMEM columns per tile slot: [0, 2NP) D0/D1, [2NP, 2NP+32) D2
 
 struct TcGeom {
     int Hs, Ws, P;          // plane size
     int total;              // n * P positions
     int ntiles;
-    int K0, K0p;            // layer-0 depth and its padding to a multiple of 16
-    int NP;                 // padded sub-network width (96 for 88, 64 for 60); also K of layers 1, 2
-    int group_bytes;        // packed bytes of one sub-network (weights + biases)
-    int off_w1, off_w2, off_bias;   // byte offsets inside the packed group
+    int K0, K0p;            // layer-0 depth; padded depth including the two bias slots
+    int G, NP;              // sub-network width (88 / 60) and its padding (96 / 64)
+    int pair_bytes;         // packed bytes of one pair of sub-networks
+    int off_w1, off_w2;     // byte offsets inside the packed pair
 };
 
+// ---- layer-0 tap geometry (LLICTI_nets.py:651-675) ------------------------------------------------
+struct BranchTc { int phase, kh, kw, padl, padt; };
+struct TapTc { int valid, phase, chan, dy, dx; };
+
+__host__ __device__ constexpr int band_branches(int band) { return band + 1; }
+__host__ __device__ constexpr BranchTc band_branch(int band, int b) {
+    return band == 0 ? BranchTc{0, 4, 4, 1, 1}                                              // 00_11
+         : band == 1 ? (b == 0 ? BranchTc{0, 3, 4, 1, 1} : BranchTc{1, 4, 3, 1, 2})         // 00_01, 11_01
+                     : (b == 0 ? BranchTc{0, 4, 3, 1, 1} : b == 1 ? BranchTc{1, 3, 4, 2, 1} // 00_10, 11_10
+                                                                  : BranchTc{2, 4, 4, 2, 1});  // 01_10
+}
+__host__ __device__ constexpr int band_k0(int band) {
+    int k = 0;
+    for (int b = 0; b < band_branches(band); ++b) k += 3 * band_branch(band, b).kh * band_branch(band, b).kw;
+    return k;
+}
+// k-th input of layer 0 in the order (branch, colour channel, dy, dx)
+__host__ __device__ constexpr TapTc band_tap(int band, int k) {
+    for (int b = 0; b < band_branches(band); ++b) {
+        const BranchTc br = band_branch(band, b);
+        const int sz = 3 * br.kh * br.kw;
+        if (k < sz) {
+            const int c = k / (br.kh * br.kw), r = k % (br.kh * br.kw);
+            return TapTc{1, br.phase, c, r / br.kw - br.padt, r % br.kw - br.padl};
+        }
+        k -= sz;
+    }
+    return TapTc{0, 0, 0, 0, 0};
+}
+
+// ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -52,6 +92,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -109,40 +152,99 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                  : "r"(taddr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// bias + ReLU + bf16 of one 16-column slab of the accumulator -> two 16-byte operand chunks.
-__device__ __forceinline__ void relu_pack16(const uint32_t *r, const float *bias, uint8_t *dst_chunk0, uint32_t chunk_stride) {
+// ReLU + bf16 of 16 accumulator columns -> two 16-byte operand chunks.
+__device__ __forceinline__ void relu_pack16(const uint32_t *r, uint8_t *dst_chunk0, uint32_t chunk_stride) {
     uint32_t w[8];
+    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const float a = fmaxf(__uint_as_float(r[2 * e]) + bias[2 * e], 0.f);
-        const float b = fmaxf(__uint_as_float(r[2 * e + 1]) + bias[2 * e + 1], 0.f);
-        const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+        const __nv_bfloat162 p = __hmax2(__floats2bfloat162_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), zero);
         w[e] = *reinterpret_cast<const uint32_t *>(&p);
     }
     *reinterpret_cast<uint4 *>(dst_chunk0) = make_uint4(w[0], w[1], w[2], w[3]);
     *reinterpret_cast<uint4 *>(dst_chunk0 + chunk_stride) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
-cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, TapTable taps, const uint8_t *__restrict__ packed,
-              float *__restrict__ params) {
+// bf16 bits of two small integers (|v| <= 255, exact): float(v) by the 1.5 * 2^23 trick, then
+// the two high halves.
+__device__ __forceinline__ uint32_t pack_int_pair(int lo, int hi) {
+    const float a = __int_as_float(0x4B400000 + lo) - 12582912.0f;
+    const float b = __int_as_float(0x4B400000 + hi) - 12582912.0f;
+    return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
+}
+
+// Compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{}).
+template <int... I, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>, F &&f) { (f(std::integral_constant<int, I>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
+
+// ---- im2col: row `row` of the A tile ---------------------------------------------------------------
+template <int BAND>
+__device__ __forceinline__ void build_a_row(const int16_t *__restrict__ planes, const TcGeom &tg, int q, uint8_t *sA, int row) {
+    constexpr int K0 = band_k0(BAND);
+    constexpr int K0p = (K0 + 2 + 15) / 16 * 16;
+    const int qq = min(q, tg.total - 1);
+    const int img = qq / tg.P, p = qq - img * tg.P;
+    const int i = p / tg.Ws, j = p - i * tg.Ws;
+    const int16_t *pl = planes + (size_t)img * 12 * tg.P;
+    int rowoff[5], col[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        rowoff[d] = min(max(i + d - 2, 0), tg.Hs - 1) * tg.Ws;      // replicate padding
+        col[d] = min(max(j + d - 2, 0), tg.Ws - 1);
+    }
+    constexpr uint32_t kOne = 0x3F80u;   // bf16 1.0
+    static_for<K0p / 8>([&](auto kc_) {
+        constexpr int kc = decltype(kc_)::value;
+        uint32_t w[4];
+        static_for<4>([&](auto e2_) {
+            constexpr int e2 = decltype(e2_)::value;
+            int v[2] = {0, 0};
+            uint32_t fixed = 0;
+            static_for<2>([&](auto h_) {
+                constexpr int h = decltype(h_)::value;
+                constexpr int k = kc * 8 + e2 * 2 + h;
+                constexpr TapTc t = band_tap(BAND, k);
+                if constexpr (t.valid != 0) v[h] = pl[(size_t)(t.phase * 3 + t.chan) * tg.P + rowoff[t.dy + 2] + col[t.dx + 2]];
+                else if constexpr (k == K0 || k == K0 + 1) fixed |= kOne << (16 * h);   // the two bias slots
+            });
+            w[e2] = pack_int_pair(v[0], v[1]) | fixed;
+        });
+        *reinterpret_cast<uint4 *>(sA + (size_t)kc * (TC_M * 16) + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    });
+}
+
+// Barrier slots in shared memory.
+enum { B_W = 0, B_AFULL = 1, B_AEMPTY = 3, B_D0FULL = 5, B_DFREE = 7, B_H0FULL = 9, B_D1FULL = 11, B_H1FULL = 13,
+       B_D2FULL = 15, B_COUNT = 17 };
+
+template <int BAND>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__restrict__ packed, float *__restrict__ params) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int K0 = band_k0(BAND);
+    constexpr int K0p = (K0 + 2 + 15) / 16 * 16;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int g = blockIdx.x & 3;                 // sub-network of this CTA
-    const int tile0 = blockIdx.x >> 2;
-    const int tile_stride = gridDim.x >> 2;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int pair = blockIdx.x & 1;                 // sub-networks 2*pair, 2*pair + 1
+    const int tile0 = blockIdx.x >> 1;
+    const int tile_stride = gridDim.x >> 1;
+    const int NP = tg.NP;
+    const int my_tiles = tile0 < tg.ntiles ? (tg.ntiles - tile0 + tile_stride - 1) / tile_stride : 0;
 
     // ---- shared memory carve-up -------------------------------------------------------------
-    uint8_t *sW0 = smem;                                         // [K0p/8][NP][16 B]
-    uint8_t *sW1 = smem + tg.off_w1;                             // [NP/8][NP][16 B]
-    uint8_t *sW2 = smem + tg.off_w2;                             // [NP/8][16][16 B]
-    const float *sBias = reinterpret_cast<const float *>(smem + tg.off_bias);   // b0[NP] b1[NP] b2[16]
-    uint8_t *sA0 = smem + ((tg.group_bytes + 127) & ~127);       // [K0p/8][128][16 B]
-    uint8_t *sH = sA0 + (tg.K0p / 8) * TC_M * 16;                // [NP/8][128][16 B]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sH + (tg.NP / 8) * TC_M * 16);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
-    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    uint8_t *sW0 = smem;                                         // [K0p/8][2NP][16 B]
+    uint8_t *sW1 = smem + tg.off_w1;                             // 2 x [NP/8][NP][16 B]
+    uint8_t *sW2 = smem + tg.off_w2;                             // 2 x [NP/8][16][16 B]
+    uint8_t *sA = smem + ((tg.pair_bytes + 127) & ~127);         // 2 stages x [K0p/8][128][16 B]
+    constexpr uint32_t a_stage = (K0p / 8) * TC_M * 16;
+    const uint32_t h_bytes = (uint32_t)(NP / 8) * TC_M * 16;
+    uint8_t *sH = sA + 2 * a_stage;                              // 2 sub-networks x [NP/8][128][16 B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sH + 2 * h_bytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int idx) { return bar0 + 8u * (uint32_t)idx; };
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -150,126 +252,144 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, TapTable taps, cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        mbar_init(bar_w, 1);
-        mbar_init(bar_mma, 1);
+        mbar_init(bar(B_W), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(B_AFULL + s), TC_M);
+            mbar_init(bar(B_AEMPTY + s), 1);
+            mbar_init(bar(B_D0FULL + s), 1);
+            mbar_init(bar(B_DFREE + s), TC_M);
+            mbar_init(bar(B_H0FULL + s), TC_M);
+            mbar_init(bar(B_D1FULL + s), 1);
+            mbar_init(bar(B_H1FULL + s), TC_M);
+            mbar_init(bar(B_D2FULL + s), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (tid == 0) {     // weights + biases of this sub-network: one TMA bulk copy
-        mbar_expect_tx(bar_w, (uint32_t)tg.group_bytes);
-        tma_bulk_g2s(smem_u32(sW0), packed + (size_t)g * tg.group_bytes, (uint32_t)tg.group_bytes, bar_w);
-    }
-    mbar_wait(bar_w, 0);
 
-    const uint32_t idescN = umma_idesc(tg.NP), idesc16 = umma_idesc(16);
-    const uint32_t d0 = tmem, d1 = tmem + (uint32_t)tg.NP, d2 = tmem + 2u * (uint32_t)tg.NP;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;     // this warp's TMEM lanes
-    const uint32_t a_lbo = TC_M * 16, w_lbo = (uint32_t)tg.NP * 16, w2_lbo = 16 * 16;
-    const float *b0 = sBias, *b1 = sBias + tg.NP, *b2 = sBias + 2 * tg.NP;
-    uint32_t phase = 0;
+    const uint32_t a_lbo = TC_M * 16;
 
-    for (int tile = tile0; tile < tg.ntiles; tile += tile_stride) {
-        // ---- im2col with replicate padding: row `tid` of the tile ------------------------------
-        const int q = tile * TC_M + tid;
-        const bool valid = q < tg.total;
-        const int qq = valid ? q : tg.total - 1;
-        const int img = qq / tg.P, p = qq - img * tg.P;
-        const int i = p / tg.Ws, j = p - i * tg.Ws;
-        const int16_t *pl = planes + (size_t)img * 12 * tg.P;
-        for (int kc = 0; kc < tg.K0p / 8; ++kc) {
-            uint32_t w[4];
+    if (warp >= 4 && warp < 8) {
+        // ================= im2col producers =================
+        const int row = tid - 128;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it & 1;
+            mbar_wait(bar(B_AEMPTY + s), ((it >> 1) & 1) ^ 1);     // MMAs that read this stage are complete
+            const int tile = tile0 + it * tile_stride;
+            build_a_row<BAND>(planes, tg, tile * TC_M + row, sA + s * a_stage, row);
+            fence_async_smem();
+            mbar_arrive(bar(B_AFULL + s));
+        }
+    } else if (warp == 8) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            mbar_expect_tx(bar(B_W), (uint32_t)tg.pair_bytes);
+            tma_bulk_g2s(smem_u32(sW0), packed + (size_t)pair * tg.pair_bytes, (uint32_t)tg.pair_bytes, bar(B_W));
+            mbar_wait(bar(B_W), 0);
+            const uint32_t idesc0 = umma_idesc(2 * NP), idesc1 = umma_idesc(NP), idesc2 = umma_idesc(16);
+            const uint32_t w0_lbo = (uint32_t)(2 * NP) * 16, w1_lbo = (uint32_t)NP * 16, w2_lbo = 16 * 16;
+            const uint32_t w1_bytes = (uint32_t)(NP / 8) * NP * 16, w2_bytes = (uint32_t)(NP / 8) * 16 * 16;
+            auto issue_l0 = [&](int it) {
+                const int s = it & 1;
+                mbar_wait(bar(B_AFULL + s), (it >> 1) & 1);
+                mbar_wait(bar(B_DFREE + s), ((it >> 1) & 1) ^ 1);     // epilogues of tile it-2 have drained this slot
+                tc_fence_after();
+                const uint32_t d0 = tmem + (uint32_t)(s * TC_SLOT_COLS);
+                const uint32_t a0 = smem_u32(sA) + s * a_stage;
 #pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-                float v[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int k = kc * 8 + e2 * 2 + h;
-                    float x = 0.f;
-                    if (k < tg.K0) {
-                        const int rr = min(max(i + taps.dy[k], 0), tg.Hs - 1);
-                        const int cc = min(max(j + taps.dx[k], 0), tg.Ws - 1);
-                        x = (float)pl[(size_t)(taps.phase[k] * 3 + taps.chan[k]) * tg.P + (size_t)rr * tg.Ws + cc];
-                    }
-                    v[h] = x;
+                for (int ks = 0; ks < K0p / 16; ++ks)
+                    umma_bf16(d0, umma_desc(a0 + ks * 2 * a_lbo, a_lbo, 128),
+                              umma_desc(smem_u32(sW0) + ks * 2 * w0_lbo, w0_lbo, 128), idesc0, ks > 0);
+                umma_commit(bar(B_D0FULL + s));
+                umma_commit(bar(B_AEMPTY + s));
+            };
+            if (my_tiles > 0) issue_l0(0);
+            for (int it = 0; it < my_tiles; ++it) {
+                if (it + 1 < my_tiles) issue_l0(it + 1);
+                const int s = it & 1;
+                const uint32_t dbase = tmem + (uint32_t)(s * TC_SLOT_COLS);
+                for (int g = 0; g < 2; ++g) {       // layer 1 of sub-network g, into D0_g's columns
+                    mbar_wait(bar(B_H0FULL + g), it & 1);
+                    tc_fence_after();
+                    const uint32_t h = smem_u32(sH) + g * h_bytes, w1 = smem_u32(sW1) + g * w1_bytes;
+                    for (int ks = 0; ks < NP / 16; ++ks)
+                        umma_bf16(dbase + (uint32_t)(g * NP), umma_desc(h + ks * 2 * a_lbo, a_lbo, 128),
+                                  umma_desc(w1 + ks * 2 * w1_lbo, w1_lbo, 128), idesc1, ks > 0);
+                    umma_commit(bar(B_D1FULL + g));
                 }
-                const __nv_bfloat162 pk = __floats2bfloat162_rn(v[0], v[1]);   // |x| <= 255: exact
-                w[e2] = *reinterpret_cast<const uint32_t *>(&pk);
+                for (int g = 0; g < 2; ++g) {       // layer 2
+                    mbar_wait(bar(B_H1FULL + g), it & 1);
+                    tc_fence_after();
+                    const uint32_t h = smem_u32(sH) + g * h_bytes, w2 = smem_u32(sW2) + g * w2_bytes;
+                    for (int ks = 0; ks < NP / 16; ++ks)
+                        umma_bf16(dbase + (uint32_t)(2 * NP + g * 16), umma_desc(h + ks * 2 * a_lbo, a_lbo, 128),
+                                  umma_desc(w2 + ks * 2 * w2_lbo, w2_lbo, 128), idesc2, ks > 0);
+                    umma_commit(bar(B_D2FULL + g));
+                }
             }
-            *reinterpret_cast<uint4 *>(sA0 + (size_t)kc * a_lbo + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-
-        // ---- layer 0 ----------------------------------------------------------------------------
-        if (tid == 0) {
+    } else {
+        // ================= epilogue warps (TMEM lane quadrant = warp) =================
+        const int row = tid;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it & 1;
+            const uint32_t dbase = tmem + lane_base + (uint32_t)(s * TC_SLOT_COLS);
+            const int tile = tile0 + it * tile_stride;
+            const int q = tile * TC_M + row;
+            // ---- layer 0 -> H0 ----
+            mbar_wait(bar(B_D0FULL + s), (it >> 1) & 1);
             tc_fence_after();
-            for (int ks = 0; ks < tg.K0p / 16; ++ks)
-                umma_bf16(d0, umma_desc(smem_u32(sA0) + ks * 2 * a_lbo, a_lbo, 128),
-                          umma_desc(smem_u32(sW0) + ks * 2 * w_lbo, w_lbo, 128), idescN, ks > 0);
-            umma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, phase);
-        phase ^= 1;
-        tc_fence_after();
-        for (int c16 = 0; c16 < tg.NP / 16; ++c16) {
-            uint32_t r[16];
-            TMEM_LD_X16(d0 + lane_base + c16 * 16, r);
-            tmem_ld_wait();
-            relu_pack16(r, b0 + c16 * 16, sH + (size_t)(c16 * 2) * a_lbo + tid * 16, a_lbo);
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-
-        // ---- layer 1 ----------------------------------------------------------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            for (int ks = 0; ks < tg.NP / 16; ++ks)
-                umma_bf16(d1, umma_desc(smem_u32(sH) + ks * 2 * a_lbo, a_lbo, 128),
-                          umma_desc(smem_u32(sW1) + ks * 2 * w_lbo, w_lbo, 128), idescN, ks > 0);
-            umma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, phase);
-        phase ^= 1;
-        tc_fence_after();
-        for (int c16 = 0; c16 < tg.NP / 16; ++c16) {
-            uint32_t r[16];
-            TMEM_LD_X16(d1 + lane_base + c16 * 16, r);
-            tmem_ld_wait();
-            relu_pack16(r, b1 + c16 * 16, sH + (size_t)(c16 * 2) * a_lbo + tid * 16, a_lbo);   // layer-1 MMAs are complete
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-
-        // ---- layer 2 ----------------------------------------------------------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            for (int ks = 0; ks < tg.NP / 16; ++ks)
-                umma_bf16(d2, umma_desc(smem_u32(sH) + ks * 2 * a_lbo, a_lbo, 128),
-                          umma_desc(smem_u32(sW2) + ks * 2 * w2_lbo, w2_lbo, 128), idesc16, ks > 0);
-            umma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, phase);
-        phase ^= 1;
-        tc_fence_after();
-        {
-            uint32_t r[16];
-            TMEM_LD_X16(d2 + lane_base, r);
-            tmem_ld_wait();
-            if (valid) {
-                float *o = params + (size_t)img * kParamCh * tg.P + (size_t)(g * 15) * tg.P + p;
+            for (int g = 0; g < 2; ++g) {
+                uint8_t *h = sH + g * h_bytes + row * 16;
+                for (int c16 = 0; c16 < NP / 16; ++c16) {
+                    uint32_t r[16];
+                    TMEM_LD_X16(dbase + (uint32_t)(g * NP + c16 * 16), r);
+                    tmem_ld_wait();
+                    relu_pack16(r, h + (size_t)(c16 * 2) * a_lbo, a_lbo);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar(B_H0FULL + g));
+            }
+            // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(bar(B_D1FULL + g), it & 1);
+                tc_fence_after();
+                uint8_t *h = sH + g * h_bytes + row * 16;
+                for (int c16 = 0; c16 < NP / 16; ++c16) {
+                    uint32_t r[16];
+                    TMEM_LD_X16(dbase + (uint32_t)(g * NP + c16 * 16), r);
+                    tmem_ld_wait();
+                    relu_pack16(r, h + (size_t)(c16 * 2) * a_lbo, a_lbo);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar(B_H1FULL + g));
+            }
+            mbar_arrive(bar(B_DFREE + s));      // D0/D1 columns of this slot may be overwritten by tile it+2
+            // ---- layer 2 -> params (fp32) ----
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(bar(B_D2FULL + g), it & 1);
+                tc_fence_after();
+                uint32_t r[16];
+                TMEM_LD_X16(dbase + (uint32_t)(2 * NP + g * 16), r);
+                tmem_ld_wait();
+                if (q < tg.total) {
+                    const int img = q / tg.P, p = q - img * tg.P;
+                    float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + g) * 15) * tg.P + p;
 #pragma unroll
-                for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]) + b2[c];
+                    for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
+                }
             }
+            tc_fence_before();
         }
-        tc_fence_before();     // TMEM reads of this tile are ordered before the next tile's MMAs by the next barrier
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
@@ -279,7 +399,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, TapTable taps, cons
 // Host side: packing and launch
 // ---------------------------------------------------------------------------------------------
 struct TcBand {
-    uint8_t *packed = nullptr;   // device: 4 sub-networks back to back
+    uint8_t *packed = nullptr;   // device: 2 pairs of sub-networks back to back
     TcGeom g{};                  // shape-independent fields filled at pack time
     size_t smem_bytes = 0;
 };
@@ -293,58 +413,80 @@ static uint16_t f2bf(float f) {   // round to nearest even
     const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(r >> 16);
 }
-
-struct BranchDefTc { int band, kh, kw; };
-static const BranchDefTc kBr[6] = {{0, 4, 4}, {1, 3, 4}, {1, 4, 3}, {2, 4, 3}, {2, 3, 4}, {2, 4, 4}};
+static float bf2f(uint16_t b) {
+    const uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
 
 int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
     const int G = ctx->cfg.chs, Ch = 4 * G;
-    const int NP = (G + 15) / 16 * 16;   // 88 -> 96, 60 -> 64
+    const int NP = (G + 2 + 15) / 16 * 16;   // 88 -> 96, 60 -> 64 (two bias slots included)
+    LLICTI_REQUIRE(G + 2 <= NP, "no room for the bias slots");
     TcWeights *tw = new TcWeights();
     for (int band = 0; band < 3; ++band) {
-        const int K0 = ctx->taps[band].K0, K0p = (K0 + 15) / 16 * 16;
-        const int w0_bytes = (K0p / 8) * NP * 16, w1_bytes = (NP / 8) * NP * 16, w2_bytes = (NP / 8) * 16 * 16;
-        const int bias_bytes = (2 * NP + 16) * 4;
-        const int group_bytes = w0_bytes + w1_bytes + w2_bytes + bias_bytes;
-        std::vector<uint8_t> host((size_t)4 * group_bytes, 0);
+        const int K0 = band_k0(band), K0p = (K0 + 2 + 15) / 16 * 16;
+        LLICTI_REQUIRE(K0 == ctx->taps[band].K0, "tap tables disagree for band %d", band);
+        const int w0_bytes = (K0p / 8) * (2 * NP) * 16, w1_bytes = 2 * (NP / 8) * NP * 16, w2_bytes = 2 * (NP / 8) * 16 * 16;
+        const int pair_bytes = w0_bytes + w1_bytes + w2_bytes;
+        std::vector<uint8_t> host((size_t)2 * pair_bytes, 0);
         // layer-0 weights in the kernel's k order (branch, c, dy, dx), scaled by 1/255 (the kernel
         // feeds integer sample values, the reference feeds value/255)
         std::vector<float> w0((size_t)K0 * Ch, 0.f), b0(Ch, 0.f);
-        int k = 0;
-        for (int br = 0; br < 6; ++br) {
-            if (kBr[br].band != band) continue;
+        int k = 0, brn = 0;
+        for (int b = 0; b < band_branches(band); ++b) {
+            const BranchTc bd = band_branch(band, b);
+            int br = 0;   // index into llicti_weights.l0_*: 00_11 | 00_01, 11_01 | 00_10, 11_10, 01_10
+            br = (band == 0 ? 0 : band == 1 ? 1 : 3) + b;
             for (int c = 0; c < 3; ++c)
-                for (int dy = 0; dy < kBr[br].kh; ++dy)
-                    for (int dx = 0; dx < kBr[br].kw; ++dx, ++k)
+                for (int dy = 0; dy < bd.kh; ++dy)
+                    for (int dx = 0; dx < bd.kw; ++dx, ++k)
                         for (int ch = 0; ch < Ch; ++ch)
-                            w0[(size_t)k * Ch + ch] =
-                                w.l0_w[br][(((size_t)ch * 3 + c) * kBr[br].kh + dy) * kBr[br].kw + dx] / 255.0f;
+                            w0[(size_t)k * Ch + ch] = w.l0_w[br][(((size_t)ch * 3 + c) * bd.kh + dy) * bd.kw + dx] / 255.0f;
             for (int ch = 0; ch < Ch; ++ch) b0[ch] += w.l0_b[br][ch];
+            ++brn;
         }
-        for (int g = 0; g < 4; ++g) {
-            uint8_t *base = host.data() + (size_t)g * group_bytes;
-            uint16_t *p0 = reinterpret_cast<uint16_t *>(base);
-            for (int kk = 0; kk < K0; ++kk)
-                for (int n = 0; n < G; ++n)
-                    p0[((size_t)(kk / 8) * NP + n) * 8 + kk % 8] = f2bf(w0[(size_t)kk * Ch + g * G + n]);
-            uint16_t *p1 = reinterpret_cast<uint16_t *>(base + w0_bytes);
-            for (int in = 0; in < G; ++in)
-                for (int n = 0; n < G; ++n)
-                    p1[((size_t)(in / 8) * NP + n) * 8 + in % 8] = f2bf(w.l1_w[band][(size_t)(g * G + n) * G + in]);
-            uint16_t *p2 = reinterpret_cast<uint16_t *>(base + w0_bytes + w1_bytes);
-            for (int in = 0; in < G; ++in)
-                for (int n = 0; n < 15; ++n)
-                    p2[((size_t)(in / 8) * 16 + n) * 8 + in % 8] = f2bf(w.l2_w[band][(size_t)(g * 15 + n) * G + in]);
-            float *pb = reinterpret_cast<float *>(base + w0_bytes + w1_bytes + w2_bytes);
-            for (int n = 0; n < G; ++n) { pb[n] = b0[g * G + n]; pb[NP + n] = w.l1_b[band][g * G + n]; }
-            for (int n = 0; n < 15; ++n) pb[2 * NP + n] = w.l2_b[band][g * 15 + n];
+        auto put = [](uint16_t *base, int rows, int n, int kk, uint16_t v) { base[((size_t)(kk / 8) * rows + n) * 8 + kk % 8] = v; };
+        auto put_bias = [&](uint16_t *base, int rows, int n, int kk, float b) {   // hi + lo pair in slots kk, kk + 1
+            const uint16_t hi = f2bf(b);
+            put(base, rows, n, kk, hi);
+            put(base, rows, n, kk + 1, f2bf(b - bf2f(hi)));
+        };
+        const uint16_t one = f2bf(1.0f);
+        for (int pr = 0; pr < 2; ++pr) {
+            uint8_t *base = host.data() + (size_t)pr * pair_bytes;
+            uint16_t *p0 = reinterpret_cast<uint16_t *>(base);            // [K0p/8][2NP][8]
+            for (int gl = 0; gl < 2; ++gl) {
+                const int g = 2 * pr + gl;
+                for (int n = 0; n < G; ++n) {
+                    for (int kk = 0; kk < K0; ++kk) put(p0, 2 * NP, gl * NP + n, kk, f2bf(w0[(size_t)kk * Ch + g * G + n]));
+                    put_bias(p0, 2 * NP, gl * NP + n, K0, b0[g * G + n]);
+                }
+                // hidden units G, G+1 reproduce the constant one (the next layer's bias slots)
+                put(p0, 2 * NP, gl * NP + G, K0, one);
+                put(p0, 2 * NP, gl * NP + G + 1, K0, one);
+                uint16_t *p1 = reinterpret_cast<uint16_t *>(base + w0_bytes) + (size_t)gl * (NP / 8) * NP * 8;   // [NP/8][NP][8]
+                for (int n = 0; n < G; ++n) {
+                    for (int in = 0; in < G; ++in) put(p1, NP, n, in, f2bf(w.l1_w[band][(size_t)(g * G + n) * G + in]));
+                    put_bias(p1, NP, n, G, w.l1_b[band][g * G + n]);
+                }
+                put(p1, NP, G, G, one);
+                put(p1, NP, G + 1, G, one);
+                uint16_t *p2 = reinterpret_cast<uint16_t *>(base + w0_bytes + w1_bytes) + (size_t)gl * (NP / 8) * 16 * 8;   // [NP/8][16][8]
+                for (int n = 0; n < 15; ++n) {
+                    for (int in = 0; in < G; ++in) put(p2, 16, n, in, f2bf(w.l2_w[band][(size_t)(g * 15 + n) * G + in]));
+                    put_bias(p2, 16, n, G, w.l2_b[band][g * 15 + n]);
+                }
+            }
         }
         TcBand &tb = tw->band[band];
         LLICTI_CUDA(cudaMalloc((void **)&tb.packed, host.size()));
         LLICTI_CUDA(cudaMemcpy(tb.packed, host.data(), host.size(), cudaMemcpyHostToDevice));
-        tb.g.K0 = K0; tb.g.K0p = K0p; tb.g.NP = NP; tb.g.group_bytes = group_bytes;
-        tb.g.off_w1 = w0_bytes; tb.g.off_w2 = w0_bytes + w1_bytes; tb.g.off_bias = w0_bytes + w1_bytes + w2_bytes;
-        tb.smem_bytes = (size_t)((group_bytes + 127) & ~127) + (size_t)(K0p / 8) * TC_M * 16 + (size_t)(NP / 8) * TC_M * 16 + 64;
+        tb.g.K0 = K0; tb.g.K0p = K0p; tb.g.G = G; tb.g.NP = NP; tb.g.pair_bytes = pair_bytes;
+        tb.g.off_w1 = w0_bytes; tb.g.off_w2 = w0_bytes + w1_bytes;
+        tb.smem_bytes = (size_t)((pair_bytes + 127) & ~127) + 2 * (size_t)(K0p / 8) * TC_M * 16 + 2 * (size_t)(NP / 8) * TC_M * 16 +
+                        B_COUNT * 8 + 16;
     }
     ctx->tc_weights = tw;
     return LLICTI_OK;
@@ -366,7 +508,7 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
     TcGeom tg = tb.g;
     tg.Hs = Hs; tg.Ws = Ws; tg.P = Hs * Ws;
     const long long total = (long long)n * tg.P;
-    LLICTI_REQUIRE(total < (1ll << 31), "batch too large for one CNN launch");
+    LLICTI_REQUIRE(total < (1ll << 31) - TC_M, "batch too large for one CNN launch");
     tg.total = (int)total;
     tg.ntiles = (tg.total + TC_M - 1) / TC_M;
     static int sm_count = 0;
@@ -376,13 +518,19 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
         LLICTI_CUDA(cudaGetDevice(&dev));
         LLICTI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    if (tb.smem_bytes > attr_smem) {
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb.smem_bytes));
-        attr_smem = tb.smem_bytes;
+    size_t mx = 0;
+    for (auto &b : tw->band) mx = std::max(mx, b.smem_bytes);
+    if (mx > attr_smem) {
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        attr_smem = mx;
     }
-    // persistent grid: 2 CTAs per SM, a multiple of 4 (one sub-network per CTA), no more than the work
-    int ctas = std::min(2 * sm_count / 4 * 4, tg.ntiles * 4);
-    cnn_tc_kernel<<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, ctx->taps[band], tb.packed, params);
+    // persistent grid: one CTA per SM, an even number (one sub-network pair per CTA), no more than the work
+    const int ctas = std::min(sm_count / 2 * 2, tg.ntiles * 2);
+    if (band == 0) cnn_tc_kernel<0><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params);
+    else if (band == 1) cnn_tc_kernel<1><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params);
+    else cnn_tc_kernel<2><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params);
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;
