@@ -203,16 +203,20 @@ def run_b200(args, rank, world, local_rank):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    enc_out = [None]                      # device output buffers, allocated by the first (untimed) step
+    rec_out = [None]
+
     def dev_step(timed):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         flush.zero_()
         ev[0].record()
-        blob, off, mm = codec.encode_dev(rgb_d)
+        enc_out[0] = codec.encode_dev(rgb_d, enc_out[0])
+        blob, off, mm = enc_out[0]
         ev[1].record()
         flush.zero_()                      # decode starts cold as well (outside both timed spans)
         ev2 = torch.cuda.Event(enable_timing=True)
         ev2.record()
-        rec = codec.decode_dev(blob, off, mm, x00_d, n_img, H, W)
+        rec_out[0] = rec = codec.decode_dev(blob, off, mm, x00_d, n_img, H, W, rec_out[0])
         ev[2].record()
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[1]), ev2.elapsed_time(ev[2]), blob, off, rec

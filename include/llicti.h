@@ -205,8 +205,8 @@ LLICTI_API int llicti_profile_read(llicti_ctx *ctx, double *ms, int64_t *count);
 
 /* Decode-side counters since the last reset (synchronises the device): out8[0] symbols that
  * fell outside their pre-computed CDF window and took the full analytic search, out8[1] polls
- * of consumer warps waiting for windows, out8[2] polls of producer warps waiting for decoded
- * samples (piped schedule).  Diagnostics for bench.py; not on the data path. */
+ * of consumer warps waiting for windows (piped schedule), out8[3] 8-symbol chunks whose
+ * branch-free decode was redone with the careful path.  Diagnostics for bench.py; not on the data path. */
 LLICTI_API int llicti_decode_stats(llicti_ctx *ctx, uint64_t *out8, int reset);
 
 #ifdef __cplusplus

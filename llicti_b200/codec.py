@@ -143,7 +143,7 @@ class Codec:
         """Decode-side diagnostics: window misses and pipeline waits since the last reset."""
         out = (C.c_uint64 * 8)()
         L.check(self.lib.llicti_decode_stats(self._ctx, out, int(reset)))
-        return {"slow_path_symbols": int(out[0]), "consumer_polls": int(out[1]), "producer_polls": int(out[2])}
+        return {"slow_path_symbols": int(out[0]), "consumer_polls": int(out[1]), "chunks_redone": int(out[3])}
 
     # -- full path, host buffers (the timed end-to-end call) -------------------------------
     def encode_host(self, rgb: np.ndarray, out: Optional[np.ndarray] = None):
@@ -177,24 +177,30 @@ class Codec:
         return out
 
     # -- full path, device buffers (asynchronous) --------------------------------------------
-    def encode_dev(self, rgb: torch.Tensor):
-        """rgb uint8 [n,3,H,W] CUDA tensor.  Returns CUDA tensors (blob, stream_off, minmax)."""
+    def encode_dev(self, rgb: torch.Tensor, out=None):
+        """rgb uint8 [n,3,H,W] CUDA tensor.  Returns CUDA tensors (blob, stream_off, minmax);
+        `out` = a previous return value to write into (no allocation on the timed path)."""
         assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
         n, _, H, W = rgb.shape
         self.reserve(n, H, W)
         g = self.geometry(H, W)
         ns = 9 * self.cfg.num_scales
-        blob = torch.empty(n * int(g.max_stream_bytes), dtype=torch.uint8, device=self.device)
-        off = torch.empty(n * ns + 1, dtype=torch.int64, device=self.device)
-        mm = torch.empty((n, 6), dtype=torch.int16, device=self.device)
+        if out is not None:
+            blob, off, mm = out
+            assert blob.numel() >= n * int(g.max_stream_bytes) and off.numel() == n * ns + 1 and mm.shape == (n, 6)
+        else:
+            blob = torch.empty(n * int(g.max_stream_bytes), dtype=torch.uint8, device=self.device)
+            off = torch.empty(n * ns + 1, dtype=torch.int64, device=self.device)
+            mm = torch.empty((n, 6), dtype=torch.int16, device=self.device)
         L.check(self.lib.llicti_encode_dev(self._ctx, rgb.data_ptr(), n, H, W, blob.data_ptr(), blob.numel(),
                                            off.data_ptr(), mm.data_ptr(), self._stream()))
         return blob, off, mm
 
     def decode_dev(self, blob: torch.Tensor, off: torch.Tensor, mm: torch.Tensor, x00: torch.Tensor, n: int, H: int,
-                   W: int) -> torch.Tensor:
+                   W: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         self.reserve(n, H, W)
-        out = torch.empty((n, 3, H, W), dtype=torch.uint8, device=self.device)
+        if out is None:
+            out = torch.empty((n, 3, H, W), dtype=torch.uint8, device=self.device)
         L.check(self.lib.llicti_decode_dev(self._ctx, blob.data_ptr(), off.data_ptr(), mm.data_ptr(), x00.data_ptr(),
                                            n, H, W, out.data_ptr(), self._stream()))
         return out

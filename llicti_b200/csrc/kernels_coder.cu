@@ -112,22 +112,171 @@ __device__ __forceinline__ void encode_strided(AcEncoder &enc, const uint32_t *_
     }
 }
 
-// Warp-per-chain variant for when chains are few and long (torchac-compatible streams): the
-// lanes fetch 32 bounds with one coalesced load a block ahead and all mirror the (uniform) coder
-// state, so there is neither divergence between chains nor memory latency on the serial chain.
-__device__ __forceinline__ void encode_strided_warp(AcEncoder &enc, const uint32_t *__restrict__ b, int j, int n_sym, int S,
-                                                    int lane) {
+// ------------------------------------------------------------------------------------------
+// Warp-per-chain encoder for few, long chains (torchac-compatible streams).
+//
+// The only serial part of arithmetic ENcoding is the interval recurrence (low, high) -> (low,
+// high); which bits a step emits depends on that step alone plus the count of pending underflow
+// bits.  So a block of 32 symbols runs in two phases:
+//   A  serial, 32 steps: the recurrence only (~20 instructions per symbol); lane s keeps step
+//      s's record (the n bits it shifts out, n, the underflow count k);
+//   B  parallel, one step per lane: pending counts by a segmented prefix sum, bit offsets by a
+//      prefix sum, then every lane ORs its bit string into a shared staging buffer, and the
+//      completed 32-bit words go out with one coalesced store.
+// The bit stream is identical to torchac's bit-plus-follow output.
+// ------------------------------------------------------------------------------------------
+constexpr int kStageWords = 96;          // staging capacity per warp (3072 bits); see block_fits()
+
+struct WarpEncoder {
+    uint32_t low, high, pending;
+    uint32_t *stage;       // shared, kStageWords + 2 words, zero except for emitted bits
+    uint32_t *out;         // 4-byte aligned slot
+    uint32_t cap_words, nwords, carry;   // slot capacity, words written, valid bits in stage[0..] not yet written
+    int overflow, lane;
+
+    __device__ __forceinline__ void init(uint8_t *slot, uint32_t cap_bytes, uint32_t *stage_, int lane_) {
+        low = 0; high = 0xFFFFFFFFu; pending = 0;
+        stage = stage_; out = reinterpret_cast<uint32_t *>(slot); cap_words = cap_bytes / 4; nwords = 0; carry = 0;
+        overflow = 0; lane = lane_;
+        for (int w = lane; w < kStageWords + 2; w += 32) stage[w] = 0u;
+        __syncwarp();
+    }
+    // OR `cnt` (<= 32) bits, right aligned in val, at bit position pos (MSB first)
+    __device__ __forceinline__ void or_bits(uint32_t pos, uint32_t val, int cnt) {
+        if (cnt <= 0) return;
+        const uint64_t t = (((uint64_t)val) << (64 - cnt)) >> (pos & 31u);
+        const uint32_t hi = (uint32_t)(t >> 32), lo = (uint32_t)t;
+        if (hi) atomicOr(&stage[pos >> 5], hi);
+        if (lo) atomicOr(&stage[(pos >> 5) + 1], lo);
+    }
+    __device__ __forceinline__ void or_ones(uint32_t pos, uint32_t cnt) {
+        while (cnt > 0) {
+            const uint32_t c = min(cnt, 32u);
+            or_bits(pos, 0xFFFFFFFFu >> (32 - c), (int)c);
+            pos += c;
+            cnt -= c;
+        }
+    }
+    // Write out the completed words of stage[] (bits [0, carry + added)), keep the partial one.
+    __device__ __forceinline__ void flush(uint32_t added) {
+        __syncwarp();
+        const uint32_t bits = carry + added, nw = bits >> 5;
+        const uint32_t partial = stage[nw];
+        for (uint32_t w = lane; w < nw; w += 32) {
+            if (nwords + w < cap_words) out[nwords + w] = __byte_perm(stage[w], 0, 0x0123);
+        }
+        if (nwords + nw > cap_words) overflow = 1;
+        __syncwarp();
+        for (uint32_t w = lane; w <= nw + 1; w += 32) stage[w] = w == 0 ? partial : 0u;
+        nwords += nw;
+        carry = bits & 31u;
+        __syncwarp();
+    }
+    // One emitting step, written by lane 0 alone with flushes as needed (rare paths and finish()).
+    __device__ __forceinline__ void emit_serial(uint32_t b, uint32_t run, uint32_t rest, int rest_cnt) {
+        uint32_t added = 0;
+        if (lane == 0) or_bits(carry, b, 1);
+        added = 1;
+        while (run > 0) {
+            const uint32_t c = min(run, 1024u);
+            if (lane == 0 && !b) or_ones(carry + added, c);     // the run repeats the complement of b
+            added += c;
+            run -= c;
+            flush(added);
+            added = 0;
+        }
+        if (lane == 0) or_bits(carry + added, rest, rest_cnt);
+        added += rest_cnt;
+        flush(added);
+    }
+
+    // 32 (or fewer) symbols: bounds in `cur` (one per lane), m valid.
+    __device__ __forceinline__ void encode_block(uint32_t cur, int m) {
+        // ---- phase A: the interval recurrence ----
+        uint32_t rec_bits = 0;
+        int rec_n = 0, rec_k = 0;
+#pragma unroll 4
+        for (int s = 0; s < m; ++s) {
+            const uint32_t v = __shfl_sync(0xffffffffu, cur, s);
+            const uint32_t c_low = v & 0xFFFFu, c_high = (v >> 16) + 1u;
+            const uint32_t sm1 = high - low;                               // span - 1; span * c = sm1 * c + c
+            const uint32_t nl = low + (uint32_t)(((uint64_t)sm1 * c_low + c_low) >> 16);
+            const uint32_t nh = (low - 1u) + (uint32_t)(((uint64_t)sm1 * c_high + c_high) >> 16);
+            const uint32_t d = nl ^ nh;
+            const int n = __clz(d);
+            const int sh = __clz(d & ~((nl & ~nh) << 1));                  // n + underflow run (see AcEncoder::encode)
+            if (lane == s) { rec_bits = __funnelshift_l(nl, 0u, n); rec_n = n; rec_k = sh - n; }
+            low = (nl << sh) & 0x7FFFFFFFu;
+            high = (nh << sh) | ~(0xFFFFFFFFu << sh) | 0x80000000u;
+        }
+        // ---- phase B: bit output of the 32 steps in parallel ----
+        int kx = rec_k;                                                   // inclusive scan of k
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, kx, o); if (lane >= o) kx += y; }
+        const int ktot = __shfl_sync(0xffffffffu, kx, 31);
+        kx -= rec_k;                                                      // exclusive
+        const uint32_t emask = __ballot_sync(0xffffffffu, rec_n > 0);
+        const uint32_t prev = emask & ((1u << lane) - 1u);
+        const int kx_prev = __shfl_sync(0xffffffffu, kx, prev ? 31 - __clz(prev) : 0);
+        const uint32_t P = prev ? (uint32_t)(kx - kx_prev) : pending + (uint32_t)kx;   // pending bits when this step emits
+        const uint32_t L = rec_n > 0 ? (uint32_t)rec_n + P : 0u;
+        uint32_t ox = L;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ox, o); if (lane >= o) ox += y; }
+        const uint32_t ltot = __shfl_sync(0xffffffffu, ox, 31);
+        ox -= L;
+        const int kx_last = __shfl_sync(0xffffffffu, kx, emask ? 31 - __clz(emask) : 0);
+        const uint32_t pending_out = emask ? (uint32_t)(ktot - kx_last) : pending + (uint32_t)ktot;
+        if (carry + ltot <= (uint32_t)kStageWords * 32u) {
+            if (rec_n > 0) {
+                const uint32_t pos = carry + ox;
+                if (P == 0) {
+                    or_bits(pos, rec_bits, rec_n);
+                } else {
+                    const uint32_t b = rec_bits >> (rec_n - 1);
+                    or_bits(pos, b, 1);
+                    if (!b) or_ones(pos + 1, P);
+                    or_bits(pos + 1 + P, rec_bits & ~(1u << (rec_n - 1)), rec_n - 1);
+                }
+            }
+            flush(ltot);
+        } else {
+            // more pending bits than the staging buffer holds (astronomically rare): step by step
+            for (int s = 0; s < 32; ++s) {
+                const int n_s = __shfl_sync(0xffffffffu, rec_n, s);
+                const uint32_t bits_s = __shfl_sync(0xffffffffu, rec_bits, s), P_s = __shfl_sync(0xffffffffu, P, s);
+                if (n_s > 0) emit_serial(bits_s >> (n_s - 1), P_s, bits_s & ~(1u << (n_s - 1)), n_s - 1);
+            }
+        }
+        pending = pending_out;
+    }
+
+    __device__ __forceinline__ uint32_t finish() {
+        pending += 1;
+        const uint32_t b = low < 0x40000000u ? 0u : 1u;
+        emit_serial(b, pending, 0u, 0);
+        // zero-pad to a byte boundary: carry (< 32) bits are left in stage[0]
+        const uint32_t nb = (carry + 7) >> 3;
+        const uint32_t word = stage[0];
+        uint8_t *tail = reinterpret_cast<uint8_t *>(out + nwords);
+        if (lane == 0)
+            for (uint32_t i = 0; i < nb; ++i) {
+                if (nwords * 4 + i < cap_words * 4) tail[i] = (uint8_t)(word >> (24 - 8 * i));
+                else overflow = 1;
+            }
+        overflow = __shfl_sync(0xffffffffu, overflow, 0) | overflow;
+        return nwords * 4 + nb;
+    }
+};
+
+__device__ __forceinline__ void encode_strided_warp(WarpEncoder &enc, const uint32_t *__restrict__ b, int j, int n_sym, int S) {
+    const int lane = enc.lane;
     const int n_steps = (n_sym - j + S - 1) / S;
     uint32_t cur = lane < n_steps ? b[(size_t)j + (size_t)lane * S] : 0u;
     for (int t0 = 0; t0 < n_steps; t0 += 32) {
         const int t1 = t0 + 32 + lane;
-        const uint32_t nxt = t1 < n_steps ? b[(size_t)j + (size_t)t1 * S] : 0u;
-        const int m = min(32, n_steps - t0);
-#pragma unroll 4
-        for (int s = 0; s < m; ++s) {
-            const uint32_t v = __shfl_sync(0xffffffffu, cur, s);
-            enc.encode(v & 0xFFFFu, (v >> 16) + 1u);
-        }
+        const uint32_t nxt = t1 < n_steps ? b[(size_t)j + (size_t)t1 * S] : 0u;   // a block ahead of the coder
+        enc.encode_block(cur, min(32, n_steps - t0));
         cur = nxt;
     }
 }
@@ -137,6 +286,7 @@ encode_all_warp_kernel(const StreamDesc *__restrict__ sd_g, int n_streams, int t
                        const uint32_t *__restrict__ bounds, int64_t sym_stride, uint8_t *__restrict__ scratch,
                        int64_t scratch_stride, uint32_t *__restrict__ sublen, int32_t *__restrict__ status) {
     __shared__ StreamDesc sd[kMaxStreams];
+    __shared__ uint32_t stage[4][kStageWords + 2];
     for (int e = threadIdx.x; e < n_streams; e += blockDim.x) sd[e] = sd_g[e];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -147,29 +297,31 @@ encode_all_warp_kernel(const StreamDesc *__restrict__ sd_g, int n_streams, int t
     const StreamDesc &d = sd[k];
     const int j = item - d.sub_first;
     const uint32_t *b = bounds + (size_t)img * sym_stride + d.sym_off;
-    AcEncoder enc;
-    enc.init(scratch + (size_t)img * scratch_stride + d.slot_off + (size_t)j * d.slot_bytes, (uint32_t)d.slot_bytes, lane == 0);
-    encode_strided_warp(enc, b, j, d.n_sym, d.S, lane);
+    WarpEncoder enc;
+    enc.init(scratch + (size_t)img * scratch_stride + d.slot_off + (size_t)j * d.slot_bytes, (uint32_t)d.slot_bytes,
+             stage[threadIdx.x >> 5], lane);
+    encode_strided_warp(enc, b, j, d.n_sym, d.S);
     const uint32_t nb = enc.finish();
     if (lane == 0) {
         sublen[(size_t)img * total_sub + item] = nb;
-        if (enc.bw.overflow) atomicExch(status, LLICTI_E_NOMEM);
+        if (enc.overflow) atomicExch(status, LLICTI_E_NOMEM);
     }
 }
 
 __global__ void __launch_bounds__(128)
 encode_flat_warp_kernel(const uint32_t *__restrict__ bounds, int n_sym, int S, uint8_t *__restrict__ out, int slot_bytes,
                         uint32_t *__restrict__ lens, int32_t *__restrict__ status) {
+    __shared__ uint32_t stage[4][kStageWords + 2];
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= S) return;
-    AcEncoder enc;
-    enc.init(out + (size_t)j * slot_bytes, (uint32_t)slot_bytes, lane == 0);
-    encode_strided_warp(enc, bounds, j, n_sym, S, lane);
+    WarpEncoder enc;
+    enc.init(out + (size_t)j * slot_bytes, (uint32_t)slot_bytes, stage[threadIdx.x >> 5], lane);
+    encode_strided_warp(enc, bounds, j, n_sym, S);
     const uint32_t nb = enc.finish();
     if (lane == 0) {
         lens[j] = nb;
-        if (enc.bw.overflow) atomicExch(status, LLICTI_E_NOMEM);
+        if (enc.overflow) atomicExch(status, LLICTI_E_NOMEM);
     }
 }
 

@@ -32,7 +32,7 @@
 
 namespace llicti {
 
-__device__ unsigned long long g_decode_stats[8];   // 0 slow-path symbols, 1 consumer flag polls, 2 producer sample polls
+__device__ unsigned long long g_decode_stats[8];   // 0 slow-path symbols, 1 consumer flag polls, 2 unused, 3 chunks redone carefully
 
 constexpr int kWin = 31;                 // table entries per window (lane 31 carries `base`)
 constexpr int16_t kSentinel = (int16_t)0x8080;   // memset(0x80): never a sample value (|v| <= 255)
@@ -166,57 +166,68 @@ __device__ __noinline__ uint64_t slow_symbol(const float *__restrict__ pp, const
     return (uint64_t)c_low | ((uint64_t)(c_high - 1u) << 16) | ((uint64_t)(uint32_t)sym << 32);
 }
 
-// Serial coder state of one chain: torchac's (low, high, value) registers over a bit window that
-// always holds at least 32 upcoming bits, refilled from two look-ahead words AFTER each step, so
-// neither a memory access nor a refill sits between two symbols.
+// Serial coder state of one chain: torchac's (low, high, value) registers over a 160-bit window
+// of upcoming stream bits held in registers.  The window is topped up BETWEEN 8-step chunks from
+// two look-ahead words, so inside a chunk there is no memory access, no refill and no branch.
 struct ChainCoder {
     uint32_t low, high, value;
-    const uint32_t *w;           // 4-byte aligned base (<= stream start)
-    uint32_t lo_byte, hi_byte;   // valid bytes [lo, hi) relative to w
-    uint32_t idx, a0, a1;        // next word index, the two upcoming words
-    uint32_t bhi, blo;           // upcoming bits, left aligned in bhi:blo
-    int avail;
+    uint32_t b0, b1, b2, b3, b4;   // upcoming bits, left aligned in b0:b1:b2:b3:b4
+    int avail;                     // valid bits in the window
+    const uint32_t *w;             // 4-byte aligned base (<= stream start)
+    uint32_t lo_byte, hi_byte;     // valid bytes [lo, hi) relative to w
+    uint32_t idx, a0, a1;          // next word index, the two upcoming words
 
     __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
-        const uint32_t b0 = i * 4u;
+        const uint32_t p0 = i * 4u;
         uint32_t v = 0u;
-        if (b0 < hi_byte) {
+        if (p0 < hi_byte) {
             v = __byte_perm(__ldg(w + i), 0, 0x0123);   // first stream byte in the most significant position
-            if (b0 < lo_byte) v &= 0xFFFFFFFFu >> (8u * (lo_byte - b0));
-            if (b0 + 4u > hi_byte) v &= 0xFFFFFFFFu << (8u * (b0 + 4u - hi_byte));   // torchac reads zeros past the end
+            if (p0 < lo_byte) v &= 0xFFFFFFFFu >> (8u * (lo_byte - p0));
+            if (p0 + 4u > hi_byte) v &= 0xFFFFFFFFu << (8u * (p0 + 4u - hi_byte));   // torchac reads zeros past the end
         }
         return v;
     }
-    __device__ __forceinline__ void skip(int sh) {      // 0 <= sh <= 32; keeps >= 32 bits in the window
-        const uint64_t b = (((uint64_t)bhi << 32) | blo) << sh;
-        bhi = (uint32_t)(b >> 32);
-        blo = (uint32_t)b;
-        avail -= sh;
-        if (__builtin_expect(avail < 32, 0)) {
-            const uint64_t ins = (uint64_t)a0 << (32 - avail);
-            bhi |= (uint32_t)(ins >> 32);
-            blo |= (uint32_t)ins;
+    // Append look-ahead words while at most 96 bits are valid: afterwards 97..128 bits are.
+    __device__ __forceinline__ void topup() {
+        while (avail <= 96) {
+            const int wi = avail >> 5, r = avail & 31;
+            const uint64_t t = ((uint64_t)a0 << 32) >> r;
+            const uint32_t hi = (uint32_t)(t >> 32), lo = (uint32_t)t;
+            b0 |= wi == 0 ? hi : 0u;
+            b1 |= wi == 0 ? lo : wi == 1 ? hi : 0u;
+            b2 |= wi == 1 ? lo : wi == 2 ? hi : 0u;
+            b3 |= wi == 2 ? lo : wi == 3 ? hi : 0u;
+            b4 |= wi == 3 ? lo : 0u;
             avail += 32;
             a0 = a1;
             a1 = fetch(idx++);
         }
+    }
+    __device__ __forceinline__ void shift(int sh) {     // 0 <= sh <= 31
+        b0 = __funnelshift_l(b1, b0, sh);
+        b1 = __funnelshift_l(b2, b1, sh);
+        b2 = __funnelshift_l(b3, b2, sh);
+        b3 = __funnelshift_l(b4, b3, sh);
+        b4 <<= sh;
+        avail -= sh;
     }
     __device__ __forceinline__ void init(const uint8_t *ptr, uint32_t n) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
         w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         lo_byte = (uint32_t)(a & 3);
         hi_byte = lo_byte + n;
-        const uint64_t b = (uint64_t)fetch(0) << (32 + 8 * lo_byte);
-        bhi = (uint32_t)(b >> 32);
-        blo = (uint32_t)b;
+        b0 = fetch(0) << (8 * lo_byte);
+        b1 = b2 = b3 = b4 = 0u;
         avail = 32 - 8 * (int)lo_byte;
         a0 = fetch(1);
         a1 = fetch(2);
         idx = 3;
-        skip(0);
+        topup();
         low = 0; high = 0xFFFFFFFFu;
-        value = bhi;
-        skip(32);
+        value = b0;
+        b0 = b1; b1 = b2; b2 = b3; b3 = b4; b4 = 0u;
+        avail -= 32;
+        topup();
     }
 };
 
@@ -263,9 +274,11 @@ struct ChainCtx {       // what the (rare) slow path needs
 //   low + ((span * q(s)) >> 16) <= value          (<=> q(s) <= floor(((value-low+1) 2^16 - 1) / span),
 // torchac's search key), so a ballot picks the lane and four shuffles fetch its state.  The only
 // work after the ballot is the selection.
-template <bool kPipe>
-__device__ __forceinline__ int decode_step(ChainCoder &cc, uint32_t raw, int last, long long i, const ChainCtx &cx,
-                                           const CdfGrid &g, const NumericsProfile &np, int lane) {
+//
+// Fast variant: no branch at all.  A symbol outside its window, or a window of stream bits that
+// ran low, only raises `bad`; the caller validates once per chunk and redoes a bad chunk with the
+// careful variant from a snapshot (about 1 chunk in 100).
+__device__ __forceinline__ int decode_step_fast(ChainCoder &cc, uint32_t raw, int last, int lane, uint32_t &bad) {
     // window geometry and the upper bound of each candidate: data only, off the serial chain
     const uint32_t info = __shfl_sync(kFull, raw, 31);
     const int base = (int)(info & 511u), nq = (int)(info >> 9);
@@ -274,13 +287,35 @@ __device__ __forceinline__ int decode_step(ChainCoder &cc, uint32_t raw, int las
     const uint32_t vmask = (1u << nq) - 1u;
     const uint32_t zmask = base == 0 ? 1u : 0u;          // target below q(0): torchac's search returns symbol 0
     const uint32_t lim = base + nq < last ? (uint32_t)(nq - 1) : 31u;   // li >= lim: beyond the window
-    const NextState ns = next_state(cc.low, cc.high, cc.value, cc.bhi, raw, c_high);
+    const NextState ns = next_state(cc.low, cc.high, cc.value, cc.b0, raw, c_high);
+    const uint32_t li = (uint32_t)__popc((__ballot_sync(kFull, cc.value >= ns.nl) & vmask) | zmask) - 1u;
+    bad |= (li >= lim ? 1u : 0u) | (cc.avail < 32 ? 1u : 0u);   // li = -1: below a window that does not start at 0
+    const uint32_t lic = min(li, 31u);
+    cc.low = __shfl_sync(kFull, ns.low, lic);
+    cc.high = __shfl_sync(kFull, ns.high, lic);
+    cc.value = __shfl_sync(kFull, ns.value, lic);
+    cc.shift(__shfl_sync(kFull, ns.sh, lic));
+    return base + (int)li;
+}
+
+template <bool kPipe>
+__device__ __noinline__ int decode_step_careful(ChainCoder &cc, uint32_t raw, int last, long long i, const ChainCtx &cx,
+                                               const CdfGrid &g, const NumericsProfile &np, int lane) {
+    cc.topup();
+    const uint32_t info = __shfl_sync(kFull, raw, 31);
+    const int base = (int)(info & 511u), nq = (int)(info >> 9);
+    const uint32_t up = __shfl_down_sync(kFull, raw, 1);
+    const uint32_t c_high = lane + 1 < nq ? up : 0x10000u;
+    const uint32_t vmask = (1u << nq) - 1u;
+    const uint32_t zmask = base == 0 ? 1u : 0u;
+    const uint32_t lim = base + nq < last ? (uint32_t)(nq - 1) : 31u;
+    const NextState ns = next_state(cc.low, cc.high, cc.value, cc.b0, raw, c_high);
     const uint32_t li = (uint32_t)__popc((__ballot_sync(kFull, cc.value >= ns.nl) & vmask) | zmask) - 1u;
     int sym, sh;
-    if (__builtin_expect(li >= lim, 0)) {                 // includes li = -1: below a window that does not start at 0
+    if (li >= lim) {
         const uint64_t pk = slow_symbol(cx.pp, cx.syms, cx.sym_cap, cx.P, cx.crop_w, cx.Ws, i, cx.clr, cx.lo0, cx.lo1, g, np,
                                         cc.low, cc.high, cc.value, lane, kPipe ? 1 : 0);
-        const NextState s2 = next_state(cc.low, cc.high, cc.value, cc.bhi, (uint32_t)pk & 0xFFFFu,
+        const NextState s2 = next_state(cc.low, cc.high, cc.value, cc.b0, (uint32_t)pk & 0xFFFFu,
                                         (((uint32_t)pk >> 16) & 0xFFFFu) + 1u);
         cc.low = s2.low; cc.high = s2.high; cc.value = s2.value; sh = s2.sh;
         sym = (int)(pk >> 32);
@@ -291,8 +326,13 @@ __device__ __forceinline__ int decode_step(ChainCoder &cc, uint32_t raw, int las
         sh = __shfl_sync(kFull, ns.sh, li);
         sym = base + (int)li;
     }
-    cc.skip(sh);     // (torchac does not update after the last symbol; the state is dead by then)
+    cc.shift(sh);     // (torchac does not update after the last symbol; the state is dead by then)
     return sym;
+}
+
+__device__ __forceinline__ uint32_t chunk_entry_dyn(const uint4 &q, int e) {
+    const uint32_t w = (e >> 1) == 0 ? q.x : (e >> 1) == 1 ? q.y : (e >> 1) == 2 ? q.z : q.w;
+    return (e & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
 // `out` = compact symbol array of this (image, channel) in coding order; chain j writes j, j+S, ...
@@ -307,7 +347,8 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
     const int n_items = (n_steps + 31) >> 5;      // an item = 4 chunks of 8 steps (one uint4 per lane each)
     const int n_full = n_steps >> 3, tail = n_steps & 7;
     const int last = g.Lp - 1;
-    unsigned long long polls = 0;
+    const bool vec_store = S == 1 && j == 0;      // 8 consecutive symbols = one aligned 16-byte store
+    unsigned long long polls = 0, redone = 0;
 
     ChainCoder cc;
     cc.init(stream, stream_len);
@@ -338,25 +379,45 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
 #pragma unroll 1
         for (int v = 0; v < full_here; ++v) {
             const uint4 q = v == 0 ? q0 : v == 1 ? q1 : v == 2 ? q2 : q3;
+            cc.topup();
+            const ChainCoder snap = cc;
+            uint32_t bad = 0;
+            int sym[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int sym = decode_step<kPipe>(cc, chunk_entry(q, e), last, i, cx, g, np, lane);
-                if (lane == 0) {
-                    if (kPipe) st_relaxed_s16(dst, sym); else *dst = (int16_t)sym;
+            for (int e = 0; e < 8; ++e) sym[e] = decode_step_fast(cc, chunk_entry(q, e), last, lane, bad);
+            if (__builtin_expect(bad != 0u, 0)) {
+                cc = snap;
+                ++redone;
+#pragma unroll 1
+                for (int e = 0; e < 8; ++e) {
+                    const int sy = decode_step_careful<kPipe>(cc, chunk_entry_dyn(q, e), last, i + (long long)e * S, cx, g, np, lane);
+#pragma unroll
+                    for (int e2 = 0; e2 < 8; ++e2) sym[e2] = e2 == e ? sy : sym[e2];
                 }
-                i += S;
-                dst += S;
             }
+            if (lane == 0) {
+                if (vec_store) {
+                    const uint4 pk = make_uint4((uint32_t)(sym[0] & 0xFFFF) | ((uint32_t)sym[1] << 16),
+                                                (uint32_t)(sym[2] & 0xFFFF) | ((uint32_t)sym[3] << 16),
+                                                (uint32_t)(sym[4] & 0xFFFF) | ((uint32_t)sym[5] << 16),
+                                                (uint32_t)(sym[6] & 0xFFFF) | ((uint32_t)sym[7] << 16));
+                    if (kPipe) __stcg(reinterpret_cast<uint4 *>(dst), pk); else *reinterpret_cast<uint4 *>(dst) = pk;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dst[(size_t)e * S] = (int16_t)sym[e];
+                }
+            }
+            i += 8ll * S;
+            dst += (size_t)8 * S;
         }
         if (it == n_items - 1 && tail) {
             const int v = max(full_here, 0);
             const uint4 q = v == 0 ? q0 : v == 1 ? q1 : v == 2 ? q2 : q3;
 #pragma unroll 1
             for (int e = 0; e < tail; ++e) {
-                const uint32_t w = (e >> 1) == 0 ? q.x : (e >> 1) == 1 ? q.y : (e >> 1) == 2 ? q.z : q.w;
-                const int sym = decode_step<kPipe>(cc, (e & 1) ? (w >> 16) : (w & 0xFFFFu), last, i, cx, g, np, lane);
+                const int sy = decode_step_careful<kPipe>(cc, chunk_entry_dyn(q, e), last, i, cx, g, np, lane);
                 if (lane == 0) {
-                    if (kPipe) st_relaxed_s16(dst, sym); else *dst = (int16_t)sym;
+                    if (kPipe) st_relaxed_s16(dst, sy); else *dst = (int16_t)sy;
                 }
                 i += S;
                 dst += S;
@@ -370,7 +431,10 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
         q0 = n0; q1 = n1; q2 = n2; q3 = n3;
         f_next = f_next2;
     }
-    if (kPipe && lane == 0 && polls) atomicAdd(&g_decode_stats[1], polls);
+    if (lane == 0) {
+        if (kPipe && polls) atomicAdd(&g_decode_stats[1], polls);
+        if (redone) atomicAdd(&g_decode_stats[3], redone);
+    }
 }
 
 // Compact symbols of a decoded band -> centred samples in the planes, with the replicate padding
