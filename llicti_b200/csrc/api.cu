@@ -283,7 +283,7 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_x00, n * 3 * (size_t)g.Hs[S - 1] * g.Ws[S - 1]));
     ctx->items_cap = (int64_t)n * decode_items_per_image(p);
     LLICTI_CUDA(cudaMalloc(&ctx->d_items, (size_t)ctx->items_cap * 2048));
-    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)ctx->items_cap * sizeof(uint32_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)decode_flag_words(ctx->items_cap) * sizeof(uint32_t)));
     ctx->sym_cap = ((int64_t)g.Hs[0] * g.Ws[0] + 63) / 64 * 64;
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_syms, n * 3 * (size_t)ctx->sym_cap * sizeof(int16_t)));
     ctx->ws_images = max_images; ctx->ws_H = H; ctx->ws_W = W;

@@ -194,6 +194,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
                        const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
                        const uint32_t *sublen, cudaStream_t st);
 int64_t decode_items_per_image(const Plan &p);
+int64_t decode_flag_words(int64_t items_cap);
 int read_decode_stats(uint64_t *out, int reset);
 int launch_decode_table(llicti_ctx *ctx, const int16_t *table, int n_sym, int Lp, int S, const uint8_t *in,
                         const uint32_t *offs, int16_t *sym, cudaStream_t st);

@@ -175,23 +175,23 @@ struct ChainCoder {
     int avail;                     // valid bits in the window
     const uint32_t *w;             // 4-byte aligned base (<= stream start)
     uint32_t lo_byte, hi_byte;     // valid bytes [lo, hi) relative to w
-    uint32_t idx, a0, a1;          // next word index, the two upcoming words
+    uint32_t idx, a0, a1;          // index of the word in a0; a0, a1 = the two upcoming words as loaded (raw)
 
-    __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
+    // Raw load only: the value is not touched until it is inserted one or two chunks later, so the
+    // load latency never stalls the chain.
+    __device__ __forceinline__ uint32_t fetch_raw(uint32_t i) const { return i * 4u < hi_byte ? __ldg(w + i) : 0u; }
+    __device__ __forceinline__ uint32_t cook(uint32_t raw, uint32_t i) const {
         const uint32_t p0 = i * 4u;
-        uint32_t v = 0u;
-        if (p0 < hi_byte) {
-            v = __byte_perm(__ldg(w + i), 0, 0x0123);   // first stream byte in the most significant position
-            if (p0 < lo_byte) v &= 0xFFFFFFFFu >> (8u * (lo_byte - p0));
-            if (p0 + 4u > hi_byte) v &= 0xFFFFFFFFu << (8u * (p0 + 4u - hi_byte));   // torchac reads zeros past the end
-        }
+        uint32_t v = __byte_perm(raw, 0, 0x0123);       // first stream byte in the most significant position
+        if (p0 < lo_byte) v &= 0xFFFFFFFFu >> (8u * (lo_byte - p0));
+        if (p0 + 4u > hi_byte) v &= p0 < hi_byte ? 0xFFFFFFFFu << (8u * (p0 + 4u - hi_byte)) : 0u;   // torchac reads zeros past the end
         return v;
     }
     // Append look-ahead words while at most 96 bits are valid: afterwards 97..128 bits are.
     __device__ __forceinline__ void topup() {
         while (avail <= 96) {
             const int wi = avail >> 5, r = avail & 31;
-            const uint64_t t = ((uint64_t)a0 << 32) >> r;
+            const uint64_t t = ((uint64_t)cook(a0, idx) << 32) >> r;
             const uint32_t hi = (uint32_t)(t >> 32), lo = (uint32_t)t;
             b0 |= wi == 0 ? hi : 0u;
             b1 |= wi == 0 ? lo : wi == 1 ? hi : 0u;
@@ -200,7 +200,8 @@ struct ChainCoder {
             b4 |= wi == 3 ? lo : 0u;
             avail += 32;
             a0 = a1;
-            a1 = fetch(idx++);
+            ++idx;
+            a1 = fetch_raw(idx + 1);
         }
     }
     __device__ __forceinline__ void shift(int sh) {     // 0 <= sh <= 31
@@ -216,12 +217,12 @@ struct ChainCoder {
         w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         lo_byte = (uint32_t)(a & 3);
         hi_byte = lo_byte + n;
-        b0 = fetch(0) << (8 * lo_byte);
+        b0 = cook(fetch_raw(0), 0) << (8 * lo_byte);
         b1 = b2 = b3 = b4 = 0u;
         avail = 32 - 8 * (int)lo_byte;
-        a0 = fetch(1);
-        a1 = fetch(2);
-        idx = 3;
+        idx = 1;
+        a0 = fetch_raw(1);
+        a1 = fetch_raw(2);
         topup();
         low = 0; high = 0xFFFFFFFFu;
         value = b0;
@@ -299,7 +300,7 @@ __device__ __forceinline__ int decode_step_fast(ChainCoder &cc, uint32_t raw, in
 }
 
 template <bool kPipe>
-__device__ __noinline__ int decode_step_careful(ChainCoder &cc, uint32_t raw, int last, long long i, const ChainCtx &cx,
+__device__ __forceinline__ int decode_step_careful(ChainCoder &cc, uint32_t raw, int last, long long i, const ChainCtx &cx,
                                                const CdfGrid &g, const NumericsProfile &np, int lane) {
     cc.topup();
     const uint32_t info = __shfl_sync(kFull, raw, 31);
@@ -512,10 +513,21 @@ consume_kernel(const float *__restrict__ params, int16_t *__restrict__ syms, siz
                          sublen[e], lane);
 }
 
-// ---- piped schedule (S == 1): grid of one-warp CTAs, consumers first --------------------------
+// ---- piped schedule (S == 1): one grid of one-warp CTAs, all co-resident ----------------------
+// Roles are claimed at run time so that the serial consumer warps get SMs of their own: the first
+// cons_per_sm CTAs to arrive on an SM draw consumer tickets (one chain each, at most one per
+// scheduler); once the tickets are gone the remaining SMs are producer SMs, and CTAs that land on
+// a consumer SM without a ticket leave.  Producers draw window items through per-channel tickets
+// in (step block, image) order: Y items wait for nothing; a Co (Cg) item waits for the Y (and Co)
+// symbols of its 32 positions, i.e. for consumers that only depend on items earlier in the same
+// orders -- the holder of the earliest unfinished ticket can always run, so the grid cannot
+// deadlock as long as it is co-resident.
+constexpr int kConsPerSmMax = 4;
+constexpr int kCtlWords = 1024;     // [0,256) arrivals per SM, [256,512) role per SM, 512 consumer / 513 producer / 514.. item tickets
+
 __global__ void __launch_bounds__(32)
 decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t sym_cap, const int32_t *__restrict__ minmax,
-                        DecodeGeom dg, NumericsProfile np, uint4 *items, uint32_t *flags,
+                        DecodeGeom dg, NumericsProfile np, uint4 *items, uint32_t *ctl, uint32_t *flags, int cons_per_sm,
                         const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
                         const uint32_t *__restrict__ sublen, int total_sub, int n) {
     __shared__ __align__(16) uint16_t stage[32 * 34];
@@ -524,42 +536,64 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
     const int n_cons = 3 * n;
     int lo[3];
     CdfGrid g[3];
-    if ((int)blockIdx.x < n_cons) {
-        const int img = blockIdx.x / 3, clr = blockIdx.x - 3 * img;
+
+    // ---- role ----
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    smid &= 255u;
+    int chain = -1, producer_id = -1;
+    if (lane == 0) {
+        const uint32_t slot = atomicAdd(&ctl[smid], 1u);
+        if (slot < (uint32_t)cons_per_sm) {
+            const uint32_t t = atomicAdd(&ctl[512], 1u);
+            if (t < (uint32_t)n_cons) chain = (int)t;
+            if (slot == 0) st_release_u32(&ctl[256 + smid], chain >= 0 ? 1u : 2u);
+        }
+        if (chain < 0) {
+            uint32_t role;
+            while ((role = ld_relaxed_u32(&ctl[256 + smid])) == 0u) __nanosleep(100);
+            if (role == 2u) producer_id = (int)atomicAdd(&ctl[513], 1u);
+        }
+    }
+    chain = __shfl_sync(kFull, chain, 0);
+    producer_id = __shfl_sync(kFull, producer_id, 0);
+
+    if (chain >= 0) {
+        const int img = chain / 3, clr = chain - 3 * img;
         band_grids(minmax + img * 4, lo, g);
         int16_t *isyms = syms + (size_t)img * 3 * sym_cap;
         const ChainCtx cx = {params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], 1};
         const size_t e = (size_t)img * total_sub + dg.sub_first[clr];
-        const size_t chain = (size_t)img * 3 + clr;
-        consume_chain<true>(cx, dg.n_sym, g[clr], 0, np, isyms + (size_t)clr * sym_cap, items + chain * dg.items_per_chain * 128,
-                            flags + chain * dg.items_per_chain, blob + suboff[e], sublen[e], lane);
+        consume_chain<true>(cx, dg.n_sym, g[clr], 0, np, isyms + (size_t)clr * sym_cap,
+                            items + (size_t)chain * dg.items_per_chain * 128, flags + (size_t)chain * dg.items_per_chain,
+                            blob + suboff[e], sublen[e], lane);
         return;
     }
-    // Producers are split into three groups, one per colour channel, each walking its channel's
-    // items in (step block, image) order.  Y items wait for nothing; a Co (Cg) item waits for the
-    // Y (and Co) symbols of its 32 positions, i.e. for consumers that only depend on items earlier
-    // in the same orders -- the earliest unfinished item of every group can always run.
-    const int np_total = (int)gridDim.x - n_cons;
-    const int p = (int)blockIdx.x - n_cons;
-    const int gy = max(np_total / 5, 1), gco = max((np_total - gy) / 2, 1);
-    int clr, gp, gsize;
-    if (p < gy) { clr = 0; gp = p; gsize = gy; }
-    else if (p < gy + gco) { clr = 1; gp = p - gy; gsize = gco; }
-    else { clr = 2; gp = p - gy - gco; gsize = np_total - gy - gco; }
-    const long long total = (long long)dg.items_per_chain * n;
-    for (long long w = gp; w < total; w += gsize) {
-        const int tb = (int)(w / n);
-        const int img = (int)(w - (long long)tb * n);
-        const int chain = img * 3 + clr;
-        band_grids(minmax + img * 4, lo, g);
-        uint4 *item = items + ((size_t)chain * dg.items_per_chain + tb) * 128;
-        produce_item<true>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
-                           g[clr], 0, tb, np, item, stage, lane);
-        // every lane's stores happen before the flag store: warp barrier, then a cumulative fence
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            st_release_u32(flags + (size_t)chain * dg.items_per_chain + tb, 1u);
+    if (producer_id < 0) return;       // on a consumer SM without a ticket
+
+    const int r5 = producer_id % 5;    // Y : Co : Cg producers start 1 : 2 : 2, then help the other channels
+    const int clr0 = r5 == 0 ? 0 : r5 <= 2 ? 1 : 2;
+    const uint32_t total = (uint32_t)dg.items_per_chain * (uint32_t)n;
+    for (int c = 0; c < 3; ++c) {
+        const int clr = (clr0 + c) % 3;
+        for (;;) {
+            uint32_t w = 0;
+            if (lane == 0) w = atomicAdd(&ctl[514 + clr], 1u);
+            w = __shfl_sync(kFull, w, 0);
+            if (w >= total) break;
+            const int tb = (int)(w / (uint32_t)n);
+            const int img = (int)(w - (uint32_t)tb * (uint32_t)n);
+            const int ch = img * 3 + clr;
+            band_grids(minmax + img * 4, lo, g);
+            uint4 *item = items + ((size_t)ch * dg.items_per_chain + tb) * 128;
+            produce_item<true>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
+                               g[clr], 0, tb, np, item, stage, lane);
+            // every lane's stores happen before the flag store: warp barrier, then a cumulative fence
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                st_release_u32(flags + (size_t)ch * dg.items_per_chain + tb, 1u);
+            }
         }
     }
 }
@@ -652,6 +686,8 @@ static DecodeGeom make_decode_geom(const Plan &p, int scale, int band) {
 }
 
 // Window items (2 KB each) one image needs for its largest band.
+int64_t decode_flag_words(int64_t items_cap) { return items_cap + kCtlWords; }
+
 int64_t decode_items_per_image(const Plan &p) {
     int64_t m = 0;
     for (int s = 0; s < p.g.num_scales; ++s)
@@ -702,17 +738,24 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
     const size_t sym_cap = (size_t)ctx->sym_cap;
     const long long items_band = 3ll * n * dg.S * dg.items_per_chain;
     LLICTI_REQUIRE(items && syms && items_band <= ctx->items_cap && (size_t)dg.n_sym <= sym_cap, "decode workspace too small");
-    // one-warp CTAs: 32 resident per SM at most; keep well below so the whole grid is co-resident
-    const int resident = sm_count * 24;
-    const int producers = (int)std::min<long long>(items_band, (long long)sm_count * env_int("LLICTI_PIPE_PRODUCERS_PER_SM", 4));
-    const bool piped = dg.S == 1 && producers >= 5 && 3 * n + producers <= resident && !env_int("LLICTI_NO_PIPE", 0);
+    // piped: a grid of sm_count x ctas_per_sm one-warp CTAs (32 resident per SM at most, so the grid
+    // is co-resident); consumers claim ceil(3n / 4) SMs, the rest produce
+    // consumers run fastest alone on an SM (measured: 1 per SM 54.8 ms, 2 per SM 59.4 ms on c1); give them up
+    // to half of the SMs, the other half produces
+    const int cons_auto = (3 * n + sm_count / 2 - 1) / (sm_count / 2);
+    const int cons_per_sm = std::min(std::max(env_int("LLICTI_PIPE_CONS_PER_SM", cons_auto), 1), kConsPerSmMax);
+    const int ctas_per_sm = std::min(std::max(env_int("LLICTI_PIPE_CTAS_PER_SM", 12), cons_per_sm + 1), 24);
+    const int cons_sms = (3 * n + cons_per_sm - 1) / cons_per_sm;
+    const bool piped = dg.S == 1 && cons_sms <= sm_count / 2 && 3 * n <= kConsPerSmMax * (sm_count / 2) && sm_count <= 256 &&
+                       !env_int("LLICTI_NO_PIPE", 0);
     if (piped) {
         ProfScope prof_(ctx, KC_DECODE, st);
-        // sentinels over the symbol arrays (data = flag), zeros over the item flags
+        // sentinels over the symbol arrays (data = flag), zeros over the role/ticket words and item flags
         LLICTI_CUDA(cudaMemsetAsync(syms, 0x80, (size_t)n * 3 * sym_cap * sizeof(int16_t), st));
-        LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, (size_t)items_band * sizeof(uint32_t), st));
-        decode_band_pipe_kernel<<<3 * n + producers, 32, 0, st>>>(params, syms, sym_cap, minmax, dg, ctx->num, items,
-                                                                 ctx->d_item_flags, blob, suboff, sublen, total_sub, n);
+        LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, ((size_t)items_band + kCtlWords) * sizeof(uint32_t), st));
+        decode_band_pipe_kernel<<<sm_count * ctas_per_sm, 32, 0, st>>>(params, syms, sym_cap, minmax, dg, ctx->num, items,
+                                                                      ctx->d_item_flags, ctx->d_item_flags + kCtlWords, cons_per_sm, blob,
+                                                                      suboff, sublen, total_sub, n);
         ctx->launches += 1;
     } else {
         const long long win_warps = (long long)n * dg.S * dg.items_per_chain;
