@@ -152,7 +152,13 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def algorithmic_work(geom, chs, n, blob_bytes, decode_impl=0):
+# How each kernel class is bounded: the CNN by the tensor pipe, everything else is
+# byte/integer work whose ceiling is HBM bandwidth -- the serial coder chains and the erfc-heavy
+# CDF kernels sit far below it by nature (latency / instruction issue), which the fractions show.
+BOUND = {"cnn": "tensor"}
+
+
+def algorithmic_work(geom, chs, n, blob_bytes, decode_impl=0, piped=False):
     """Per-step algorithmic bytes / flops of each kernel class for n images."""
     S = geom.num_scales
     pos = [geom.Hs[s] * geom.Ws[s] for s in range(S)]
@@ -165,11 +171,18 @@ def algorithmic_work(geom, chs, n, blob_bytes, decode_impl=0):
         "cnn": n * sum(pos[s] * (2 * 3 * (b + 1) + 240) for s in range(S) for b in range(3)),
         "bounds": n * coded_pos * (240 + 6 + 12),                               # 258 B per (position, band)
         "encode": n * geom.symbols * 4 + blob_bytes,                            # 4 B bounds in + bytes out
-        "window": n * coded_pos * (240 + 6 + 3 * 64),                           # params + samples in, 3 window rows out
-        "decode": (n * coded_pos * (3 * 64 + 6) + blob_bytes) if decode_impl == 0   # window rows + bytes in, symbols out
-        else (n * coded_pos * (240 + 6) + blob_bytes),                          # legacy: params in, symbols out, bytes in
+        "window": n * coded_pos * (240 + 6 + 3 * 64),                           # params + symbols in, 3 window rows out
+        # split schedule: window rows + stream bytes in, symbols out; piped schedule: the one kernel also
+        # produces the windows; legacy: params in, symbols out
+        "decode": (n * coded_pos * ((240 + 6 + 3 * 64) * piped + 3 * 64 + 6) + blob_bytes) if decode_impl == 0
+        else (n * coded_pos * (240 + 6) + blob_bytes),
         "merge": n * (2 * 12 * sum(pos) + 3 * geom.H * geom.W),
     }
+
+
+def kernel_ms_has_no_window(prof):
+    """True when the decode ran the piped schedule (windows produced inside the decode kernel)."""
+    return prof.get("window", (0.0, 0))[1] == 0
 
 
 def run_b200(args, rank, world, local_rank):
@@ -189,7 +202,11 @@ def run_b200(args, rank, world, local_rank):
     geom = codec.geometry(H, W)
     S = geom.num_scales
     st = 2 ** S
-    rgb_h = torch.from_numpy(synthetic_batch(n_img, H, W, 1000 * rank)).pin_memory()
+    from llicti_b200.shard import shard_range, reduce_stats
+    # weak scaling: the job is world * n_img images, rank r codes its contiguous shard; no data-path collective
+    first, last = shard_range(world * n_img, rank, world)
+    assert last - first == n_img
+    rgb_h = torch.from_numpy(synthetic_batch(n_img, H, W, 1000 + first)).pin_memory()
     rgb_np = rgb_h.numpy()
     rgb_d = rgb_h.to(dev)
     x00_np = np.ascontiguousarray(rgb_np[:, :, ::st, ::st])
@@ -261,7 +278,6 @@ def run_b200(args, rank, world, local_rank):
     codec.profile(False)
     dstats = codec.decode_stats()
     launches = codec.launches - launches0
-    clk = clocks.stop()
 
     # ---- timed region: end to end through host buffers ------------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
@@ -273,16 +289,12 @@ def run_b200(args, rank, world, local_rank):
         h_enc += a
         h_dec += b
     barrier()
+    clk = clocks.stop()        # sampled over both timed regions (device-resident and end-to-end)
     assert np.array_equal(hrec, rgb_np), "host round trip is not lossless"
 
     # ---- reduce over ranks (max time, summed work) ---------------------------------------------
-    vals = torch.tensor([t_enc, t_dec, h_enc, h_dec], dtype=torch.float64, device=dev)
-    work = torch.tensor([n_img * H * W, blob_bytes, launches, h2d, d2h], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.MAX)
-        torch.distributed.all_reduce(work, op=torch.distributed.ReduceOp.SUM)   # NCCL: rate statistics only
-    t_enc, t_dec, h_enc, h_dec = vals.tolist()
-    px_total, bytes_total, launches_total, h2d_total, d2h_total = work.tolist()
+    (px_total, bytes_total, launches_total, h2d_total, d2h_total), (t_enc, t_dec, h_enc, h_dec) = reduce_stats(
+        [n_img * H * W, blob_bytes, launches, h2d, d2h], [t_enc, t_dec, h_enc, h_dec], device=dev)   # NCCL: rate statistics only
     if rank != 0:
         return
     K = args.steps
@@ -297,20 +309,42 @@ def run_b200(args, rank, world, local_rank):
         pk = json.load(open(pk_path))
         peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops_sustained": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
                  "src": "measured"}
-    work_step = algorithmic_work(geom, ocfg.chs, n_img, blob_bytes, args.decode_impl)
+    piped = sub_len == 0 and kernel_ms_has_no_window(prof)
+    work_step = algorithmic_work(geom, ocfg.chs, n_img, blob_bytes, args.decode_impl, piped)
     kernel_ms = {k: v[0] / K for k, v in prof.items()}
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic_db = json.load(open(tpath)).get(args.workload, {})
+    coded_symbols = n_img * geom.symbols
+
+    def roofline_of(cls):
+        """Algorithmic work of one average launch group / its average duration (CUDA events on the
+        launching stream during the timed region)."""
+        groups = max(prof[cls][1] / K, 1.0)
+        ms = kernel_ms[cls] / groups
+        if ms <= 0:
+            return None
+        if BOUND.get(cls) == "tensor" and args.cnn == 1:
+            ach = work_step["cnn_flops"] / groups / (ms * 1e-3) / 1e12
+            r = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s"}
+        else:
+            ach = work_step[cls] / groups / (ms * 1e-3) / 1e9
+            r = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+        r["frac"] = r["achieved"] / r["peak"]
+        t = traffic_db.get(cls)      # dram bytes of one captured launch (ncu --set full), scaled by work units to the average launch
+        r["traffic"] = (t["dram_bytes"] / t["units"] * (n_img * t["units_per_image_step"] / groups)) if t else None
+        r.update({"kernel": cls, "launch_groups_per_step": groups, "ms_per_launch_group": ms,
+                  "share_of_step": kernel_ms[cls] / ((t_enc + t_dec) / K)})
+        if t:
+            r["traffic_source"] = t["source"]
+        return r
+
     dom = max(kernel_ms, key=kernel_ms.get)
-    if dom == "cnn" and args.cnn == 1:
-        ach = work_step["cnn_flops"] / (kernel_ms["cnn"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None}
-    else:
-        key = dom if dom in work_step else "merge"
-        ach = work_step[key] / (kernel_ms[dom] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                "traffic": None}
-    roof.update({"kernel": dom, "peak_source": peaks["src"], "launch_groups_per_step": prof[dom][1] / K,
-                 "ms_per_step": kernel_ms[dom], "share_of_step": kernel_ms[dom] / ((t_enc + t_dec) / K)})
+    roof = roofline_of(dom)
+    roof["peak_source"] = peaks["src"]
+    rooflines = {c: {k: v for k, v in r.items() if k in ("bound", "achieved", "peak", "unit", "frac", "share_of_step")}
+                 for c in kernel_ms if kernel_ms[c] > 0 and c in work_step for r in [roofline_of(c)] if r}
     cnn_tflops = work_step["cnn_flops"] / (max(kernel_ms["cnn"], 1e-9) * 1e-3) / 1e12
 
     # ---- CPU baseline: the oracle on a bounded sample (rank 0, N=1 only) -----------------------------
@@ -335,7 +369,7 @@ def run_b200(args, rank, world, local_rank):
         "encode_mpps": mp * K / (t_enc / 1e3), "decode_mpps": mp * K / (t_dec / 1e3),
         "encode_ms_per_step": t_enc / K, "decode_ms_per_step": t_dec / K,
         "bpsp": bytes_total * 8 / (px_total * 3), "compressed_bytes_per_step": bytes_total,
-        "roofline": roof, "kernel_ms_per_step": kernel_ms, "cnn_tflops": cnn_tflops,
+        "roofline": roof, "rooflines_all_kernels": rooflines, "kernel_ms_per_step": kernel_ms, "cnn_tflops": cnn_tflops,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                 "encode_mpps": mp * K / (h_enc / 1e3), "decode_mpps": mp * K / (h_dec / 1e3),
