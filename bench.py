@@ -167,8 +167,8 @@ def algorithmic_work(geom, chs, n, blob_bytes, decode_impl=0, piped=False):
     coded_pos = sum(sum(sym_band[s]) for s in range(S))
     return {
         "split": n * (3 * geom.H * geom.W + 2 * 12 * sum(pos)),                 # u8 in, int16 planes out
-        "cnn_flops": n * 2.0 * macs,
-        "cnn": n * sum(pos[s] * (2 * 3 * (b + 1) + 240) for s in range(S) for b in range(3)),
+        "cnn_flops": 2 * n * 2.0 * macs,                                        # the CNN runs in both directions
+        "cnn": 2 * n * sum(pos[s] * (2 * 3 * (b + 1) + 240) for s in range(S) for b in range(3)),
         "bounds": n * coded_pos * (240 + 6 + 12),                               # 258 B per (position, band)
         "encode": n * geom.symbols * 4 + blob_bytes,                            # 4 B bounds in + bytes out
         "window": n * coded_pos * (240 + 6 + 3 * 64),                           # params + symbols in, 3 window rows out

@@ -6,15 +6,15 @@
 // bf16 weights (<= 92 KB) arrive once by a TMA bulk copy and stay in shared memory while the CTA
 // walks over 128-position tiles.  Nine warps, three roles:
 //
-//   warps 4-7  im2col producers: row t of the A tile = the receptive field of position t, gathered
+//   warps 8-15 im2col producers (two threads per tile row): row t of the A tile = the receptive field of position t, gathered
 //              from the int16 planes with replicate padding (integers, exact in bf16), two stages;
-//   warp  8    one elected lane issues every tcgen05.mma:
+//   warp  16   one elected lane issues every tcgen05.mma:
 //                L0  D0[128 x 2NP]  = A[128 x K0p] * W0^T          (both sub-networks at once)
 //                L1  D1_g[128 x NP] = H0_g * W1_g^T                (into D0_g's TMEM columns)
 //                L2  D2_g[128 x 16] = H1_g * W2_g^T
 //              L0 of tile t+1 is issued before L1/L2 of tile t, so the tensor pipe works on the
 //              next tile while the epilogue warps turn D0/D1 of this one into operands;
-//   warps 0-3  epilogue: TMEM -> registers -> ReLU -> bf16 -> shared (K-major operand of the next
+//   warps 0-7  epilogue (four warps per sub-network): TMEM -> registers -> ReLU -> bf16 -> shared (K-major operand of the next
 //              layer); layer 2 -> fp32 params in global memory.
 //
 // Two tiles are in flight in TMEM (2 x (2NP + 32) <= 448 columns).  Biases ride in two spare K
@@ -41,14 +41,15 @@
 namespace llicti {
 
 constexpr int TC_M = 128;            // positions per tile = UMMA_M
-constexpr int TC_THREADS = 288;      // 4 epilogue warps, 4 im2col warps, 1 MMA warp
+constexpr int TC_THREADS = 544;      // 8 epilogue warps (4 per sub-network), 8 im2col warps, 1 MMA warp
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_SLOT_COLS = 256;    // TMEM columns per tile slot: [0, 2NP) D0/D1, [2NP, 2NP+32) D2
 
 struct TcGeom {
     int Hs, Ws, P;          // plane size
-    int total;              // n * P positions
-    int ntiles;
+    int n;                  // images
+    int tpr;                // tiles per plane row: a tile = up to 128 consecutive positions of ONE row
+    int ntiles;             // n * Hs * tpr
     int K0, K0p;            // layer-0 depth; padded depth including the two bias slots
     int G, NP;              // sub-network width (88 / 60) and its padding (96 / 64)
     int pair_bytes;         // packed bytes of one pair of sub-networks
@@ -151,27 +152,40 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                    "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),          \
                    "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                                                \
                  : "r"(taddr))
+#define TMEM_LD_X32(taddr, r)                                                                           \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                              \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "             \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),  \
+                   "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),          \
+                   "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),       \
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),       \
+                   "=r"(r[31])                                                                          \
+                 : "r"(taddr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ReLU + bf16 of 16 accumulator columns -> two 16-byte operand chunks.
 __device__ __forceinline__ void relu_pack16(const uint32_t *r, uint8_t *dst_chunk0, uint32_t chunk_stride) {
     uint32_t w[8];
-    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const __nv_bfloat162 p = __hmax2(__floats2bfloat162_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), zero);
-        w[e] = *reinterpret_cast<const uint32_t *>(&p);
-    }
+    for (int e = 0; e < 8; ++e)     // one instruction per column pair: round to bf16 with ReLU (element 2e in the low half)
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(__uint_as_float(r[2 * e + 1])), "f"(__uint_as_float(r[2 * e])));
     *reinterpret_cast<uint4 *>(dst_chunk0) = make_uint4(w[0], w[1], w[2], w[3]);
     *reinterpret_cast<uint4 *>(dst_chunk0 + chunk_stride) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// bf16 bits of two small integers (|v| <= 255, exact): float(v) by the 1.5 * 2^23 trick, then
-// the two high halves.
-__device__ __forceinline__ uint32_t pack_int_pair(int lo, int hi) {
-    const float a = __int_as_float(0x4B400000 + lo) - 12582912.0f;
-    const float b = __int_as_float(0x4B400000 + hi) - 12582912.0f;
-    return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
+// One hidden layer's epilogue for one sub-network: all NP accumulator columns of this thread's row
+// are fetched with back-to-back TMEM loads and ONE wait (the loads overlap each other and the
+// conversion of 8 independent column pairs per 16-byte chunk pipelines), then ReLU + bf16 + store.
+template <int NP>
+__device__ __forceinline__ void epilogue_hidden(uint32_t taddr, uint8_t *h_row, uint32_t chunk_stride) {
+    uint32_t r[NP];
+#pragma unroll
+    for (int c = 0; c < NP / 32; ++c) TMEM_LD_X32(taddr + (uint32_t)(c * 32), (r + c * 32));
+    tmem_ld_wait();
+#pragma unroll
+    for (int c16 = 0; c16 < NP / 16; ++c16) relu_pack16(r + c16 * 16, h_row + (size_t)(c16 * 2) * chunk_stride, chunk_stride);
 }
 
 // Compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{}).
@@ -180,37 +194,97 @@ __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>
 template <int N, class F>
 __device__ __forceinline__ void static_for(F &&f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
 
-// ---- im2col: row `row` of the A tile ---------------------------------------------------------------
-template <int BAND>
-__device__ __forceinline__ void build_a_row(const int16_t *__restrict__ planes, const TcGeom &tg, int q, uint8_t *sA, int row) {
+// ---- im2col ----------------------------------------------------------------------------------------
+// A tile = up to 128 consecutive positions (i, j0 .. j0+127) of one plane row.  Its receptive
+// field is a handful of 132-sample row segments (columns j0-2 .. j0+129 of rows i+dy of the
+// planes the band reads), which the 128 producer threads first stage in shared memory as bf16
+// -- every sample is loaded from global memory (coalesced) and converted ONCE, with the
+// reference's replicate padding applied by clamping -- and then each thread gathers its own A row
+// from the staged segments with constant offsets.
+struct SegTc { int phase, chan, dy; };
+__host__ __device__ constexpr int branch_rows_lo(const BranchTc &b) { return -b.padt; }
+__host__ __device__ constexpr int band_phase_lo(int band, int phase) {       // smallest dy used on this phase, 99 if unused
+    int lo = 99;
+    for (int b = 0; b < band_branches(band); ++b)
+        if (band_branch(band, b).phase == phase && -band_branch(band, b).padt < lo) lo = -band_branch(band, b).padt;
+    return lo;
+}
+__host__ __device__ constexpr int band_phase_hi(int band, int phase) {
+    int hi = -99;
+    for (int b = 0; b < band_branches(band); ++b)
+        if (band_branch(band, b).phase == phase && band_branch(band, b).kh - 1 - band_branch(band, b).padt > hi)
+            hi = band_branch(band, b).kh - 1 - band_branch(band, b).padt;
+    return hi;
+}
+__host__ __device__ constexpr int band_nseg(int band) {
+    int n = 0;
+    for (int ph = 0; ph <= band; ++ph) n += 3 * (band_phase_hi(band, ph) - band_phase_lo(band, ph) + 1);
+    return n;
+}
+// segment s -> (phase, channel, dy); order: phase, channel, dy
+__host__ __device__ constexpr SegTc band_seg(int band, int s) {
+    for (int ph = 0; ph <= band; ++ph) {
+        const int rows = band_phase_hi(band, ph) - band_phase_lo(band, ph) + 1;
+        if (s < 3 * rows) return SegTc{ph, s / rows, band_phase_lo(band, ph) + s % rows};
+        s -= 3 * rows;
+    }
+    return SegTc{0, 0, 0};
+}
+__host__ __device__ constexpr int band_seg_index(int band, int phase, int chan, int dy) {
+    int base = 0;
+    for (int ph = 0; ph < phase; ++ph) base += 3 * (band_phase_hi(band, ph) - band_phase_lo(band, ph) + 1);
+    const int rows = band_phase_hi(band, phase) - band_phase_lo(band, phase) + 1;
+    return base + chan * rows + (dy - band_phase_lo(band, phase));
+}
+constexpr int TC_SEG_PITCH = 136;      // staged samples per segment (132 used), bf16
+
+// bf16 bits of a small integer (|v| <= 255, exact): the sample enters as unsigned 16 bits; xor 0x8000 makes it
+// v + 32768, which or-ed into the mantissa of 2^23 gives the float 2^23 + 32768 + v; subtracting the offset
+// leaves float(v), whose low 16 bits are zero.
+__device__ __forceinline__ uint16_t bf16_of_sample(uint16_t u) {
+    const float f = __uint_as_float(0x4B008000u ^ (uint32_t)u) - 8421376.0f;
+    return (uint16_t)(__float_as_uint(f) >> 16);
+}
+
+template <int BAND, int HALF>
+__device__ __forceinline__ void stage_segments(const int16_t *__restrict__ planes, const TcGeom &tg, int img, int i, int j0,
+                                               uint16_t *sSeg, int t) {
+    constexpr int NSEG = band_nseg(BAND);
+    const uint16_t *pl = reinterpret_cast<const uint16_t *>(planes) + (size_t)img * 12 * tg.P;
+    const int c_main = min(max(j0 - 2 + t, 0), tg.Ws - 1);           // replicate padding
+    const int c_extra = min(max(j0 + 126 + t, 0), tg.Ws - 1);        // threads 0..3: columns j0+126 .. j0+129
+    int rowoff[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) rowoff[d] = min(max(i + d - 2, 0), tg.Hs - 1) * tg.Ws;
+    static_for<(NSEG + 1 - HALF) / 2>([&](auto s_) {          // the two producer groups stage alternate segments
+        constexpr int sg = 2 * decltype(s_)::value + HALF;
+        constexpr SegTc seg = band_seg(BAND, sg);
+        const uint16_t *src = pl + (size_t)(seg.phase * 3 + seg.chan) * tg.P + rowoff[seg.dy + 2];
+        sSeg[sg * TC_SEG_PITCH + t] = bf16_of_sample(src[c_main]);
+        if (t < 4) sSeg[sg * TC_SEG_PITCH + 128 + t] = bf16_of_sample(src[c_extra]);
+    });
+}
+
+template <int BAND, int HALF>
+__device__ __forceinline__ void build_a_row(const uint16_t *sSeg, uint8_t *sA, int row) {
     constexpr int K0 = band_k0(BAND);
     constexpr int K0p = (K0 + 2 + 15) / 16 * 16;
-    const int qq = min(q, tg.total - 1);
-    const int img = qq / tg.P, p = qq - img * tg.P;
-    const int i = p / tg.Ws, j = p - i * tg.Ws;
-    const int16_t *pl = planes + (size_t)img * 12 * tg.P;
-    int rowoff[5], col[5];
-#pragma unroll
-    for (int d = 0; d < 5; ++d) {
-        rowoff[d] = min(max(i + d - 2, 0), tg.Hs - 1) * tg.Ws;      // replicate padding
-        col[d] = min(max(j + d - 2, 0), tg.Ws - 1);
-    }
     constexpr uint32_t kOne = 0x3F80u;   // bf16 1.0
-    static_for<K0p / 8>([&](auto kc_) {
-        constexpr int kc = decltype(kc_)::value;
+    const uint16_t *my = sSeg + row + 2;
+    static_for<K0p / 16>([&](auto kc_) {                       // ... and build alternate 16-byte chunks of every row
+        constexpr int kc = 2 * decltype(kc_)::value + HALF;
         uint32_t w[4];
         static_for<4>([&](auto e2_) {
             constexpr int e2 = decltype(e2_)::value;
-            int v[2] = {0, 0};
-            uint32_t fixed = 0;
+            uint32_t v[2] = {0u, 0u};
             static_for<2>([&](auto h_) {
                 constexpr int h = decltype(h_)::value;
                 constexpr int k = kc * 8 + e2 * 2 + h;
                 constexpr TapTc t = band_tap(BAND, k);
-                if constexpr (t.valid != 0) v[h] = pl[(size_t)(t.phase * 3 + t.chan) * tg.P + rowoff[t.dy + 2] + col[t.dx + 2]];
-                else if constexpr (k == K0 || k == K0 + 1) fixed |= kOne << (16 * h);   // the two bias slots
+                if constexpr (t.valid != 0) v[h] = my[band_seg_index(BAND, t.phase, t.chan, t.dy) * TC_SEG_PITCH + t.dx];
+                else if constexpr (k == K0 || k == K0 + 1) v[h] = kOne;   // the two bias slots
             });
-            w[e2] = pack_int_pair(v[0], v[1]) | fixed;
+            w[e2] = v[0] | (v[1] << 16);
         });
         *reinterpret_cast<uint4 *>(sA + (size_t)kc * (TC_M * 16) + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     });
@@ -242,7 +316,9 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     constexpr uint32_t a_stage = (K0p / 8) * TC_M * 16;
     const uint32_t h_bytes = (uint32_t)(NP / 8) * TC_M * 16;
     uint8_t *sH = sA + 2 * a_stage;                              // 2 sub-networks x [NP/8][128][16 B]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sH + 2 * h_bytes);
+    uint16_t *sSeg = reinterpret_cast<uint16_t *>(sH + 2 * h_bytes);   // staged row segments, [NSEG][TC_SEG_PITCH] bf16
+    constexpr uint32_t seg_bytes = (band_nseg(BAND) * TC_SEG_PITCH * 2 + 15) / 16 * 16;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sH + 2 * h_bytes + seg_bytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int idx) { return bar0 + 8u * (uint32_t)idx; };
@@ -255,10 +331,10 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     if (tid == 0) {
         mbar_init(bar(B_W), 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(B_AFULL + s), TC_M);
+            mbar_init(bar(B_AFULL + s), 2 * TC_M);
             mbar_init(bar(B_AEMPTY + s), 1);
             mbar_init(bar(B_D0FULL + s), 1);
-            mbar_init(bar(B_DFREE + s), TC_M);
+            mbar_init(bar(B_DFREE + s), 2 * TC_M);
             mbar_init(bar(B_H0FULL + s), TC_M);
             mbar_init(bar(B_D1FULL + s), 1);
             mbar_init(bar(B_H1FULL + s), TC_M);
@@ -273,18 +349,25 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
 
     const uint32_t a_lbo = TC_M * 16;
 
-    if (warp >= 4 && warp < 8) {
-        // ================= im2col producers =================
-        const int row = tid - 128;
+    if (warp >= 8 && warp < 16) {
+        // ================= im2col producers: two threads per tile row =================
+        const int row = (tid - 256) & (TC_M - 1), half = (tid - 256) >> 7;
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
             mbar_wait(bar(B_AEMPTY + s), ((it >> 1) & 1) ^ 1);     // MMAs that read this stage are complete
             const int tile = tile0 + it * tile_stride;
-            build_a_row<BAND>(planes, tg, tile * TC_M + row, sA + s * a_stage, row);
+            const int rowid = tile / tg.tpr, jb = tile - rowid * tg.tpr;       // (image, plane row), column block
+            const int img = rowid / tg.Hs, i = rowid - img * tg.Hs;
+            asm volatile("bar.sync 1, 256;" ::: "memory");                      // everyone is done reading the previous segments
+            if (half == 0) stage_segments<BAND, 0>(planes, tg, img, i, jb * TC_M, sSeg, row);
+            else stage_segments<BAND, 1>(planes, tg, img, i, jb * TC_M, sSeg, row);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0) build_a_row<BAND, 0>(sSeg, sA + s * a_stage, row);
+            else build_a_row<BAND, 1>(sSeg, sA + s * a_stage, row);
             fence_async_smem();
             mbar_arrive(bar(B_AFULL + s));
         }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         // ================= MMA issuer =================
         if (lane == 0) {
             mbar_expect_tx(bar(B_W), (uint32_t)tg.pair_bytes);
@@ -333,58 +416,44 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             }
         }
     } else {
-        // ================= epilogue warps (TMEM lane quadrant = warp) =================
-        const int row = tid;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        // ================= epilogue warps: warps 0-3 sub-network 0, warps 4-7 sub-network 1 =================
+        // (a warp reaches the TMEM lanes 32 * (warp % 4) .. +31, so each quadrant of rows has one warp per sub-network)
+        const int row = tid & (TC_M - 1), g = tid >> 7;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint8_t *h = sH + g * h_bytes + row * 16;
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
             const uint32_t dbase = tmem + lane_base + (uint32_t)(s * TC_SLOT_COLS);
             const int tile = tile0 + it * tile_stride;
-            const int q = tile * TC_M + row;
+            const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + row;   // this thread's position: plane row, column
             // ---- layer 0 -> H0 ----
             mbar_wait(bar(B_D0FULL + s), (it >> 1) & 1);
             tc_fence_after();
-            for (int g = 0; g < 2; ++g) {
-                uint8_t *h = sH + g * h_bytes + row * 16;
-                for (int c16 = 0; c16 < NP / 16; ++c16) {
-                    uint32_t r[16];
-                    TMEM_LD_X16(dbase + (uint32_t)(g * NP + c16 * 16), r);
-                    tmem_ld_wait();
-                    relu_pack16(r, h + (size_t)(c16 * 2) * a_lbo, a_lbo);
-                }
-                fence_async_smem();
-                tc_fence_before();
-                mbar_arrive(bar(B_H0FULL + g));
-            }
+            if (NP == 96) epilogue_hidden<96>(dbase + (uint32_t)(g * NP), h, a_lbo);
+            else epilogue_hidden<64>(dbase + (uint32_t)(g * NP), h, a_lbo);
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar(B_H0FULL + g));
             // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
-            for (int g = 0; g < 2; ++g) {
-                mbar_wait(bar(B_D1FULL + g), it & 1);
-                tc_fence_after();
-                uint8_t *h = sH + g * h_bytes + row * 16;
-                for (int c16 = 0; c16 < NP / 16; ++c16) {
-                    uint32_t r[16];
-                    TMEM_LD_X16(dbase + (uint32_t)(g * NP + c16 * 16), r);
-                    tmem_ld_wait();
-                    relu_pack16(r, h + (size_t)(c16 * 2) * a_lbo, a_lbo);
-                }
-                fence_async_smem();
-                tc_fence_before();
-                mbar_arrive(bar(B_H1FULL + g));
-            }
+            mbar_wait(bar(B_D1FULL + g), it & 1);
+            tc_fence_after();
+            if (NP == 96) epilogue_hidden<96>(dbase + (uint32_t)(g * NP), h, a_lbo);
+            else epilogue_hidden<64>(dbase + (uint32_t)(g * NP), h, a_lbo);
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar(B_H1FULL + g));
             mbar_arrive(bar(B_DFREE + s));      // D0/D1 columns of this slot may be overwritten by tile it+2
             // ---- layer 2 -> params (fp32) ----
-            for (int g = 0; g < 2; ++g) {
-                mbar_wait(bar(B_D2FULL + g), it & 1);
-                tc_fence_after();
-                uint32_t r[16];
-                TMEM_LD_X16(dbase + (uint32_t)(2 * NP + g * 16), r);
-                tmem_ld_wait();
-                if (q < tg.total) {
-                    const int img = q / tg.P, p = q - img * tg.P;
-                    float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + g) * 15) * tg.P + p;
+            mbar_wait(bar(B_D2FULL + g), it & 1);
+            tc_fence_after();
+            uint32_t r[16];
+            TMEM_LD_X16(dbase + (uint32_t)(2 * NP + g * 16), r);
+            tmem_ld_wait();
+            if (jcol < tg.Ws) {
+                const int img = rowid / tg.Hs, p = (rowid - img * tg.Hs) * tg.Ws + jcol;
+                float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + g) * 15) * tg.P + p;
 #pragma unroll
-                    for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
-                }
+                for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
             }
             tc_fence_before();
         }
@@ -487,7 +556,7 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
         tb.g.K0 = K0; tb.g.K0p = K0p; tb.g.G = G; tb.g.NP = NP; tb.g.pair_bytes = pair_bytes;
         tb.g.off_w1 = w0_bytes; tb.g.off_w2 = w0_bytes + w1_bytes;
         tb.smem_bytes = (size_t)((pair_bytes + 127) & ~127) + 2 * (size_t)(K0p / 8) * TC_M * 16 + 2 * (size_t)(NP / 8) * TC_M * 16 +
-                        B_COUNT * 8 + 16;
+                        (size_t)(band_nseg(band) * TC_SEG_PITCH * 2 + 15) / 16 * 16 + B_COUNT * 8 + 16;
     }
     ctx->tc_weights = tw;
     return LLICTI_OK;
@@ -510,8 +579,11 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
     tg.Hs = Hs; tg.Ws = Ws; tg.P = Hs * Ws;
     const long long total = (long long)n * tg.P;
     LLICTI_REQUIRE(total < (1ll << 31) - TC_M, "batch too large for one CNN launch");
-    tg.total = (int)total;
-    tg.ntiles = (tg.total + TC_M - 1) / TC_M;
+    tg.n = n;
+    tg.tpr = (Ws + TC_M - 1) / TC_M;
+    const long long ntiles = (long long)n * Hs * tg.tpr;
+    LLICTI_REQUIRE(ntiles < (1ll << 31), "batch too large for one CNN launch");
+    tg.ntiles = (int)ntiles;
     static int sm_count = 0;
     static size_t attr_smem = 0;
     if (!sm_count) {
