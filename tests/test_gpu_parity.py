@@ -271,7 +271,7 @@ def test_decoder_reads_reference_golden_streams(L, name):
 
 
 # ---------------------------------------------------------------------------- full path (a)
-@pytest.mark.parametrize("impl", [(0, 0), (1, 0), (0, 1)], ids=["fp32-warp", "tcgen05-warp", "fp32-scalar"])
+@pytest.mark.parametrize("impl", [(0, 0), (1, 0), (0, 1)], ids=["fp32-windows", "tcgen05-windows", "fp32-legacy"])
 @pytest.mark.parametrize("sub_len", [0, 64, 2048])
 @pytest.mark.parametrize("name", list(EDGE_IMAGES))
 def test_round_trip_lossless(L, name, sub_len, impl):
@@ -284,8 +284,8 @@ def test_round_trip_lossless(L, name, sub_len, impl):
     assert np.array_equal(rec, img)
 
 
-def test_scalar_and_warp_decoders_agree(L):
-    """Both decode kernels read the same streams (they find the symbol torchac's search finds)."""
+def test_window_and_legacy_decoders_agree(L):
+    """Both decode implementations read the same streams (they find the symbol torchac's search finds)."""
     ocfg = O.OracleConfig()
     sd = O.synthetic_state_dict(ocfg)
     img = O.synthetic_image(95, 161, 3)
@@ -295,6 +295,79 @@ def test_scalar_and_warp_decoders_agree(L):
         for decode_impl in (0, 1):
             dec = make_codec(L, ocfg, sd, sub_len=sub_len, decode_impl=decode_impl)
             assert np.array_equal(dec.decompress_images(bsl)[0], img)
+
+
+# ------------------------------------------------------------------ full sizes of BASELINE.json (a)
+FULL_SIZE_CASES = [
+    # (id, model config, H, W, images, sub_len)
+    ("c1-kodak-compat-B", dict(dwtlevels=(0, 1), chs=60), 512, 768, 6, 0),
+    ("c0-kodak-compat-A", dict(), 512, 768, 3, 0),
+    ("c2-div2k-substreams", dict(), 1356, 2040, 2, 2048),
+    ("c3-4k-substreams", dict(), 2160, 3840, 1, 2048),
+    ("c4-openimages-substreams", dict(), 512, 512, 16, 2048),
+]
+
+
+@pytest.mark.parametrize("case", FULL_SIZE_CASES, ids=[c[0] for c in FULL_SIZE_CASES])
+def test_full_size_round_trip(L, case):
+    """Size-independent property at the shapes BASELINE.json names: decode(encode(x)) == x for every
+    image of a batch, through the batch entry points with the tcgen05 CNN, and the statistics of
+    the decoder show the pre-computed windows carry (almost) every symbol."""
+    _, over, H, W, n, sub_len = case
+    ocfg = O.OracleConfig(**over)
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=sub_len, cnn_impl=L.CNN_TCGEN05)
+    imgs = np.stack([O.synthetic_image(H, W, 100 + i) for i in range(n)])
+    if n > 1:
+        imgs[1] = np.random.default_rng(7).integers(0, 256, size=imgs[1].shape, dtype=np.uint8)   # worst case: noise
+    blob, off, mm = codec.encode_host(imgs)
+    S = len(ocfg.dwtlevels)
+    x00 = np.ascontiguousarray(imgs[:, :, ::2 ** S, ::2 ** S])
+    rec = codec.decode_host(blob, off, mm, x00, n, H, W)
+    assert np.array_equal(rec, imgs)
+    # photographic content: (almost) every symbol is found in its pre-computed window; the noise image
+    # above is the opposite extreme and decodes through the full analytic search
+    ns = 9 * S
+    codec.decode_stats()
+    rec0 = codec.decode_host(blob[: int(off[ns])], off[: ns + 1], mm[:1], x00[:1], 1, H, W)
+    assert np.array_equal(rec0, imgs[:1])
+    st = codec.decode_stats()
+    assert st["slow_path_symbols"] < 0.02 * codec.geometry(H, W).symbols, st
+    # streams of an image do not depend on its batch neighbours
+    blob1, off1, _ = codec.encode_host(imgs[:1])
+    assert bytes(blob1[: int(off1[ns])]) == bytes(blob[: int(off[ns])])
+    codec.close()
+
+
+def test_piped_and_split_schedules_agree(L, monkeypatch):
+    """torchac-compatible streams decode identically through the one-kernel-per-band pipeline and
+    through the six-launch split schedule, and through the legacy decoder."""
+    ocfg = O.OracleConfig(dwtlevels=(0, 1), chs=60)
+    sd = O.synthetic_state_dict(ocfg)
+    imgs = np.stack([O.synthetic_image(150, 212, i) for i in range(3)])
+    enc = make_codec(L, ocfg, sd, sub_len=0, cnn_impl=L.CNN_TCGEN05)
+    bsls = enc.compress_images(imgs)
+    assert np.array_equal(enc.decompress_images(bsls), imgs)
+    monkeypatch.setenv("LLICTI_NO_PIPE", "1")
+    assert np.array_equal(enc.decompress_images(bsls), imgs)
+    monkeypatch.delenv("LLICTI_NO_PIPE")
+    legacy = make_codec(L, ocfg, sd, sub_len=0, cnn_impl=L.CNN_TCGEN05, decode_impl=1)
+    assert np.array_equal(legacy.decompress_images(bsls), imgs)
+
+
+def test_constant_and_extreme_images_at_scale(L):
+    """Lp = 2 alphabets (constant image), full-range chroma (0/255 checkerboard) and saturated
+    noise in one batch of 768x512 images."""
+    ocfg = O.OracleConfig()
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=1024, cnn_impl=L.CNN_TCGEN05)
+    H, W = 512, 768
+    yy, xx = np.mgrid[0:H, 0:W]
+    chk = (((yy + xx) & 1) * 255).astype(np.uint8)
+    imgs = np.stack([np.full((3, H, W), 200, np.uint8),
+                     np.stack([chk, 255 - chk, chk]),
+                     np.random.default_rng(3).choice(np.array([0, 255], np.uint8), size=(3, H, W))])
+    for batch in (imgs, imgs[:1], imgs[1:2]):      # per-image alphabets differ: each batch composition must work
+        bsls = codec.compress_images(batch)
+        assert np.array_equal(codec.decompress_images(bsls), batch)
 
 
 @pytest.mark.parametrize("cnn_impl", [0, 1])
