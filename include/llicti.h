@@ -203,6 +203,10 @@ LLICTI_API int64_t llicti_launch_count(const llicti_ctx *ctx);
 LLICTI_API int llicti_profile(llicti_ctx *ctx, int enable);
 LLICTI_API int llicti_profile_read(llicti_ctx *ctx, double *ms, int64_t *count);
 
+/* Self-test of the CDF stage's hoisted IEEE division (csrc/gmm.cuh: fdiv_hoisted) against div.rn.f32 on
+ * n_pairs random operand pairs from the stage's domain; *mismatches must come back 0. */
+LLICTI_API int llicti_selftest_fdiv(llicti_ctx *ctx, int64_t n_pairs, uint64_t seed, uint64_t *mismatches);
+
 /* Decode-side counters since the last reset (synchronises the device): out8[0] symbols that
  * fell outside their pre-computed CDF window and took the full analytic search, out8[1] polls
  * of consumer warps waiting for windows (piped schedule), out8[3] 8-symbol chunks whose

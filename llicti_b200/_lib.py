@@ -79,6 +79,7 @@ _PROTOS = {
     "llicti_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "llicti_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "llicti_decode_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
+    "llicti_selftest_fdiv": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 
 EXPORTS = tuple(_PROTOS)

@@ -139,6 +139,12 @@ class Codec:
         L.check(self.lib.llicti_profile_read(self._ctx, ms, cnt))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(L.KERNEL_CLASSES)}
 
+    def selftest_fdiv(self, n_pairs: int, seed: int = 1) -> int:
+        """Mismatches between the CDF stage's hoisted division and div.rn.f32 on n_pairs random operand pairs."""
+        bad = C.c_uint64(0)
+        L.check(self.lib.llicti_selftest_fdiv(self._ctx, n_pairs, seed, C.byref(bad)))
+        return int(bad.value)
+
     def decode_stats(self, reset: bool = True):
         """Decode-side diagnostics: window misses and pipeline waits since the last reset."""
         out = (C.c_uint64 * 8)()

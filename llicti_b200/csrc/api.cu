@@ -323,6 +323,21 @@ int llicti_decode_stats(llicti_ctx *ctx, uint64_t *out8, int reset) {
     return read_decode_stats(out8, reset);
 }
 
+int llicti_selftest_fdiv(llicti_ctx *ctx, int64_t n_pairs, uint64_t seed, uint64_t *mismatches) {
+    LLICTI_REQUIRE(ctx && mismatches && n_pairs > 0, "bad argument");
+    unsigned long long *d = nullptr, h = 0;
+    LLICTI_CUDA(cudaMalloc((void **)&d, sizeof(h)));
+    LLICTI_CUDA(cudaMemset(d, 0, sizeof(h)));
+    int rc = launch_selftest_fdiv(ctx, n_pairs, seed, d, nullptr);
+    if (rc == LLICTI_OK) {
+        cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("selftest: %s", cudaGetErrorString(e)); rc = LLICTI_E_CUDA; }
+    }
+    cudaFree(d);
+    *mismatches = h;
+    return rc;
+}
+
 // ---- stage-level ------------------------------------------------------------------------
 int llicti_color_split(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, int16_t *const *planes_dev,
                        int32_t *minmax_dev, void *stream) {

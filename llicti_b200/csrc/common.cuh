@@ -196,6 +196,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
 int64_t decode_items_per_image(const Plan &p);
 int64_t decode_flag_words(int64_t items_cap);
 int read_decode_stats(uint64_t *out, int reset);
+int launch_selftest_fdiv(llicti_ctx *ctx, long long n_pairs, uint64_t seed, unsigned long long *mismatches_dev, cudaStream_t st);
 int launch_decode_table(llicti_ctx *ctx, const int16_t *table, int n_sym, int Lp, int S, const uint8_t *in,
                         const uint32_t *offs, int16_t *sym, cudaStream_t st);
 

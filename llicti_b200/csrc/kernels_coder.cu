@@ -559,6 +559,60 @@ decode_table_kernel(const int16_t *__restrict__ table, int n_sym, int Lp, int S,
 }
 
 // ------------------------------------------------------------------------------------------
+// Self-test of the hoisted division (gmm.cuh: fdiv_hoisted) against div.rn.f32 on random operands
+// drawn from the domain the CDF stage produces: sampling points of every alphabet, means near and
+// far from them, spreads from the clamp value to 2^20 including hard mantissas.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t &s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+selftest_fdiv_kernel(uint64_t seed, int per_thread, NumericsProfile np, unsigned long long *mismatches) {
+    uint64_t s = seed + 0x1234567ull * (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x);
+    unsigned long long bad = 0;
+    for (int it = 0; it < per_thread; ++it) {
+        const uint64_t r0 = splitmix64(s), r1 = splitmix64(s);
+        // spread: log-uniform over [2^-12, 2^20] with a random mantissa; every 8th one has a hard mantissa
+        const int e = (int)(r0 % 33) - 12;
+        uint32_t mant = (uint32_t)(r0 >> 8) & 0x7FFFFFu;
+        if (((r0 >> 40) & 7) == 0) mant = ((r0 >> 43) & 1) ? 0x7FFFFFu - (uint32_t)((r0 >> 44) & 3) : (uint32_t)((r0 >> 44) & 3);
+        float sigma = __uint_as_float(((uint32_t)(e + 127) << 23) | mant);
+        sigma = fmaxf(sigma, (float)(0.11 / 255.0));
+        // sampling point of a random alphabet, mean: near the point (a few ulps), image-range, or far
+        const int min_val = (int)(r1 % 511) - 255, k = (int)((r1 >> 16) % 512);
+        const CdfGrid g = make_grid(min_val, min_val + 510);
+        const float pt = grid_point(g, k, np);
+        const uint32_t sel = (uint32_t)(r1 >> 32) & 3u;
+        float mu;
+        if (sel == 0) mu = __uint_as_float(__float_as_uint(pt) + (uint32_t)((r1 >> 34) & 15) - 8u);
+        else if (sel == 1) mu = (float)((r1 >> 34) & 0xFFFFF) * (1.5f / 1048576.0f) - 0.25f;
+        else if (sel == 2) mu = ((float)((r1 >> 34) & 0xFFFFF) - 524288.0f) * (1.0f / 512.0f);
+        else mu = pt - sigma * ((float)((r1 >> 34) & 0xFFFF) * (1.0f / 4096.0f) - 8.0f);
+        GmmChannel c;
+#pragma unroll
+        for (int m = 0; m < kM; ++m) { c.sigma[m] = sigma; c.mu[m] = mu; c.w[m] = 0.2f; }
+        gmm_prepare(c, np);
+        if (!c.fast) continue;
+        const float x = __fsub_rn(pt, c.mu[0]);
+        const float a = fdiv_hoisted(x, c.sigma[0], c.rinv[0], 1), b = __fdiv_rn(x, c.sigma[0]);
+        bad += __float_as_uint(a) != __float_as_uint(b);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+int launch_selftest_fdiv(llicti_ctx *ctx, long long n_pairs, uint64_t seed, unsigned long long *mismatches_dev, cudaStream_t st) {
+    const int threads = 256, blocks = 1184, per_thread = (int)((n_pairs + (long long)threads * blocks - 1) / ((long long)threads * blocks));
+    selftest_fdiv_kernel<<<blocks, threads, 0, st>>>(seed, per_thread, ctx->num, mismatches_dev);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Launchers
 // ------------------------------------------------------------------------------------------
 int launch_cdf_table(llicti_ctx *ctx, const float *params, const int16_t *yband, int clr, int min_val, int max_val,

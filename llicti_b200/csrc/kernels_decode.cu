@@ -34,6 +34,7 @@ namespace llicti {
 
 __device__ unsigned long long g_decode_stats[8];   // 0 slow-path symbols, 1 consumer flag polls, 2 unused, 3 chunks redone carefully
 
+constexpr int kStageU16 = 32 * 34 + 32 * 6 * 8;   // per warp: window staging (17-word pitch) + prepared channels of 32 steps
 constexpr int kWin = 31;                 // table entries per window (lane 31 carries `base`)
 constexpr int16_t kSentinel = (int16_t)0x8080;   // memset(0x80): never a sample value (|v| <= 255)
 
@@ -95,7 +96,8 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
     const long long i = (long long)j + (long long)t * dg.S;
     GmmChannel ch;
 #pragma unroll
-    for (int m = 0; m < kM; ++m) { ch.sigma[m] = 1.f; ch.mu[m] = 0.f; ch.w[m] = 0.2f; }
+    for (int m = 0; m < kM; ++m) { ch.sigma[m] = 1.f; ch.mu[m] = 0.f; ch.w[m] = 0.2f; ch.rinv[m] = 1.f; }
+    ch.fast = 1;
     int base = 0;
     if (i < dg.n_sym) {
         const int r = (int)(i / dg.crop_w), c = (int)(i - (long long)r * dg.crop_w);
@@ -111,20 +113,35 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
         base = min(max(kc - kWin / 2, 0), max(last - (kWin - 1), 0));
     }
     const int nv = min(32, (dg.n_sym - j + dg.S - 1) / dg.S - tb * 32);   // valid steps of this item (warp-uniform)
+    // the prepared channel of every step goes through shared memory: 6 broadcast 16-byte reads per step
+    float4 *prm = reinterpret_cast<float4 *>(stage + 32 * 34);            // [32 steps][6 x float4]
+    {
+        float4 *mine = prm + lane * 6;
+        mine[0] = make_float4(ch.sigma[0], ch.sigma[1], ch.sigma[2], ch.sigma[3]);
+        mine[1] = make_float4(ch.sigma[4], ch.mu[0], ch.mu[1], ch.mu[2]);
+        mine[2] = make_float4(ch.mu[3], ch.mu[4], ch.w[0], ch.w[1]);
+        mine[3] = make_float4(ch.w[2], ch.w[3], ch.w[4], ch.rinv[0]);
+        mine[4] = make_float4(ch.rinv[1], ch.rinv[2], ch.rinv[3], ch.rinv[4]);
+        mine[5] = make_float4(__int_as_float(base), __int_as_float(ch.fast), 0.f, 0.f);
+    }
+    __syncwarp();
     uint16_t *my = stage + lane * 34;     // 17-word pitch: conflict-free writes and reads
 #pragma unroll 1
     for (int s = 0; s < nv; ++s) {
+        const float4 *src = prm + s * 6;
+        const float4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4], v5 = src[5];
         GmmChannel b;
-#pragma unroll
-        for (int m = 0; m < kM; ++m) {
-            b.sigma[m] = __shfl_sync(kFull, ch.sigma[m], s);
-            b.mu[m] = __shfl_sync(kFull, ch.mu[m], s);
-            b.w[m] = __shfl_sync(kFull, ch.w[m], s);
-        }
-        const int bs = __shfl_sync(kFull, base, s);
+        b.sigma[0] = v0.x; b.sigma[1] = v0.y; b.sigma[2] = v0.z; b.sigma[3] = v0.w; b.sigma[4] = v1.x;
+        b.mu[0] = v1.y; b.mu[1] = v1.z; b.mu[2] = v1.w; b.mu[3] = v2.x; b.mu[4] = v2.y;
+        b.w[0] = v2.z; b.w[1] = v2.w; b.w[2] = v3.x; b.w[3] = v3.y; b.w[4] = v3.z;
+        b.rinv[0] = v3.w; b.rinv[1] = v4.x; b.rinv[2] = v4.y; b.rinv[3] = v4.z; b.rinv[4] = v4.w;
+        const int bs = __float_as_int(v5.x);
+        b.fast = __float_as_int(v5.y);
         const int k = bs + lane;
-        uint32_t q = window_info(bs, last);
-        if (lane < kWin) q = k < last ? cdf_q(b, g, k, np) : 0u;
+        // every lane evaluates an entry (the warp-uniform erfc skip votes over all 32 lanes); lanes beyond
+        // the table and lane 31 evaluate a clamped index and discard it
+        const uint32_t qe = cdf_q<true>(b, g, min(k, last - 1), np);
+        const uint32_t q = lane < kWin ? (k < last ? qe : 0u) : window_info(bs, last);
         my[s] = (uint16_t)q;
     }
     __syncwarp();
@@ -461,9 +478,11 @@ scatter_band_kernel(const int16_t *__restrict__ syms, size_t sym_cap, int16_t *_
     if (last_c && last_r) dst[dg.Ws + 1] = v;
 }
 
-static __device__ __forceinline__ void band_grids(const int32_t *mm, int (&lo)[3], CdfGrid (&g)[3]) {
+// Alphabet of every colour channel of an image: Y is fixed, Co / Cg come from the header's min / max.
+// (Selected by value: a CdfGrid array indexed by a run-time channel would live in local memory.)
+static __device__ __forceinline__ CdfGrid band_grids(const int32_t *mm, int clr, int (&lo)[3]) {
     lo[0] = -127; lo[1] = mm[0]; lo[2] = mm[1];
-    g[0] = make_grid(-127, 128); g[1] = make_grid(mm[0], mm[2]); g[2] = make_grid(mm[1], mm[3]);
+    return clr == 0 ? make_grid(-127, 128) : clr == 1 ? make_grid(mm[0], mm[2]) : make_grid(mm[1], mm[3]);
 }
 
 // ---- split schedule ---------------------------------------------------------------------------
@@ -471,7 +490,7 @@ __global__ void __launch_bounds__(128)
 window_kernel(const float *__restrict__ params, const int16_t *__restrict__ syms, size_t sym_cap,
               const int32_t *__restrict__ minmax, DecodeGeom dg, int clr, NumericsProfile np, uint4 *__restrict__ items,
               int n) {
-    __shared__ __align__(16) uint16_t stage[4][32 * 34];
+    __shared__ __align__(16) uint16_t stage[4][kStageU16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long per_img = (long long)dg.S * dg.items_per_chain;
     const long long total = per_img * n;
@@ -484,11 +503,10 @@ window_kernel(const float *__restrict__ params, const int16_t *__restrict__ syms
         if ((long long)j + (long long)tb * 32 * dg.S >= dg.n_sym) continue;
         const size_t P = (size_t)dg.Hs * dg.Ws;
         int lo[3];
-        CdfGrid g[3];
-        band_grids(minmax + img * 4, lo, g);
+        const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
         uint4 *item = items + ((((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain + tb) * 128;
         produce_item<false>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
-                            g[clr], j, tb, np, item, stage[wib], lane);
+                            g, j, tb, np, item, stage[wib], lane);
     }
 }
 
@@ -503,13 +521,12 @@ consume_kernel(const float *__restrict__ params, int16_t *__restrict__ syms, siz
     const int img = (int)(w / dg.S), j = (int)(w - (long long)img * dg.S);
     const size_t P = (size_t)dg.Hs * dg.Ws;
     int lo[3];
-    CdfGrid g[3];
-    band_grids(minmax + img * 4, lo, g);
+    const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
     int16_t *isyms = syms + (size_t)img * 3 * sym_cap;
     const ChainCtx cx = {params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], dg.S};
     const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
     const uint4 *chain_items = items + (((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain * 128;
-    consume_chain<false>(cx, dg.n_sym, g[clr], j, np, isyms + (size_t)clr * sym_cap, chain_items, nullptr, blob + suboff[e],
+    consume_chain<false>(cx, dg.n_sym, g, j, np, isyms + (size_t)clr * sym_cap, chain_items, nullptr, blob + suboff[e],
                          sublen[e], lane);
 }
 
@@ -530,12 +547,11 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
                         DecodeGeom dg, NumericsProfile np, uint4 *items, uint32_t *ctl, uint32_t *flags, int cons_per_sm,
                         const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
                         const uint32_t *__restrict__ sublen, int total_sub, int n) {
-    __shared__ __align__(16) uint16_t stage[32 * 34];
+    __shared__ __align__(16) uint16_t stage[kStageU16];
     const int lane = threadIdx.x;
     const size_t P = (size_t)dg.Hs * dg.Ws;
     const int n_cons = 3 * n;
     int lo[3];
-    CdfGrid g[3];
 
     // ---- role ----
     uint32_t smid;
@@ -560,11 +576,11 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
 
     if (chain >= 0) {
         const int img = chain / 3, clr = chain - 3 * img;
-        band_grids(minmax + img * 4, lo, g);
+        const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
         int16_t *isyms = syms + (size_t)img * 3 * sym_cap;
         const ChainCtx cx = {params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], 1};
         const size_t e = (size_t)img * total_sub + dg.sub_first[clr];
-        consume_chain<true>(cx, dg.n_sym, g[clr], 0, np, isyms + (size_t)clr * sym_cap,
+        consume_chain<true>(cx, dg.n_sym, g, 0, np, isyms + (size_t)clr * sym_cap,
                             items + (size_t)chain * dg.items_per_chain * 128, flags + (size_t)chain * dg.items_per_chain,
                             blob + suboff[e], sublen[e], lane);
         return;
@@ -584,10 +600,10 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
             const int tb = (int)(w / (uint32_t)n);
             const int img = (int)(w - (uint32_t)tb * (uint32_t)n);
             const int ch = img * 3 + clr;
-            band_grids(minmax + img * 4, lo, g);
+            const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
             uint4 *item = items + ((size_t)ch * dg.items_per_chain + tb) * 128;
             produce_item<true>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
-                               g[clr], 0, tb, np, item, stage, lane);
+                               g, 0, tb, np, item, stage, lane);
             // every lane's stores happen before the flag store: warp barrier, then a cumulative fence
             __syncwarp();
             if (lane == 0) {

@@ -213,6 +213,15 @@ def test_cdf_tables_vs_cpu_oracle_counted(L, scale, band):
         assert (delta != 0).mean() < 5e-3, (delta != 0).mean()
 
 
+def test_hoisted_division_is_ieee_division(L):
+    """gmm.cuh hoists the reciprocal refinement of (p - mu) / sigma out of the per-entry loop; the
+    result must be div.rn.f32's, bit for bit (2^28 random operand pairs per seed from the stage's domain)."""
+    ocfg = O.OracleConfig()
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg))
+    for seed in (1, 2, 3, 4):
+        assert codec.selftest_fdiv(1 << 28, seed) == 0
+
+
 def test_cdf_bounds_equal_table_entries(L):
     ocfg, sd, d = stage_c_inputs()
     codec = make_codec(L, ocfg, sd)
