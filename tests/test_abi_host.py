@@ -173,3 +173,30 @@ def test_model_state_dict_names_match_reference_layout():
     m.load_state_dict(sd)
     assert torch.equal(m.state_dict()["entropymodel.entmdls_scale_band.0.1.layer0_11_01.weight"],
                        sd["entropymodel.entmdls_scale_band.0.1.layer0_11_01.weight"])
+
+
+def test_llicti_file_round_trip_and_validation():
+    """.llicti container: the reference's bytestream_list, length-prefixed."""
+    from llicti_b200 import container, fileformat
+    rng = np.random.default_rng(5)
+    S, H, W = 2, 37, 53
+    planes, flags, pad_int = O.pyramid_split(np.zeros((3, H, W), dtype=np.int16), (0, 1))
+    h_last, w_last = planes[-1].shape[1:]
+    rgb = rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)
+    lens = rng.integers(0, 40, size=9 * S)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    blob = rng.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    mm = rng.integers(-255, 256, size=(1, 6)).astype(np.int16)
+    for sub_len in (0, 256):
+        bsl = container.assemble(S, sub_len, h_last, w_last, pad_int, rgb, blob, off, mm)[0]
+        data = fileformat.dumps(bsl, sub_len, H, W)
+        bsl2, sub2, H2, W2 = fileformat.loads(data)
+        assert (sub2, H2, W2) == (sub_len, H, W) and bsl2 == [list(map(bytes, r)) for r in bsl]
+        assert len(data) == 21 + 4 * 9 * (S + 1) + sum(len(e) for r in bsl for e in r)
+        for bad in (data[:-1], data + b"x", b"XLICTI" + data[6:], data[:6] + bytes([9]) + data[7:]):
+            with pytest.raises(ValueError):
+                fileformat.loads(bad)
+        with pytest.raises(ValueError):
+            fileformat.dumps(bsl, sub_len + 1, H, W)
+        with pytest.raises(ValueError):
+            fileformat.loads(fileformat.dumps(bsl, sub_len, H + 1, W))

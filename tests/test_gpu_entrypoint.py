@@ -40,3 +40,18 @@ def test_main_eval_model(tmp_path, cfg_name, ocfg):
     assert log.count("(Check: Decoded img matches original)") == 2, log[-2000:]
     assert "Checkpoint loaded successfully" in log
     assert (ckdir / "checkpoint.pth.tar").exists()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sub_len", [0, 512])
+def test_cli_encode_decode_files(tmp_path, sub_len):
+    """PNG -> .llicti -> PNG through the command-line front end is lossless."""
+    from PIL import Image
+    from llicti_b200 import cli
+    img = O.synthetic_image(75, 109, 4)
+    src, mid, dst = tmp_path / "in.png", tmp_path / "x.llicti", tmp_path / "out.png"
+    Image.fromarray(np.ascontiguousarray(img.transpose(1, 2, 0)), "RGB").save(src)
+    cfg = os.path.join(ROOT, "configs", "llicti_A.json")
+    assert cli.main(["encode", str(src), str(mid), "--config", cfg, "--sub-len", str(sub_len)]) == 0
+    assert cli.main(["decode", str(mid), str(dst), "--config", cfg]) == 0
+    assert np.array_equal(np.asarray(Image.open(dst)).transpose(2, 0, 1), img)
