@@ -70,15 +70,28 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
 
 // Decoded symbol of coding-order index i of one (image, channel); in the piped schedule the
 // array starts as sentinels and the consumer's store is the publication (data = flag).
+// Waits inside the piped grid are bounded: a wait that outlives any legitimate kernel run time (a
+// programming error, or a grid that is not co-resident) traps instead of hanging the GPU.
+constexpr uint32_t kMaxPolls = 1u << 25;      // x >= 100 ns per poll: several seconds
+
 template <bool kPipe>
 __device__ __forceinline__ int read_symbol(const int16_t *p) {
     if (!kPipe) return (int)*p;
     int v = ld_relaxed_s16(p);
-    while (v == (int)kSentinel) {       // not decoded yet
+    for (uint32_t polls = 0; v == (int)kSentinel; ++polls) {       // not decoded yet
+        if (polls > kMaxPolls) __trap();
         __nanosleep(200);
         v = ld_relaxed_s16(p);
     }
     return v;
+}
+
+__device__ __forceinline__ void wait_flag(const uint32_t *flag, unsigned long long &polls) {
+    for (uint32_t spins = 0; ld_relaxed_u32(flag) == 0u; ++spins) {
+        if (spins > kMaxPolls) __trap();
+        ++polls;
+        __nanosleep(100);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -373,8 +386,7 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
     long long i = j;
     int16_t *dst = out + j;
 
-    if (kPipe)
-        while (ld_relaxed_u32(flags) == 0u) { ++polls; __nanosleep(100); }
+    if (kPipe) wait_flag(flags, polls);
     const uint4 *src = items + lane;
     uint4 q0 = load_chunk<kPipe>(src), q1 = load_chunk<kPipe>(src + 32), q2 = load_chunk<kPipe>(src + 64),
           q3 = load_chunk<kPipe>(src + 96);
@@ -442,7 +454,7 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
             }
         }
         if (!have_next) {
-            while (ld_relaxed_u32(flags + it + 1) == 0u) { ++polls; __nanosleep(100); }
+            wait_flag(flags + it + 1, polls);
             const uint4 *nx = src + (size_t)(it + 1) * 128;
             n0 = load_chunk<kPipe>(nx); n1 = load_chunk<kPipe>(nx + 32); n2 = load_chunk<kPipe>(nx + 64); n3 = load_chunk<kPipe>(nx + 96);
         }
@@ -567,7 +579,10 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
         }
         if (chain < 0) {
             uint32_t role;
-            while ((role = ld_relaxed_u32(&ctl[256 + smid])) == 0u) __nanosleep(100);
+            for (uint32_t spins = 0; (role = ld_relaxed_u32(&ctl[256 + smid])) == 0u; ++spins) {
+                if (spins > kMaxPolls) __trap();
+                __nanosleep(100);
+            }
             if (role == 2u) producer_id = (int)atomicAdd(&ctl[513], 1u);
         }
     }
@@ -760,9 +775,12 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
     // to half of the SMs, the other half produces
     const int cons_auto = (3 * n + sm_count / 2 - 1) / (sm_count / 2);
     const int cons_per_sm = std::min(std::max(env_int("LLICTI_PIPE_CONS_PER_SM", cons_auto), 1), kConsPerSmMax);
-    const int ctas_per_sm = std::min(std::max(env_int("LLICTI_PIPE_CTAS_PER_SM", 12), cons_per_sm + 1), 24);
+    static int pipe_resident = 0;       // one-warp CTAs of the piped kernel that fit on one SM
+    if (!pipe_resident)
+        LLICTI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pipe_resident, decode_band_pipe_kernel, 32, 0));
+    const int ctas_per_sm = std::min(std::min(std::max(env_int("LLICTI_PIPE_CTAS_PER_SM", 12), cons_per_sm + 1), 24), pipe_resident);
     const int cons_sms = (3 * n + cons_per_sm - 1) / cons_per_sm;
-    const bool piped = dg.S == 1 && cons_sms <= sm_count / 2 && 3 * n <= kConsPerSmMax * (sm_count / 2) && sm_count <= 256 &&
+    const bool piped = dg.S == 1 && ctas_per_sm > cons_per_sm && cons_sms <= sm_count / 2 && 3 * n <= kConsPerSmMax * (sm_count / 2) && sm_count <= 256 &&
                        !env_int("LLICTI_NO_PIPE", 0);
     if (piped) {
         ProfScope prof_(ctx, KC_DECODE, st);
