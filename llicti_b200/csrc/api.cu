@@ -161,6 +161,7 @@ static void free_workspace(llicti_ctx *ctx) {
     cudaFree(ctx->d_x00); ctx->d_x00 = nullptr;
     cudaFree(ctx->d_items); ctx->d_items = nullptr; ctx->items_cap = 0;
     cudaFree(ctx->d_item_flags); ctx->d_item_flags = nullptr;
+    cudaFree(ctx->d_chain_state_raw); ctx->d_chain_state_raw = nullptr; ctx->wave_ws = false;
     cudaFree(ctx->d_syms); ctx->d_syms = nullptr; ctx->sym_cap = 0;
     ctx->ws_images = 0;
 }
@@ -237,6 +238,17 @@ int llicti_create(const llicti_config *cfg, const llicti_weights *w, llicti_ctx 
     int rc = pack_weights(ctx, *w);
     if (rc == LLICTI_OK) rc = tc_pack_weights(ctx, *w);
     if (rc == LLICTI_OK) {
+        cudaStream_t s2 = nullptr;
+        cudaEvent_t e1 = nullptr, e2 = nullptr;
+        if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("cannot create the side stream of the wavefront decode");
+            rc = LLICTI_E_CUDA;
+        }
+        ctx->side_stream = s2; ctx->ev_fork = e1; ctx->ev_join = e2;
+    }
+    if (rc == LLICTI_OK) {
         cudaError_t e = cudaMalloc((void **)&ctx->d_status, sizeof(int32_t));
         if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(int32_t));
         if (e != cudaSuccess) { set_error("cudaMalloc(status): %s", cudaGetErrorString(e)); rc = LLICTI_E_CUDA; }
@@ -251,6 +263,9 @@ void llicti_destroy(llicti_ctx *ctx) {
     free_workspace(ctx);
     for (auto &b : ctx->wf32) { cudaFree(b.w0); cudaFree(b.b0); cudaFree(b.w1); cudaFree(b.b1); cudaFree(b.w2); cudaFree(b.b2); }
     tc_free_weights(ctx);
+    if (ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy((cudaStream_t)ctx->side_stream);
     cudaFree(ctx->d_status);
     delete ctx;
 }
@@ -271,7 +286,9 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
     for (int s = 0; s < S; ++s) LLICTI_CUDA(cudaMalloc((void **)&ctx->d_planes[s], n * p.plane_elems[s] * sizeof(int16_t)));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_minmax, n * 4 * sizeof(int32_t)));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_minmax16, n * 6 * sizeof(int16_t)));
-    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_params, n * kParamCh * (size_t)g.Hs[0] * g.Ws[0] * sizeof(float)));
+    // the wavefront decode keeps the network outputs, windows and symbols of all three bands of a scale in flight
+    const size_t wb = (size_t)wave_bands_in_workspace(ctx->cfg, max_images);
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_params, wb * n * kParamCh * (size_t)g.Hs[0] * g.Ws[0] * sizeof(float)));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_bounds, n * (size_t)g.symbols * sizeof(uint32_t)));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_scratch, n * (size_t)p.scratch_bytes));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_sublen, n * (size_t)g.substreams * sizeof(uint32_t)));
@@ -282,10 +299,12 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_blob, ctx->blob_cap));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_x00, n * 3 * (size_t)g.Hs[S - 1] * g.Ws[S - 1]));
     ctx->items_cap = (int64_t)n * decode_items_per_image(p);
-    LLICTI_CUDA(cudaMalloc(&ctx->d_items, (size_t)ctx->items_cap * 2048));
-    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)decode_flag_words(ctx->items_cap) * sizeof(uint32_t)));
+    LLICTI_CUDA(cudaMalloc(&ctx->d_items, wb * (size_t)ctx->items_cap * 2048));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)decode_flag_words(wb * ctx->items_cap) * sizeof(uint32_t)));
+    LLICTI_CUDA(cudaMalloc(&ctx->d_chain_state_raw, n * 9 * 64));
+    ctx->wave_ws = wb == 3;
     ctx->sym_cap = ((int64_t)g.Hs[0] * g.Ws[0] + 63) / 64 * 64;
-    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_syms, n * 3 * (size_t)ctx->sym_cap * sizeof(int16_t)));
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_syms, wb * n * 3 * (size_t)ctx->sym_cap * sizeof(int16_t)));
     ctx->ws_images = max_images; ctx->ws_H = H; ctx->ws_W = W;
     return LLICTI_OK;
 }
@@ -447,11 +466,17 @@ int llicti_decode_dev(llicti_ctx *ctx, const uint8_t *blob_dev, const uint64_t *
     if ((rc = launch_index_streams(ctx, p, n, blob_dev, stream_off_dev, ctx->d_suboff, ctx->d_sublen, st))) return rc;
     if ((rc = launch_x00_from_header(ctx, p, x00_rgb_dev, n, ctx->d_planes[S - 1], st))) return rc;
     for (int s = S - 1; s >= 0; --s) {
-        for (int b = 0; b < 3; ++b) {
-            if ((rc = cnn(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st))) return rc;
-            if ((rc = launch_decode_band(ctx, p, s, b, ctx->d_params, ctx->d_planes[s], ctx->d_minmax, n, blob_dev,
-                                         ctx->d_suboff, ctx->d_sublen, st)))
+        if (wave_eligible(ctx, p, s, n)) {       // the three bands concurrently, two strips of rows apart
+            if ((rc = launch_decode_scale_wave(ctx, p, s, ctx->d_planes[s], ctx->d_minmax, n, blob_dev, ctx->d_suboff,
+                                               ctx->d_sublen, st)))
                 return rc;
+        } else {
+            for (int b = 0; b < 3; ++b) {
+                if ((rc = cnn(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st))) return rc;
+                if ((rc = launch_decode_band(ctx, p, s, b, ctx->d_params, ctx->d_planes[s], ctx->d_minmax, n, blob_dev,
+                                             ctx->d_suboff, ctx->d_sublen, st)))
+                    return rc;
+            }
         }
         if (s > 0 && (rc = launch_interleave(ctx, p, s, ctx->d_planes[s], ctx->d_planes[s - 1], n, st))) return rc;
     }

@@ -49,7 +49,8 @@ struct TcGeom {
     int Hs, Ws, P;          // plane size
     int n;                  // images
     int tpr;                // tiles per plane row: a tile = up to 128 consecutive positions of ONE row
-    int ntiles;             // n * Hs * tpr
+    int row0, nrows;        // plane rows [row0, row0 + nrows) are evaluated (a strip of the wavefront decode, or all)
+    int ntiles;             // n * nrows * tpr
     int K0, K0p;            // layer-0 depth; padded depth including the two bias slots
     int G, NP;              // sub-network width (88 / 60) and its padding (96 / 64)
     int pair_bytes;         // packed bytes of one pair of sub-networks
@@ -357,7 +358,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             mbar_wait(bar(B_AEMPTY + s), ((it >> 1) & 1) ^ 1);     // MMAs that read this stage are complete
             const int tile = tile0 + it * tile_stride;
             const int rowid = tile / tg.tpr, jb = tile - rowid * tg.tpr;       // (image, plane row), column block
-            const int img = rowid / tg.Hs, i = rowid - img * tg.Hs;
+            const int img = rowid / tg.nrows, i = tg.row0 + rowid - img * tg.nrows;
             asm volatile("bar.sync 1, 256;" ::: "memory");                      // everyone is done reading the previous segments
             if (half == 0) stage_segments<BAND, 0>(planes, tg, img, i, jb * TC_M, sSeg, row);
             else stage_segments<BAND, 1>(planes, tg, img, i, jb * TC_M, sSeg, row);
@@ -450,7 +451,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             TMEM_LD_X16(dbase + (uint32_t)(2 * NP + g * 16), r);
             tmem_ld_wait();
             if (jcol < tg.Ws) {
-                const int img = rowid / tg.Hs, p = (rowid - img * tg.Hs) * tg.Ws + jcol;
+                const int img = rowid / tg.nrows, p = (tg.row0 + rowid - img * tg.nrows) * tg.Ws + jcol;
                 float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + g) * 15) * tg.P + p;
 #pragma unroll
                 for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
@@ -570,7 +571,8 @@ void tc_free_weights(llicti_ctx *ctx) {
     ctx->tc_weights = nullptr;
 }
 
-int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params, cudaStream_t st) {
+int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params, cudaStream_t st,
+                  int row0, int nrows) {
     ProfScope prof_(ctx, KC_CNN, st);
     TcWeights *tw = static_cast<TcWeights *>(ctx->tc_weights);
     LLICTI_REQUIRE(tw, "tcgen05 weights are not packed");
@@ -579,9 +581,12 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
     tg.Hs = Hs; tg.Ws = Ws; tg.P = Hs * Ws;
     const long long total = (long long)n * tg.P;
     LLICTI_REQUIRE(total < (1ll << 31) - TC_M, "batch too large for one CNN launch");
+    if (nrows < 0) nrows = Hs - row0;
+    LLICTI_REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= Hs, "bad row range");
     tg.n = n;
     tg.tpr = (Ws + TC_M - 1) / TC_M;
-    const long long ntiles = (long long)n * Hs * tg.tpr;
+    tg.row0 = row0; tg.nrows = nrows;
+    const long long ntiles = (long long)n * nrows * tg.tpr;
     LLICTI_REQUIRE(ntiles < (1ll << 31), "batch too large for one CNN launch");
     tg.ntiles = (int)ntiles;
     static int sm_count = 0;

@@ -122,6 +122,9 @@ struct llicti_ctx {
     int64_t items_cap = 0;             // in items
     int16_t *d_syms = nullptr;         // [n][3][sym_cap] compact decoded symbols of the band in flight
     int64_t sym_cap = 0;
+    void *d_chain_state_raw = nullptr;
+    void *side_stream = nullptr, *ev_fork = nullptr, *ev_join = nullptr;   // second stream of the wavefront decode (consumer kernel)
+    bool wave_ws = false;              // workspace holds three bands' worth of decode buffers (wavefront schedule)
     uint32_t *d_item_flags = nullptr;  // [items_cap] readiness flags of the piped decode schedule
     int32_t *d_status = nullptr;       // device-side error flag
 };
@@ -171,7 +174,7 @@ int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int
 int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w);
 void tc_free_weights(llicti_ctx *ctx);
 int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
-                  cudaStream_t st);
+                  cudaStream_t st, int row0 = 0, int nrows = -1);
 
 // kernels_coder.cu
 int launch_cdf_table(llicti_ctx *ctx, const float *params, const int16_t *yband, int clr, int min_val,
@@ -194,6 +197,10 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
                        const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
                        const uint32_t *sublen, cudaStream_t st);
 int64_t decode_items_per_image(const Plan &p);
+bool wave_eligible(const llicti_ctx *ctx, const llicti::Plan &p, int scale, int n);
+int wave_bands_in_workspace(const llicti_config &cfg, int max_images);
+int launch_decode_scale_wave(llicti_ctx *ctx, const llicti::Plan &p, int scale, int16_t *planes, const int32_t *minmax, int n,
+                             const uint8_t *blob, const uint64_t *suboff, const uint32_t *sublen, cudaStream_t st);
 int64_t decode_flag_words(int64_t items_cap);
 int read_decode_stats(uint64_t *out, int reset);
 int launch_selftest_fdiv(llicti_ctx *ctx, long long n_pairs, uint64_t seed, unsigned long long *mismatches_dev, cudaStream_t st);

@@ -366,16 +366,25 @@ __device__ __forceinline__ uint32_t chunk_entry_dyn(const uint4 &q, int e) {
     return (e & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
+// Coder registers of a chain between two launches of the wavefront schedule (the chain is decoded a
+// strip of items at a time).
+struct ChainState { uint32_t low, high, value, b0, b1, b2, b3, b4, avail, idx, a0, a1; };
+
 // `out` = compact symbol array of this (image, channel) in coding order; chain j writes j, j+S, ...
+// Items [it_begin, it_end) of the chain are decoded; it_begin > 0 resumes from *state, it_end short
+// of the chain's end saves to it.
 template <bool kPipe>
 __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, const CdfGrid &g, int j,
                                               const NumericsProfile &np, int16_t *out, const uint4 *__restrict__ items,
                                               uint32_t *flags, const uint8_t *__restrict__ stream, uint32_t stream_len,
-                                              int lane) {
+                                              int lane, int it_begin = 0, int it_end = 0x7FFFFFFF,
+                                              ChainState *state = nullptr) {
     const int S = cx.S;
     const int n_steps = (n_sym - j + S - 1) / S;
     if (n_steps <= 0) return;
-    const int n_items = (n_steps + 31) >> 5;      // an item = 4 chunks of 8 steps (one uint4 per lane each)
+    const int n_items_all = (n_steps + 31) >> 5;      // an item = 4 chunks of 8 steps (one uint4 per lane each)
+    const int n_items = min(n_items_all, it_end);     // decode up to here in this call
+    if (it_begin >= n_items) return;
     const int n_full = n_steps >> 3, tail = n_steps & 7;
     const int last = g.Lp - 1;
     const bool vec_store = S == 1 && j == 0;      // 8 consecutive symbols = one aligned 16-byte store
@@ -383,17 +392,24 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
 
     ChainCoder cc;
     cc.init(stream, stream_len);
-    long long i = j;
-    int16_t *dst = out + j;
+    if (it_begin > 0) {
+        const ChainState s = *state;
+        cc.low = s.low; cc.high = s.high; cc.value = s.value;
+        cc.b0 = s.b0; cc.b1 = s.b1; cc.b2 = s.b2; cc.b3 = s.b3; cc.b4 = s.b4;
+        cc.avail = (int)s.avail; cc.idx = s.idx; cc.a0 = s.a0; cc.a1 = s.a1;
+    }
+    long long i = j + (long long)it_begin * 32 * S;
+    int16_t *dst = out + i;
 
-    if (kPipe) wait_flag(flags, polls);
+    if (kPipe) wait_flag(flags + it_begin, polls);
     const uint4 *src = items + lane;
-    uint4 q0 = load_chunk<kPipe>(src), q1 = load_chunk<kPipe>(src + 32), q2 = load_chunk<kPipe>(src + 64),
-          q3 = load_chunk<kPipe>(src + 96);
+    const uint4 *first = src + (size_t)it_begin * 128;
+    uint4 q0 = load_chunk<kPipe>(first), q1 = load_chunk<kPipe>(first + 32), q2 = load_chunk<kPipe>(first + 64),
+          q3 = load_chunk<kPipe>(first + 96);
     uint4 n0 = q0, n1 = q1, n2 = q2, n3 = q3;
-    uint32_t f_next = kPipe && n_items > 1 ? ld_relaxed_u32(flags + 1) : 1u;   // readiness of item 1, looked at one item later
+    uint32_t f_next = kPipe && it_begin + 1 < n_items ? ld_relaxed_u32(flags + it_begin + 1) : 1u;   // looked at one item later
 
-    for (int it = 0; it < n_items; ++it) {
+    for (int it = it_begin; it < n_items; ++it) {
         // the next item is fetched while this one is decoded (32 steps of distance)
         bool have_next = it + 1 >= n_items;
         uint32_t f_next2 = 1u;
@@ -440,7 +456,7 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
             i += 8ll * S;
             dst += (size_t)8 * S;
         }
-        if (it == n_items - 1 && tail) {
+        if (it == n_items_all - 1 && tail) {
             const int v = max(full_here, 0);
             const uint4 q = v == 0 ? q0 : v == 1 ? q1 : v == 2 ? q2 : q3;
 #pragma unroll 1
@@ -461,6 +477,13 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
         q0 = n0; q1 = n1; q2 = n2; q3 = n3;
         f_next = f_next2;
     }
+    if (state != nullptr && n_items < n_items_all && lane == 0) {
+        ChainState s;
+        s.low = cc.low; s.high = cc.high; s.value = cc.value;
+        s.b0 = cc.b0; s.b1 = cc.b1; s.b2 = cc.b2; s.b3 = cc.b3; s.b4 = cc.b4;
+        s.avail = (uint32_t)cc.avail; s.idx = cc.idx; s.a0 = cc.a0; s.a1 = cc.a1;
+        *state = s;
+    }
     if (lane == 0) {
         if (kPipe && polls) atomicAdd(&g_decode_stats[1], polls);
         if (redone) atomicAdd(&g_decode_stats[3], redone);
@@ -471,10 +494,10 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
 // of the short phases (_pad_decoded_tensor, LLICTI_nets.py:512-530).
 __global__ void __launch_bounds__(256)
 scatter_band_kernel(const int16_t *__restrict__ syms, size_t sym_cap, int16_t *__restrict__ planes,
-                    const int32_t *__restrict__ minmax, DecodeGeom dg, int n) {
+                    const int32_t *__restrict__ minmax, DecodeGeom dg, int n, int sym0, int sym1) {
     const int img = blockIdx.y / 3, clr = blockIdx.y - 3 * img;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dg.n_sym) return;
+    const int i = sym0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sym1) return;
     const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
     const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
     const size_t P = (size_t)dg.Hs * dg.Ws;
@@ -624,6 +647,114 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
             if (lane == 0) {
                 __threadfence();
                 st_release_u32(flags + (size_t)ch * dg.items_per_chain + tb, 1u);
+            }
+        }
+    }
+}
+
+// ---- wavefront schedule: the three bands of a scale decoded concurrently, a strip of rows apart ----
+// Band b+1 of a scale needs the network outputs computed from band b, but only from rows i-2 .. i+2:
+// once band b is two strips ahead, band b+1 can follow.  One launch of this kernel decodes one strip
+// of up to three bands at once (the same consumer / producer roles as decode_band_pipe_kernel, with the
+// coder registers of every chain carried from launch to launch in ChainState); between launches the
+// host runs the CNN of the next strips and scatters the finished ones into the planes.  The serial
+// chain of a scale shrinks from 3 * n_sym steps to about (1 + 4 / strips) * n_sym.
+struct WaveBand {
+    DecodeGeom dg;
+    const float *params;     // [n][60][P] network outputs of this band
+    int16_t *syms;           // [n][3][sym_cap]
+    uint4 *items;            // [n][3][items_per_chain][128]
+    uint32_t *flags;         // [n][3][items_per_chain]
+    int it0, it1;            // items of every chain decoded by this launch (it0 == it1: band idle)
+};
+struct WaveArgs { WaveBand b[3]; };
+
+// Consumers and producers of a wavefront step are two kernels running concurrently on two streams
+// (they only talk through the flags / sentinels in global memory): the consumer kernel is nine
+// one-warp CTAs per image with the ~160 registers the serial loop wants; the producer kernel is
+// compiled on its own (64 registers), so three times as many producer warps fit on an SM as in the
+// single-kernel form.  The producer grid is sized to leave room for the consumer CTAs on every SM
+// (see launch_decode_scale_wave), so the consumers are resident whichever kernel starts first, and a
+// producer only holds a ticket while it runs: the earliest unfinished item can always complete.
+__global__ void __launch_bounds__(128)
+wave_consume_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsProfile np, size_t sym_cap, uint32_t *ctl,
+                    const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
+                    const uint32_t *__restrict__ sublen, int total_sub, int n, ChainState *states) {
+    // four chains per CTA, one per scheduler; the CTA claims its SM: producer CTAs that share it leave, so
+    // that nothing competes with the serial chains for issue slots and L1
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        st_release_u32(&ctl[256 + (smid & 255u)], 1u);
+    }
+    int act[3], n_act = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+        if (wa.b[b].it1 > wa.b[b].it0) act[n_act++] = b;
+    const int chain = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (chain >= 3 * n * n_act) return;
+    const int slot = chain / (3 * n), rem = chain - slot * 3 * n;
+    const int band = slot == 0 ? act[0] : slot == 1 ? act[1] : act[2];
+    const WaveBand &wb = band == 0 ? wa.b[0] : band == 1 ? wa.b[1] : wa.b[2];
+    const DecodeGeom dg = wb.dg;
+    const int img = rem / 3, clr = rem - 3 * img;
+    const size_t P = (size_t)dg.Hs * dg.Ws;
+    int lo[3];
+    const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
+    int16_t *isyms = wb.syms + (size_t)img * 3 * sym_cap;
+    const ChainCtx cx = {wb.params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], 1};
+    const size_t e = (size_t)img * total_sub + dg.sub_first[clr];
+    const size_t ch = (size_t)img * 3 + clr;
+    consume_chain<true>(cx, dg.n_sym, g, 0, np, isyms + (size_t)clr * sym_cap, wb.items + ch * dg.items_per_chain * 128,
+                        wb.flags + ch * dg.items_per_chain, blob + suboff[e], sublen[e], lane, wb.it0, wb.it1,
+                        states + ((size_t)img * 3 + band) * 3 + clr);
+}
+
+__global__ void __launch_bounds__(128, 8)
+wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsProfile np, size_t sym_cap, uint32_t *ctl, int n) {
+    __shared__ __align__(16) uint16_t stage[4][kStageU16];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int act[3], n_act = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+        if (wa.b[b].it1 > wa.b[b].it0) act[n_act++] = b;
+    if (n_act == 0) return;
+    int lo[3];
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const uint32_t *claimed = &ctl[256 + (smid & 255u)];      // set by a consumer CTA running on this SM
+    // nine ticket queues (band, channel), each in (step block, image) order; a producer warp starts in the
+    // Y : Co : Cg = 1 : 2 : 2 pattern of one active band and then walks all queues
+    const int producer_id = blockIdx.x * 4 + wib;
+    const int r = producer_id % (5 * n_act);
+    const int slot0 = r / 5, r5 = r - 5 * slot0;
+    const int q0 = (slot0 == 0 ? act[0] : slot0 == 1 ? act[1] : act[2]) * 3 + (r5 == 0 ? 0 : r5 <= 2 ? 1 : 2);
+    for (int c = 0; c < 9; ++c) {
+        const int q = (q0 + c) % 9, band = q / 3, clr = q - 3 * band;
+        const WaveBand &wb = band == 0 ? wa.b[0] : band == 1 ? wa.b[1] : wa.b[2];
+        if (wb.it1 <= wb.it0) continue;
+        const DecodeGeom dg = wb.dg;
+        const size_t P = (size_t)dg.Hs * dg.Ws;
+        const uint32_t total = (uint32_t)(wb.it1 - wb.it0) * (uint32_t)n;
+        for (;;) {
+            if (ld_relaxed_u32(claimed) != 0u) return;          // leave the SM to the consumers (no ticket is held here)
+            uint32_t w = 0;
+            if (lane == 0) w = atomicAdd(&ctl[514 + q], 1u);
+            w = __shfl_sync(kFull, w, 0);
+            if (w >= total) break;
+            const int tb = wb.it0 + (int)(w / (uint32_t)n);
+            const int img = (int)(w % (uint32_t)n);
+            const size_t ch = (size_t)img * 3 + clr;
+            const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
+            uint4 *item = wb.items + (ch * dg.items_per_chain + tb) * 128;
+            produce_item<true>(wb.params + (size_t)img * kParamCh * P, wb.syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr,
+                               lo, g, 0, tb, np, item, stage[wib], lane);
+            // every lane's stores happen before the flag store: warp barrier, then a cumulative fence
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                st_release_u32(wb.flags + ch * dg.items_per_chain + tb, 1u);
             }
         }
     }
@@ -811,8 +942,114 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
     }
     {
         ProfScope prof_(ctx, KC_MERGE, st);
-        scatter_band_kernel<<<dim3((dg.n_sym + 255) / 256, 3 * n), 256, 0, st>>>(syms, sym_cap, planes, minmax, dg, n);
+        scatter_band_kernel<<<dim3((dg.n_sym + 255) / 256, 3 * n), 256, 0, st>>>(syms, sym_cap, planes, minmax, dg, n, 0, dg.n_sym);
         ctx->launches += 1;
+    }
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+// ---- wavefront schedule, host side ------------------------------------------------------------
+static int wave_strips(int Hs) { return std::min(std::max(Hs / 32, 1), 8); }
+
+// Can the scale be decoded by the wavefront schedule?  (torchac-compatible streams, the tcgen05 CNN --
+// the only one with row ranges --, enough rows for at least two strips, few enough chains for one
+// consumer warp each, and a workspace reserved with three bands' worth of buffers.)
+bool wave_eligible(const llicti_ctx *ctx, const Plan &p, int scale, int n) {
+    if (ctx->cfg.decode_impl != 0 || ctx->cfg.cnn_impl != LLICTI_CNN_TCGEN05 || ctx->cfg.sub_len != 0) return false;
+    if (!ctx->wave_ws || env_int("LLICTI_NO_WAVE", 0) || env_int("LLICTI_NO_PIPE", 0)) return false;
+    if (wave_strips(p.g.Hs[scale]) < 2) return false;
+    return 9 * n <= kConsPerSmMax * 64;
+}
+
+int wave_bands_in_workspace(const llicti_config &cfg, int max_images) {
+    return (cfg.decode_impl == 0 && cfg.cnn_impl == LLICTI_CNN_TCGEN05 && cfg.sub_len == 0 && 9 * max_images <= kConsPerSmMax * 64) ? 3 : 1;
+}
+
+int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t *planes, const int32_t *minmax, int n,
+                             const uint8_t *blob, const uint64_t *suboff, const uint32_t *sublen, cudaStream_t st) {
+    static int sm_count = 0, prod_resident = 0;
+    if (!sm_count) {
+        int dev = 0;
+        LLICTI_CUDA(cudaGetDevice(&dev));
+        LLICTI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        LLICTI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&prod_resident, wave_produce_kernel, 128, 0));
+    }
+    LLICTI_REQUIRE(ctx->side_stream && ctx->ev_fork && ctx->ev_join, "wavefront decode: no side stream");
+    cudaStream_t side = (cudaStream_t)ctx->side_stream;
+    const int Hs = p.g.Hs[scale], Ws = p.g.Ws[scale];
+    const int K = wave_strips(Hs);
+    const size_t P0 = (size_t)p.g.Hs[0] * p.g.Ws[0];
+    const size_t sym_cap = (size_t)ctx->sym_cap;
+    const size_t nws = (size_t)ctx->ws_images;
+    const int total_sub = (int)p.g.substreams;
+    DecodeGeom dg[3];
+    float *params[3];
+    int16_t *syms[3];
+    uint4 *items[3];
+    uint32_t *flags[3];
+    const size_t items_band = (size_t)ctx->items_cap;        // items per band in the workspace
+    for (int b = 0; b < 3; ++b) {
+        dg[b] = make_decode_geom(p, scale, b);
+        LLICTI_REQUIRE(dg[b].S == 1 && 3ll * n * dg[b].items_per_chain <= ctx->items_cap && (size_t)dg[b].n_sym <= sym_cap,
+                       "wavefront decode: workspace too small");
+        params[b] = ctx->d_params + (size_t)b * nws * kParamCh * P0;
+        syms[b] = ctx->d_syms + (size_t)b * nws * 3 * sym_cap;
+        items[b] = reinterpret_cast<uint4 *>(ctx->d_items) + (size_t)b * items_band * 128;
+        flags[b] = ctx->d_item_flags + kCtlWords + (size_t)b * items_band;
+    }
+    // sentinels over the symbol arrays (data = flag), zeros over the item flags of the three bands
+    LLICTI_CUDA(cudaMemsetAsync(ctx->d_syms, 0x80, 3 * nws * 3 * sym_cap * sizeof(int16_t), st));
+    LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, (kCtlWords + 3 * items_band) * sizeof(uint32_t), st));
+
+    // producer CTAs (4 warps, 64 registers = 8 K registers each) per SM: three short of what fits, so that a consumer
+    // CTA (4 warps x ~160 registers = 20 K registers) is resident whichever kernel starts first
+    const int prod_per_sm = std::min(std::max(env_int("LLICTI_WAVE_PRODUCER_CTAS_PER_SM", 5), 1), std::max(prod_resident - 3, 1));
+    auto row_of = [&](int k) { return (int)((long long)Hs * k / K); };
+    auto item_of = [&](int b, int k) {       // items of band b complete after strip k-1
+        if (k >= K) return dg[b].items_per_chain;
+        return (int)std::min<long long>((long long)std::min(row_of(k), dg[b].crop_h) * dg[b].crop_w / 32, dg[b].items_per_chain);
+    };
+    for (int T = 0; T < K + 4; ++T) {
+        WaveArgs wa;
+        bool any = false;
+        for (int b = 0; b < 3; ++b) {
+            const int s = T - 2 * b;
+            wa.b[b].dg = dg[b];
+            wa.b[b].params = params[b]; wa.b[b].syms = syms[b]; wa.b[b].items = items[b]; wa.b[b].flags = flags[b];
+            wa.b[b].it0 = wa.b[b].it1 = 0;
+            if (s < 0 || s >= K) continue;
+            // network outputs of the rows this strip decodes (band 0 depends on x00 only: all rows at once)
+            int rc = LLICTI_OK;
+            if (b == 0) { if (s == 0) rc = launch_cnn_tc(ctx, 0, planes, n, Hs, Ws, params[0], st); }
+            else rc = launch_cnn_tc(ctx, b, planes, n, Hs, Ws, params[b], st, row_of(s), row_of(s + 1) - row_of(s));
+            if (rc) return rc;
+            wa.b[b].it0 = item_of(b, s);
+            wa.b[b].it1 = item_of(b, s + 1);
+            any |= wa.b[b].it1 > wa.b[b].it0;
+        }
+        if (any) {
+            ProfScope prof_(ctx, KC_DECODE, st);
+            LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, kCtlWords * sizeof(uint32_t), st));
+            // fork: consumers on the side stream, producers on the caller's stream; join before the scatter
+            LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_fork, st));
+            LLICTI_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)ctx->ev_fork, 0));
+            wave_consume_kernel<<<(9 * n + 3) / 4, 128, 0, side>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, blob, suboff,
+                                                                  sublen, total_sub, n,
+                                                                  reinterpret_cast<ChainState *>(ctx->d_chain_state_raw));
+            LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_join, side));
+            wave_produce_kernel<<<sm_count * prod_per_sm, 128, 0, st>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, n);
+            LLICTI_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
+            ctx->launches += 2;
+        }
+        for (int b = 0; b < 3; ++b) {
+            if (wa.b[b].it1 <= wa.b[b].it0) continue;
+            ProfScope prof_(ctx, KC_MERGE, st);
+            const int sym0 = wa.b[b].it0 * 32, sym1 = std::min(wa.b[b].it1 * 32, dg[b].n_sym);
+            scatter_band_kernel<<<dim3((sym1 - sym0 + 255) / 256, 3 * n), 256, 0, st>>>(syms[b], sym_cap, planes, minmax, dg[b], n,
+                                                                                      sym0, sym1);
+            ctx->launches += 1;
+        }
     }
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;
