@@ -687,6 +687,7 @@ wave_consume_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         st_release_u32(&ctl[256 + (smid & 255u)], 1u);
+        atomicAdd(&ctl[523], 1u);                       // consumer CTAs that are running
     }
     int act[3], n_act = 0;
 #pragma unroll
@@ -712,9 +713,19 @@ wave_consume_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
 }
 
 __global__ void __launch_bounds__(128, 8)
-wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsProfile np, size_t sym_cap, uint32_t *ctl, int n) {
+wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsProfile np, size_t sym_cap, uint32_t *ctl, int n,
+                    int safe_ctas, int consumer_ctas) {
     __shared__ __align__(16) uint16_t stage[4][kStageU16];
+    __shared__ uint32_t started;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // The first `safe_ctas` CTAs leave room on every SM for a consumer CTA.  The CTAs beyond them only
+    // stay if every consumer CTA is already running (the usual order: the consumers are launched
+    // first); otherwise they leave at once, before holding any ticket, so the consumers always fit.
+    if ((int)blockIdx.x >= safe_ctas) {
+        if (threadIdx.x == 0) started = ld_relaxed_u32(&ctl[523]);
+        __syncthreads();
+        if ((int)started < consumer_ctas) return;
+    }
     int act[3], n_act = 0;
 #pragma unroll
     for (int b = 0; b < 3; ++b)
@@ -950,7 +961,10 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
 }
 
 // ---- wavefront schedule, host side ------------------------------------------------------------
-static int wave_strips(int Hs) { return std::min(std::max(Hs / 32, 1), 8); }
+static int env_int(const char *name, int dflt);
+static int wave_strips(int Hs) {      // strips of >= 32 rows, at most 8 (measured optimum on 768x512: 4 -> 46.4 ms, 8 -> 40.5 ms, 16 -> 41.5 ms)
+    return std::min(std::max(Hs / env_int("LLICTI_WAVE_STRIP_ROWS", 32), 1), env_int("LLICTI_WAVE_MAX_STRIPS", 8));
+}
 
 // Can the scale be decoded by the wavefront schedule?  (torchac-compatible streams, the tcgen05 CNN --
 // the only one with row ranges --, enough rows for at least two strips, few enough chains for one
@@ -1002,9 +1016,12 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
     LLICTI_CUDA(cudaMemsetAsync(ctx->d_syms, 0x80, 3 * nws * 3 * sym_cap * sizeof(int16_t), st));
     LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, (kCtlWords + 3 * items_band) * sizeof(uint32_t), st));
 
-    // producer CTAs (4 warps, 64 registers = 8 K registers each) per SM: three short of what fits, so that a consumer
-    // CTA (4 warps x ~160 registers = 20 K registers) is resident whichever kernel starts first
-    const int prod_per_sm = std::min(std::max(env_int("LLICTI_WAVE_PRODUCER_CTAS_PER_SM", 5), 1), std::max(prod_resident - 3, 1));
+    // producer CTAs (4 warps, 64 registers = 8 K registers each): `safe` per SM leave room for a consumer CTA (4 warps x
+    // ~160 registers = 20 K registers) whichever kernel starts first; the CTAs beyond them stay only when the consumers
+    // are already running (wave_produce_kernel)
+    const int safe_per_sm = std::max(prod_resident - 3, 1);
+    const int prod_per_sm = std::min(std::max(env_int("LLICTI_WAVE_PRODUCER_CTAS_PER_SM", prod_resident - 1), 1), std::max(prod_resident, 1));
+    const int consumer_ctas = (9 * n + 3) / 4;
     auto row_of = [&](int k) { return (int)((long long)Hs * k / K); };
     auto item_of = [&](int b, int k) {       // items of band b complete after strip k-1
         if (k >= K) return dg[b].items_per_chain;
@@ -1031,14 +1048,15 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
         if (any) {
             ProfScope prof_(ctx, KC_DECODE, st);
             LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, kCtlWords * sizeof(uint32_t), st));
-            // fork: consumers on the side stream, producers on the caller's stream; join before the scatter
+            // fork: consumers on the caller's stream (they start first), producers on the side stream; join before the scatter
             LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_fork, st));
             LLICTI_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)ctx->ev_fork, 0));
-            wave_consume_kernel<<<(9 * n + 3) / 4, 128, 0, side>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, blob, suboff,
-                                                                  sublen, total_sub, n,
-                                                                  reinterpret_cast<ChainState *>(ctx->d_chain_state_raw));
+            wave_consume_kernel<<<consumer_ctas, 128, 0, st>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, blob, suboff,
+                                                              sublen, total_sub, n,
+                                                              reinterpret_cast<ChainState *>(ctx->d_chain_state_raw));
+            wave_produce_kernel<<<sm_count * prod_per_sm, 128, 0, side>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, n,
+                                                                         sm_count * std::min(safe_per_sm, prod_per_sm), consumer_ctas);
             LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_join, side));
-            wave_produce_kernel<<<sm_count * prod_per_sm, 128, 0, st>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, n);
             LLICTI_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
             ctx->launches += 2;
         }
