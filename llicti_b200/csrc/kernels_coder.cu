@@ -192,22 +192,28 @@ struct WarpEncoder {
 
     // 32 (or fewer) symbols: bounds in `cur` (one per lane), m valid.
     __device__ __forceinline__ void encode_block(uint32_t cur, int m) {
-        // ---- phase A: the interval recurrence ----
-        uint32_t rec_bits = 0;
-        int rec_n = 0, rec_k = 0;
-#pragma unroll 4
+        // ---- phase A: the interval recurrence, nothing else (lane s keeps (nl, nh) of step s) ----
+        const uint32_t my_low = cur & 0xFFFFu, my_high = (cur >> 16) + 1u;   // bounds unpacked in parallel, off the chain
+        uint32_t rec_nl = 0, rec_nh = 0xFFFFFFFFu;
+#pragma unroll 8
         for (int s = 0; s < m; ++s) {
-            const uint32_t v = __shfl_sync(0xffffffffu, cur, s);
-            const uint32_t c_low = v & 0xFFFFu, c_high = (v >> 16) + 1u;
+            const uint32_t c_low = __shfl_sync(0xffffffffu, my_low, s), c_high = __shfl_sync(0xffffffffu, my_high, s);
             const uint32_t sm1 = high - low;                               // span - 1; span * c = sm1 * c + c
             const uint32_t nl = low + (uint32_t)(((uint64_t)sm1 * c_low + c_low) >> 16);
             const uint32_t nh = (low - 1u) + (uint32_t)(((uint64_t)sm1 * c_high + c_high) >> 16);
-            const uint32_t d = nl ^ nh;
-            const int n = __clz(d);
-            const int sh = __clz(d & ~((nl & ~nh) << 1));                  // n + underflow run (see AcEncoder::encode)
-            if (lane == s) { rec_bits = __funnelshift_l(nl, 0u, n); rec_n = n; rec_k = sh - n; }
+            const int sh = __clz((nl ^ nh) & ~((nl & ~nh) << 1));         // equal leading bits + underflow run (AcEncoder::encode)
+            if (lane == s) { rec_nl = nl; rec_nh = nh; }
             low = (nl << sh) & 0x7FFFFFFFu;
             high = (nh << sh) | ~(0xFFFFFFFFu << sh) | 0x80000000u;
+        }
+        // per-step record, derived in parallel: the n bits shifted out, n, the underflow count k
+        int rec_n = 0, rec_k = 0;
+        uint32_t rec_bits = 0;
+        if (lane < m) {
+            const uint32_t d = rec_nl ^ rec_nh;
+            rec_n = __clz(d);
+            rec_k = __clz(d & ~((rec_nl & ~rec_nh) << 1)) - rec_n;
+            rec_bits = __funnelshift_l(rec_nl, 0u, rec_n);
         }
         // ---- phase B: bit output of the 32 steps in parallel ----
         int kx = rec_k;                                                   // inclusive scan of k
