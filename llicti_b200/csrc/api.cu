@@ -247,6 +247,7 @@ int llicti_create(const llicti_config *cfg, const llicti_weights *w, llicti_ctx 
             rc = LLICTI_E_CUDA;
         }
         ctx->side_stream = s2; ctx->ev_fork = e1; ctx->ev_join = e2;
+        if (rc == LLICTI_OK) rc = probe_concurrent_kernels(ctx, &ctx->concurrent_kernels);
     }
     if (rc == LLICTI_OK) {
         cudaError_t e = cudaMalloc((void **)&ctx->d_status, sizeof(int32_t));

@@ -124,6 +124,7 @@ struct llicti_ctx {
     int64_t sym_cap = 0;
     void *d_chain_state_raw = nullptr;
     void *side_stream = nullptr, *ev_fork = nullptr, *ev_join = nullptr;   // second stream of the wavefront decode (consumer kernel)
+    bool concurrent_kernels = false;   // two kernels on two streams really overlap (false under kernel-serialising profilers)
     bool wave_ws = false;              // workspace holds three bands' worth of decode buffers (wavefront schedule)
     uint32_t *d_item_flags = nullptr;  // [items_cap] readiness flags of the piped decode schedule
     int32_t *d_status = nullptr;       // device-side error flag
@@ -199,6 +200,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
 int64_t decode_items_per_image(const Plan &p);
 bool wave_eligible(const llicti_ctx *ctx, const llicti::Plan &p, int scale, int n);
 int wave_bands_in_workspace(const llicti_config &cfg, int max_images);
+int probe_concurrent_kernels(llicti_ctx *ctx, bool *ok);
 int launch_decode_scale_wave(llicti_ctx *ctx, const llicti::Plan &p, int scale, int16_t *planes, const int32_t *minmax, int n,
                              const uint8_t *blob, const uint64_t *suboff, const uint32_t *sublen, cudaStream_t st);
 int64_t decode_flag_words(int64_t items_cap);

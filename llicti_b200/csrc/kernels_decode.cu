@@ -961,6 +961,49 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
 }
 
 // ---- wavefront schedule, host side ------------------------------------------------------------
+// The wavefront step needs two kernels that really run at the same time.  Tools that serialise
+// kernel launches (Nsight Compute's kernel replay does) would make the consumer kernel wait for a
+// producer kernel that cannot start, so the capability is probed once per context: a kernel waits a
+// few milliseconds for a flag that only a second kernel on another stream can set.
+__global__ void probe_wait_kernel(volatile uint32_t *flag, uint32_t *result) {
+    const long long t0 = clock64();
+    while (*flag == 0u && clock64() - t0 < 8000000ll) __nanosleep(1000);      // ~4 ms at 2 GHz
+    *result = *flag;
+}
+__global__ void probe_set_kernel(volatile uint32_t *flag) { *flag = 1u; }
+
+int probe_concurrent_kernels(llicti_ctx *ctx, bool *ok) {
+    *ok = false;
+    uint32_t *d = nullptr, h = 0;
+    LLICTI_CUDA(cudaMalloc((void **)&d, 2 * sizeof(uint32_t)));
+    cudaStream_t side = (cudaStream_t)ctx->side_stream, second = nullptr;
+    LLICTI_CUDA(cudaStreamCreateWithFlags(&second, cudaStreamNonBlocking));
+    // load every kernel that later runs next to a waiting kernel now (lazy module loading may have to
+    // synchronise the context on a first launch), and run the probe pair once back to back
+    cudaFuncAttributes fa;
+    LLICTI_CUDA(cudaFuncGetAttributes(&fa, probe_wait_kernel));
+    LLICTI_CUDA(cudaFuncGetAttributes(&fa, probe_set_kernel));
+    LLICTI_CUDA(cudaFuncGetAttributes(&fa, wave_consume_kernel));
+    LLICTI_CUDA(cudaFuncGetAttributes(&fa, wave_produce_kernel));
+    LLICTI_CUDA(cudaFuncGetAttributes(&fa, scatter_band_kernel));
+    LLICTI_CUDA(cudaMemset(d, 0, 2 * sizeof(uint32_t)));
+    probe_set_kernel<<<1, 1, 0, second>>>(d);
+    probe_wait_kernel<<<1, 1, 0, second>>>(d, d + 1);
+    LLICTI_CUDA(cudaStreamSynchronize(second));
+    LLICTI_CUDA(cudaMemset(d, 0, 2 * sizeof(uint32_t)));
+    LLICTI_CUDA(cudaDeviceSynchronize());
+    probe_wait_kernel<<<1, 1, 0, side>>>(d, d + 1);
+    probe_set_kernel<<<1, 1, 0, second>>>(d);
+    cudaError_t e = cudaStreamSynchronize(side);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(second);
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d + 1, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaStreamDestroy(second);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("concurrency probe: %s", cudaGetErrorString(e)); return LLICTI_E_CUDA; }
+    *ok = h != 0u;
+    return LLICTI_OK;
+}
+
 static int env_int(const char *name, int dflt);
 static int wave_strips(int Hs) {      // strips of >= 32 rows, at most 8 (measured optimum on 768x512: 4 -> 46.4 ms, 8 -> 40.5 ms, 16 -> 41.5 ms)
     return std::min(std::max(Hs / env_int("LLICTI_WAVE_STRIP_ROWS", 32), 1), env_int("LLICTI_WAVE_MAX_STRIPS", 8));
@@ -971,7 +1014,7 @@ static int wave_strips(int Hs) {      // strips of >= 32 rows, at most 8 (measur
 // consumer warp each, and a workspace reserved with three bands' worth of buffers.)
 bool wave_eligible(const llicti_ctx *ctx, const Plan &p, int scale, int n) {
     if (ctx->cfg.decode_impl != 0 || ctx->cfg.cnn_impl != LLICTI_CNN_TCGEN05 || ctx->cfg.sub_len != 0) return false;
-    if (!ctx->wave_ws || env_int("LLICTI_NO_WAVE", 0) || env_int("LLICTI_NO_PIPE", 0)) return false;
+    if (!ctx->wave_ws || !ctx->concurrent_kernels || env_int("LLICTI_NO_WAVE", 0) || env_int("LLICTI_NO_PIPE", 0)) return false;
     if (wave_strips(p.g.Hs[scale]) < 2) return false;
     return 9 * n <= kConsPerSmMax * 64;
 }
