@@ -654,11 +654,11 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
 
 // ---- wavefront schedule: the three bands of a scale decoded concurrently, a strip of rows apart ----
 // Band b+1 of a scale needs the network outputs computed from band b, but only from rows i-2 .. i+2:
-// once band b is two strips ahead, band b+1 can follow.  One launch of this kernel decodes one strip
+// once band b is one (slightly shifted) strip ahead, band b+1 can follow.  One launch of this kernel decodes one strip
 // of up to three bands at once (the same consumer / producer roles as decode_band_pipe_kernel, with the
 // coder registers of every chain carried from launch to launch in ChainState); between launches the
 // host runs the CNN of the next strips and scatters the finished ones into the planes.  The serial
-// chain of a scale shrinks from 3 * n_sym steps to about (1 + 4 / strips) * n_sym.
+// chain of a scale shrinks from 3 * n_sym steps to about (1 + 2 / strips) * n_sym.
 struct WaveBand {
     DecodeGeom dg;
     const float *params;     // [n][60][P] network outputs of this band
@@ -1065,16 +1065,24 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
     const int safe_per_sm = std::max(prod_resident - 3, 1);
     const int prod_per_sm = std::min(std::max(env_int("LLICTI_WAVE_PRODUCER_CTAS_PER_SM", prod_resident - 1), 1), std::max(prod_resident, 1));
     const int consumer_ctas = (9 * n + 3) / 4;
-    auto row_of = [&](int k) { return (int)((long long)Hs * k / K); };
+    // Strip k of band b covers rows [row_of(b, k), row_of(b, k+1)): the strips of band b+1 end three rows before
+    // those of band b.  The CNN of band b+1 reads band b up to two rows below the row it evaluates, and a strip is
+    // decoded in whole 32-symbol items (up to one row short of its last row), so strip k of band b+1 depends on
+    // strips <= k of band b only: the bands run ONE time step apart.
+    auto row_of = [&](int b, int k) {
+        if (k <= 0) return 0;
+        if (k >= K) return Hs;
+        return std::max((int)((long long)Hs * k / K) - 3 * b, 0);
+    };
     auto item_of = [&](int b, int k) {       // items of band b complete after strip k-1
         if (k >= K) return dg[b].items_per_chain;
-        return (int)std::min<long long>((long long)std::min(row_of(k), dg[b].crop_h) * dg[b].crop_w / 32, dg[b].items_per_chain);
+        return (int)std::min<long long>((long long)std::min(row_of(b, k), dg[b].crop_h) * dg[b].crop_w / 32, dg[b].items_per_chain);
     };
-    for (int T = 0; T < K + 4; ++T) {
+    for (int T = 0; T < K + 2; ++T) {
         WaveArgs wa;
         bool any = false;
         for (int b = 0; b < 3; ++b) {
-            const int s = T - 2 * b;
+            const int s = T - b;
             wa.b[b].dg = dg[b];
             wa.b[b].params = params[b]; wa.b[b].syms = syms[b]; wa.b[b].items = items[b]; wa.b[b].flags = flags[b];
             wa.b[b].it0 = wa.b[b].it1 = 0;
@@ -1082,7 +1090,8 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
             // network outputs of the rows this strip decodes (band 0 depends on x00 only: all rows at once)
             int rc = LLICTI_OK;
             if (b == 0) { if (s == 0) rc = launch_cnn_tc(ctx, 0, planes, n, Hs, Ws, params[0], st); }
-            else rc = launch_cnn_tc(ctx, b, planes, n, Hs, Ws, params[b], st, row_of(s), row_of(s + 1) - row_of(s));
+            else if (row_of(b, s + 1) > row_of(b, s))
+                rc = launch_cnn_tc(ctx, b, planes, n, Hs, Ws, params[b], st, row_of(b, s), row_of(b, s + 1) - row_of(b, s));
             if (rc) return rc;
             wa.b[b].it0 = item_of(b, s);
             wa.b[b].it1 = item_of(b, s + 1);
