@@ -33,7 +33,7 @@ class CodecConfig:
     num_mixtures: int = 5
     sub_len: int = 0                 # 0 = torchac-compatible streams; >0 = interleaved substreams
     numerics: int = L.NUM_TORCH_CUDA
-    cnn_impl: int = L.CNN_FP32
+    cnn_impl: int = L.CNN_TCGEN05     # CNN_FP32 = CUDA-core exactness reference
     device: int = 0
     decode_impl: int = 0             # 0 = CDF windows + serial chains, 1 = legacy one-warp-per-chain
 
