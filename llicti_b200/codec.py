@@ -149,7 +149,9 @@ class Codec:
         """Decode-side diagnostics: window misses and pipeline waits since the last reset."""
         out = (C.c_uint64 * 8)()
         L.check(self.lib.llicti_decode_stats(self._ctx, out, int(reset)))
-        return {"slow_path_symbols": int(out[0]), "consumer_polls": int(out[1]), "chunks_redone": int(out[3])}
+        return {"slow_path_symbols": int(out[0]), "consumer_polls": int(out[1]), "chunks_redone": int(out[3]),
+                "consumer_wait_cycles": int(out[4]), "consumer_cycles": int(out[5]), "consumer_runs": int(out[6]),
+                "consumer_redo_cycles": int(out[7]), "consumer_longest_run_cycles": int(out[2])}
 
     # -- full path, host buffers (the timed end-to-end call) -------------------------------
     def encode_host(self, rgb: np.ndarray, out: Optional[np.ndarray] = None):

@@ -1,5 +1,6 @@
 // C ABI of libllicti_b200.so: context, geometry, weight packing, workspace and the host-side
 // sequencing of the kernels for the full compress / decompress path.  See include/llicti.h.
+#include <cstdlib>
 #include <stdarg.h>
 #include <string.h>
 
@@ -300,7 +301,7 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_blob, ctx->blob_cap));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_x00, n * 3 * (size_t)g.Hs[S - 1] * g.Ws[S - 1]));
     ctx->items_cap = (int64_t)n * decode_items_per_image(p);
-    LLICTI_CUDA(cudaMalloc(&ctx->d_items, wb * (size_t)ctx->items_cap * 2048));
+    LLICTI_CUDA(cudaMalloc(&ctx->d_items, wb * (size_t)ctx->items_cap * decode_item_bytes()));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)decode_flag_words(wb * ctx->items_cap) * sizeof(uint32_t)));
     LLICTI_CUDA(cudaMalloc(&ctx->d_chain_state_raw, n * 9 * 64));
     ctx->wave_ws = wb == 3;
@@ -330,6 +331,7 @@ int llicti_profile_read(llicti_ctx *ctx, double *ms, int64_t *count) {
         LLICTI_CUDA(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
         ms[ctx->prof_cls[i]] += t;
         count[ctx->prof_cls[i]] += 1;
+        if (getenv("LLICTI_PROF_DUMP")) fprintf(stderr, "[llicti profile] scope %zu class %d %.4f ms\n", i, ctx->prof_cls[i], t);
     }
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     ctx->prof_ev.clear();

@@ -198,6 +198,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
                        const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
                        const uint32_t *sublen, cudaStream_t st);
 int64_t decode_items_per_image(const Plan &p);
+size_t decode_item_bytes();
 bool wave_eligible(const llicti_ctx *ctx, const llicti::Plan &p, int scale, int n);
 int wave_bands_in_workspace(const llicti_config &cfg, int max_images);
 int probe_concurrent_kernels(llicti_ctx *ctx, bool *ok);

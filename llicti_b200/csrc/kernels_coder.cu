@@ -127,6 +127,10 @@ __device__ __forceinline__ void encode_strided(AcEncoder &enc, const uint32_t *_
 // ------------------------------------------------------------------------------------------
 constexpr int kStageWords = 96;          // staging capacity per warp (3072 bits); see block_fits()
 
+// clz of a non-zero word through the exponent of a round-toward-zero int -> float conversion (I2F: ~10 cycles;
+// FLO: ~22 cycles on sm_100)
+__device__ __forceinline__ int enc_clz_nz(uint32_t x) { return 158 - (int)(__float_as_uint(__uint2float_rz(x)) >> 23); }
+
 struct WarpEncoder {
     uint32_t low, high, pending;
     uint32_t *stage;       // shared, kStageWords + 2 words, zero except for emitted bits
@@ -193,18 +197,43 @@ struct WarpEncoder {
     // 32 (or fewer) symbols: bounds in `cur` (one per lane), m valid.
     __device__ __forceinline__ void encode_block(uint32_t cur, int m) {
         // ---- phase A: the interval recurrence, nothing else (lane s keeps (nl, nh) of step s) ----
-        const uint32_t my_low = cur & 0xFFFFu, my_high = (cur >> 16) + 1u;   // bounds unpacked in parallel, off the chain
+        // 32-bit arithmetic: (span * c) >> 16 is the high word of span * (c << 16) for span < 2^32; the full range
+        // (span = 2^32, seen as 0) gives c << 16 itself, and c_high = 2^16 (c << 16 seen as 0) gives span.
+        const uint32_t my_cl16 = cur << 16, my_ch16 = ((cur >> 16) + 1u) << 16;   // bounds unpacked in parallel, off the chain
         uint32_t rec_nl = 0, rec_nh = 0xFFFFFFFFu;
-#pragma unroll 8
-        for (int s = 0; s < m; ++s) {
-            const uint32_t c_low = __shfl_sync(0xffffffffu, my_low, s), c_high = __shfl_sync(0xffffffffu, my_high, s);
-            const uint32_t sm1 = high - low;                               // span - 1; span * c = sm1 * c + c
-            const uint32_t nl = low + (uint32_t)(((uint64_t)sm1 * c_low + c_low) >> 16);
-            const uint32_t nh = (low - 1u) + (uint32_t)(((uint64_t)sm1 * c_high + c_high) >> 16);
-            const int sh = __clz((nl ^ nh) & ~((nl & ~nh) << 1));         // equal leading bits + underflow run (AcEncoder::encode)
+        auto step = [&](int s, uint32_t cl16, uint32_t ch16) {
+            const uint32_t span = high - low + 1u;
+            const bool full = span == 0u;
+            const uint32_t tl = full ? cl16 : __umulhi(span, cl16);
+            const uint32_t th = ch16 == 0u ? span : full ? ch16 : __umulhi(span, ch16);
+            const uint32_t nl = low + tl, nh = low + th - 1u;
+            const int sh = enc_clz_nz((nl ^ nh) & ~((nl & ~nh) << 1));     // equal leading bits + underflow run (AcEncoder::encode)
             if (lane == s) { rec_nl = nl; rec_nh = nh; }
             low = (nl << sh) & 0x7FFFFFFFu;
             high = (nh << sh) | ~(0xFFFFFFFFu << sh) | 0x80000000u;
+        };
+        if (m == 32) {
+            // the bounds of eight steps are broadcast while the previous eight run: no shuffle latency on the chain
+            uint32_t cl[8], ch[8], ncl[8], nch[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { cl[k] = __shfl_sync(0xffffffffu, my_cl16, k); ch[k] = __shfl_sync(0xffffffffu, my_ch16, k); }
+#pragma unroll
+            for (int b8 = 0; b8 < 4; ++b8) {
+                if (b8 < 3) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        ncl[k] = __shfl_sync(0xffffffffu, my_cl16, 8 * b8 + 8 + k);
+                        nch[k] = __shfl_sync(0xffffffffu, my_ch16, 8 * b8 + 8 + k);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) step(8 * b8 + k, cl[k], ch[k]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { cl[k] = ncl[k]; ch[k] = nch[k]; }
+            }
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < m; ++s) step(s, __shfl_sync(0xffffffffu, my_cl16, s), __shfl_sync(0xffffffffu, my_ch16, s));
         }
         // per-step record, derived in parallel: the n bits shifted out, n, the underflow count k
         int rec_n = 0, rec_k = 0;

@@ -5,9 +5,10 @@
 // The reference builds the dense H x W x Lp table for every stream and lets one CPU thread
 // binary-search it symbol by symbol.  Here the work is split by what depends on the coder state:
 //
-//   producers  (any number of warps, no coder state): for every symbol, the 31 exact table
-//              entries q(base .. base+30) around the predicted value -- a "window" -- packed
-//              with `base` into one 64-byte row.  32 symbols of one chain form a 2 KB item.
+//   producers  (any number of warps, no coder state): for every symbol, the 32 exact table
+//              entries q(base .. base+31) around the predicted value -- a "window" of 31 complete
+//              symbols, one 64-byte row.  32 symbols of one chain form an item: 2 KB of rows plus
+//              the 32 window bases.
 //   consumers  (one warp per coded chain, the serial part): per symbol one 64-bit multiply and
 //              compare per lane, a ballot, two shuffles and the interval update.  No erfc, no
 //              division, no table search on the critical path.  A symbol outside its window
@@ -32,14 +33,23 @@
 
 namespace llicti {
 
-__device__ unsigned long long g_decode_stats[8];   // 0 slow-path symbols, 1 consumer flag polls, 2 unused, 3 chunks redone carefully
+__device__ unsigned long long g_decode_stats[8];   // 0 slow-path symbols, 1 consumer flag polls, 2 longest consumer run (cycles), 3 chunks redone carefully,
+                                                   // 4 cycles consumers waited for items, 5 consumer cycles, 6 consumer runs, 7 cycles in redone chunks (piped schedules)
+
+__device__ unsigned long long g_wave_dbg[8];   // LLICTI_WAVE_DEBUG: per-launch consumer timing
+__global__ void wave_dbg_kernel(int T, int chains) {
+    printf("[wave] T=%d chains=%d max=%.3f ms avg=%.3f ms wait=%.3f redo=%.3f span=%.3f ms\n", T, chains, g_wave_dbg[0] / 1.965e6, g_wave_dbg[1] / 1.965e6 / chains,
+           g_wave_dbg[2] / 1.965e6 / chains, g_wave_dbg[3] / 1.965e6 / chains, (g_wave_dbg[5] - g_wave_dbg[4]) / 1.965e6);
+    for (int i = 0; i < 8; ++i) g_wave_dbg[i] = 0;
+    g_wave_dbg[4] = ~0ull;
+}
 
 constexpr int kStageU16 = 32 * 34 + 32 * 6 * 8;   // per warp: window staging (17-word pitch) + prepared channels of 32 steps
-constexpr int kWin = 31;                 // table entries per window (lane 31 carries `base`)
+constexpr int kWin = 31;                 // complete symbols per window (32 table entries: lane l holds q(base + l))
+constexpr int kLiBuf = 32;               // per consumer warp: the window-relative symbols of the item in flight
+constexpr int kItemU4 = 132;             // uint4 per item: [4][32 lanes] window rows, then 32 x u16 window bases
 constexpr int16_t kSentinel = (int16_t)0x8080;   // memset(0x80): never a sample value (|v| <= 255)
 
-// Lane 31 of every window row: base | nq << 9, nq = number of real table entries in the window.
-__device__ __forceinline__ uint32_t window_info(int base, int last) { return (uint32_t)base | ((uint32_t)min(kWin, max(last - base, 0)) << 9); }
 
 struct DecodeGeom {
     int Hs, Ws, crop_h, crop_w, band, padH, padW;
@@ -86,17 +96,23 @@ __device__ __forceinline__ int read_symbol(const int16_t *p) {
     return v;
 }
 
-__device__ __forceinline__ void wait_flag(const uint32_t *flag, unsigned long long &polls) {
+__device__ __forceinline__ void wait_flag(const uint32_t *flag, unsigned long long &polls, long long &waited) {
+    if (ld_relaxed_u32(flag) != 0u) return;
+    const long long t0 = clock64();
     for (uint32_t spins = 0; ld_relaxed_u32(flag) == 0u; ++spins) {
         if (spins > kMaxPolls) __trap();
         ++polls;
         __nanosleep(100);
     }
+    waited += clock64() - t0;
 }
 
 // ------------------------------------------------------------------------------------------
 // Producer: the windows of 32 consecutive steps of one chain.  Item layout: uint4 [4][32 lanes],
-// lane l holds its own entries q(base_s + l) of steps s = 8 v + e in element e of its v-th uint4.
+// lane l holds its own entries q(base_s + l) of steps s = 8 v + e in element e of its v-th uint4;
+// the entry of the alphabet's end, q(Lp - 1) = 2^16, and everything past it is stored as 0.  The
+// 32 bases follow as u16.  A window holds the 31 symbols base .. base+30 (fewer for alphabets
+// below 31 symbols, where base = 0).
 // `syms` = compact symbol arrays of this image's band, [3][sym_cap] in coding order.
 // ------------------------------------------------------------------------------------------
 template <bool kPipe>
@@ -123,7 +139,7 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
 #pragma unroll
         for (int m = 0; m < kM; ++m) mean = fmaf(ch.w[m], ch.mu[m], mean);
         const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
-        base = min(max(kc - kWin / 2, 0), max(last - (kWin - 1), 0));
+        base = min(max(kc - kWin / 2, 0), max(last - kWin, 0));
     }
     const int nv = min(32, (dg.n_sym - j + dg.S - 1) / dg.S - tb * 32);   // valid steps of this item (warp-uniform)
     // the prepared channel of every step goes through shared memory: 6 broadcast 16-byte reads per step
@@ -151,11 +167,10 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
         const int bs = __float_as_int(v5.x);
         b.fast = __float_as_int(v5.y);
         const int k = bs + lane;
-        // every lane evaluates an entry (the warp-uniform erfc skip votes over all 32 lanes); lanes beyond
-        // the table and lane 31 evaluate a clamped index and discard it
+        // every lane evaluates an entry (the warp-uniform erfc skip votes over all 32 lanes); lanes at or
+        // beyond the alphabet's end evaluate a clamped index and store 0 (= 2^16 mod 2^16)
         const uint32_t qe = cdf_q<true>(b, g, min(k, last - 1), np);
-        const uint32_t q = lane < kWin ? (k < last ? qe : 0u) : window_info(bs, last);
-        my[s] = (uint16_t)q;
+        my[s] = (uint16_t)(k < last ? qe : 0u);
     }
     __syncwarp();
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(my);
@@ -165,6 +180,8 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
         o.x = mw[4 * v + 0]; o.y = mw[4 * v + 1]; o.z = mw[4 * v + 2]; o.w = mw[4 * v + 3];
         if (kPipe) __stcg(item + v * 32 + lane, o); else item[v * 32 + lane] = o;
     }
+    unsigned short *bases = reinterpret_cast<unsigned short *>(item + 128);
+    if (kPipe) __stcg(bases + lane, (unsigned short)base); else bases[lane] = (unsigned short)base;
     __syncwarp();
 }
 
@@ -196,71 +213,82 @@ __device__ __noinline__ uint64_t slow_symbol(const float *__restrict__ pp, const
     return (uint64_t)c_low | ((uint64_t)(c_high - 1u) << 16) | ((uint64_t)(uint32_t)sym << 32);
 }
 
-// Serial coder state of one chain: torchac's (low, high, value) registers over a 160-bit window
-// of upcoming stream bits held in registers.  The window is topped up BETWEEN 8-step chunks from
-// two look-ahead words, so inside a chunk there is no memory access, no refill and no branch.
+// Serial coder state of one chain: torchac's (low, high, value) registers and the stream position.
+// The next 128 stream bits are rebuilt from memory (L1 hits) at the start of every 8-step chunk, so
+// inside a chunk there is no memory access, no refill and no branch.
 struct ChainCoder {
     uint32_t low, high, value;
-    uint32_t b0, b1, b2, b3, b4;   // upcoming bits, left aligned in b0:b1:b2:b3:b4
-    int avail;                     // valid bits in the window
+    uint32_t pos;                  // stream bits already shifted into `value`, counted from w
+    uint32_t b0, b1, b2, b3;       // the stream bits after pos, left aligned (transient: load_window)
+    int avail;                     // valid bits in b0:b1:b2:b3
     const uint32_t *w;             // 4-byte aligned base (<= stream start)
-    uint32_t lo_byte, hi_byte;     // valid bytes [lo, hi) relative to w
-    uint32_t idx, a0, a1;          // index of the word in a0; a0, a1 = the two upcoming words as loaded (raw)
+    uint32_t hi_byte;              // end of the stream relative to w, in bytes
 
-    // Raw load only: the value is not touched until it is inserted one or two chunks later, so the
-    // load latency never stalls the chain.
-    __device__ __forceinline__ uint32_t fetch_raw(uint32_t i) const { return i * 4u < hi_byte ? __ldg(w + i) : 0u; }
-    __device__ __forceinline__ uint32_t cook(uint32_t raw, uint32_t i) const {
+    // big-endian word i of the stream; torchac reads zeros past the end
+    __device__ __forceinline__ uint32_t word(uint32_t i) const {
         const uint32_t p0 = i * 4u;
-        uint32_t v = __byte_perm(raw, 0, 0x0123);       // first stream byte in the most significant position
-        if (p0 < lo_byte) v &= 0xFFFFFFFFu >> (8u * (lo_byte - p0));
-        if (p0 + 4u > hi_byte) v &= p0 < hi_byte ? 0xFFFFFFFFu << (8u * (p0 + 4u - hi_byte)) : 0u;   // torchac reads zeros past the end
+        if (p0 >= hi_byte) return 0u;
+        uint32_t v = __byte_perm(__ldg(w + i), 0, 0x0123);       // first stream byte in the most significant position
+        if (p0 + 4u > hi_byte) v &= 0xFFFFFFFFu << (8u * (p0 + 4u - hi_byte));
         return v;
     }
-    // Append look-ahead words while at most 96 bits are valid: afterwards 97..128 bits are.
-    __device__ __forceinline__ void topup() {
-        while (avail <= 96) {
-            const int wi = avail >> 5, r = avail & 31;
-            const uint64_t t = ((uint64_t)cook(a0, idx) << 32) >> r;
-            const uint32_t hi = (uint32_t)(t >> 32), lo = (uint32_t)t;
-            b0 |= wi == 0 ? hi : 0u;
-            b1 |= wi == 0 ? lo : wi == 1 ? hi : 0u;
-            b2 |= wi == 1 ? lo : wi == 2 ? hi : 0u;
-            b3 |= wi == 2 ? lo : wi == 3 ? hi : 0u;
-            b4 |= wi == 3 ? lo : 0u;
-            avail += 32;
-            a0 = a1;
-            ++idx;
-            a1 = fetch_raw(idx + 1);
+    __device__ __forceinline__ void load_window() {
+        const uint32_t wi = pos >> 5, r = pos & 31u;
+        uint32_t W0, W1, W2, W3, W4;
+        if ((wi + 5u) * 4u <= hi_byte) {        // all five words inside the stream (uniform; false only at its end)
+            W0 = __byte_perm(__ldg(w + wi), 0, 0x0123);
+            W1 = __byte_perm(__ldg(w + wi + 1), 0, 0x0123);
+            W2 = __byte_perm(__ldg(w + wi + 2), 0, 0x0123);
+            W3 = __byte_perm(__ldg(w + wi + 3), 0, 0x0123);
+            W4 = __byte_perm(__ldg(w + wi + 4), 0, 0x0123);
+            if ((wi + 70u) * 4u <= hi_byte) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + wi + 64));
+        } else {
+            W0 = word(wi); W1 = word(wi + 1); W2 = word(wi + 2); W3 = word(wi + 3); W4 = word(wi + 4);
         }
+        b0 = __funnelshift_l(W1, W0, r);
+        b1 = __funnelshift_l(W2, W1, r);
+        b2 = __funnelshift_l(W3, W2, r);
+        b3 = __funnelshift_l(W4, W3, r);
+        avail = 128;
     }
     __device__ __forceinline__ void shift(int sh) {     // 0 <= sh <= 31
         b0 = __funnelshift_l(b1, b0, sh);
         b1 = __funnelshift_l(b2, b1, sh);
         b2 = __funnelshift_l(b3, b2, sh);
-        b3 = __funnelshift_l(b4, b3, sh);
-        b4 <<= sh;
+        b3 <<= sh;
         avail -= sh;
     }
     __device__ __forceinline__ void init(const uint8_t *ptr, uint32_t n) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
         w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-        lo_byte = (uint32_t)(a & 3);
+        const uint32_t lo_byte = (uint32_t)(a & 3);
         hi_byte = lo_byte + n;
-        b0 = cook(fetch_raw(0), 0) << (8 * lo_byte);
-        b1 = b2 = b3 = b4 = 0u;
-        avail = 32 - 8 * (int)lo_byte;
-        idx = 1;
-        a0 = fetch_raw(1);
-        a1 = fetch_raw(2);
-        topup();
+        pos = 8u * lo_byte;
+        load_window();
         low = 0; high = 0xFFFFFFFFu;
         value = b0;
-        b0 = b1; b1 = b2; b2 = b3; b3 = b4; b4 = 0u;
-        avail -= 32;
-        topup();
+        pos += 32u;
     }
 };
+
+// Build-time variants (tools/step_probe.cu measures them on the GPU):
+//   LLICTI_CLZ_I2F  1  count leading zeros through the exponent of a round-toward-zero int -> float
+//                      conversion (I2F: ~10 cycles) instead of FLO (~22 cycles)
+#ifndef LLICTI_CLZ_I2F
+#define LLICTI_CLZ_I2F 1
+#endif
+#ifndef LLICTI_PROBE_X
+#define LLICTI_PROBE_X 0     // measurement-only knobs of tools/step_probe.cu (never set in the product build)
+#endif
+
+// clz of a non-zero word (the argument below is non-zero whenever nl < nh; other lanes' results are never selected)
+__device__ __forceinline__ int clz_nz(uint32_t x) {
+#if LLICTI_CLZ_I2F
+    return 158 - (int)(__float_as_uint(__uint2float_rz(x)) >> 23);
+#else
+    return __clz(x);
+#endif
+}
 
 // torchac's interval update and renormalisation for the symbol with bounds (c_low, c_high), as a
 // pure function of the coder registers.  The bit-serial E1/E2/E3 loop shifts out
@@ -270,27 +298,42 @@ struct ChainCoder {
 // d & ~(m << 1) has its first one exactly at n + k, so ONE clz gives the total shift sh = n + k.
 // After the shift the top pair is (0, 1) whether or not an underflow happened; it happened iff
 // the top bit of nl << sh is set, which is also the bit torchac flips in `value`.
-struct NextState { uint32_t low, high, value; int sh; uint32_t nl; };
-__device__ __forceinline__ NextState next_state(uint32_t low, uint32_t high, uint32_t value, uint32_t next_bits,
-                                                uint32_t c_low, uint32_t c_high) {
-    const uint32_t sm1 = high - low;                                    // span - 1; span * c = sm1 * c + c
+struct NextState { uint32_t low, high, value; int sh; uint32_t nl, nh; };
+__device__ __forceinline__ NextState renormalise(uint32_t nl, uint32_t nh, uint32_t value, uint32_t next_bits) {
     NextState o;
-    o.nl = low + (uint32_t)(((uint64_t)sm1 * c_low + c_low) >> 16);
-    const uint32_t nh = (low - 1u) + (uint32_t)(((uint64_t)sm1 * c_high + c_high) >> 16);
-    o.sh = __clz((o.nl ^ nh) & ~((o.nl & ~nh) << 1));                   // <= 31 whenever nl < nh
-    const uint32_t ls = o.nl << o.sh;
+    o.nl = nl; o.nh = nh;
+    o.sh = clz_nz((nl ^ nh) & ~((nl & ~nh) << 1));                      // <= 31 whenever nl < nh
+    const uint32_t ls = nl << o.sh;
     o.low = ls & 0x7FFFFFFFu;
     o.high = (nh << o.sh) | ~(0xFFFFFFFFu << o.sh) | 0x80000000u;
     o.value = __funnelshift_l(next_bits, value, o.sh) ^ (ls & 0x80000000u);
     return o;
 }
+// exact for every state (64-bit products, as torchac)
+__device__ __forceinline__ NextState next_state(uint32_t low, uint32_t high, uint32_t value, uint32_t next_bits,
+                                                uint32_t c_low, uint32_t c_high) {
+    const uint32_t sm1 = high - low;                                    // span - 1; span * c = sm1 * c + c
+    const uint32_t nl = low + (uint32_t)(((uint64_t)sm1 * c_low + c_low) >> 16);
+    const uint32_t nh = (low - 1u) + (uint32_t)(((uint64_t)sm1 * c_high + c_high) >> 16);
+    return renormalise(nl, nh, value, next_bits);
+}
 
 template <bool kPipe>
 __device__ __forceinline__ uint4 load_chunk(const uint4 *p) { return kPipe ? __ldcg(p) : *p; }
+template <bool kPipe>
+__device__ __forceinline__ int load_base(const uint4 *item, int lane) {
+    const unsigned short *b = reinterpret_cast<const unsigned short *>(item + 128) + lane;
+    return (int)(kPipe ? __ldcg(b) : *b);
+}
 
+// entry of step e (0..7) of a chunk word: as the 16-bit value, and shifted to the top half of a word
 __device__ __forceinline__ uint32_t chunk_entry(const uint4 &q, int e) {
     const uint32_t w = (e >> 1) == 0 ? q.x : (e >> 1) == 1 ? q.y : (e >> 1) == 2 ? q.z : q.w;
     return (e & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+__device__ __forceinline__ uint32_t chunk_entry_hi(const uint4 &q, int e) {
+    const uint32_t w = (e >> 1) == 0 ? q.x : (e >> 1) == 1 ? q.y : (e >> 1) == 2 ? q.z : q.w;
+    return (e & 1) ? (w & 0xFFFF0000u) : (w << 16);
 }
 
 struct ChainCtx {       // what the (rare) slow path needs
@@ -300,50 +343,54 @@ struct ChainCtx {       // what the (rare) slow path needs
     int crop_w, Ws, clr, lo0, lo1, S;
 };
 
-// One symbol.  Lane l holds table entry q(base + l) of this symbol's window and evaluates, for the
-// candidate "symbol = base + l", the complete next coder state; which candidate is right is
+// One symbol.  Lane l holds table entry q(base + l) of this symbol's window (cl16 = q << 16) and evaluates,
+// for the candidate "symbol = base + l", the complete next coder state; which candidate is right is
 //   low + ((span * q(s)) >> 16) <= value          (<=> q(s) <= floor(((value-low+1) 2^16 - 1) / span),
 // torchac's search key), so a ballot picks the lane and four shuffles fetch its state.  The only
 // work after the ballot is the selection.
 //
-// Fast variant: no branch at all.  A symbol outside its window, or a window of stream bits that
-// ran low, only raises `bad`; the caller validates once per chunk and redoes a bad chunk with the
-// careful variant from a snapshot (about 1 chunk in 100).
-__device__ __forceinline__ int decode_step_fast(ChainCoder &cc, uint32_t raw, int last, int lane, uint32_t &bad) {
-    // window geometry and the upper bound of each candidate: data only, off the serial chain
-    const uint32_t info = __shfl_sync(kFull, raw, 31);
-    const int base = (int)(info & 511u), nq = (int)(info >> 9);
-    const uint32_t up = __shfl_down_sync(kFull, raw, 1);
-    const uint32_t c_high = lane + 1 < nq ? up : 0x10000u;
-    const uint32_t vmask = (1u << nq) - 1u;
-    const uint32_t zmask = base == 0 ? 1u : 0u;          // target below q(0): torchac's search returns symbol 0
-    const uint32_t lim = base + nq < last ? (uint32_t)(nq - 1) : 31u;   // li >= lim: beyond the window
-    const NextState ns = next_state(cc.low, cc.high, cc.value, cc.b0, raw, c_high);
-    const uint32_t li = (uint32_t)__popc((__ballot_sync(kFull, cc.value >= ns.nl) & vmask) | zmask) - 1u;
-    bad |= (li >= lim ? 1u : 0u) | (cc.avail < 32 ? 1u : 0u);   // li = -1: below a window that does not start at 0
-    const uint32_t lic = min(li, 31u);
-    cc.low = __shfl_sync(kFull, ns.low, lic);
-    cc.high = __shfl_sync(kFull, ns.high, lic);
-    cc.value = __shfl_sync(kFull, ns.value, lic);
-    cc.shift(__shfl_sync(kFull, ns.sh, lic));
-    return base + (int)li;
+// Fast variant: no branch at all, 32-bit arithmetic.  (span * q) >> 16 is the high word of
+// span * (q << 16) whenever span < 2^32; an upper bound of 2^16 (stored as 0: the top symbol of the
+// alphabet) gives `span` itself.  A full-range state (span = 2^32), a symbol outside its window or a
+// window of stream bits that ran low only raise `bad`; the caller validates once per chunk and
+// redoes a bad chunk with the careful variant from a snapshot (about 1 chunk in 100).
+// Returns the window-relative symbol.
+__device__ __forceinline__ uint32_t decode_step_fast(ChainCoder &cc, uint32_t cl16, uint32_t vmask, uint32_t &bad) {
+    const uint32_t ch16 = __shfl_down_sync(kFull, cl16, 1);              // data only, off the serial chain
+    const uint32_t span = cc.high - cc.low + 1u;                         // 0: the full range 2^32
+    const uint32_t nl = cc.low + __umulhi(span, cl16);
+    const uint32_t nhp1 = cc.low + (ch16 == 0u ? span : __umulhi(span, ch16));   // nh + 1 = nl of the next candidate
+    const NextState ns = renormalise(nl, nhp1 - 1u, cc.value, cc.b0);
+    // beyond the window: only possible for the last candidate (for the others it contradicts the ballot)
+    const uint32_t shw = (uint32_t)ns.sh | (cc.value >= nhp1 ? 0x100u : 0u);
+#if LLICTI_PROBE_X == 4                          // redux.max instead of ballot + popc
+    const uint32_t li = __reduce_max_sync(kFull, (cc.value >= nl && ((vmask >> (threadIdx.x & 31)) & 1u)) ? (threadIdx.x & 31) + 1u : 0u) - 1u;
+#else
+    const uint32_t li = (uint32_t)__popc(__ballot_sync(kFull, cc.value >= nl) & vmask) - 1u;
+#endif
+    bad |= (span == 0u ? 1u : 0u) | (cc.avail < 32 ? 1u : 0u);
+    cc.low = __shfl_sync(kFull, ns.low, li);
+    cc.high = __shfl_sync(kFull, ns.high, li);
+    cc.value = __shfl_sync(kFull, ns.value, li);
+    const uint32_t w = __shfl_sync(kFull, shw, li);
+    bad |= (li >> 31) | (w >> 8);                                        // li = -1: below the window
+    cc.shift((int)(w & 31u));
+    return li << 8;
 }
 
+// Careful variant: exact in every state; a symbol outside its window takes the full analytic search.
+// Returns the symbol (alphabet index).
 template <bool kPipe>
-__device__ __forceinline__ int decode_step_careful(ChainCoder &cc, uint32_t raw, int last, long long i, const ChainCtx &cx,
-                                               const CdfGrid &g, const NumericsProfile &np, int lane) {
-    cc.topup();
-    const uint32_t info = __shfl_sync(kFull, raw, 31);
-    const int base = (int)(info & 511u), nq = (int)(info >> 9);
-    const uint32_t up = __shfl_down_sync(kFull, raw, 1);
-    const uint32_t c_high = lane + 1 < nq ? up : 0x10000u;
-    const uint32_t vmask = (1u << nq) - 1u;
-    const uint32_t zmask = base == 0 ? 1u : 0u;
-    const uint32_t lim = base + nq < last ? (uint32_t)(nq - 1) : 31u;
-    const NextState ns = next_state(cc.low, cc.high, cc.value, cc.b0, raw, c_high);
-    const uint32_t li = (uint32_t)__popc((__ballot_sync(kFull, cc.value >= ns.nl) & vmask) | zmask) - 1u;
+__device__ __forceinline__ int decode_step_careful(ChainCoder &cc, uint32_t slot, int base, uint32_t vmask, long long i,
+                                               const ChainCtx &cx, const CdfGrid &g, const NumericsProfile &np, int lane) {
+    cc.load_window();
+    const uint32_t up = __shfl_down_sync(kFull, slot, 1);
+    const uint32_t c_high = up == 0u ? 0x10000u : up;
+    const NextState ns = next_state(cc.low, cc.high, cc.value, cc.b0, slot, c_high);
+    const uint32_t li = (uint32_t)__popc(__ballot_sync(kFull, cc.value >= ns.nl) & vmask) - 1u;
+    const uint32_t nh_sel = __shfl_sync(kFull, ns.nh, li);
     int sym, sh;
-    if (li >= lim) {
+    if ((li >> 31) != 0u || cc.value > nh_sel) {
         const uint64_t pk = slow_symbol(cx.pp, cx.syms, cx.sym_cap, cx.P, cx.crop_w, cx.Ws, i, cx.clr, cx.lo0, cx.lo1, g, np,
                                         cc.low, cc.high, cc.value, lane, kPipe ? 1 : 0);
         const NextState s2 = next_state(cc.low, cc.high, cc.value, cc.b0, (uint32_t)pk & 0xFFFFu,
@@ -357,28 +404,25 @@ __device__ __forceinline__ int decode_step_careful(ChainCoder &cc, uint32_t raw,
         sh = __shfl_sync(kFull, ns.sh, li);
         sym = base + (int)li;
     }
-    cc.shift(sh);     // (torchac does not update after the last symbol; the state is dead by then)
+    cc.pos += (uint32_t)sh;     // (torchac does not update after the last symbol; the state is dead by then)
     return sym;
-}
-
-__device__ __forceinline__ uint32_t chunk_entry_dyn(const uint4 &q, int e) {
-    const uint32_t w = (e >> 1) == 0 ? q.x : (e >> 1) == 1 ? q.y : (e >> 1) == 2 ? q.z : q.w;
-    return (e & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
 // Coder registers of a chain between two launches of the wavefront schedule (the chain is decoded a
 // strip of items at a time).
-struct ChainState { uint32_t low, high, value, b0, b1, b2, b3, b4, avail, idx, a0, a1; };
+struct ChainState { uint32_t low, high, value, pos; };
 
 // `out` = compact symbol array of this (image, channel) in coding order; chain j writes j, j+S, ...
 // Items [it_begin, it_end) of the chain are decoded; it_begin > 0 resumes from *state, it_end short
-// of the chain's end saves to it.
+// of the chain's end saves to it.  `li_buf` = 32 words of shared memory of this warp: the window-relative
+// symbols of the item in flight; lane t adds the base of step t and stores the symbol.
 template <bool kPipe>
 __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, const CdfGrid &g, int j,
                                               const NumericsProfile &np, int16_t *out, const uint4 *__restrict__ items,
                                               uint32_t *flags, const uint8_t *__restrict__ stream, uint32_t stream_len,
-                                              int lane, int it_begin = 0, int it_end = 0x7FFFFFFF,
+                                              int lane, int *li_buf, int it_begin = 0, int it_end = 0x7FFFFFFF,
                                               ChainState *state = nullptr) {
+
     const int S = cx.S;
     const int n_steps = (n_sym - j + S - 1) / S;
     if (n_steps <= 0) return;
@@ -387,26 +431,27 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
     if (it_begin >= n_items) return;
     const int n_full = n_steps >> 3, tail = n_steps & 7;
     const int last = g.Lp - 1;
-    const bool vec_store = S == 1 && j == 0;      // 8 consecutive symbols = one aligned 16-byte store
+    const uint32_t vmask = last >= kWin ? 0x7FFFFFFFu : (1u << last) - 1u;    // candidate lanes that are symbols
     unsigned long long polls = 0, redone = 0;
+    long long waited = 0, redo_cycles = 0;
+    const long long t_begin = kPipe ? clock64() : 0;
 
     ChainCoder cc;
     cc.init(stream, stream_len);
     if (it_begin > 0) {
         const ChainState s = *state;
-        cc.low = s.low; cc.high = s.high; cc.value = s.value;
-        cc.b0 = s.b0; cc.b1 = s.b1; cc.b2 = s.b2; cc.b3 = s.b3; cc.b4 = s.b4;
-        cc.avail = (int)s.avail; cc.idx = s.idx; cc.a0 = s.a0; cc.a1 = s.a1;
+        cc.low = s.low; cc.high = s.high; cc.value = s.value; cc.pos = s.pos;
     }
     long long i = j + (long long)it_begin * 32 * S;
-    int16_t *dst = out + i;
 
-    if (kPipe) wait_flag(flags + it_begin, polls);
+    if (kPipe) wait_flag(flags + it_begin, polls, waited);
     const uint4 *src = items + lane;
-    const uint4 *first = src + (size_t)it_begin * 128;
+    const uint4 *first = src + (size_t)it_begin * kItemU4;
     uint4 q0 = load_chunk<kPipe>(first), q1 = load_chunk<kPipe>(first + 32), q2 = load_chunk<kPipe>(first + 64),
           q3 = load_chunk<kPipe>(first + 96);
+    int base_cur = load_base<kPipe>(items + (size_t)it_begin * kItemU4, lane);
     uint4 n0 = q0, n1 = q1, n2 = q2, n3 = q3;
+    int base_nxt = base_cur;
     uint32_t f_next = kPipe && it_begin + 1 < n_items ? ld_relaxed_u32(flags + it_begin + 1) : 1u;   // looked at one item later
 
     for (int it = it_begin; it < n_items; ++it) {
@@ -415,77 +460,87 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
         uint32_t f_next2 = 1u;
         if (it + 1 < n_items) {
             if (!kPipe || f_next != 0u) {
-                const uint4 *nx = src + (size_t)(it + 1) * 128;
+                const uint4 *nx = src + (size_t)(it + 1) * kItemU4;
                 n0 = load_chunk<kPipe>(nx); n1 = load_chunk<kPipe>(nx + 32); n2 = load_chunk<kPipe>(nx + 64); n3 = load_chunk<kPipe>(nx + 96);
+                base_nxt = load_base<kPipe>(items + (size_t)(it + 1) * kItemU4, lane);
                 have_next = true;
             }
             if (kPipe && it + 2 < n_items) f_next2 = ld_relaxed_u32(flags + it + 2);
         }
         const int full_here = min(4, n_full - it * 4);
-#pragma unroll 1
-        for (int v = 0; v < full_here; ++v) {
-            const uint4 q = v == 0 ? q0 : v == 1 ? q1 : v == 2 ? q2 : q3;
-            cc.topup();
-            const ChainCoder snap = cc;
-            uint32_t bad = 0;
-            int sym[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sym[e] = decode_step_fast(cc, chunk_entry(q, e), last, lane, bad);
+        for (int v = 0; v < 4; ++v) {
+            if (v >= full_here) break;
+            const uint4 q = v == 0 ? q0 : v == 1 ? q1 : v == 2 ? q2 : q3;
+            cc.load_window();
+            const uint32_t s_low = cc.low, s_high = cc.high, s_value = cc.value;
+            uint32_t bad = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) li_buf[8 * v + e] = (int)decode_step_fast(cc, chunk_entry_hi(q, e), vmask, bad);
             if (__builtin_expect(bad != 0u, 0)) {
-                cc = snap;
+                cc.low = s_low; cc.high = s_high; cc.value = s_value;      // cc.pos is only advanced below
                 ++redone;
+                const long long t_redo = kPipe ? clock64() : 0;
 #pragma unroll 1
                 for (int e = 0; e < 8; ++e) {
-                    const int sy = decode_step_careful<kPipe>(cc, chunk_entry_dyn(q, e), last, i + (long long)e * S, cx, g, np, lane);
-#pragma unroll
-                    for (int e2 = 0; e2 < 8; ++e2) sym[e2] = e2 == e ? sy : sym[e2];
+                    const int base = __shfl_sync(kFull, base_cur, 8 * v + e);
+                    const int sy = decode_step_careful<kPipe>(cc, chunk_entry(q, e), base, vmask, i + (long long)(8 * v + e) * S, cx, g, np, lane);
+                    li_buf[8 * v + e] = (int)(((uint32_t)(sy - base) & 0xFFFu) << 8);
                 }
+                if (kPipe) redo_cycles += clock64() - t_redo;
+            } else {
+                cc.pos += (uint32_t)(128 - cc.avail);
             }
-            if (lane == 0) {
-                if (vec_store) {
-                    const uint4 pk = make_uint4((uint32_t)(sym[0] & 0xFFFF) | ((uint32_t)sym[1] << 16),
-                                                (uint32_t)(sym[2] & 0xFFFF) | ((uint32_t)sym[3] << 16),
-                                                (uint32_t)(sym[4] & 0xFFFF) | ((uint32_t)sym[5] << 16),
-                                                (uint32_t)(sym[6] & 0xFFFF) | ((uint32_t)sym[7] << 16));
-                    if (kPipe) __stcg(reinterpret_cast<uint4 *>(dst), pk); else *reinterpret_cast<uint4 *>(dst) = pk;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) dst[(size_t)e * S] = (int16_t)sym[e];
-                }
-            }
-            i += 8ll * S;
-            dst += (size_t)8 * S;
         }
         if (it == n_items_all - 1 && tail) {
             const int v = max(full_here, 0);
             const uint4 q = v == 0 ? q0 : v == 1 ? q1 : v == 2 ? q2 : q3;
 #pragma unroll 1
             for (int e = 0; e < tail; ++e) {
-                const int sy = decode_step_careful<kPipe>(cc, chunk_entry_dyn(q, e), last, i, cx, g, np, lane);
-                if (lane == 0) {
-                    if (kPipe) st_relaxed_s16(dst, sy); else *dst = (int16_t)sy;
-                }
-                i += S;
-                dst += S;
+                const int base = __shfl_sync(kFull, base_cur, 8 * v + e);
+                const int sy = decode_step_careful<kPipe>(cc, chunk_entry(q, e), base, vmask, i + (long long)(8 * v + e) * S, cx, g, np, lane);
+                li_buf[8 * v + e] = (int)(((uint32_t)(sy - base) & 0xFFFu) << 8);
             }
         }
+        // lane t owns step t of the item: symbol = window base + window-relative symbol
+        __syncwarp();
+        if (lane < min(32, n_steps - it * 32)) {
+            const int sy = base_cur + (((int)((uint32_t)li_buf[lane] << 12)) >> 20);     // bits 8..19: window-relative symbol, signed
+            int16_t *dst = out + i + (long long)lane * S;
+            if (kPipe) st_relaxed_s16(dst, sy); else *dst = (int16_t)sy;
+        }
+        __syncwarp();
+        i += 32ll * S;
         if (!have_next) {
-            wait_flag(flags + it + 1, polls);
-            const uint4 *nx = src + (size_t)(it + 1) * 128;
+            wait_flag(flags + it + 1, polls, waited);
+            const uint4 *nx = src + (size_t)(it + 1) * kItemU4;
             n0 = load_chunk<kPipe>(nx); n1 = load_chunk<kPipe>(nx + 32); n2 = load_chunk<kPipe>(nx + 64); n3 = load_chunk<kPipe>(nx + 96);
+            base_nxt = load_base<kPipe>(items + (size_t)(it + 1) * kItemU4, lane);
         }
         q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+        base_cur = base_nxt;
         f_next = f_next2;
     }
     if (state != nullptr && n_items < n_items_all && lane == 0) {
         ChainState s;
-        s.low = cc.low; s.high = cc.high; s.value = cc.value;
-        s.b0 = cc.b0; s.b1 = cc.b1; s.b2 = cc.b2; s.b3 = cc.b3; s.b4 = cc.b4;
-        s.avail = (uint32_t)cc.avail; s.idx = cc.idx; s.a0 = cc.a0; s.a1 = cc.a1;
+        s.low = cc.low; s.high = cc.high; s.value = cc.value; s.pos = cc.pos;
         *state = s;
     }
     if (lane == 0) {
         if (kPipe && polls) atomicAdd(&g_decode_stats[1], polls);
+        if (kPipe) {
+            atomicAdd(&g_decode_stats[4], (unsigned long long)waited);
+            atomicAdd(&g_decode_stats[5], (unsigned long long)(clock64() - t_begin));
+            atomicAdd(&g_decode_stats[6], 1ull);
+            atomicMax(&g_decode_stats[2], (unsigned long long)(clock64() - t_begin));
+            atomicMax(&g_wave_dbg[0], (unsigned long long)(clock64() - t_begin));
+            atomicAdd(&g_wave_dbg[1], (unsigned long long)(clock64() - t_begin));
+            atomicAdd(&g_wave_dbg[2], (unsigned long long)waited);
+            atomicAdd(&g_wave_dbg[3], (unsigned long long)redo_cycles);
+            atomicMin(&g_wave_dbg[4], (unsigned long long)t_begin);
+            atomicMax(&g_wave_dbg[5], (unsigned long long)clock64());
+            atomicAdd(&g_decode_stats[7], (unsigned long long)redo_cycles);
+        }
         if (redone) atomicAdd(&g_decode_stats[3], redone);
     }
 }
@@ -539,7 +594,7 @@ window_kernel(const float *__restrict__ params, const int16_t *__restrict__ syms
         const size_t P = (size_t)dg.Hs * dg.Ws;
         int lo[3];
         const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
-        uint4 *item = items + ((((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain + tb) * 128;
+        uint4 *item = items + ((((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain + tb) * kItemU4;
         produce_item<false>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
                             g, j, tb, np, item, stage[wib], lane);
     }
@@ -550,6 +605,7 @@ consume_kernel(const float *__restrict__ params, int16_t *__restrict__ syms, siz
                const int32_t *__restrict__ minmax, DecodeGeom dg, int clr, NumericsProfile np,
                const uint4 *__restrict__ items, const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
                const uint32_t *__restrict__ sublen, int total_sub, int n) {
+    __shared__ __align__(16) int li_buf[4][kLiBuf];
     const int lane = threadIdx.x & 31;
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= (long long)n * dg.S) return;
@@ -560,9 +616,9 @@ consume_kernel(const float *__restrict__ params, int16_t *__restrict__ syms, siz
     int16_t *isyms = syms + (size_t)img * 3 * sym_cap;
     const ChainCtx cx = {params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], dg.S};
     const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
-    const uint4 *chain_items = items + (((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain * 128;
+    const uint4 *chain_items = items + (((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain * kItemU4;
     consume_chain<false>(cx, dg.n_sym, g, j, np, isyms + (size_t)clr * sym_cap, chain_items, nullptr, blob + suboff[e],
-                         sublen[e], lane);
+                         sublen[e], lane, li_buf[threadIdx.x >> 5]);
 }
 
 // ---- piped schedule (S == 1): one grid of one-warp CTAs, all co-resident ----------------------
@@ -583,6 +639,7 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
                         const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
                         const uint32_t *__restrict__ sublen, int total_sub, int n) {
     __shared__ __align__(16) uint16_t stage[kStageU16];
+    __shared__ __align__(16) int li_buf[kLiBuf];
     const int lane = threadIdx.x;
     const size_t P = (size_t)dg.Hs * dg.Ws;
     const int n_cons = 3 * n;
@@ -619,8 +676,8 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
         const ChainCtx cx = {params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], 1};
         const size_t e = (size_t)img * total_sub + dg.sub_first[clr];
         consume_chain<true>(cx, dg.n_sym, g, 0, np, isyms + (size_t)clr * sym_cap,
-                            items + (size_t)chain * dg.items_per_chain * 128, flags + (size_t)chain * dg.items_per_chain,
-                            blob + suboff[e], sublen[e], lane);
+                            items + (size_t)chain * dg.items_per_chain * kItemU4, flags + (size_t)chain * dg.items_per_chain,
+                            blob + suboff[e], sublen[e], lane, li_buf);
         return;
     }
     if (producer_id < 0) return;       // on a consumer SM without a ticket
@@ -639,7 +696,7 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
             const int img = (int)(w - (uint32_t)tb * (uint32_t)n);
             const int ch = img * 3 + clr;
             const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
-            uint4 *item = items + ((size_t)ch * dg.items_per_chain + tb) * 128;
+            uint4 *item = items + ((size_t)ch * dg.items_per_chain + tb) * kItemU4;
             produce_item<true>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
                                g, 0, tb, np, item, stage, lane);
             // every lane's stores happen before the flag store: warp barrier, then a cumulative fence
@@ -676,12 +733,15 @@ struct WaveArgs { WaveBand b[3]; };
 // single-kernel form.  The producer grid is sized to leave room for the consumer CTAs on every SM
 // (see launch_decode_scale_wave), so the consumers are resident whichever kernel starts first, and a
 // producer only holds a ticket while it runs: the earliest unfinished item can always complete.
-__global__ void __launch_bounds__(128)
+constexpr int kWaveChainsMax = 12;       // chains (warps) per consumer CTA, at most
+
+__global__ void __launch_bounds__(32 * kWaveChainsMax)
 wave_consume_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsProfile np, size_t sym_cap, uint32_t *ctl,
                     const uint8_t *__restrict__ blob, const uint64_t *__restrict__ suboff,
                     const uint32_t *__restrict__ sublen, int total_sub, int n, ChainState *states) {
-    // four chains per CTA, one per scheduler; the CTA claims its SM: producer CTAs that share it leave, so
-    // that nothing competes with the serial chains for issue slots and L1
+    // blockDim.x / 32 chains per CTA, spread over the four schedulers; the CTA claims its SM: producer CTAs
+    // that share it leave, so that nothing competes with the serial chains for issue slots and L1
+    __shared__ __align__(16) int li_buf[kWaveChainsMax][kLiBuf];
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         uint32_t smid;
@@ -693,7 +753,7 @@ wave_consume_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
 #pragma unroll
     for (int b = 0; b < 3; ++b)
         if (wa.b[b].it1 > wa.b[b].it0) act[n_act++] = b;
-    const int chain = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (chain >= 3 * n * n_act) return;
     const int slot = chain / (3 * n), rem = chain - slot * 3 * n;
     const int band = slot == 0 ? act[0] : slot == 1 ? act[1] : act[2];
@@ -707,14 +767,14 @@ wave_consume_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
     const ChainCtx cx = {wb.params + (size_t)img * kParamCh * P, isyms, sym_cap, P, dg.crop_w, dg.Ws, clr, lo[0], lo[1], 1};
     const size_t e = (size_t)img * total_sub + dg.sub_first[clr];
     const size_t ch = (size_t)img * 3 + clr;
-    consume_chain<true>(cx, dg.n_sym, g, 0, np, isyms + (size_t)clr * sym_cap, wb.items + ch * dg.items_per_chain * 128,
-                        wb.flags + ch * dg.items_per_chain, blob + suboff[e], sublen[e], lane, wb.it0, wb.it1,
+    consume_chain<true>(cx, dg.n_sym, g, 0, np, isyms + (size_t)clr * sym_cap, wb.items + ch * dg.items_per_chain * kItemU4,
+                        wb.flags + ch * dg.items_per_chain, blob + suboff[e], sublen[e], lane, li_buf[threadIdx.x >> 5], wb.it0, wb.it1,
                         states + ((size_t)img * 3 + band) * 3 + clr);
 }
 
 __global__ void __launch_bounds__(128, 8)
 wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsProfile np, size_t sym_cap, uint32_t *ctl, int n,
-                    int safe_ctas, int consumer_ctas) {
+                    int safe_ctas, int consumer_ctas, int share, int pattern) {
     __shared__ __align__(16) uint16_t stage[4][kStageU16];
     __shared__ uint32_t started;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -735,37 +795,42 @@ wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     const uint32_t *claimed = &ctl[256 + (smid & 255u)];      // set by a consumer CTA running on this SM
-    // nine ticket queues (band, channel), each in (step block, image) order; a producer warp starts in the
-    // Y : Co : Cg = 1 : 2 : 2 pattern of one active band and then walks all queues
-    const int producer_id = blockIdx.x * 4 + wib;
-    const int r = producer_id % (5 * n_act);
-    const int slot0 = r / 5, r5 = r - 5 * slot0;
-    const int q0 = (slot0 == 0 ? act[0] : slot0 == 1 ? act[1] : act[2]) * 3 + (r5 == 0 ? 0 : r5 <= 2 ? 1 : 2);
-    for (int c = 0; c < 9; ++c) {
-        const int q = (q0 + c) % 9, band = q / 3, clr = q - 3 * band;
-        const WaveBand &wb = band == 0 ? wa.b[0] : band == 1 ? wa.b[1] : wa.b[2];
-        if (wb.it1 <= wb.it0) continue;
-        const DecodeGeom dg = wb.dg;
-        const size_t P = (size_t)dg.Hs * dg.Ws;
-        const uint32_t total = (uint32_t)(wb.it1 - wb.it0) * (uint32_t)n;
-        for (;;) {
-            if (ld_relaxed_u32(claimed) != 0u) return;          // leave the SM to the consumers (no ticket is held here)
-            uint32_t w = 0;
-            if (lane == 0) w = atomicAdd(&ctl[514 + q], 1u);
-            w = __shfl_sync(kFull, w, 0);
-            if (w >= total) break;
-            const int tb = wb.it0 + (int)(w / (uint32_t)n);
-            const int img = (int)(w % (uint32_t)n);
-            const size_t ch = (size_t)img * 3 + clr;
-            const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
-            uint4 *item = wb.items + (ch * dg.items_per_chain + tb) * 128;
-            produce_item<true>(wb.params + (size_t)img * kParamCh * P, wb.syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr,
-                               lo, g, 0, tb, np, item, stage[wib], lane);
-            // every lane's stores happen before the flag store: warp barrier, then a cumulative fence
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                st_release_u32(wb.flags + ch * dg.items_per_chain + tb, 1u);
+    // Nine ticket queues (band, channel), each in (step block, image) order.  A producer warp starts in the
+    // Y : Co : Cg = a : b : c pattern (pattern = 100 a + 10 b + c, default 1 : 2 : 2) of one active band and then walks
+    // all nine queues; a drawn ticket is produced as soon as the symbols it needs arrive.  (Measured alternatives
+    // that changed nothing on c1: other patterns, earliest-needed-first drawing of ready tickets only, producers
+    // sharing the consumers' SMs -- the step is bound by the Y -> Co -> Cg hand-over latency, not by capacity.)
+    {
+        const int pa = pattern / 100, pb = pattern / 10 % 10, pc = pattern % 10, pt = pa + pb + pc;
+        const int producer_id = blockIdx.x * 4 + wib;
+        const int r = producer_id % (pt * n_act);
+        const int slot0 = r / pt, r5 = r - pt * slot0;
+        const int q0 = (slot0 == 0 ? act[0] : slot0 == 1 ? act[1] : act[2]) * 3 + (r5 < pa ? 0 : r5 < pa + pb ? 1 : 2);
+        for (int c = 0; c < 9; ++c) {
+            const int q = (q0 + c) % 9, band = q / 3, clr = q - 3 * band;
+            const WaveBand &wb = band == 0 ? wa.b[0] : band == 1 ? wa.b[1] : wa.b[2];
+            if (wb.it1 <= wb.it0) continue;
+            const DecodeGeom dg = wb.dg;
+            const size_t P = (size_t)dg.Hs * dg.Ws;
+            const uint32_t total = (uint32_t)(wb.it1 - wb.it0) * (uint32_t)n;
+            for (;;) {
+                if (!share && ld_relaxed_u32(claimed) != 0u) return;          // leave the SM to the consumers (no ticket is held here)
+                uint32_t w = 0;
+                if (lane == 0) w = atomicAdd(&ctl[514 + q], 1u);
+                w = __shfl_sync(kFull, w, 0);
+                if (w >= total) break;
+                const int tb = wb.it0 + (int)(w / (uint32_t)n);
+                const int img = (int)(w % (uint32_t)n);
+                const size_t ch = (size_t)img * 3 + clr;
+                const CdfGrid g = band_grids(minmax + img * 4, clr, lo);
+                uint4 *item = wb.items + (ch * dg.items_per_chain + tb) * kItemU4;
+                produce_item<true>(wb.params + (size_t)img * kParamCh * P, wb.syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr,
+                                   lo, g, 0, tb, np, item, stage[wib], lane);
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    st_release_u32(wb.flags + ch * dg.items_per_chain + tb, 1u);
+                }
             }
         }
     }
@@ -858,7 +923,9 @@ static DecodeGeom make_decode_geom(const Plan &p, int scale, int band) {
     return dg;
 }
 
-// Window items (2 KB each) one image needs for its largest band.
+size_t decode_item_bytes() { return (size_t)kItemU4 * sizeof(uint4); }
+
+// Window items one image needs for its largest band.
 int64_t decode_flag_words(int64_t items_cap) { return items_cap + kCtlWords; }
 
 int64_t decode_items_per_image(const Plan &p) {
@@ -1025,12 +1092,18 @@ int wave_bands_in_workspace(const llicti_config &cfg, int max_images) {
 
 int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t *planes, const int32_t *minmax, int n,
                              const uint8_t *blob, const uint64_t *suboff, const uint32_t *sublen, cudaStream_t st) {
-    static int sm_count = 0, prod_resident = 0;
+    static int sm_count = 0, prod_resident = 0, regs_per_sm = 0, cons_regs = 0, prod_regs = 0;
     if (!sm_count) {
         int dev = 0;
         LLICTI_CUDA(cudaGetDevice(&dev));
         LLICTI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        LLICTI_CUDA(cudaDeviceGetAttribute(&regs_per_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
         LLICTI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&prod_resident, wave_produce_kernel, 128, 0));
+        cudaFuncAttributes fa;
+        LLICTI_CUDA(cudaFuncGetAttributes(&fa, wave_consume_kernel));
+        cons_regs = (fa.numRegs + 7) / 8 * 8;
+        LLICTI_CUDA(cudaFuncGetAttributes(&fa, wave_produce_kernel));
+        prod_regs = (fa.numRegs + 7) / 8 * 8;
     }
     LLICTI_REQUIRE(ctx->side_stream && ctx->ev_fork && ctx->ev_join, "wavefront decode: no side stream");
     cudaStream_t side = (cudaStream_t)ctx->side_stream;
@@ -1052,7 +1125,7 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
                        "wavefront decode: workspace too small");
         params[b] = ctx->d_params + (size_t)b * nws * kParamCh * P0;
         syms[b] = ctx->d_syms + (size_t)b * nws * 3 * sym_cap;
-        items[b] = reinterpret_cast<uint4 *>(ctx->d_items) + (size_t)b * items_band * 128;
+        items[b] = reinterpret_cast<uint4 *>(ctx->d_items) + (size_t)b * items_band * kItemU4;
         flags[b] = ctx->d_item_flags + kCtlWords + (size_t)b * items_band;
     }
     // sentinels over the symbol arrays (data = flag), zeros over the item flags of the three bands
@@ -1062,9 +1135,16 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
     // producer CTAs (4 warps, 64 registers = 8 K registers each): `safe` per SM leave room for a consumer CTA (4 warps x
     // ~160 registers = 20 K registers) whichever kernel starts first; the CTAs beyond them stay only when the consumers
     // are already running (wave_produce_kernel)
-    const int safe_per_sm = std::max(prod_resident - 3, 1);
+    // chains per consumer CTA: one per scheduler is fastest (measured on c1, decode kernels per batch: 4 per CTA 31.0 ms,
+    // 6: 33.2 ms, 8: 33.7 ms, 10: 36.7 ms -- a second chain on a scheduler slows both more than the freed SMs help)
+    const int cpc = std::min(std::max(env_int("LLICTI_WAVE_CHAINS_PER_CTA", 4), 1), kWaveChainsMax);
+    const int consumer_ctas = (9 * n + cpc - 1) / cpc;
+    LLICTI_REQUIRE(consumer_ctas <= sm_count, "wavefront decode: more consumer CTAs than SMs");
+    const int room = (regs_per_sm - cpc * 32 * cons_regs) / (128 * prod_regs);     // producer CTAs next to a consumer CTA (registers)
+    const int room_thr = (2048 - cpc * 32) / 128;
+    const int safe_per_sm = std::max(std::min(std::min(room, room_thr), prod_resident), 0);
+    LLICTI_REQUIRE(safe_per_sm >= 1, "wavefront decode: no room for producers next to a consumer CTA");
     const int prod_per_sm = std::min(std::max(env_int("LLICTI_WAVE_PRODUCER_CTAS_PER_SM", prod_resident - 1), 1), std::max(prod_resident, 1));
-    const int consumer_ctas = (9 * n + 3) / 4;
     // Strip k of band b covers rows [row_of(b, k), row_of(b, k+1)): the strips of band b+1 end three rows before
     // those of band b.  The CNN of band b+1 reads band b up to two rows below the row it evaluates, and a strip is
     // decoded in whole 32-symbol items (up to one row short of its last row), so strip k of band b+1 depends on
@@ -1103,14 +1183,15 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
             // fork: consumers on the caller's stream (they start first), producers on the side stream; join before the scatter
             LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_fork, st));
             LLICTI_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)ctx->ev_fork, 0));
-            wave_consume_kernel<<<consumer_ctas, 128, 0, st>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, blob, suboff,
+            wave_consume_kernel<<<consumer_ctas, 32 * cpc, 0, st>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, blob, suboff,
                                                               sublen, total_sub, n,
                                                               reinterpret_cast<ChainState *>(ctx->d_chain_state_raw));
             wave_produce_kernel<<<sm_count * prod_per_sm, 128, 0, side>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, n,
-                                                                         sm_count * std::min(safe_per_sm, prod_per_sm), consumer_ctas);
+                                                                         sm_count * std::min(safe_per_sm, prod_per_sm), consumer_ctas, env_int("LLICTI_WAVE_SHARE_SMS", 0), std::max(env_int("LLICTI_WAVE_PATTERN", 122), 1));
             LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_join, side));
             LLICTI_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
             ctx->launches += 2;
+            if (env_int("LLICTI_WAVE_DEBUG", 0)) wave_dbg_kernel<<<1, 1, 0, st>>>(T, 9 * n);
         }
         for (int b = 0; b < 3; ++b) {
             if (wa.b[b].it1 <= wa.b[b].it0) continue;
