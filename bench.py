@@ -31,6 +31,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ENCODE_ONLY = bool(os.environ.get("LLICTI_BENCH_ENCODE_ONLY"))   # debugging aid: time the encoder alone
+
 WORKLOADS = {
     # name: (description, config, per-GPU images, H, W, sub_len)
     "c1": ("configs[1]: llicti_B eval_model, 24 synthetic 768x512 RGB images, torchac-compatible streams",
@@ -233,12 +235,18 @@ def run_b200(args, rank, world, local_rank):
         flush.zero_()                      # decode starts cold as well (outside both timed spans)
         ev2 = torch.cuda.Event(enable_timing=True)
         ev2.record()
+        if ENCODE_ONLY:                    # kernel experiments whose streams are not decodable (tools/)
+            ev[2].record()
+            torch.cuda.synchronize()
+            return ev[0].elapsed_time(ev[1]), 1e-3, blob, off, rgb_d
         rec_out[0] = rec = codec.decode_dev(blob, off, mm, x00_d, n_img, H, W, rec_out[0])
         ev[2].record()
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[1]), ev2.elapsed_time(ev[2]), blob, off, rec
 
     def host_step():
+        if ENCODE_ONLY:
+            return 1e-3, 1e-3, 0, 0, None, rgb_np
         flush.zero_()
         torch.cuda.synchronize()
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))

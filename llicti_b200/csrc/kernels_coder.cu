@@ -7,6 +7,8 @@
 // and ships them to a single CPU thread; here nothing but 4 bytes per symbol (encode) or
 // the 60 network outputs per position (decode) ever leave the chip's caches.
 #include "common.cuh"
+
+#include <cstdlib>
 #include "gmm.cuh"
 #include "rangecoder.cuh"
 
@@ -196,11 +198,17 @@ struct WarpEncoder {
 
     // 32 (or fewer) symbols: bounds in `cur` (one per lane), m valid.
     __device__ __forceinline__ void encode_block(uint32_t cur, int m) {
-        // ---- phase A: the interval recurrence, nothing else (lane s keeps (nl, nh) of step s) ----
+        uint32_t rec_nl, rec_nh;
+        recur_block(cur, m, rec_nl, rec_nh);
+        emit_block(rec_nl, rec_nh, m);
+    }
+
+    // ---- phase A: the interval recurrence, nothing else (lane s keeps (nl, nh) of step s); uses low / high only ----
+    __device__ __forceinline__ void recur_block(uint32_t cur, int m, uint32_t &rec_nl, uint32_t &rec_nh) {
         // 32-bit arithmetic: (span * c) >> 16 is the high word of span * (c << 16) for span < 2^32; the full range
         // (span = 2^32, seen as 0) gives c << 16 itself, and c_high = 2^16 (c << 16 seen as 0) gives span.
         const uint32_t my_cl16 = cur << 16, my_ch16 = ((cur >> 16) + 1u) << 16;   // bounds unpacked in parallel, off the chain
-        uint32_t rec_nl = 0, rec_nh = 0xFFFFFFFFu;
+        rec_nl = 0; rec_nh = 0xFFFFFFFFu;
         auto step = [&](int s, uint32_t cl16, uint32_t ch16) {
             const uint32_t span = high - low + 1u;
             const bool full = span == 0u;
@@ -235,6 +243,10 @@ struct WarpEncoder {
 #pragma unroll 1
             for (int s = 0; s < m; ++s) step(s, __shfl_sync(0xffffffffu, my_cl16, s), __shfl_sync(0xffffffffu, my_ch16, s));
         }
+    }
+
+    // ---- phase B: bit output of the 32 steps in parallel; uses pending and the staging buffer only ----
+    __device__ __forceinline__ void emit_block(uint32_t rec_nl, uint32_t rec_nh, int m) {
         // per-step record, derived in parallel: the n bits shifted out, n, the underflow count k
         int rec_n = 0, rec_k = 0;
         uint32_t rec_bits = 0;
@@ -244,7 +256,6 @@ struct WarpEncoder {
             rec_k = __clz(d & ~((rec_nl & ~rec_nh) << 1)) - rec_n;
             rec_bits = __funnelshift_l(rec_nl, 0u, rec_n);
         }
-        // ---- phase B: bit output of the 32 steps in parallel ----
         int kx = rec_k;                                                   // inclusive scan of k
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, kx, o); if (lane >= o) kx += y; }
@@ -336,6 +347,67 @@ encode_all_warp_kernel(const StreamDesc *__restrict__ sd_g, int n_streams, int t
     enc.init(scratch + (size_t)img * scratch_stride + d.slot_off + (size_t)j * d.slot_bytes, (uint32_t)d.slot_bytes,
              stage[threadIdx.x >> 5], lane);
     encode_strided_warp(enc, b, j, d.n_sym, d.S);
+    const uint32_t nb = enc.finish();
+    if (lane == 0) {
+        sublen[(size_t)img * total_sub + item] = nb;
+        if (enc.overflow) atomicExch(status, LLICTI_E_NOMEM);
+    }
+}
+
+// Two warps per chain: warp A runs the recurrence of block k + 1 while warp B packs the bits of block k.  The
+// per-step records (nl, nh) travel through a double buffer in shared memory, handed over with named barriers
+// (bar.arrive by the writer, bar.sync by the reader; 64 = both warps).  Two chains per 128-thread CTA:
+// warps 0, 1 recur, warps 2, 3 pack; barriers 1 + 4 pair + {0, 1} = full[buf], + {2, 3} = empty[buf].
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(128)
+encode_all_pair_kernel(const StreamDesc *__restrict__ sd_g, int n_streams, int total_sub,
+                       const uint32_t *__restrict__ bounds, int64_t sym_stride, uint8_t *__restrict__ scratch,
+                       int64_t scratch_stride, uint32_t *__restrict__ sublen, int32_t *__restrict__ status) {
+    __shared__ StreamDesc sd[kMaxStreams];
+    __shared__ uint32_t stage[2][kStageWords + 2];
+    __shared__ uint2 rec[2][2][32];           // [pair][buffer][step]
+    __shared__ uint32_t final_low[2];
+    for (int e = threadIdx.x; e < n_streams; e += blockDim.x) sd[e] = sd_g[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = warp & 1, packer = warp >> 1;
+    const int item = blockIdx.x * 2 + pair;
+    const int img = blockIdx.y;
+    if (item >= total_sub) return;            // both warps of the pair leave
+    const int k = find_stream(sd, n_streams, item);
+    const StreamDesc &d = sd[k];
+    const int j = item - d.sub_first;
+    const int n_steps = (d.n_sym - j + d.S - 1) / d.S;
+    const int n_blocks = (n_steps + 31) >> 5;
+    const int bar0 = 1 + 4 * pair;
+    WarpEncoder enc;
+    enc.init(scratch + (size_t)img * scratch_stride + d.slot_off + (size_t)j * d.slot_bytes, (uint32_t)d.slot_bytes,
+             stage[pair], lane);
+    if (!packer) {
+        const uint32_t *b = bounds + (size_t)img * sym_stride + d.sym_off;
+        uint32_t cur = lane < n_steps ? b[(size_t)j + (size_t)lane * d.S] : 0u;
+        for (int kb = 0; kb < n_blocks; ++kb) {
+            const int t1 = kb * 32 + 32 + lane;
+            const uint32_t nxt = t1 < n_steps ? b[(size_t)j + (size_t)t1 * d.S] : 0u;   // a block ahead of the coder
+            uint32_t nl, nh;
+            enc.recur_block(cur, min(32, n_steps - kb * 32), nl, nh);
+            if (kb >= 2) pair_sync(bar0 + 2 + (kb & 1));          // the packer has read block kb - 2 out of this buffer
+            rec[pair][kb & 1][lane] = make_uint2(nl, nh);
+            if (kb == n_blocks - 1 && lane == 0) final_low[pair] = enc.low;
+            pair_arrive(bar0 + (kb & 1));
+            cur = nxt;
+        }
+        return;
+    }
+    for (int kb = 0; kb < n_blocks; ++kb) {
+        pair_sync(bar0 + (kb & 1));
+        const uint2 r = rec[pair][kb & 1][lane];
+        if (kb == n_blocks - 1) enc.low = final_low[pair];
+        if (kb + 2 < n_blocks) pair_arrive(bar0 + 2 + (kb & 1));
+        enc.emit_block(r.x, r.y, min(32, n_steps - kb * 32));
+    }
     const uint32_t nb = enc.finish();
     if (lane == 0) {
         sublen[(size_t)img * total_sub + item] = nb;
@@ -692,9 +764,15 @@ int launch_encode_all(llicti_ctx *ctx, const Plan &p, const uint32_t *bounds, in
     ProfScope prof_(ctx, KC_ENCODE, st);
     const int total_sub = (int)p.g.substreams;
     if ((long long)total_sub * n <= kWarpChainLimit) {      // few, long chains: one warp each
-        dim3 grid((total_sub + 3) / 4, n);
-        encode_all_warp_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
-                                                     scratch_stride, sublen, ctx->d_status);
+        if (getenv("LLICTI_ENC_SINGLE_WARP")) {                 // A/B: one warp does both phases
+            dim3 grid((total_sub + 3) / 4, n);
+            encode_all_warp_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
+                                                         scratch_stride, sublen, ctx->d_status);
+        } else {
+            dim3 grid((total_sub + 1) / 2, n);
+            encode_all_pair_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
+                                                         scratch_stride, sublen, ctx->d_status);
+        }
     } else {
         dim3 grid((total_sub + 127) / 128, n);
         encode_all_kernel<<<grid, 128, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, bounds, sym_stride, scratch,
