@@ -33,6 +33,10 @@
 
 namespace llicti {
 
+#ifndef LLICTI_WAIT_SLEEP
+#define LLICTI_WAIT_SLEEP 0      // ns a consumer sleeps between two looks at an item flag (it has its scheduler to itself)
+#endif
+
 __device__ unsigned long long g_decode_stats[8];   // 0 slow-path symbols, 1 consumer flag polls, 2 longest consumer run (cycles), 3 chunks redone carefully,
                                                    // 4 cycles consumers waited for items, 5 consumer cycles, 6 consumer runs, 7 cycles in redone chunks (piped schedules)
 
@@ -100,9 +104,9 @@ __device__ __forceinline__ void wait_flag(const uint32_t *flag, unsigned long lo
     if (ld_relaxed_u32(flag) != 0u) return;
     const long long t0 = clock64();
     for (uint32_t spins = 0; ld_relaxed_u32(flag) == 0u; ++spins) {
-        if (spins > kMaxPolls) __trap();
+        if (spins > kMaxPolls * 4u) __trap();
         ++polls;
-        __nanosleep(100);
+        if (LLICTI_WAIT_SLEEP) __nanosleep(LLICTI_WAIT_SLEEP);
     }
     waited += clock64() - t0;
 }
@@ -194,7 +198,7 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
 __device__ __noinline__ uint64_t slow_symbol(const float *__restrict__ pp, const int16_t *syms, size_t sym_cap, size_t P,
                                              int crop_w, int Ws, long long i, int clr, int lo0, int lo1, CdfGrid g,
                                              NumericsProfile np, uint32_t low, uint32_t high, uint32_t value, int lane,
-                                             int pipe) {
+                                             int pipe, int first_base) {
     if (lane == 0) atomicAdd(&g_decode_stats[0], 1ull);
     const int r = (int)(i / crop_w), c = (int)(i - (long long)r * crop_w);
     const size_t pidx = (size_t)r * Ws + c;
@@ -209,7 +213,7 @@ __device__ __noinline__ uint64_t slow_symbol(const float *__restrict__ pp, const
     const uint64_t num = (((uint64_t)value - (uint64_t)low + 1ull) << 16) - 1ull;
     const uint32_t target = (uint32_t)(num / span) & 0xFFFFu;
     uint32_t c_low, c_high;
-    const int sym = warp_search(ch, g, target, np, lane, c_low, c_high);
+    const int sym = warp_search(ch, g, target, np, lane, c_low, c_high, first_base);
     return (uint64_t)c_low | ((uint64_t)(c_high - 1u) << 16) | ((uint64_t)(uint32_t)sym << 32);
 }
 
@@ -392,7 +396,8 @@ __device__ __forceinline__ int decode_step_careful(ChainCoder &cc, uint32_t slot
     int sym, sh;
     if ((li >> 31) != 0u || cc.value > nh_sel) {
         const uint64_t pk = slow_symbol(cx.pp, cx.syms, cx.sym_cap, cx.P, cx.crop_w, cx.Ws, i, cx.clr, cx.lo0, cx.lo1, g, np,
-                                        cc.low, cc.high, cc.value, lane, kPipe ? 1 : 0);
+                                        cc.low, cc.high, cc.value, lane, kPipe ? 1 : 0,
+                                        (li >> 31) != 0u ? max(base - 31, 0) : base + kWin);   // right below / above the window that missed
         const NextState s2 = next_state(cc.low, cc.high, cc.value, cc.b0, (uint32_t)pk & 0xFFFFu,
                                         (((uint32_t)pk >> 16) & 0xFFFFu) + 1u);
         cc.low = s2.low; cc.high = s2.high; cc.value = s2.value; sh = s2.sh;

@@ -55,15 +55,23 @@ __device__ __forceinline__ void warp_channel(const WarpParams &wp, int clr, int 
 // Largest m in [0, Lp-2] with q(m) <= target, found by rounds of 32 parallel probes: first a
 // unit-stride window around the predicted value, then (rarely) a coarse round over what is left
 // of [0, Lp-1] and a final unit-stride round.  Entry Lp-1 acts as the 0x10000 sentinel.
+// `first_base` >= 0 overrides the first window (the decode slow path knows on which side of the
+// predicted window the symbol lies and starts right next to it).
 __device__ __forceinline__ int warp_search(const GmmChannel &c, const CdfGrid &g, uint32_t target,
-                                           const NumericsProfile &np, int lane, uint32_t &c_low, uint32_t &c_high) {
+                                           const NumericsProfile &np, int lane, uint32_t &c_low, uint32_t &c_high,
+                                           int first_base = -1) {
     const int last = g.Lp - 1;
-    float mean = 0.f;
-#pragma unroll
-    for (int m = 0; m < kM; ++m) mean = fmaf(c.w[m], c.mu[m], mean);
-    const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
     int lo = 0, hi = last;
-    int base = min(max(kc - 15, 0), max(last - 31, 0));
+    int base;
+    if (first_base >= 0) {
+        base = min(first_base, max(last - 31, 0));
+    } else {
+        float mean = 0.f;
+#pragma unroll
+        for (int m = 0; m < kM; ++m) mean = fmaf(c.w[m], c.mu[m], mean);
+        const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
+        base = min(max(kc - 15, 0), max(last - 31, 0));
+    }
     int stride = 1;
     for (;;) {
         const int k = base + lane * stride;
