@@ -42,7 +42,28 @@ EDGE_IMAGES = {
     "noise_32x64": lambda: np.random.default_rng(4).integers(0, 256, size=(3, 32, 64), dtype=np.uint8),
     "checker_35x32": lambda: np.stack([(((np.add.outer(np.arange(35), np.arange(32))) & 1) * 255).astype(np.uint8)] * 3),
     "tiny_17x17": lambda: O.synthetic_image(17, 17, 5),
+    # chroma alphabets below the 31 symbols of a decode window (Co, Cg ranges of a few levels)
+    "lowchroma_48x80": lambda: _low_chroma(48, 80),
+    # windows clamped to both ends of the alphabet: large saturated black and white areas with a little noise
+    "saturated_64x64": lambda: _saturated(64, 64),
+    "gray_40x56": lambda: np.repeat(O.synthetic_image(40, 56, 6)[1:2], 3, axis=0),
 }
+
+
+def _low_chroma(H, W):
+    y = O.synthetic_image(H, W, 8)[0].astype(np.int16)
+    rng = np.random.default_rng(8)
+    img = np.stack([y + rng.integers(-2, 3, size=y.shape), y, y + rng.integers(-3, 4, size=y.shape)])
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def _saturated(H, W):
+    rng = np.random.default_rng(9)
+    img = np.zeros((3, H, W), np.int16)
+    img[:, :, W // 2:] = 255
+    img[:, H // 3:H // 2, :] = 128
+    img += rng.integers(-1, 2, size=img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
 
 
 # ---------------------------------------------------------------------------- stage K1-K3, K12
