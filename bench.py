@@ -274,7 +274,6 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     clocks.start()
     launches0 = codec.launches
-    codec.profile(True)
     codec.decode_stats()
     t_enc = t_dec = 0.0
     for _ in range(args.steps):
@@ -282,10 +281,21 @@ def run_b200(args, rank, world, local_rank):
         t_enc += a
         t_dec += b
     barrier()
-    prof = codec.profile_read()
-    codec.profile(False)
     dstats = codec.decode_stats()
     launches = codec.launches - launches0
+
+    # ---- the same K steps once more with the library's per-kernel-class events (they need eager launches: the decode
+    #      of the timed region above is replayed as one CUDA graph) ----------------------------------------------
+    codec.profile(True)
+    p_enc = p_dec = 0.0
+    for _ in range(args.steps):
+        a, b, *_ = dev_step(True)
+        p_enc += a
+        p_dec += b
+    prof = codec.profile_read()
+    codec.profile(False)
+    codec.decode_stats()
+    barrier()
 
     # ---- timed region: end to end through host buffers ------------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
@@ -343,7 +353,7 @@ def run_b200(args, rank, world, local_rank):
         t = traffic_db.get(cls)      # dram bytes of one captured launch (ncu --set full), scaled by work units to the average launch
         r["traffic"] = (t["dram_bytes"] / t["units"] * (n_img * t["units_per_image_step"] / groups)) if t else None
         r.update({"kernel": cls, "launch_groups_per_step": groups, "ms_per_launch_group": ms,
-                  "share_of_step": kernel_ms[cls] / ((t_enc + t_dec) / K)})
+                  "share_of_step": kernel_ms[cls] / ((p_enc + p_dec) / K)})
         if t:
             r["traffic_source"] = t["source"]
         return r
@@ -359,9 +369,9 @@ def run_b200(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         sh, sw = (H, W) if H * W <= 768 * 512 else (512, 768)
-        r = cpu_oracle_pass(cfg, sh, sw, 1, 0)
+        r = cpu_oracle_pass(cfg, sh, sw, 4, 0)      # ~15-20 s of CPU work
         cpu = {"value": r["value"], "unit": "MP/s", "cores": r["cores"], "kind": "port",
-               "sample": f"1 synthetic {sw}x{sh} image, compress+decompres once, {r['cores']} torch threads",
+               "sample": f"4 synthetic {sw}x{sh} images, compress+decompres of each once, {r['cores']} torch threads",
                "encode_mpps": r["encode_mpps"], "decode_mpps": r["decode_mpps"]}
 
     line = {
@@ -378,6 +388,9 @@ def run_b200(args, rank, world, local_rank):
         "encode_ms_per_step": t_enc / K, "decode_ms_per_step": t_dec / K,
         "bpsp": bytes_total * 8 / (px_total * 3), "compressed_bytes_per_step": bytes_total,
         "roofline": roof, "rooflines_all_kernels": rooflines, "kernel_ms_per_step": kernel_ms, "cnn_tflops": cnn_tflops,
+        "kernel_profile_pass": {"note": "per-kernel-class CUDA events (llicti_profile) over a second pass of the same K steps "
+                                        "right after the timed region; the timed region replays the decode as one CUDA graph",
+                                "encode_ms_per_step": p_enc / K, "decode_ms_per_step": p_dec / K},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                 "encode_mpps": mp * K / (h_enc / 1e3), "decode_mpps": mp * K / (h_dec / 1e3),

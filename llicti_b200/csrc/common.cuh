@@ -127,6 +127,14 @@ struct llicti_ctx {
     bool concurrent_kernels = false;   // two kernels on two streams really overlap (false under kernel-serialising profilers)
     bool wave_ws = false;              // workspace holds three bands' worth of decode buffers (wavefront schedule)
     uint32_t *d_item_flags = nullptr;  // [items_cap] readiness flags of the piped decode schedule
+
+    // llicti_decode_dev as a CUDA graph: the launch sequence of a decode is fixed by its arguments, so the second
+    // call with the same arguments captures it and later calls replay it with one launch (api.cu)
+    void *dec_capture_stream = nullptr, *dec_graph_exec = nullptr;
+    const void *dec_key_ptr[5] = {};
+    long long dec_key_dim[4] = {};
+    bool dec_key_seen = false;
+    int64_t dec_graph_launches = 0;
     int32_t *d_status = nullptr;       // device-side error flag
 };
 
