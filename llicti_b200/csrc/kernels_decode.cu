@@ -486,16 +486,29 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
                 cc.low = s_low; cc.high = s_high; cc.value = s_value;      // cc.pos is only advanced below
                 ++redone;
                 const long long t_redo = kPipe ? clock64() : 0;
+                // step by step over one window of stream bits: the fast step, validated at once; only the step that
+                // fails is repeated carefully (cc.pos moves to that step first, the window is rebuilt after it)
+                cc.load_window();
 #pragma unroll 1
                 for (int e = 0; e < 8; ++e) {
-                    const int base = __shfl_sync(kFull, base_cur, 8 * v + e);
-                    const int sy = decode_step_careful<kPipe>(cc, chunk_entry(q, e), base, vmask, i + (long long)(8 * v + e) * S, cx, g, np, lane);
-                    li_buf[8 * v + e] = (int)(((uint32_t)(sy - base) & 0xFFFu) << 8);
+                    const uint32_t r_low = cc.low, r_high = cc.high, r_value = cc.value, r0 = cc.b0, r1 = cc.b1, r2 = cc.b2, r3 = cc.b3;
+                    const int r_avail = cc.avail;
+                    uint32_t bad1 = 0;
+                    const uint32_t wfast = decode_step_fast(cc, chunk_entry_hi(q, e), vmask, bad1);
+                    if (bad1 == 0u) {
+                        li_buf[8 * v + e] = (int)wfast;
+                    } else {
+                        cc.low = r_low; cc.high = r_high; cc.value = r_value; cc.b0 = r0; cc.b1 = r1; cc.b2 = r2; cc.b3 = r3;
+                        cc.pos += (uint32_t)(128 - r_avail);
+                        const int base = __shfl_sync(kFull, base_cur, 8 * v + e);
+                        const int sy = decode_step_careful<kPipe>(cc, chunk_entry(q, e), base, vmask, i + (long long)(8 * v + e) * S, cx, g, np, lane);
+                        li_buf[8 * v + e] = (int)(((uint32_t)(sy - base) & 0xFFFu) << 8);
+                        cc.load_window();
+                    }
                 }
                 if (kPipe) redo_cycles += clock64() - t_redo;
-            } else {
-                cc.pos += (uint32_t)(128 - cc.avail);
             }
+            cc.pos += (uint32_t)(128 - cc.avail);
         }
         if (it == n_items_all - 1 && tail) {
             const int v = max(full_here, 0);
