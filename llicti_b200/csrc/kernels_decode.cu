@@ -1019,21 +1019,43 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
                                                                       suboff, sublen, total_sub, n);
         ctx->launches += 1;
     } else {
-        const long long win_warps = (long long)n * dg.S * dg.items_per_chain;
-        const int win_blocks = (int)std::min<long long>((win_warps + 3) / 4, (long long)sm_count * 16);
-        const long long chains = (long long)n * dg.S;
-        const int con_blocks = (int)((chains + 3) / 4);
-        for (int clr = 0; clr < 3; ++clr) {
-            {
-                ProfScope prof_(ctx, KC_WINDOW, st);
-                window_kernel<<<win_blocks, 128, 0, st>>>(params, syms, sym_cap, minmax, dg, clr, ctx->num, items, n);
+        // The window kernel is issue bound (erfc), the chain kernel latency bound: the batch is cut in two halves that
+        // run one kernel out of phase on two streams, so the windows of one half overlap the chains of the other.  (Not
+        // while the per-class profile is on: its events would time overlapping kernels.)
+        const bool halves = n >= 2 && !ctx->prof_on && ctx->side_stream && ctx->ev_fork && ctx->ev_join && !env_int("LLICTI_NO_HALVES", 0);
+        const int n_a = halves ? (n + 1) / 2 : n;
+        const size_t P = (size_t)dg.Hs * dg.Ws;
+        auto run_half = [&](int img0, int cnt, cudaStream_t s, bool fork_after_first) {
+            const long long win_warps = (long long)cnt * dg.S * dg.items_per_chain;
+            const int win_blocks = (int)std::min<long long>((win_warps + 3) / 4, (long long)sm_count * 16);
+            const int con_blocks = (int)(((long long)cnt * dg.S + 3) / 4);
+            const float *pr = params + (size_t)img0 * kParamCh * P;
+            int16_t *sy = syms + (size_t)img0 * 3 * sym_cap;
+            const int32_t *mm = minmax + (size_t)img0 * 4;
+            uint4 *itm = items + (size_t)img0 * 3 * dg.S * dg.items_per_chain * kItemU4;
+            const uint64_t *so = suboff + (size_t)img0 * total_sub;
+            const uint32_t *sl = sublen + (size_t)img0 * total_sub;
+            for (int clr = 0; clr < 3; ++clr) {
+                {
+                    ProfScope prof_(ctx, KC_WINDOW, s);
+                    window_kernel<<<win_blocks, 128, 0, s>>>(pr, sy, sym_cap, mm, dg, clr, ctx->num, itm, cnt);
+                }
+                if (clr == 0 && fork_after_first) {
+                    cudaEventRecord((cudaEvent_t)ctx->ev_fork, s);
+                    cudaStreamWaitEvent((cudaStream_t)ctx->side_stream, (cudaEvent_t)ctx->ev_fork, 0);
+                }
+                {
+                    ProfScope prof_(ctx, KC_DECODE, s);
+                    consume_kernel<<<con_blocks, 128, 0, s>>>(pr, sy, sym_cap, mm, dg, clr, ctx->num, itm, blob, so, sl, total_sub, cnt);
+                }
+                ctx->launches += 2;
             }
-            {
-                ProfScope prof_(ctx, KC_DECODE, st);
-                consume_kernel<<<con_blocks, 128, 0, st>>>(params, syms, sym_cap, minmax, dg, clr, ctx->num, items, blob,
-                                                           suboff, sublen, total_sub, n);
-            }
-            ctx->launches += 2;
+        };
+        run_half(0, n_a, st, halves);
+        if (halves) {
+            run_half(n_a, n - n_a, (cudaStream_t)ctx->side_stream, false);
+            LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_join, (cudaStream_t)ctx->side_stream));
+            LLICTI_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
         }
     }
     {
