@@ -173,7 +173,7 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
         const int k = bs + lane;
         // every lane evaluates an entry (the warp-uniform erfc skip votes over all 32 lanes); lanes at or
         // beyond the alphabet's end evaluate a clamped index and store 0 (= 2^16 mod 2^16)
-        const uint32_t qe = cdf_q<true>(b, g, min(k, last - 1), np);
+        const uint32_t qe = b.fast ? cdf_q<true, true>(b, g, min(k, last - 1), np) : cdf_q<true, false>(b, g, min(k, last - 1), np);
         my[s] = (uint16_t)(k < last ? qe : 0u);
     }
     __syncwarp();
