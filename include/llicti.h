@@ -183,7 +183,10 @@ LLICTI_API int llicti_encode_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n,
  *   blob / stream_off  as produced by encode
  *   minmax             int16 [n][6]
  *   x00_rgb            uint8 [n][3][h_last][w_last] raw coarsest band (:350, :429)
- *   rgb_out            uint8 [n][3][H][W] */
+ *   rgb_out            uint8 [n][3][H][W]
+ * The launch sequence of a decode depends only on its arguments (pointers, n, H, W), not on the stream contents: from
+ * the third consecutive call with the same arguments on it is replayed as one CUDA graph (LLICTI_NO_GRAPH=1 in the
+ * environment keeps every call eager).  Nothing is retained beyond the pointers passed to the call being made. */
 LLICTI_API int llicti_decode_host(llicti_ctx *ctx, const uint8_t *blob, const uint64_t *stream_off,
                        const int16_t *minmax, const uint8_t *x00_rgb, int n, int H, int W,
                        uint8_t *rgb_out, void *stream);
