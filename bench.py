@@ -300,6 +300,25 @@ def run_b200(args, rank, world, local_rank):
     codec.decode_stats()
     barrier()
 
+    # ---- rate of the substream container against the torchac-compatible streams (= the reference's bytes) of the
+    #      same images, untimed, on a few images of the batch ----------------------------------------------------
+    bpp_delta = None
+    if sub_len > 0 and rank == 0 and not ENCODE_ONLY:
+        m = min(n_img, 4)
+        ns = 9 * S
+        compat = Codec(CodecConfig.from_json_dict(cfg, sub_len=0, numerics=L.NUM_TORCH_CUDA, cnn_impl=args.cnn,
+                                                  device=local_rank, decode_impl=args.decode_impl), sd)
+        _, c_off, _ = compat.encode_dev(rgb_d[:m].contiguous())
+        compat_bytes = int(c_off[-1].item())
+        sub_bytes = int(off[m * ns].item()) + 5 * m          # + the container's mode tag in the header row
+        compat.close()
+        del compat
+        torch.cuda.empty_cache()
+        bpp_delta = {"value": (sub_bytes - compat_bytes) / compat_bytes, "images": m, "substream_bytes": sub_bytes,
+                     "torchac_compatible_bytes": compat_bytes,
+                     "note": "(substream container - torchac-compatible streams) / torchac-compatible streams, all "
+                             "length tables and flush bytes counted; the compatible streams are the reference's bytes"}
+
     # ---- timed region: end to end through host buffers ------------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
         host_step()
@@ -390,7 +409,8 @@ def run_b200(args, rank, world, local_rank):
                                   f"{n_img}-image synthetic set (identical work per GPU)"},
         "encode_mpps": mp * K / (t_enc / 1e3), "decode_mpps": mp * K / (t_dec / 1e3),
         "encode_ms_per_step": t_enc / K, "decode_ms_per_step": t_dec / K,
-        "bpsp": bytes_total * 8 / (px_total * 3), "compressed_bytes_per_step": bytes_total,
+        "bpsp": bytes_total * 8 / (px_total * 3), "bpp": bytes_total * 8 / px_total, "bpp_delta_vs_reference_streams": bpp_delta,
+        "compressed_bytes_per_step": bytes_total,
         "roofline": roof, "rooflines_all_kernels": rooflines, "kernel_ms_per_step": kernel_ms, "cnn_tflops": cnn_tflops,
         "kernel_profile_pass": {"note": "per-kernel-class CUDA events (llicti_profile) over a second pass of the same K steps "
                                         "right after the timed region; the timed region replays the decode as one CUDA graph",

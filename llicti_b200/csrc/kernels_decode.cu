@@ -42,10 +42,10 @@ __device__ unsigned long long g_decode_stats[8];   // 0 slow-path symbols, 1 con
 
 __device__ unsigned long long g_wave_dbg[8];   // LLICTI_WAVE_DEBUG: per-launch consumer timing
 __global__ void wave_dbg_kernel(int T, int chains) {
-    printf("[wave] T=%d chains=%d max=%.3f ms avg=%.3f ms wait=%.3f redo=%.3f span=%.3f ms\n", T, chains, g_wave_dbg[0] / 1.965e6, g_wave_dbg[1] / 1.965e6 / chains,
-           g_wave_dbg[2] / 1.965e6 / chains, g_wave_dbg[3] / 1.965e6 / chains, (g_wave_dbg[5] - g_wave_dbg[4]) / 1.965e6);
+    printf("[wave] T=%d chains=%d max=%.3f ms avg=%.3f ms wait=%.3f (Y %.3f Co %.3f Cg %.3f per chain of the channel, first item %.3f) redo=%.3f\n", T, chains,
+           g_wave_dbg[0] / 1.965e6, g_wave_dbg[1] / 1.965e6 / chains, g_wave_dbg[2] / 1.965e6 / chains, g_wave_dbg[4] / 1.965e6 / (chains / 3),
+           g_wave_dbg[5] / 1.965e6 / (chains / 3), g_wave_dbg[6] / 1.965e6 / (chains / 3), g_wave_dbg[7] / 1.965e6 / chains, g_wave_dbg[3] / 1.965e6 / chains);
     for (int i = 0; i < 8; ++i) g_wave_dbg[i] = 0;
-    g_wave_dbg[4] = ~0ull;
 }
 
 constexpr int kStageU16 = 32 * 34 + 32 * 6 * 8;   // per warp: window staging (17-word pitch) + prepared channels of 32 steps
@@ -132,6 +132,21 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
     for (int m = 0; m < kM; ++m) { ch.sigma[m] = 1.f; ch.mu[m] = 0.f; ch.w[m] = 0.2f; ch.rinv[m] = 1.f; }
     ch.fast = 1;
     int base = 0;
+    if (kPipe && clr >= 1) {
+        // Wait for the previous channel's symbols with ONE lane on the item's last symbol (the consumer stores the 32
+        // symbols of an item with one instruction; a Co symbol implies the Y symbols before it).  Thousands of producer
+        // warps wait here at any time: polled by every lane, their loads alone are a large share of the L2 traffic.
+        if (lane == 0) {
+            const long long steps = (dg.n_sym - j + dg.S - 1) / dg.S;
+            const long long i_last = (long long)j + (min((long long)tb * 32 + 31, steps - 1)) * dg.S;
+            const int16_t *p = syms + (size_t)(clr - 1) * sym_cap + i_last;
+            for (uint32_t polls = 0; ld_relaxed_s16(p) == (int)kSentinel; ++polls) {
+                if (polls > kMaxPolls) __trap();
+                __nanosleep(500);
+            }
+        }
+        __syncwarp();
+    }
     if (i < dg.n_sym) {
         const int r = (int)(i / dg.crop_w), c = (int)(i - (long long)r * dg.crop_w);
         const size_t pidx = (size_t)r * dg.Ws + c;
@@ -450,6 +465,7 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
     long long i = j + (long long)it_begin * 32 * S;
 
     if (kPipe) wait_flag(flags + it_begin, polls, waited);
+    const long long first_wait = waited;
     const uint4 *src = items + lane;
     const uint4 *first = src + (size_t)it_begin * kItemU4;
     uint4 q0 = load_chunk<kPipe>(first), q1 = load_chunk<kPipe>(first + 32), q2 = load_chunk<kPipe>(first + 64),
@@ -555,8 +571,8 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
             atomicAdd(&g_wave_dbg[1], (unsigned long long)(clock64() - t_begin));
             atomicAdd(&g_wave_dbg[2], (unsigned long long)waited);
             atomicAdd(&g_wave_dbg[3], (unsigned long long)redo_cycles);
-            atomicMin(&g_wave_dbg[4], (unsigned long long)t_begin);
-            atomicMax(&g_wave_dbg[5], (unsigned long long)clock64());
+            atomicAdd(&g_wave_dbg[4 + min(cx.clr, 2)], (unsigned long long)waited);     // waiting per colour channel
+            atomicAdd(&g_wave_dbg[7], (unsigned long long)first_wait);
             atomicAdd(&g_decode_stats[7], (unsigned long long)redo_cycles);
         }
         if (redone) atomicAdd(&g_decode_stats[3], redone);
@@ -597,17 +613,19 @@ static __device__ __forceinline__ CdfGrid band_grids(const int32_t *mm, int clr,
 __global__ void __launch_bounds__(128)
 window_kernel(const float *__restrict__ params, const int16_t *__restrict__ syms, size_t sym_cap,
               const int32_t *__restrict__ minmax, DecodeGeom dg, int clr, NumericsProfile np, uint4 *__restrict__ items,
-              int n) {
+              int n, int tb0, int ntb, uint32_t *__restrict__ flags) {
+    // items [tb0, tb0 + ntb) of every chain; `flags` (wavefront schedule: the Y windows of a strip, produced ahead of the
+    // consumer / producer pair) = per-item readiness words to set
     __shared__ __align__(16) uint16_t stage[4][kStageU16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long per_img = (long long)dg.S * dg.items_per_chain;
+    const long long per_img = (long long)dg.S * ntb;
     const long long total = per_img * n;
     for (long long w = (long long)blockIdx.x * 4 + wib; w < total; w += (long long)gridDim.x * 4) {
         const int img = (int)(w / per_img);
         const long long rem = w - (long long)img * per_img;
         // chain-minor order: neighbouring warps work on neighbouring chains of the same step block,
         // so their (strided) parameter reads share sectors
-        const int tb = (int)(rem / dg.S), j = (int)(rem - (long long)tb * dg.S);
+        const int tb = tb0 + (int)(rem / dg.S), j = (int)(rem % dg.S);
         if ((long long)j + (long long)tb * 32 * dg.S >= dg.n_sym) continue;
         const size_t P = (size_t)dg.Hs * dg.Ws;
         int lo[3];
@@ -615,6 +633,7 @@ window_kernel(const float *__restrict__ params, const int16_t *__restrict__ syms
         uint4 *item = items + ((((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain + tb) * kItemU4;
         produce_item<false>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
                             g, j, tb, np, item, stage[wib], lane);
+        if (flags != nullptr && lane == 0) flags[(((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain + tb] = 1u;
     }
 }
 
@@ -792,7 +811,7 @@ wave_consume_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
 
 __global__ void __launch_bounds__(128, 8)
 wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsProfile np, size_t sym_cap, uint32_t *ctl, int n,
-                    int safe_ctas, int consumer_ctas, int share, int pattern) {
+                    int safe_ctas, int consumer_ctas, int share, int pattern, int skip_y) {
     __shared__ __align__(16) uint16_t stage[4][kStageU16];
     __shared__ uint32_t started;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -827,7 +846,7 @@ wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
         for (int c = 0; c < 9; ++c) {
             const int q = (q0 + c) % 9, band = q / 3, clr = q - 3 * band;
             const WaveBand &wb = band == 0 ? wa.b[0] : band == 1 ? wa.b[1] : wa.b[2];
-            if (wb.it1 <= wb.it0) continue;
+            if (wb.it1 <= wb.it0 || (skip_y && clr == 0)) continue;
             const DecodeGeom dg = wb.dg;
             const size_t P = (size_t)dg.Hs * dg.Ws;
             const uint32_t total = (uint32_t)(wb.it1 - wb.it0) * (uint32_t)n;
@@ -1038,7 +1057,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
             for (int clr = 0; clr < 3; ++clr) {
                 {
                     ProfScope prof_(ctx, KC_WINDOW, s);
-                    window_kernel<<<win_blocks, 128, 0, s>>>(pr, sy, sym_cap, mm, dg, clr, ctx->num, itm, cnt);
+                    window_kernel<<<win_blocks, 128, 0, s>>>(pr, sy, sym_cap, mm, dg, clr, ctx->num, itm, cnt, 0, dg.items_per_chain, nullptr);
                 }
                 if (clr == 0 && fork_after_first) {
                     cudaEventRecord((cudaEvent_t)ctx->ev_fork, s);
@@ -1217,8 +1236,24 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
             wa.b[b].it1 = item_of(b, s + 1);
             any |= wa.b[b].it1 > wa.b[b].it0;
         }
+        const int y_ahead = env_int("LLICTI_WAVE_Y_AHEAD", 0);
         if (any) {
             ProfScope prof_(ctx, KC_DECODE, st);
+            // Option (off): the Y windows of the strips need no decoded symbol and can be produced first, by the whole GPU.
+            // With all three channels on 94 SMs the producers do not keep up with 216 chains (the Y chains alone wait
+            // 0.47 of 1.8 ms per step); produced ahead, the waiting goes (average chain 1.78 -> 1.36 ms) -- but a step
+            // lasts as long as its slowest chain, which is the image with the most redone chunks (1.9 - 2.5 ms either
+            // way), and the extra launches cost more than they save: 29.0 -> 31.2 ms per c1 batch.
+            if (y_ahead)
+                for (int b = 0; b < 3; ++b) {
+                    const int ntb = wa.b[b].it1 - wa.b[b].it0;
+                    if (ntb <= 0) continue;
+                    const long long warps = (long long)n * ntb;
+                    const int blocks = (int)std::min<long long>((warps + 3) / 4, (long long)sm_count * 16);
+                    window_kernel<<<blocks, 128, 0, st>>>(params[b], syms[b], sym_cap, minmax, dg[b], 0, ctx->num, items[b], n, wa.b[b].it0,
+                                                          ntb, flags[b]);
+                    ctx->launches += 1;
+                }
             LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, kCtlWords * sizeof(uint32_t), st));
             // fork: consumers on the caller's stream (they start first), producers on the side stream; join before the scatter
             LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_fork, st));
@@ -1227,7 +1262,8 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
                                                               sublen, total_sub, n,
                                                               reinterpret_cast<ChainState *>(ctx->d_chain_state_raw));
             wave_produce_kernel<<<sm_count * prod_per_sm, 128, 0, side>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, n,
-                                                                         sm_count * std::min(safe_per_sm, prod_per_sm), consumer_ctas, env_int("LLICTI_WAVE_SHARE_SMS", 0), std::max(env_int("LLICTI_WAVE_PATTERN", 122), 1));
+                                                                         sm_count * std::min(safe_per_sm, prod_per_sm), consumer_ctas, env_int("LLICTI_WAVE_SHARE_SMS", 0),
+                                                                         std::max(env_int("LLICTI_WAVE_PATTERN", y_ahead ? 11 : 122), 1), y_ahead);
             LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_join, side));
             LLICTI_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
             ctx->launches += 2;
