@@ -51,7 +51,8 @@ __global__ void wave_dbg_kernel(int T, int chains) {
 constexpr int kStageU16 = 32 * 34 + 32 * 6 * 8;   // per warp: window staging (17-word pitch) + prepared channels of 32 steps
 constexpr int kWin = 31;                 // complete symbols per window (32 table entries: lane l holds q(base + l))
 constexpr int kLiBuf = 32;               // per consumer warp: the window-relative symbols of the item in flight
-constexpr int kItemU4 = 132;             // uint4 per item: [4][32 lanes] window rows, then 32 x u16 window bases
+constexpr int kItemU4 = 132 + 192;       // uint4 per item: [4][32 lanes] window rows, 32 x u16 window bases, then (piped schedules
+                                         // only) the prepared GMM channel of every step, [32][6] float4, for the consumer's slow path
 constexpr int16_t kSentinel = (int16_t)0x8080;   // memset(0x80): never a sample value (|v| <= 255)
 
 
@@ -201,6 +202,11 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
     }
     unsigned short *bases = reinterpret_cast<unsigned short *>(item + 128);
     if (kPipe) __stcg(bases + lane, (unsigned short)base); else bases[lane] = (unsigned short)base;
+    if (kPipe) {      // few, long chains: a symbol outside its window should not cost the consumer a reload of 60 planes
+        float4 *dst = reinterpret_cast<float4 *>(item + 132);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) __stcg(dst + k * 32 + lane, prm[k * 32 + lane]);
+    }
     __syncwarp();
 }
 
@@ -229,6 +235,26 @@ __device__ __noinline__ uint64_t slow_symbol(const float *__restrict__ pp, const
     const uint32_t target = (uint32_t)(num / span) & 0xFFFFu;
     uint32_t c_low, c_high;
     const int sym = warp_search(ch, g, target, np, lane, c_low, c_high, first_base);
+    return (uint64_t)c_low | ((uint64_t)(c_high - 1u) << 16) | ((uint64_t)(uint32_t)sym << 32);
+}
+
+// The same from the prepared channel the producer left beside the item (piped schedules): six broadcast loads
+// instead of 60 strided planes, two symbols, the coupling and the weight normalisation.
+__device__ __noinline__ uint64_t slow_symbol_prepared(const float4 *__restrict__ prm, CdfGrid g, NumericsProfile np, uint32_t low,
+                                                      uint32_t high, uint32_t value, int lane, int first_base) {
+    if (lane == 0) atomicAdd(&g_decode_stats[0], 1ull);
+    const float4 v0 = __ldcg(prm), v1 = __ldcg(prm + 1), v2 = __ldcg(prm + 2), v3 = __ldcg(prm + 3), v4 = __ldcg(prm + 4), v5 = __ldcg(prm + 5);
+    GmmChannel b;
+    b.sigma[0] = v0.x; b.sigma[1] = v0.y; b.sigma[2] = v0.z; b.sigma[3] = v0.w; b.sigma[4] = v1.x;
+    b.mu[0] = v1.y; b.mu[1] = v1.z; b.mu[2] = v1.w; b.mu[3] = v2.x; b.mu[4] = v2.y;
+    b.w[0] = v2.z; b.w[1] = v2.w; b.w[2] = v3.x; b.w[3] = v3.y; b.w[4] = v3.z;
+    b.rinv[0] = v3.w; b.rinv[1] = v4.x; b.rinv[2] = v4.y; b.rinv[3] = v4.z; b.rinv[4] = v4.w;
+    b.fast = __float_as_int(v5.y);
+    const uint64_t span = (uint64_t)high - (uint64_t)low + 1ull;
+    const uint64_t num = (((uint64_t)value - (uint64_t)low + 1ull) << 16) - 1ull;
+    const uint32_t target = (uint32_t)(num / span) & 0xFFFFu;
+    uint32_t c_low, c_high;
+    const int sym = warp_search(b, g, target, np, lane, c_low, c_high, first_base);
     return (uint64_t)c_low | ((uint64_t)(c_high - 1u) << 16) | ((uint64_t)(uint32_t)sym << 32);
 }
 
@@ -401,7 +427,8 @@ __device__ __forceinline__ uint32_t decode_step_fast(ChainCoder &cc, uint32_t cl
 // Returns the symbol (alphabet index).
 template <bool kPipe>
 __device__ __forceinline__ int decode_step_careful(ChainCoder &cc, uint32_t slot, int base, uint32_t vmask, long long i,
-                                               const ChainCtx &cx, const CdfGrid &g, const NumericsProfile &np, int lane) {
+                                               const ChainCtx &cx, const CdfGrid &g, const NumericsProfile &np, int lane,
+                                               const float4 *prm) {
     cc.load_window();
     const uint32_t up = __shfl_down_sync(kFull, slot, 1);
     const uint32_t c_high = up == 0u ? 0x10000u : up;
@@ -410,9 +437,10 @@ __device__ __forceinline__ int decode_step_careful(ChainCoder &cc, uint32_t slot
     const uint32_t nh_sel = __shfl_sync(kFull, ns.nh, li);
     int sym, sh;
     if ((li >> 31) != 0u || cc.value > nh_sel) {
-        const uint64_t pk = slow_symbol(cx.pp, cx.syms, cx.sym_cap, cx.P, cx.crop_w, cx.Ws, i, cx.clr, cx.lo0, cx.lo1, g, np,
-                                        cc.low, cc.high, cc.value, lane, kPipe ? 1 : 0,
-                                        (li >> 31) != 0u ? max(base - 31, 0) : base + kWin);   // right below / above the window that missed
+        const int first_base = (li >> 31) != 0u ? max(base - 31, 0) : base + kWin;      // right below / above the window that missed
+        const uint64_t pk = kPipe ? slow_symbol_prepared(prm, g, np, cc.low, cc.high, cc.value, lane, first_base)
+                                  : slow_symbol(cx.pp, cx.syms, cx.sym_cap, cx.P, cx.crop_w, cx.Ws, i, cx.clr, cx.lo0, cx.lo1, g, np,
+                                                cc.low, cc.high, cc.value, lane, 0, first_base);
         const NextState s2 = next_state(cc.low, cc.high, cc.value, cc.b0, (uint32_t)pk & 0xFFFFu,
                                         (((uint32_t)pk >> 16) & 0xFFFFu) + 1u);
         cc.low = s2.low; cc.high = s2.high; cc.value = s2.value; sh = s2.sh;
@@ -489,6 +517,7 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
             if (kPipe && it + 2 < n_items) f_next2 = ld_relaxed_u32(flags + it + 2);
         }
         const int full_here = min(4, n_full - it * 4);
+        const float4 *item_prm = reinterpret_cast<const float4 *>(items + (size_t)it * kItemU4 + 132);   // prepared channels (piped schedules)
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             if (v >= full_here) break;
@@ -517,7 +546,8 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
                         cc.low = r_low; cc.high = r_high; cc.value = r_value; cc.b0 = r0; cc.b1 = r1; cc.b2 = r2; cc.b3 = r3;
                         cc.pos += (uint32_t)(128 - r_avail);
                         const int base = __shfl_sync(kFull, base_cur, 8 * v + e);
-                        const int sy = decode_step_careful<kPipe>(cc, chunk_entry(q, e), base, vmask, i + (long long)(8 * v + e) * S, cx, g, np, lane);
+                        const int sy = decode_step_careful<kPipe>(cc, chunk_entry(q, e), base, vmask, i + (long long)(8 * v + e) * S, cx, g, np, lane,
+                                                                  item_prm + (8 * v + e) * 6);
                         li_buf[8 * v + e] = (int)(((uint32_t)(sy - base) & 0xFFFu) << 8);
                         cc.load_window();
                     }
@@ -532,7 +562,8 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
 #pragma unroll 1
             for (int e = 0; e < tail; ++e) {
                 const int base = __shfl_sync(kFull, base_cur, 8 * v + e);
-                const int sy = decode_step_careful<kPipe>(cc, chunk_entry(q, e), base, vmask, i + (long long)(8 * v + e) * S, cx, g, np, lane);
+                const int sy = decode_step_careful<kPipe>(cc, chunk_entry(q, e), base, vmask, i + (long long)(8 * v + e) * S, cx, g, np, lane,
+                                                                  item_prm + (8 * v + e) * 6);
                 li_buf[8 * v + e] = (int)(((uint32_t)(sy - base) & 0xFFFu) << 8);
             }
         }
@@ -567,12 +598,10 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
             atomicAdd(&g_decode_stats[5], (unsigned long long)(clock64() - t_begin));
             atomicAdd(&g_decode_stats[6], 1ull);
             atomicMax(&g_decode_stats[2], (unsigned long long)(clock64() - t_begin));
-            atomicMax(&g_wave_dbg[0], (unsigned long long)(clock64() - t_begin));
             atomicAdd(&g_wave_dbg[1], (unsigned long long)(clock64() - t_begin));
             atomicAdd(&g_wave_dbg[2], (unsigned long long)waited);
             atomicAdd(&g_wave_dbg[3], (unsigned long long)redo_cycles);
             atomicAdd(&g_wave_dbg[4 + min(cx.clr, 2)], (unsigned long long)waited);     // waiting per colour channel
-            atomicAdd(&g_wave_dbg[7], (unsigned long long)first_wait);
             atomicAdd(&g_decode_stats[7], (unsigned long long)redo_cycles);
         }
         if (redone) atomicAdd(&g_decode_stats[3], redone);
