@@ -484,7 +484,7 @@ int llicti_decode_dev(llicti_ctx *ctx, const uint8_t *blob_dev, const uint64_t *
     static const char *const knobs[] = {"LLICTI_WAVE_STRIP_ROWS", "LLICTI_WAVE_MAX_STRIPS", "LLICTI_NO_WAVE", "LLICTI_NO_PIPE",
                                         "LLICTI_WAVE_CHAINS_PER_CTA", "LLICTI_WAVE_SHARE_SMS", "LLICTI_WAVE_PATTERN",
                                         "LLICTI_WAVE_PRODUCER_CTAS_PER_SM", "LLICTI_PIPE_CONS_PER_SM", "LLICTI_PIPE_CTAS_PER_SM",
-                                        "LLICTI_WAVE_DEBUG", "LLICTI_NO_HALVES", "LLICTI_WAVE_Y_AHEAD"};
+                                        "LLICTI_WAVE_DEBUG", "LLICTI_NO_HALVES"};
     unsigned long long h = 1469598103934665603ull;
     for (const char *k : knobs) {
         const char *v = getenv(k);

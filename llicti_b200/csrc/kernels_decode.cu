@@ -642,19 +642,17 @@ static __device__ __forceinline__ CdfGrid band_grids(const int32_t *mm, int clr,
 __global__ void __launch_bounds__(128)
 window_kernel(const float *__restrict__ params, const int16_t *__restrict__ syms, size_t sym_cap,
               const int32_t *__restrict__ minmax, DecodeGeom dg, int clr, NumericsProfile np, uint4 *__restrict__ items,
-              int n, int tb0, int ntb, uint32_t *__restrict__ flags) {
-    // items [tb0, tb0 + ntb) of every chain; `flags` (wavefront schedule: the Y windows of a strip, produced ahead of the
-    // consumer / producer pair) = per-item readiness words to set
+              int n) {
     __shared__ __align__(16) uint16_t stage[4][kStageU16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long per_img = (long long)dg.S * ntb;
+    const long long per_img = (long long)dg.S * dg.items_per_chain;
     const long long total = per_img * n;
     for (long long w = (long long)blockIdx.x * 4 + wib; w < total; w += (long long)gridDim.x * 4) {
         const int img = (int)(w / per_img);
         const long long rem = w - (long long)img * per_img;
         // chain-minor order: neighbouring warps work on neighbouring chains of the same step block,
         // so their (strided) parameter reads share sectors
-        const int tb = tb0 + (int)(rem / dg.S), j = (int)(rem % dg.S);
+        const int tb = (int)(rem / dg.S), j = (int)(rem % dg.S);
         if ((long long)j + (long long)tb * 32 * dg.S >= dg.n_sym) continue;
         const size_t P = (size_t)dg.Hs * dg.Ws;
         int lo[3];
@@ -662,7 +660,6 @@ window_kernel(const float *__restrict__ params, const int16_t *__restrict__ syms
         uint4 *item = items + ((((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain + tb) * kItemU4;
         produce_item<false>(params + (size_t)img * kParamCh * P, syms + (size_t)img * 3 * sym_cap, sym_cap, P, dg, clr, lo,
                             g, j, tb, np, item, stage[wib], lane);
-        if (flags != nullptr && lane == 0) flags[(((size_t)img * 3 + clr) * dg.S + j) * dg.items_per_chain + tb] = 1u;
     }
 }
 
@@ -840,7 +837,7 @@ wave_consume_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
 
 __global__ void __launch_bounds__(128, 8)
 wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsProfile np, size_t sym_cap, uint32_t *ctl, int n,
-                    int safe_ctas, int consumer_ctas, int share, int pattern, int skip_y) {
+                    int safe_ctas, int consumer_ctas, int share, int pattern) {
     __shared__ __align__(16) uint16_t stage[4][kStageU16];
     __shared__ uint32_t started;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -875,7 +872,7 @@ wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
         for (int c = 0; c < 9; ++c) {
             const int q = (q0 + c) % 9, band = q / 3, clr = q - 3 * band;
             const WaveBand &wb = band == 0 ? wa.b[0] : band == 1 ? wa.b[1] : wa.b[2];
-            if (wb.it1 <= wb.it0 || (skip_y && clr == 0)) continue;
+            if (wb.it1 <= wb.it0) continue;
             const DecodeGeom dg = wb.dg;
             const size_t P = (size_t)dg.Hs * dg.Ws;
             const uint32_t total = (uint32_t)(wb.it1 - wb.it0) * (uint32_t)n;
@@ -1086,7 +1083,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
             for (int clr = 0; clr < 3; ++clr) {
                 {
                     ProfScope prof_(ctx, KC_WINDOW, s);
-                    window_kernel<<<win_blocks, 128, 0, s>>>(pr, sy, sym_cap, mm, dg, clr, ctx->num, itm, cnt, 0, dg.items_per_chain, nullptr);
+                    window_kernel<<<win_blocks, 128, 0, s>>>(pr, sy, sym_cap, mm, dg, clr, ctx->num, itm, cnt);
                 }
                 if (clr == 0 && fork_after_first) {
                     cudaEventRecord((cudaEvent_t)ctx->ev_fork, s);
@@ -1265,24 +1262,13 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
             wa.b[b].it1 = item_of(b, s + 1);
             any |= wa.b[b].it1 > wa.b[b].it0;
         }
-        const int y_ahead = env_int("LLICTI_WAVE_Y_AHEAD", 0);
         if (any) {
             ProfScope prof_(ctx, KC_DECODE, st);
-            // Option (off): the Y windows of the strips need no decoded symbol and can be produced first, by the whole GPU.
-            // With all three channels on 94 SMs the producers do not keep up with 216 chains (the Y chains alone wait
-            // 0.47 of 1.8 ms per step); produced ahead, the waiting goes (average chain 1.78 -> 1.36 ms) -- but a step
-            // lasts as long as its slowest chain, which is the image with the most redone chunks (1.9 - 2.5 ms either
-            // way), and the extra launches cost more than they save: 29.0 -> 31.2 ms per c1 batch.
-            if (y_ahead)
-                for (int b = 0; b < 3; ++b) {
-                    const int ntb = wa.b[b].it1 - wa.b[b].it0;
-                    if (ntb <= 0) continue;
-                    const long long warps = (long long)n * ntb;
-                    const int blocks = (int)std::min<long long>((warps + 3) / 4, (long long)sm_count * 16);
-                    window_kernel<<<blocks, 128, 0, st>>>(params[b], syms[b], sym_cap, minmax, dg[b], 0, ctx->num, items[b], n, wa.b[b].it0,
-                                                          ntb, flags[b]);
-                    ctx->launches += 1;
-                }
+            // (Measured and dropped: producing the Y windows of the strips ahead of the pair with the whole GPU.  With all
+            // three channels on 94 SMs the producers do not keep up with 216 chains -- the Y chains alone wait 0.47 of
+            // 1.8 ms per step -- and produced ahead the waiting goes (average chain 1.78 -> 1.36 ms); but a step lasts as
+            // long as its slowest chain, the image with the most redone chunks, and the extra launches cost more than
+            // they saved: 29.0 -> 31.2 ms per c1 batch.)
             LLICTI_CUDA(cudaMemsetAsync(ctx->d_item_flags, 0, kCtlWords * sizeof(uint32_t), st));
             // fork: consumers on the caller's stream (they start first), producers on the side stream; join before the scatter
             LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_fork, st));
@@ -1292,7 +1278,7 @@ int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t 
                                                               reinterpret_cast<ChainState *>(ctx->d_chain_state_raw));
             wave_produce_kernel<<<sm_count * prod_per_sm, 128, 0, side>>>(wa, minmax, ctx->num, sym_cap, ctx->d_item_flags, n,
                                                                          sm_count * std::min(safe_per_sm, prod_per_sm), consumer_ctas, env_int("LLICTI_WAVE_SHARE_SMS", 0),
-                                                                         std::max(env_int("LLICTI_WAVE_PATTERN", y_ahead ? 11 : 122), 1), y_ahead);
+                                                                         std::max(env_int("LLICTI_WAVE_PATTERN", 122), 1));
             LLICTI_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_join, side));
             LLICTI_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
             ctx->launches += 2;
