@@ -864,6 +864,7 @@ wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
     // that changed nothing on c1: other patterns, earliest-needed-first drawing of ready tickets only, producers
     // sharing the consumers' SMs -- the step is bound by the Y -> Co -> Cg hand-over latency, not by capacity.)
     {
+        bool stay = false;
         const int pa = pattern / 100, pb = pattern / 10 % 10, pc = pattern % 10, pt = pa + pb + pc;
         const int producer_id = blockIdx.x * 4 + wib;
         const int r = producer_id % (pt * n_act);
@@ -877,7 +878,12 @@ wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
             const size_t P = (size_t)dg.Hs * dg.Ws;
             const uint32_t total = (uint32_t)(wb.it1 - wb.it0) * (uint32_t)n;
             for (;;) {
-                if (!share && ld_relaxed_u32(claimed) != 0u) return;          // leave the SM to the consumers (no ticket is held here)
+                if (!stay && ld_relaxed_u32(claimed) != 0u) {                  // a consumer CTA runs on this SM (no ticket is held here):
+                    uint32_t slot = 0;                                        // all but `share` producer warps leave it to the chains
+                    if (lane == 0) slot = atomicAdd(&ctl[600 + (smid & 255u)], 1u);
+                    if (__shfl_sync(kFull, slot, 0) >= (uint32_t)share) return;
+                    stay = true;
+                }
                 uint32_t w = 0;
                 if (lane == 0) w = atomicAdd(&ctl[514 + q], 1u);
                 w = __shfl_sync(kFull, w, 0);
