@@ -494,14 +494,15 @@ def test_reference_model_interface(L):
     assert mdl.get_params(y).shape == (1, 60, 9, 11)
 
 
-@pytest.mark.parametrize("sub_len", [0, 512])
-def test_decode_graph_replay(L, sub_len, monkeypatch):
+@pytest.mark.parametrize("sub_len,H,W", [(0, 96, 160), (512, 96, 160), (0, 128, 192)],
+                         ids=["piped", "substreams", "wavefront"])
+def test_decode_graph_replay(L, sub_len, H, W, monkeypatch):
     """llicti_decode_dev replays its launch sequence as one CUDA graph from the third call with the same
     arguments on: same pixels, same launch count as the eager calls, new content through the same buffers is
     decoded correctly, and LLICTI_NO_GRAPH=1 gives the eager path."""
     ocfg = O.OracleConfig(dwtlevels=(0, 1), chs=60)
     codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=sub_len, cnn_impl=L.CNN_TCGEN05)
-    H, W, n = 96, 160, 3
+    n = 3
     st = 2 ** len(ocfg.dwtlevels)
 
     def batch(seed):
