@@ -32,6 +32,16 @@ def image_size_from_header(num_scales: int, h_last: int, w_last: int, pad_int: i
     return h, w
 
 
+def stream_size(bsl):
+    """(H, W) of the image a bytestream_list codes, from its header row alone."""
+    hdr = bsl[0]
+    ns, h_last, w_last = (int(v) for v in np.frombuffer(hdr[0], dtype=np.uint8))
+    if len(bsl) != ns + 1:
+        raise ValueError(f"header says {ns} scales, list has {len(bsl) - 1}")
+    pad_int = int(np.frombuffer(hdr[2], dtype=np.uint16)[0])
+    return image_size_from_header(ns, h_last, w_last, pad_int)
+
+
 def assemble(num_scales: int, sub_len: int, h_last: int, w_last: int, pad_int: int, rgb: np.ndarray,
              blob, off: np.ndarray, minmax: np.ndarray):
     """(blob, off, minmax) of a batch -> list of bytestream_lists
