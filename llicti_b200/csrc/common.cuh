@@ -118,7 +118,7 @@ struct llicti_ctx {
     uint8_t *d_blob = nullptr;         // compacted output / decode input
     size_t blob_cap = 0;
     uint8_t *d_x00 = nullptr;          // [n][3][h_last][w_last]
-    void *d_items = nullptr;           // decode windows: 2 KB items of 32 steps of one chain (kernels_decode.cu)
+    void *d_items = nullptr;           // decode windows: one item slot per 32 steps of one chain (kernels_decode.cu)
     int64_t items_cap = 0;             // in items
     int16_t *d_syms = nullptr;         // [n][3][sym_cap] compact decoded symbols of the band in flight
     int64_t sym_cap = 0;

@@ -7,22 +7,25 @@
 //
 //   producers  (any number of warps, no coder state): for every symbol, the 32 exact table
 //              entries q(base .. base+31) around the predicted value -- a "window" of 31 complete
-//              symbols, one 64-byte row.  32 symbols of one chain form an item: 2 KB of rows plus
-//              the 32 window bases.
-//   consumers  (one warp per coded chain, the serial part): per symbol one 64-bit multiply and
-//              compare per lane, a ballot, two shuffles and the interval update.  No erfc, no
+//              symbols, one 64-byte row.  32 symbols of one chain form an item: 2 KB of rows, the 32
+//              window bases and (piped schedules) the prepared GMM channel of every step.
+//   consumers  (one warp per coded chain, the serial part): per symbol two high-word multiplies
+//              and a compare per lane, a ballot, four shuffles and the interval update.  No erfc, no
 //              division, no table search on the critical path.  A symbol outside its window
-//              (rare) takes the slow path: the full analytic search of `warp_search`.
+//              (rare) takes the slow path: the analytic search of `warp_search`.
 //
-// Two schedules use the same two device functions:
-//   split   six launches per band (window Y, consume Y, window Co, ...): any number of
-//           substreams; the Y -> Co -> Cg coupling is ordered by the launches.
-//   piped   one launch per band when every stream is a single torchac chain (sub_len = 0):
-//           three consumer warps per image (Y, Co, Cg) run concurrently with the producers in
-//           one grid of one-warp CTAs that are all co-resident.  Consumers publish decoded samples
-//           by writing them over a sentinel in the planes (data = flag, no fence on the serial
-//           path); producers publish items through per-item flags.  The serial chain per band is
-//           n_sym steps instead of 3 * n_sym.
+// Three schedules use the same two device functions:
+//   split      six launches per band (window Y, consume Y, window Co, ...): any number of
+//              substreams; the Y -> Co -> Cg coupling is ordered by the launches; two half batches
+//              run one kernel out of phase on two streams.
+//   piped      one launch per band when every stream is a single torchac chain (sub_len = 0):
+//              three consumer warps per image (Y, Co, Cg) run concurrently with the producers in
+//              one grid of one-warp CTAs that are all co-resident.  Consumers publish decoded
+//              samples by writing them over a sentinel (data = flag, no fence on the serial
+//              path); producers publish items through per-item flags.  The serial chain per band
+//              is n_sym steps instead of 3 * n_sym.
+//   wavefront  (default for sub_len = 0) the three bands of a scale run concurrently a strip of
+//              rows apart: a consumer and a producer kernel side by side per time step.
 #include "common.cuh"
 #include "gmm.cuh"
 #include "rangecoder.cuh"
@@ -791,7 +794,7 @@ struct WaveArgs { WaveBand b[3]; };
 
 // Consumers and producers of a wavefront step are two kernels running concurrently on two streams
 // (they only talk through the flags / sentinels in global memory): the consumer kernel is nine
-// one-warp CTAs per image with the ~160 registers the serial loop wants; the producer kernel is
+// one-warp CTAs per image with the ~150 registers the serial loop wants; the producer kernel is
 // compiled on its own (64 registers), so three times as many producer warps fit on an SM as in the
 // single-kernel form.  The producer grid is sized to leave room for the consumer CTAs on every SM
 // (see launch_decode_scale_wave), so the consumers are resident whichever kernel starts first, and a
