@@ -57,7 +57,7 @@ def log(*a):
 def synthetic_batch(n, H, W, seed0):
     """n distinct photographic-like images; a pool of 8 generated images is tiled with cheap
     per-image perturbations so that large batches do not take minutes of host time."""
-    from oracle.llicti_oracle import synthetic_image
+    from llicti_b200.synth import synthetic_image
     pool = [synthetic_image(H, W, seed0 + i) for i in range(min(n, 8))]
     out = np.empty((n, 3, H, W), dtype=np.uint8)
     for i in range(n):
@@ -189,7 +189,7 @@ def kernel_ms_has_no_window(prof):
 
 def run_b200(args, rank, world, local_rank):
     from llicti_b200 import Codec, CodecConfig, _lib as L
-    from oracle import llicti_oracle as O   # synthetic weights / images + cpu_baseline only
+    from llicti_b200 import synth           # synthetic weights / images; the oracle is used by the cpu_baseline leg only
 
     desc, cfg_name, n_img, H, W, sub_len = WORKLOADS[args.workload]
     if args.images:
@@ -197,10 +197,10 @@ def run_b200(args, rank, world, local_rank):
     cfg = load_cfg(cfg_name)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    ocfg = O.OracleConfig.from_dict(cfg)
-    sd = O.synthetic_state_dict(ocfg)
-    codec = Codec(CodecConfig.from_json_dict(cfg, sub_len=sub_len, numerics=L.NUM_TORCH_CUDA, cnn_impl=args.cnn,
-                                             device=local_rank, decode_impl=args.decode_impl), sd)
+    ccfg = CodecConfig.from_json_dict(cfg, sub_len=sub_len, numerics=L.NUM_TORCH_CUDA, cnn_impl=args.cnn,
+                                      device=local_rank, decode_impl=args.decode_impl)
+    sd = synth.synthetic_state_dict(ccfg.chs, ccfg.num_mixtures, int(cfg["Evens"][0]), int(cfg["Odds"][0]))
+    codec = Codec(ccfg, sd)
     geom = codec.geometry(H, W)
     S = geom.num_scales
     st = 2 ** S
@@ -350,7 +350,7 @@ def run_b200(args, rank, world, local_rank):
         peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops_sustained": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
                  "src": "measured"}
     piped = sub_len == 0 and kernel_ms_has_no_window(prof)
-    work_step = algorithmic_work(geom, ocfg.chs, n_img, blob_bytes, args.decode_impl, piped)
+    work_step = algorithmic_work(geom, ccfg.chs, n_img, blob_bytes, args.decode_impl, piped)
     kernel_ms = {k: v[0] / K for k, v in prof.items()}
     traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -403,7 +403,7 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": desc, "model_config": cfg_name, "images_per_gpu": n_img, "height": H, "width": W,
                    "sub_len": sub_len, "cnn_impl": "tcgen05" if args.cnn == 1 else "fp32-cuda-core",
                    "decode_impl": "windows+chains" if args.decode_impl == 0 else "legacy-warp",
-                   "weights": "oracle.synthetic_state_dict(seed=1337) (shipped checkpoint absent)",
+                   "weights": "llicti_b200.synth.synthetic_state_dict(seed=1337) (shipped checkpoint absent)",
                    "l2": "256 MiB buffer written before every timed encode and decode (L2 flushed)",
                    "parallelism": f"images sharded over {world} GPU(s), no data-path collective; every shard is the same "
                                   f"{n_img}-image synthetic set (identical work per GPU)"},

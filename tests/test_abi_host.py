@@ -200,3 +200,38 @@ def test_llicti_file_round_trip_and_validation():
             fileformat.dumps(bsl, sub_len + 1, H, W)
         with pytest.raises(ValueError):
             fileformat.loads(fileformat.dumps(bsl, sub_len, H + 1, W))
+
+
+def test_synthetic_inputs_of_bench_equal_the_oracle_generators():
+    """bench.py and the tools take their synthetic images / weights from llicti_b200.synth (the product path imports
+    nothing from oracle/); both generators must produce the same bytes."""
+    from llicti_b200 import synth
+    for cfg in (O.OracleConfig(), O.OracleConfig(dwtlevels=(0, 1), chs=60)):
+        a = O.synthetic_state_dict(cfg)
+        b = synth.synthetic_state_dict(cfg.chs, cfg.num_mixtures, cfg.evens, cfg.odds)
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+    for H, W, i in ((33, 47, 0), (64, 96, 5), (17, 17, 9)):
+        assert np.array_equal(O.synthetic_image(H, W, i), synth.synthetic_image(H, W, i))
+
+
+def test_product_sources_do_not_import_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs may use oracle/."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "llicti_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "oracle/" in text and f.endswith((".cu", ".cuh", ".h")) and "#include" in text and re.search(r'#include\s+"[^"]*oracle', text):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    bench = open(os.path.join(root, "bench.py")).read()
+    body = bench[bench.index("def run_b200("):bench.index("# ---- CPU baseline")]
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", body, re.M), "bench.py's product arm imports the oracle"
+    main = open(os.path.join(root, "main.py")).read()
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", main, re.M)
