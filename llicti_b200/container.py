@@ -32,9 +32,19 @@ def image_size_from_header(num_scales: int, h_last: int, w_last: int, pad_int: i
     return h, w
 
 
+def _header_row(bsl):
+    """The header row of a bytestream_list, shape-checked (LLICTI_nets.py:346-354)."""
+    if len(bsl) < 2 or len(bsl[0]) < 4:
+        raise ValueError("bytestream_list has no header row")
+    hdr = bsl[0]
+    if len(hdr[0]) != 3 or len(hdr[1]) != 12 or len(hdr[2]) != 2:
+        raise ValueError("malformed header row (expected 3 + 12 + 2 bytes of dims, min/max and pad word)")
+    return hdr
+
+
 def stream_size(bsl):
     """(H, W) of the image a bytestream_list codes, from its header row alone."""
-    hdr = bsl[0]
+    hdr = _header_row(bsl)
     ns, h_last, w_last = (int(v) for v in np.frombuffer(hdr[0], dtype=np.uint8))
     if len(bsl) != ns + 1:
         raise ValueError(f"header says {ns} scales, list has {len(bsl) - 1}")
@@ -76,7 +86,7 @@ def parse(num_scales: int, sub_len: int, bsls: Sequence):
     mm = np.empty((n, 6), dtype=np.int16)
     x00s, parts, offs, pos = [], [], [0], 0
     for i, bsl in enumerate(bsls):
-        hdr = bsl[0]
+        hdr = _header_row(bsl)
         ns, h_last, w_last = (int(v) for v in np.frombuffer(hdr[0], dtype=np.uint8))
         if ns != S or len(bsl) != S + 1:
             raise ValueError(f"stream has {ns} scales, model has {S}")               # LLICTI_nets.py:424
