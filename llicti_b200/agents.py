@@ -6,7 +6,6 @@ compress -> rate table -> decompres -> lossless check loop and its log lines).
 Training / validation modes are outside the B200 hot path and raise NotImplementedError.
 """
 import logging
-import os
 import shutil
 import time
 
