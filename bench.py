@@ -1,20 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the LLICTI compress/decompress hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c0..c4] [--impl b200|reference]
 
-A step = one pass of the hot path (compress then decompress) over one batch of synthetic
-images.  Default workload (N=1) is BASELINE.json configs[1]: llicti_B, 24 synthetic 768x512
-images, torchac-compatible streams.  Rank 0 prints ONE JSON line on stdout.
+A step = one pass of the hot path (compress then decompres) over ONE batch of synthetic images.
+Workloads are BASELINE.json's configs:
 
-  value     whole-job round-trip throughput (MP/s) with the batch already resident in HBM
-  e2e       the same through llicti_encode_host / llicti_decode_host with pinned HOST buffers
-            (host<->device copies inside the timed region)
-  roofline  dominant kernel class: algorithmic bytes (or flops) / its CUDA-event time
-  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample
+  c0  configs[0]  llicti_A, 24 x 768x512, torchac-compatible streams (the reference's own CPU-runnable case)
+  c1  configs[1]  llicti_B, the same 24 images, torchac-compatible byte-exact mode
+  c2  configs[2]  llicti_A, 100 x 2040x1356 in 4 batches of 25, interleaved-substream coder      <- default at N = 1
+  c3  configs[3]  llicti_A, 512 x 3840x2160 sharded over the N GPUs (512 / N distinct images per rank, batches of 16)
+                                                                                                <- default at N > 1
+  c4  configs[4]  llicti_A, 50,000 x 512x512 sharded over the N GPUs (batches of 256)
 
-`--impl reference` times the CPU oracle alone (the reference is pure Python/PyTorch and cannot
-travel to the GPU box; oracle/llicti_oracle.py keeps its cost structure).
+Every rank generates ITS OWN images (seeded by global image index); step k codes batch k mod (resident batches).
+Rank 0 prints ONE JSON line on stdout:
+
+  value         whole-job round-trip throughput (MP/s), batches resident in HBM, max over ranks of the device time
+  e2e           the same through llicti_encode_host / llicti_decode_host with pinned HOST buffers
+  roofline      dominant kernel class: algorithmic bytes (or flops) per launch / its CUDA-event time
+  per_config    short passes over the other configs (N = 1: c0, c1, c3, c4; N > 1: c4), same code path
+  cpu_baseline  the CPU oracle on a bounded sample, run in a fresh process (`bench.py --impl reference`); a failure
+                there is recorded in the JSON line and never discards the GPU measurement
+
+`--impl reference` times the CPU oracle alone (the reference is a Python script tree and cannot travel to the GPU
+box; oracle/llicti_oracle.py restates it with the same cost structure).
 """
 import argparse
 import json
@@ -34,17 +44,19 @@ sys.path.insert(0, ROOT)
 ENCODE_ONLY = bool(os.environ.get("LLICTI_BENCH_ENCODE_ONLY"))   # debugging aid: time the encoder alone
 
 WORKLOADS = {
-    # name: (description, config, per-GPU images, H, W, sub_len)
-    "c1": ("configs[1]: llicti_B eval_model, 24 synthetic 768x512 RGB images, torchac-compatible streams",
-           "llicti_B.json", 24, 512, 768, 0),
-    "c2": ("configs[2]: llicti_A, synthetic 2040x1356 images, interleaved-substream coder",
-           "llicti_A.json", 25, 1356, 2040, 2048),
-    "c3": ("configs[3]: llicti_A, synthetic 3840x2160 images, interleaved-substream coder",
-           "llicti_A.json", 8, 2160, 3840, 2048),
-    "c4": ("configs[4]: llicti_A, synthetic 512x512 images, interleaved-substream coder",
-           "llicti_A.json", 256, 512, 512, 2048),
-    "c0": ("configs[0]: llicti_A eval_model, 24 synthetic 768x512 RGB images, torchac-compatible streams",
-           "llicti_A.json", 24, 512, 768, 0),
+    # name: description, config, images per batch, H, W, sub_len, images of the whole job (sharded over the ranks)
+    "c0": dict(desc="configs[0]: llicti_A eval_model, 24 synthetic 768x512 RGB images, torchac-compatible streams",
+               cfg="llicti_A.json", batch=24, H=512, W=768, sub_len=0, total=24, shard=False),
+    "c1": dict(desc="configs[1]: llicti_B eval_model, 24 synthetic 768x512 RGB images, torchac-compatible byte-exact mode",
+               cfg="llicti_B.json", batch=24, H=512, W=768, sub_len=0, total=24, shard=False),
+    "c2": dict(desc="configs[2]: llicti_A, 100 synthetic 2040x1356 images in 4 batches of 25, interleaved-substream coder",
+               cfg="llicti_A.json", batch=25, H=1356, W=2040, sub_len=2048, total=100, shard=False),
+    "c3": dict(desc="configs[3]: llicti_A, 512 synthetic 3840x2160 images sharded over the GPUs, batches of 16, "
+                    "interleaved-substream coder",
+               cfg="llicti_A.json", batch=16, H=2160, W=3840, sub_len=2048, total=512, shard=True),
+    "c4": dict(desc="configs[4]: llicti_A, 50,000 synthetic 512x512 images sharded over the GPUs, batches of 256, "
+                    "interleaved-substream coder",
+               cfg="llicti_A.json", batch=256, H=512, W=512, sub_len=2048, total=50000, shard=True),
 }
 METRIC = "encode+decode round-trip megapixels/s (compress then decompres of every image)"
 MAC_PER_POS = {88: (53152, 61600, 78496), 60: (29520, 35280, 46800)}
@@ -52,21 +64,6 @@ MAC_PER_POS = {88: (53152, 61600, 78496), 60: (29520, 35280, 46800)}
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
-
-
-def synthetic_batch(n, H, W, seed0):
-    """n distinct photographic-like images; a pool of 8 generated images is tiled with cheap
-    per-image perturbations so that large batches do not take minutes of host time."""
-    from llicti_b200.synth import synthetic_image
-    pool = [synthetic_image(H, W, seed0 + i) for i in range(min(n, 8))]
-    out = np.empty((n, 3, H, W), dtype=np.uint8)
-    for i in range(n):
-        img = pool[i % len(pool)]
-        if i >= len(pool):
-            img = np.roll(img, shift=(7 * i) % W, axis=2)
-            img = np.clip(img.astype(np.int16) + ((i // len(pool)) % 5 - 2), 0, 255).astype(np.uint8)
-        out[i] = img
-    return out
 
 
 class ClockSampler:
@@ -110,8 +107,12 @@ def load_cfg(name):
         return json.load(f)
 
 
+# =============================================================================================
+# reference arm / cpu_baseline: the CPU oracle, one image per step
+# =============================================================================================
 def cpu_oracle_pass(cfg_json, H, W, steps, warmup, seed0=0):
-    """Time the CPU oracle (compress + decompress of one image per step)."""
+    """Time the CPU oracle (compress + decompress of one image per step).  Every image must round-trip;
+    a mismatch is diagnosed (which stream's table differs between encode and decode) before raising."""
     from oracle import llicti_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     ocfg = O.OracleConfig.from_dict(cfg_json)
@@ -124,7 +125,8 @@ def cpu_oracle_pass(cfg_json, H, W, steps, warmup, seed0=0):
         t1 = time.perf_counter()
         rec = codec.decompress(bsl)
         t2 = time.perf_counter()
-        assert np.array_equal(rec, img)
+        if not np.array_equal(rec, img):
+            raise RuntimeError(f"CPU oracle round trip of image {seed0 + it} is not lossless: " + O.diagnose_round_trip(codec, img))
         log(f"[cpu oracle] step {it}: enc {t1 - t0:.2f}s dec {t2 - t1:.2f}s")
         if it >= warmup:
             times.append((t1 - t0, t2 - t1))
@@ -135,33 +137,63 @@ def cpu_oracle_pass(cfg_json, H, W, steps, warmup, seed0=0):
             "ms_per_step": 1e3 * (enc + dec) / len(times), "cores": torch.get_num_threads()}
 
 
+def reference_sample_shape(wl):
+    """The reference materialises dense H x W x Lp CDF tables (5 fp32 temporaries of that size): a 2040x1356 image takes
+    minutes and ~10 GB, a 4K image cannot be held at all.  Its cost per pixel does not depend on the image size, so
+    big shapes are sampled as 768x512 images of the same generator."""
+    return (wl["H"], wl["W"]) if wl["H"] * wl["W"] <= 768 * 512 else (512, 768)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    desc, cfg_name, n_img, H, W, sub_len = WORKLOADS[args.workload]
-    cfg = load_cfg(cfg_name)
-    # the reference cannot hold a 4K image's dense CDF tables; time 768x512 crops for big shapes
-    sh, sw = (H, W) if H * W <= 768 * 512 else (512, 768)
+    wl = WORKLOADS[args.workload]
+    cfg = load_cfg(wl["cfg"])
+    sh, sw = reference_sample_shape(wl)
     r = cpu_oracle_pass(cfg, sh, sw, args.steps, args.warmup)
-    sample = f"{args.steps} step(s) of 1 synthetic {sw}x{sh} image each, compress+decompres, {r['cores']} torch threads"
+    sample = (f"{args.steps} step(s) of 1 synthetic {sw}x{sh} image each, compress+decompres, {r['cores']} torch threads, "
+              f"model config {wl['cfg']}")
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "model_config": cfg_name, "sample": sample},
+            "config": {"workload": wl["desc"], "model_config": wl["cfg"], "sample": sample},
             "encode_mpps": r["encode_mpps"], "decode_mpps": r["decode_mpps"],
             "cpu_baseline": {"value": r["value"], "unit": "MP/s", "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": r["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_leg(workload, steps=4):
+    """The CPU oracle on a bounded sample, in a FRESH process (the state the reference arm runs in): whatever this
+    process has loaded (CUDA, NCCL, the codec library, pinned allocations) cannot disturb it, and a failure becomes
+    an "error" entry of the JSON line instead of discarding the GPU measurement."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", str(steps),
+           "--warmup", "0"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        line = next((ln for ln in reversed(r.stdout.splitlines()) if ln.startswith("{")), None)
+        if r.returncode != 0 or line is None:
+            return {"error": f"cpu oracle process exited {r.returncode}: {r.stderr.strip().splitlines()[-1:] or ''}", "kind": "port"}
+        d = json.loads(line)
+        cb = d["cpu_baseline"]
+        cb.update({"encode_mpps": d["encode_mpps"], "decode_mpps": d["decode_mpps"]})
+        return cb
+    except Exception as e:       # noqa: BLE001 -- a diagnostic leg must never take the measurement down
+        return {"error": f"{type(e).__name__}: {e}", "kind": "port"}
+
+
+# =============================================================================================
+# B200 arm
+# =============================================================================================
 # How each kernel class is bounded (DESIGN.md section 4): the CNN by the tensor pipe, everything else is
 # byte/integer work whose ceiling is HBM bandwidth -- the serial coder chains and the erfc-heavy
 # CDF kernels sit far below it by nature (latency / instruction issue), which the fractions show.
 BOUND = {"cnn": "tensor"}
 
 
-def algorithmic_work(geom, chs, n, blob_bytes, decode_impl=0, piped=False):
-    """Per-step algorithmic bytes / flops of each kernel class for n images."""
+def algorithmic_work(geom, chs, n, blob_bytes):
+    """Per-step ALGORITHMIC bytes / flops of each kernel class for n images:
+    what the stage has to read and write by definition, not what a particular schedule moves internally."""
     S = geom.num_scales
     pos = [geom.Hs[s] * geom.Ws[s] for s in range(S)]
     sym_band = [[geom.crop_h[s][b] * geom.crop_w[s][b] for b in range(3)] for s in range(S)]
@@ -173,197 +205,251 @@ def algorithmic_work(geom, chs, n, blob_bytes, decode_impl=0, piped=False):
         "cnn": 2 * n * sum(pos[s] * (2 * 3 * (b + 1) + 240) for s in range(S) for b in range(3)),
         "bounds": n * coded_pos * (240 + 6 + 12),                               # 258 B per (position, band)
         "encode": n * geom.symbols * 4 + blob_bytes,                            # 4 B bounds in + bytes out
-        "window": n * coded_pos * (240 + 6 + 3 * 64),                           # params + symbols in, 3 window rows out
-        # split schedule: window rows + stream bytes in, symbols out; piped schedule: the one kernel also
-        # produces the windows; legacy: params in, symbols out
-        "decode": (n * coded_pos * ((240 + 6 + 3 * 64) * piped + 3 * 64 + 6) + blob_bytes) if decode_impl == 0
-        else (n * coded_pos * (240 + 6) + blob_bytes),
+        "window": n * coded_pos * (240 + 6),                                    # params + symbols in (the rows it writes are internal)
+        "decode": n * coded_pos * (240 + 6) + blob_bytes,                       # params + stream bytes in, symbols out
         "merge": n * (2 * 12 * sum(pos) + 3 * geom.H * geom.W),
     }
 
 
-def kernel_ms_has_no_window(prof):
-    """True when the decode ran the piped schedule (windows produced inside the decode kernel)."""
-    return prof.get("window", (0.0, 0))[1] == 0
-
-
-def run_b200(args, rank, world, local_rank):
-    from llicti_b200 import Codec, CodecConfig, _lib as L
-    from llicti_b200 import synth           # synthetic weights / images; the oracle is used by the cpu_baseline leg only
-
-    desc, cfg_name, n_img, H, W, sub_len = WORKLOADS[args.workload]
-    if args.images:
-        n_img = args.images
-    cfg = load_cfg(cfg_name)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    ccfg = CodecConfig.from_json_dict(cfg, sub_len=sub_len, numerics=L.NUM_TORCH_CUDA, cnn_impl=args.cnn,
-                                      device=local_rank, decode_impl=args.decode_impl)
-    sd = synth.synthetic_state_dict(ccfg.chs, ccfg.num_mixtures, int(cfg["Evens"][0]), int(cfg["Odds"][0]))
-    codec = Codec(ccfg, sd)
-    geom = codec.geometry(H, W)
+def internal_traffic(geom, n, prof):
+    """Bytes the windowed decode schedules move through HBM on top of the algorithmic ones: 3 x 64 B of window rows per
+    (position, band) written by the producers and read back by the chains."""
     S = geom.num_scales
-    st = 2 ** S
-    from llicti_b200.shard import shard_range, reduce_stats
-    # weak scaling: the job is world * n_img images, rank r codes its contiguous shard; no data-path collective
-    first, last = shard_range(world * n_img, rank, world)
-    assert last - first == n_img
-    # Every shard holds the same synthetic image set: decode time depends on content (symbols outside their window take
-    # the slow path; measured spread between image sets at N=8: 32 -> 38 ms per batch), and the weak-scaling number is
-    # meant to show the system, not which rank drew the hardest pictures.
-    rgb_h = torch.from_numpy(synthetic_batch(n_img, H, W, 1000)).pin_memory()
-    rgb_np = rgb_h.numpy()
-    rgb_d = rgb_h.to(dev)
-    x00_np = np.ascontiguousarray(rgb_np[:, :, ::st, ::st])
-    x00_d = torch.from_numpy(x00_np).to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    out_pinned = torch.empty(n_img * int(geom.max_stream_bytes), dtype=torch.uint8).pin_memory().numpy()
-    rec_pinned = torch.empty((n_img, 3, H, W), dtype=torch.uint8).pin_memory().numpy()
+    coded_pos = sum(geom.crop_h[s][b] * geom.crop_w[s][b] for s in range(S) for b in range(3))
+    windows = prof.get("window", (0.0, 0))[1] > 0 or prof.get("decode", (0.0, 0))[1] > 0
+    return {"window_rows_written": n * coded_pos * 3 * 64 if windows else 0,
+            "window_rows_read": n * coded_pos * 3 * 64 if windows else 0}
 
-    def barrier():
-        if world > 1:
+
+class Workload:
+    """One config on this rank: its codec, its resident batches and the timed loops over them."""
+
+    def __init__(self, name, args, rank, world, local_rank, max_batches):
+        from llicti_b200 import Codec, CodecConfig, _lib as L
+        from llicti_b200 import synth
+        from llicti_b200.shard import shard_range
+        self.name, self.wl, self.args = name, WORKLOADS[name], args
+        wl = self.wl
+        self.rank, self.world = rank, world
+        self.cfg = load_cfg(wl["cfg"])
+        self.dev = torch.device("cuda", local_rank)
+        self.L = L
+        self.ccfg = CodecConfig.from_json_dict(self.cfg, sub_len=wl["sub_len"], numerics=L.NUM_TORCH_CUDA, cnn_impl=args.cnn,
+                                               device=local_rank, decode_impl=args.decode_impl)
+        self.sd = synth.synthetic_state_dict(self.ccfg.chs, self.ccfg.num_mixtures, int(self.cfg["Evens"][0]), int(self.cfg["Odds"][0]))
+        self.codec = Codec(self.ccfg, self.sd)
+        H, W = wl["H"], wl["W"]
+        self.H, self.W = H, W
+        self.geom = self.codec.geometry(H, W)
+        self.st = 2 ** self.geom.num_scales
+        # the job's images: sharded configs give every rank its contiguous block of distinct images; the single-GPU
+        # configs (c0-c2) are replicated per rank with rank-specific seeds (distinct images as well)
+        total = args.images * world if args.images and wl["shard"] else (args.images or wl["total"])
+        if wl["shard"]:
+            first, last = shard_range(total, rank, world)
+        else:
+            first, last = rank * total, (rank + 1) * total
+        self.job_images, self.shard_images = (total if wl["shard"] else total * world), last - first
+        self.n = min(wl["batch"], self.shard_images)
+        self.job_batches = -(-self.shard_images // self.n)                    # batches this rank would code for the whole job
+        nb = max(1, min(self.job_batches, max_batches))
+        t0 = time.perf_counter()
+        self.batches = []
+        for b in range(nb):
+            k0 = first + b * self.n
+            cnt = min(self.n, last - k0)
+            if cnt < self.n:                      # ragged tail of the shard: wrap around to keep the batch shape
+                k0 = last - self.n
+            self.batches.append(synth.synthetic_batch_torch(self.n, H, W, 1000 + k0, self.dev))
+        torch.cuda.synchronize()
+        self.gen_s = time.perf_counter() - t0
+        self.x00 = [b[:, :, ::self.st, ::self.st].contiguous() for b in self.batches]
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
+        self.enc_out = None
+        self.rec_out = None
+
+    def close(self):
+        self.codec.close()
+        del self.batches, self.x00, self.flush, self.enc_out, self.rec_out
+        torch.cuda.empty_cache()
+
+    def barrier(self):
+        if self.world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    enc_out = [None]                      # device output buffers, allocated by the first (untimed) step
-    rec_out = [None]
-
-    def dev_step(timed):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        flush.zero_()
+    def dev_step(self, k):
+        rgb_d, x00_d = self.batches[k % len(self.batches)], self.x00[k % len(self.batches)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        self.flush.zero_()
         ev[0].record()
-        enc_out[0] = codec.encode_dev(rgb_d, enc_out[0])
-        blob, off, mm = enc_out[0]
+        self.enc_out = self.codec.encode_dev(rgb_d, self.enc_out)
+        blob, off, mm = self.enc_out
         ev[1].record()
-        flush.zero_()                      # decode starts cold as well (outside both timed spans)
-        ev2 = torch.cuda.Event(enable_timing=True)
-        ev2.record()
-        if ENCODE_ONLY:                    # kernel experiments whose streams are not decodable (tools/)
-            ev[2].record()
-            torch.cuda.synchronize()
-            return ev[0].elapsed_time(ev[1]), 1e-3, blob, off, rgb_d
-        rec_out[0] = rec = codec.decode_dev(blob, off, mm, x00_d, n_img, H, W, rec_out[0])
+        self.flush.zero_()                      # decode starts cold as well (outside both timed spans)
         ev[2].record()
+        if ENCODE_ONLY:                         # kernel experiments whose streams are not decodable (tools/)
+            ev[3].record()
+            torch.cuda.synchronize()
+            return ev[0].elapsed_time(ev[1]), 1e-3, off, rgb_d, rgb_d
+        self.rec_out = self.codec.decode_dev(blob, off, mm, x00_d, self.n, self.H, self.W, self.rec_out)
+        ev[3].record()
         torch.cuda.synchronize()
-        return ev[0].elapsed_time(ev[1]), ev2.elapsed_time(ev[2]), blob, off, rec
+        return ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3]), off, self.rec_out, rgb_d
 
-    def host_step():
+    def measure_device(self, steps, warmup, profile=True):
+        """W warm-up steps, then K timed steps with the batches resident in HBM; returns the raw per-rank numbers."""
+        codec = self.codec
+        for k in range(max(warmup, 1)):
+            _, _, off, rec, rgb_d = self.dev_step(k)
+            assert torch.equal(rec, rgb_d), f"{self.name}: device round trip is not lossless"
+        codec.check_status()
+        self.barrier()
+        launches0 = codec.launches
+        codec.decode_stats()
+        t_enc = t_dec = 0.0
+        blob_bytes = 0
+        per_step = []
+        for k in range(steps):
+            a, b, off, rec, rgb_d = self.dev_step(warmup + k)
+            t_enc += a
+            t_dec += b
+            per_step.append(a + b)
+            blob_bytes += int(off[-1].item())
+        ok = torch.equal(rec, rgb_d)
+        self.barrier()
+        assert ok, f"{self.name}: device round trip is not lossless"
+        out = {"t_enc": t_enc, "t_dec": t_dec, "blob_bytes": blob_bytes / steps, "launches": codec.launches - launches0,
+               "dstats": codec.decode_stats(), "per_step_ms": per_step}
+        if profile:
+            # the same K steps once more with the library's per-kernel-class events (they need eager launches: the
+            # decode of the timed region above may be replayed as one CUDA graph)
+            codec.profile(True)
+            p_enc = p_dec = 0.0
+            for k in range(steps):
+                a, b, *_ = self.dev_step(warmup + k)
+                p_enc += a
+                p_dec += b
+            out["prof"] = codec.profile_read()
+            out["p_enc"], out["p_dec"] = p_enc, p_dec
+            codec.profile(False)
+            codec.decode_stats()
+            self.barrier()
+        return out
+
+    def measure_host(self, steps, warmup):
+        """The same K steps through the *_host entry points: pinned host buffers, host<->device copies inside the timed
+        region.  Host copies exist for at most 4 of the resident batches (pinned memory is not free)."""
         if ENCODE_ONLY:
-            return 1e-3, 1e-3, 0, 0, None, rgb_np
-        flush.zero_()
-        torch.cuda.synchronize()
-        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-        e0.record()
-        blob, off, mm = codec.encode_host(rgb_np, out_pinned)
-        e1.record()
-        flush.zero_()
-        e2.record()
-        rec = codec.decode_host(blob, off, mm, x00_np, n_img, H, W, rec_pinned)
-        e3.record()
-        torch.cuda.synchronize()
-        h2d = rgb_np.nbytes + blob.nbytes + off.nbytes + mm.nbytes + x00_np.nbytes
-        d2h = blob.nbytes + off.nbytes + mm.nbytes + rec.nbytes
-        return e0.elapsed_time(e1), e2.elapsed_time(e3), h2d, d2h, blob, rec
+            return {"h_enc": 1e-3 * steps, "h_dec": 1e-3 * steps, "h2d": 0, "d2h": 0}
+        codec, n, H, W = self.codec, self.n, self.H, self.W
+        nb = min(len(self.batches), 4)
+        rgb_h = [self.batches[b].cpu().pin_memory().numpy() for b in range(nb)]
+        x00_h = [np.ascontiguousarray(r[:, :, ::self.st, ::self.st]) for r in rgb_h]
+        out_pinned = torch.empty(n * int(self.geom.max_stream_bytes), dtype=torch.uint8).pin_memory().numpy()
+        rec_pinned = torch.empty((n, 3, H, W), dtype=torch.uint8).pin_memory().numpy()
 
-    # ---- warm-up ---------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        dev_step(False)
-    enc_ms, dec_ms, blob, off, rec = dev_step(False)
-    assert torch.equal(rec, rgb_d), "device round trip is not lossless"
-    blob_bytes = int(off[-1].item())
+        def host_step(k):
+            rgb_np, x00_np = rgb_h[k % nb], x00_h[k % nb]
+            self.flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
+            blob, off, mm = codec.encode_host(rgb_np, out_pinned)
+            e1.record()
+            self.flush.zero_()
+            e2.record()
+            rec = codec.decode_host(blob, off, mm, x00_np, n, H, W, rec_pinned)
+            e3.record()
+            torch.cuda.synchronize()
+            h2d = rgb_np.nbytes + blob.nbytes + off.nbytes + mm.nbytes + x00_np.nbytes
+            d2h = blob.nbytes + off.nbytes + mm.nbytes + rec.nbytes
+            return e0.elapsed_time(e1), e2.elapsed_time(e3), h2d, d2h, rec, rgb_np
 
-    # ---- timed region: device-resident -------------------------------------------------------
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    launches0 = codec.launches
-    codec.decode_stats()
-    t_enc = t_dec = 0.0
-    for _ in range(args.steps):
-        a, b, *_ = dev_step(True)
-        t_enc += a
-        t_dec += b
-    barrier()
-    dstats = codec.decode_stats()
-    launches = codec.launches - launches0
+        for k in range(max(1, min(warmup, 2))):
+            host_step(k)
+        self.barrier()
+        h_enc = h_dec = 0.0
+        for k in range(steps):
+            a, b, h2d, d2h, rec, rgb_np = host_step(k)
+            h_enc += a
+            h_dec += b
+        ok = np.array_equal(rec, rgb_np)
+        self.barrier()
+        assert ok, f"{self.name}: host round trip is not lossless"
+        return {"h_enc": h_enc, "h_dec": h_dec, "h2d": h2d, "d2h": d2h}
 
-    # ---- the same K steps once more with the library's per-kernel-class events (they need eager launches: the decode
-    #      of the timed region above is replayed as one CUDA graph) ----------------------------------------------
-    codec.profile(True)
-    p_enc = p_dec = 0.0
-    for _ in range(args.steps):
-        a, b, *_ = dev_step(True)
-        p_enc += a
-        p_dec += b
-    prof = codec.profile_read()
-    codec.profile(False)
-    codec.decode_stats()
-    barrier()
-
-    # ---- rate of the substream container against the torchac-compatible streams (= the reference's bytes) of the
-    #      same images, untimed, on a few images of the batch ----------------------------------------------------
-    bpp_delta = None
-    if sub_len > 0 and rank == 0 and not ENCODE_ONLY:
-        m = min(n_img, 4)
-        ns = 9 * S
-        compat = Codec(CodecConfig.from_json_dict(cfg, sub_len=0, numerics=L.NUM_TORCH_CUDA, cnn_impl=args.cnn,
-                                                  device=local_rank, decode_impl=args.decode_impl), sd)
-        _, c_off, _ = compat.encode_dev(rgb_d[:m].contiguous())
+    def bpp_delta(self):
+        """Rate of the substream container against the torchac-compatible streams (= the reference's bytes when the
+        network outputs agree) of the same images, untimed, on a few images of the first batch."""
+        from llicti_b200 import Codec, CodecConfig
+        if self.wl["sub_len"] <= 0 or ENCODE_ONLY:
+            return None
+        m = min(self.n, 4)
+        ns = 9 * self.geom.num_scales
+        sub = self.codec.encode_dev(self.batches[0][:m].contiguous())
+        sub_bytes = int(sub[1][m * ns].item()) + 5 * m          # + the container's mode tag in the header row
+        compat = Codec(CodecConfig.from_json_dict(self.cfg, sub_len=0, numerics=self.L.NUM_TORCH_CUDA, cnn_impl=self.args.cnn,
+                                                  device=self.dev.index, decode_impl=self.args.decode_impl), self.sd)
+        _, c_off, _ = compat.encode_dev(self.batches[0][:m].contiguous())
         compat_bytes = int(c_off[-1].item())
-        sub_bytes = int(off[m * ns].item()) + 5 * m          # + the container's mode tag in the header row
         compat.close()
         del compat
         torch.cuda.empty_cache()
-        bpp_delta = {"value": (sub_bytes - compat_bytes) / compat_bytes, "images": m, "substream_bytes": sub_bytes,
-                     "torchac_compatible_bytes": compat_bytes,
-                     "note": "(substream container - torchac-compatible streams) / torchac-compatible streams, all "
-                             "length tables and flush bytes counted; the compatible streams are the reference's bytes"}
+        return {"value": (sub_bytes - compat_bytes) / compat_bytes, "images": m, "substream_bytes": sub_bytes,
+                "torchac_compatible_bytes": compat_bytes,
+                "note": "(substream container - torchac-compatible streams) / torchac-compatible streams, all length "
+                        "tables and flush bytes counted"}
 
-    # ---- timed region: end to end through host buffers ------------------------------------------
-    for _ in range(max(1, min(args.warmup, 2))):
-        host_step()
-    barrier()
-    h_enc = h_dec = 0.0
-    for _ in range(args.steps):
-        a, b, h2d, d2h, hblob, hrec = host_step()
-        h_enc += a
-        h_dec += b
-    barrier()
-    clk = clocks.stop()        # sampled over both timed regions (device-resident and end-to-end)
-    assert np.array_equal(hrec, rgb_np), "host round trip is not lossless"
 
-    # ---- reduce over ranks (max time, summed work) ---------------------------------------------
-    (px_total, bytes_total, launches_total, h2d_total, d2h_total), (t_enc, t_dec, h_enc, h_dec) = reduce_stats(
-        [n_img * H * W, blob_bytes, launches, h2d, d2h], [t_enc, t_dec, h_enc, h_dec], device=dev)   # NCCL: rate statistics only
-    if rank != 0:
-        return
-    K = args.steps
+def reduce_workload(w, dev_r, host_r, steps):
+    """Max over ranks of the times, sum over ranks of the work; every rank returns the same dict."""
+    from llicti_b200.shard import reduce_stats
+    px = w.n * w.H * w.W
+    sums = [px, dev_r["blob_bytes"], dev_r["launches"], host_r["h2d"] if host_r else 0, host_r["d2h"] if host_r else 0]
+    maxs = [dev_r["t_enc"], dev_r["t_dec"], dev_r["t_enc"] + dev_r["t_dec"],
+            host_r["h_enc"] if host_r else 0, host_r["h_dec"] if host_r else 0,
+            (host_r["h_enc"] + host_r["h_dec"]) if host_r else 0, -dev_r["t_dec"], w.job_batches]
+    (px_total, bytes_total, launches_total, h2d_total, d2h_total), mx = reduce_stats(sums, maxs, device=w.dev)
+    t_enc, t_dec, t_rt, h_enc, h_dec, h_rt, neg_min_dec, job_batches = mx
     mp = px_total / 1e6
-    value = mp * K / ((t_enc + t_dec) / 1e3)
-    e2e = mp * K / ((h_enc + h_dec) / 1e3)
+    K = steps
+    res = {"value": mp * K / (t_rt / 1e3), "ms_per_step": t_rt / K, "encode_mpps": mp * K / (t_enc / 1e3),
+           "decode_mpps": mp * K / (t_dec / 1e3), "encode_ms_per_step": t_enc / K, "decode_ms_per_step": t_dec / K,
+           "decode_ms_per_step_rank_min_max": [-neg_min_dec / K, t_dec / K],
+           "bpp": bytes_total * 8 / px_total, "bpsp": bytes_total * 8 / (px_total * 3), "compressed_bytes_per_step": bytes_total,
+           "gpu_launches": int(launches_total), "px_per_step": px_total,
+           # strong-scaling view of the sharded configs: the slowest rank's share of the whole job at the measured rate
+           "job": {"images": w.job_images, "images_per_rank": w.shard_images, "batches_per_rank": int(job_batches),
+                   "seconds_for_whole_job": job_batches * t_rt / K / 1e3}}
+    if host_r:
+        res["e2e"] = {"value": mp * K / (h_rt / 1e3), "unit": "MP/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
+                      "encode_mpps": mp * K / (h_enc / 1e3), "decode_mpps": mp * K / (h_dec / 1e3),
+                      "api": "llicti_encode_host + llicti_decode_host, pinned host buffers"}
+    return res
 
-    # ---- roofline of the dominant kernel class (rank 0's events) ------------------------------------
-    peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+def rooflines(w, dev_r, args, steps):
+    """Per-class roofline entries from rank 0's per-kernel-class events."""
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
         pk = json.load(open(pk_path))
         peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops_sustained": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
-                 "src": "measured"}
-    piped = sub_len == 0 and kernel_ms_has_no_window(prof)
-    work_step = algorithmic_work(geom, ccfg.chs, n_img, blob_bytes, args.decode_impl, piped)
+                 "src": "measured (MEASURED_PEAKS.json; sustained bf16 figure: the kernels are timed inside a long step)"}
+    prof, K = dev_r["prof"], steps
+    work_step = algorithmic_work(w.geom, w.ccfg.chs, w.n, dev_r["blob_bytes"])
     kernel_ms = {k: v[0] / K for k, v in prof.items()}
+    step_ms = (dev_r["p_enc"] + dev_r["p_dec"]) / K
     traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic_db = json.load(open(tpath)).get(args.workload, {})
-    coded_symbols = n_img * geom.symbols
+        traffic_db = json.load(open(tpath)).get(w.name, {})
 
     def roofline_of(cls):
-        """Algorithmic work of one average launch group / its average duration (CUDA events on the
-        launching stream during the timed region)."""
         groups = max(prof[cls][1] / K, 1.0)
         ms = kernel_ms[cls] / groups
-        if ms <= 0:
+        if ms <= 0 or cls not in work_step:
             return None
         if BOUND.get(cls) == "tensor" and args.cnn == 1:
             ach = work_step["cnn_flops"] / groups / (ms * 1e-3) / 1e12
@@ -373,54 +459,98 @@ def run_b200(args, rank, world, local_rank):
             r = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
         r["frac"] = r["achieved"] / r["peak"]
         t = traffic_db.get(cls)      # dram bytes of one captured launch (ncu --set full), scaled by work units to the average launch
-        r["traffic"] = (t["dram_bytes"] / t["units"] * (n_img * t["units_per_image_step"] / groups)) if t else None
+        r["traffic"] = (t["dram_bytes"] / t["units"] * (w.n * t["units_per_image_step"] / groups)) if t else None
         r.update({"kernel": cls, "launch_groups_per_step": groups, "ms_per_launch_group": ms,
-                  "share_of_step": kernel_ms[cls] / ((p_enc + p_dec) / K)})
+                  "algorithmic_per_launch_group": (work_step["cnn_flops"] if r["bound"] == "tensor" else work_step[cls]) / groups,
+                  "share_of_step": kernel_ms[cls] / step_ms})
         if t:
             r["traffic_source"] = t["source"]
         return r
 
-    dom = max(kernel_ms, key=kernel_ms.get)
+    dom = max((c for c in kernel_ms if c in work_step), key=lambda c: kernel_ms[c])
     roof = roofline_of(dom)
     roof["peak_source"] = peaks["src"]
-    rooflines = {c: {k: v for k, v in r.items() if k in ("bound", "achieved", "peak", "unit", "frac", "share_of_step")}
-                 for c in kernel_ms if kernel_ms[c] > 0 and c in work_step for r in [roofline_of(c)] if r}
+    allr = {c: {k: v for k, v in r.items() if k in ("bound", "achieved", "peak", "unit", "frac", "share_of_step")}
+            for c in kernel_ms if kernel_ms[c] > 0 for r in [roofline_of(c)] if r}
     cnn_tflops = work_step["cnn_flops"] / (max(kernel_ms["cnn"], 1e-9) * 1e-3) / 1e12
+    return roof, allr, kernel_ms, cnn_tflops, internal_traffic(w.geom, w.n, prof)
 
-    # ---- CPU baseline: the oracle on a bounded sample (rank 0, N=1 only) -----------------------------
+
+def run_b200(args, rank, world, local_rank):
+    torch.cuda.set_device(local_rank)
+    primary = args.workload or ("c2" if world == 1 else "c3")
+    K, Wm = args.steps, args.warmup
+
+    # ---- primary workload: full measurement -------------------------------------------------------
+    w = Workload(primary, args, rank, world, local_rank, max_batches=Wm + K)
+    clocks = ClockSampler(local_rank)
+    w.barrier()
+    clocks.start()
+    dev_r = w.measure_device(K, Wm, profile=True)
+    host_r = w.measure_host(K, Wm)
+    clk = clocks.stop()          # sampled over both timed regions (device-resident and end-to-end)
+    res = reduce_workload(w, dev_r, host_r, K)
+    bpp_delta = w.bpp_delta() if rank == 0 else None
+    roof = allr = kernel_ms = cnn_tflops = internal = None
+    if rank == 0:
+        roof, allr, kernel_ms, cnn_tflops, internal = rooflines(w, dev_r, args, K)
+    wl = w.wl
+    cfg_entry = {"workload": wl["desc"], "model_config": wl["cfg"], "images_per_step_per_gpu": w.n, "height": w.H, "width": w.W,
+                 "sub_len": wl["sub_len"], "cnn_impl": "tcgen05" if args.cnn == 1 else "fp32-cuda-core",
+                 "decode_impl": "default" if args.decode_impl == 0 else "legacy-warp",
+                 "distinct_batches_resident_per_gpu": len(w.batches),
+                 "weights": "llicti_b200.synth.synthetic_state_dict(seed=1337) (shipped checkpoint absent)",
+                 "images": f"llicti_b200.synth.synthetic_batch_torch, image k of the job seeded by 1000 + k; generated in {w.gen_s:.1f} s",
+                 "l2": "256 MiB buffer written before every timed encode and decode (L2 flushed)",
+                 "parallelism": (f"{w.job_images} images sharded over {world} GPU(s): {w.shard_images} distinct images per rank"
+                                 if wl["shard"] else f"{w.shard_images} distinct images per rank on {world} GPU(s)") +
+                                ", no data-path collective; NCCL only reduces the statistics"}
+    dstats = {k: v / K for k, v in dev_r["dstats"].items()}
+    p_enc, p_dec = dev_r["p_enc"], dev_r["p_dec"]
+    w.close()
+
+    # ---- the other configs: short passes, same code path (device-resident timing only) ------------------
+    per_config = {}
+    others = [] if args.no_per_config else ([c for c in ("c0", "c1", "c3", "c4") if c != primary] if world == 1 else
+                                            [c for c in ("c4",) if c != primary])
+    for name in others:
+        try:
+            ks, ws = min(K, 3), min(Wm, 2)
+            o = Workload(name, args, rank, world, local_rank, max_batches=ks + ws)
+            r = o.measure_device(ks, ws, profile=False)
+            rr = reduce_workload(o, r, None, ks)
+            per_config[name] = {"workload": o.wl["desc"], "value": rr["value"], "unit": "MP/s", "steps": ks, "warmup": ws,
+                                "images_per_step_per_gpu": o.n, "encode_mpps": rr["encode_mpps"], "decode_mpps": rr["decode_mpps"],
+                                "ms_per_step": rr["ms_per_step"], "bpp": rr["bpp"], "job": rr["job"],
+                                "decode_ms_per_step_rank_min_max": rr["decode_ms_per_step_rank_min_max"]}
+            o.close()
+        except Exception as e:       # noqa: BLE001 -- a side pass never takes the headline down
+            per_config[name] = {"error": f"{type(e).__name__}: {e}"}
+            if world > 1:
+                raise
+    if rank != 0:
+        return
+
     cpu = None
     if world == 1 and not args.no_cpu:
-        sh, sw = (H, W) if H * W <= 768 * 512 else (512, 768)
-        r = cpu_oracle_pass(cfg, sh, sw, 4, 0)      # ~15-20 s of CPU work
-        cpu = {"value": r["value"], "unit": "MP/s", "cores": r["cores"], "kind": "port",
-               "sample": f"4 synthetic {sw}x{sh} images, compress+decompres of each once, {r['cores']} torch threads",
-               "encode_mpps": r["encode_mpps"], "decode_mpps": r["decode_mpps"]}
+        cpu = cpu_baseline_leg(primary)      # ~15-25 s of CPU work in a fresh process; never fatal
 
     line = {
-        "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
-        "ms_per_step": (t_enc + t_dec) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "model_config": cfg_name, "images_per_gpu": n_img, "height": H, "width": W,
-                   "sub_len": sub_len, "cnn_impl": "tcgen05" if args.cnn == 1 else "fp32-cuda-core",
-                   "decode_impl": "windows+chains" if args.decode_impl == 0 else "legacy-warp",
-                   "weights": "llicti_b200.synth.synthetic_state_dict(seed=1337) (shipped checkpoint absent)",
-                   "l2": "256 MiB buffer written before every timed encode and decode (L2 flushed)",
-                   "parallelism": f"images sharded over {world} GPU(s), no data-path collective; every shard is the same "
-                                  f"{n_img}-image synthetic set (identical work per GPU)"},
-        "encode_mpps": mp * K / (t_enc / 1e3), "decode_mpps": mp * K / (t_dec / 1e3),
-        "encode_ms_per_step": t_enc / K, "decode_ms_per_step": t_dec / K,
-        "bpsp": bytes_total * 8 / (px_total * 3), "bpp": bytes_total * 8 / px_total, "bpp_delta_vs_reference_streams": bpp_delta,
-        "compressed_bytes_per_step": bytes_total,
-        "roofline": roof, "rooflines_all_kernels": rooflines, "kernel_ms_per_step": kernel_ms, "cnn_tflops": cnn_tflops,
+        "metric": METRIC, "value": res["value"], "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg_entry,
+        "encode_mpps": res["encode_mpps"], "decode_mpps": res["decode_mpps"],
+        "encode_ms_per_step": res["encode_ms_per_step"], "decode_ms_per_step": res["decode_ms_per_step"],
+        "decode_ms_per_step_rank_min_max": res["decode_ms_per_step_rank_min_max"],
+        "bpsp": res["bpsp"], "bpp": res["bpp"], "bpp_delta_vs_reference_streams": bpp_delta,
+        "compressed_bytes_per_step": res["compressed_bytes_per_step"], "job": res["job"],
+        "roofline": roof, "rooflines_all_kernels": allr, "kernel_ms_per_step": kernel_ms, "cnn_tflops": cnn_tflops,
+        "internal_traffic_per_step": internal,
         "kernel_profile_pass": {"note": "per-kernel-class CUDA events (llicti_profile) over a second pass of the same K steps "
-                                        "right after the timed region; the timed region replays the decode as one CUDA graph",
+                                        "right after the timed region",
                                 "encode_ms_per_step": p_enc / K, "decode_ms_per_step": p_dec / K},
-        "cpu_baseline": cpu,
-        "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
-                "encode_mpps": mp * K / (h_enc / 1e3), "decode_mpps": mp * K / (h_dec / 1e3),
-                "api": "llicti_encode_host + llicti_decode_host, pinned host buffers"},
-        "gpu_launches": int(launches_total), "clocks": clk,
-        "decode_stats_per_step": {k: v / K for k, v in dstats.items()},
+        "cpu_baseline": cpu, "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clk,
+        "decode_stats_per_step": dstats, "per_config": per_config,
     }
     print(json.dumps(line), flush=True)
 
@@ -428,19 +558,23 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
-    ap.add_argument("--images", type=int, default=0, help="override images per GPU")
+    ap.add_argument("--workload", default="", choices=[""] + sorted(WORKLOADS),
+                    help="default: c2 on one GPU, c3 (sharded) on several")
+    ap.add_argument("--images", type=int, default=0, help="override the job's images per GPU")
     ap.add_argument("--cnn", type=int, default=int(os.environ.get("LLICTI_CNN", "1")), help="0 fp32 CUDA cores, 1 tcgen05")
-    ap.add_argument("--decode-impl", type=int, default=0, help="0 windows + serial chains, 1 legacy one-warp-per-chain")
+    ap.add_argument("--decode-impl", type=int, default=0, help="0 default schedules, 1 legacy one-warp-per-chain")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the short passes over the other configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if not args.workload:
+            args.workload = "c2" if world == 1 else "c3"
         run_reference(args, rank, world)
         return
     if not torch.cuda.is_available():

@@ -75,7 +75,9 @@ typedef struct {
     int32_t numerics;     /* LLICTI_NUM_*                                          */
     int32_t cnn_impl;     /* LLICTI_CNN_*                                          */
     int32_t device;       /* CUDA device ordinal                                   */
-    int32_t decode_impl;  /* 0: CDF windows + serial coder chains (default); 1: legacy, one warp per chain does both */
+    int32_t decode_impl;  /* 0 (default): substream container -> one lane group per chain evaluates the few table entries
+                             it needs; torchac-compatible streams -> CDF windows + serial coder chains;
+                             1: legacy, one warp per chain; 2: CDF windows + chains for every container (A/B) */
 } llicti_config;
 
 /* fp32 host pointers in PyTorch's own layouts (state_dict keys in SURVEY.md 8b).
@@ -193,6 +195,11 @@ LLICTI_API int llicti_decode_host(llicti_ctx *ctx, const uint8_t *blob, const ui
 LLICTI_API int llicti_decode_dev(llicti_ctx *ctx, const uint8_t *blob_dev, const uint64_t *stream_off_dev,
                       const int16_t *minmax_dev, const uint8_t *x00_rgb_dev, int n, int H, int W,
                       uint8_t *rgb_out_dev, void *stream);
+
+/* Device-side error flag of the asynchronous *_dev entry points (an encoder that ran out of output
+ * capacity: LLICTI_E_NOMEM; a malformed container or stream offsets: LLICTI_E_STREAM).  Waits for
+ * `stream`, returns the flag (0 = none) and clears it.  The *_host entry points do this themselves. */
+LLICTI_API int llicti_status(llicti_ctx *ctx, void *stream);
 
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 LLICTI_API int64_t llicti_launch_count(const llicti_ctx *ctx);

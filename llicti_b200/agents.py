@@ -89,6 +89,13 @@ class LLICTIAgent(BaseAgent):
     @torch.no_grad()
     def eval_model(self):
         self.model.eval()
+        codec = self.model._codec()
+        cc = self.model.codec_config
+        self.logger.info(" B200 path: cnn_impl={} ({}), sub_len={} ({}), stream fingerprint {}".format(
+            cc.cnn_impl, "tcgen05 tensor cores, bf16 operands" if cc.cnn_impl == 1 else "fp32 CUDA cores",
+            cc.sub_len, "interleaved substreams" if cc.sub_len > 0 else "torchac-compatible streams",
+            codec.fingerprint.hex()))
+        codec.profile(True)          # per-kernel-class launch groups of this run, logged below
         for batch_idx, x in enumerate(self.test_loader):
             x = x.to(self.device)
             text = "{:3d} {:3d}x{:3d} ".format(batch_idx, x.shape[2], x.shape[3])
@@ -109,6 +116,10 @@ class LLICTIAgent(BaseAgent):
                 self.logger.info(text + "bpsp= {:.3f} Enc/Dec-Times:{:.3f}/{:.3f} "
                                         "(Check: Decoded img matches original)".format(total / torch.numel(x), enc_time,
                                                                                       dec_time))
+        prof = codec.profile_read()
+        codec.profile(False)
+        self.logger.info(" B200 kernel classes launched: " + ", ".join(
+            "{}{}={}".format(k, "[tcgen05]" if k == "cnn" and cc.cnn_impl == 1 else "", int(v[1])) for k, v in prof.items() if v[1]))
         if self.test_logger.rate:
             self.test_logger.display(lr=0.0, typ="te")
 

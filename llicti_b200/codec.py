@@ -8,6 +8,7 @@ streams only; every computation happens inside the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
+import zlib
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -97,6 +98,11 @@ class Codec:
         with torch.cuda.device(self.device):
             L.check(self.lib.llicti_create(C.byref(self._ccfg), C.byref(w), C.byref(self._ctx)))
         self._reserved = (0, 0, 0)
+        crc = 0
+        for a in keep:                     # fixed order: l0 (w, b) x 6 branches, then per band l1 w, b, l2 w, b
+            crc = zlib.crc32(a.data, crc)
+        self.weights_crc = crc & 0xFFFFFFFF
+        self.fingerprint = container.fingerprint(cfg.cnn_impl, cfg.numerics, self.weights_crc)
         del keep
 
     def close(self):
@@ -128,6 +134,10 @@ class Codec:
     @property
     def launches(self) -> int:
         return int(self.lib.llicti_launch_count(self._ctx))
+
+    def check_status(self):
+        """Raise if a kernel of an asynchronous *_dev call flagged an error (waits for the stream)."""
+        L.check(self.lib.llicti_status(self._ctx, self._stream()))
 
     def profile(self, enable: bool):
         L.check(self.lib.llicti_profile(self._ctx, int(enable)))
@@ -217,11 +227,12 @@ class Codec:
     def to_bytestream_lists(self, rgb: np.ndarray, blob: np.ndarray, off: np.ndarray, mm: np.ndarray):
         S = self.cfg.num_scales
         g = self.geometry(rgb.shape[2], rgb.shape[3])
-        return container.assemble(S, self.cfg.sub_len, g.Hs[S - 1], g.Ws[S - 1], g.pad_int, rgb, blob, off, mm)
+        return container.assemble(S, self.cfg.sub_len, g.Hs[S - 1], g.Ws[S - 1], g.pad_int, rgb, blob, off, mm,
+                                  fp=self.fingerprint, checksum=True)
 
     def from_bytestream_lists(self, bsls: Sequence):
         """Parse headers; returns (blob, off, minmax, x00, n, H, W)."""
-        return container.parse(self.cfg.num_scales, self.cfg.sub_len, bsls)
+        return container.parse(self.cfg.num_scales, self.cfg.sub_len, bsls, fp=self.fingerprint)
 
     def compress_images(self, rgb: np.ndarray):
         """uint8 [n,3,H,W] -> list of n bytestream_lists."""
@@ -230,7 +241,13 @@ class Codec:
 
     def decompress_images(self, bsls: Sequence) -> np.ndarray:
         blob, off, mm, x00, n, H, W = self.from_bytestream_lists(bsls)
-        return self.decode_host(blob, off, mm, x00, n, H, W)
+        rgb = self.decode_host(blob, off, mm, x00, n, H, W)
+        for i, bsl in enumerate(bsls):     # streams that carry the checksum of their image are verified
+            want = container.image_checksum(bsl[0])
+            if want is not None and (zlib.crc32(rgb[i].data) & 0xFFFFFFFF) != want:
+                raise ValueError(f"image {i}: the decoded pixels fail the stream's checksum (corrupt stream, or coded with "
+                                 "other weights / another CNN implementation than this codec's)")
+        return rgb
 
     # -- stage-level calls (parity tests) --------------------------------------------------------
     def color_split(self, rgb: torch.Tensor):

@@ -1,6 +1,7 @@
 """Pure host logic around the reference's `bytestream_list` (no GPU needed):
 header assembly / parsing (LLICTI_nets.py:346-354, 420-431, 533-542) and the flat
 (blob, offsets) form the C ABI works on."""
+import zlib
 from typing import Sequence
 
 import numpy as np
@@ -20,6 +21,42 @@ def parse_mode_tag(tag: bytes) -> int:
     if len(tag) != 5 or tag[0] != 1:
         raise ValueError("unknown container tag in header slot 4")
     return int.from_bytes(tag[1:5], "little")
+
+
+def fingerprint(cnn_impl: int, numerics: int, weights_crc: int) -> bytes:
+    """Header slot 5 (b'' in the reference): what the decoder must share with the encoder for the CDFs to agree --
+    [2, cnn_impl, numerics, crc32 of the fp32 weights as u32 LE].  Streams are decodable only by a codec with the same
+    fingerprint: the tcgen05 CNN (bf16 operands) and the fp32 CNN give different network outputs, hence different tables."""
+    return bytes([2, cnn_impl & 0xFF, numerics & 0xFF]) + int(weights_crc & 0xFFFFFFFF).to_bytes(4, "little")
+
+
+def describe_fingerprint(fp: bytes) -> str:
+    if len(fp) != 7 or fp[0] != 2:
+        return "unknown fingerprint"
+    return f"cnn_impl={fp[1]}, numerics={fp[2]}, weights crc32={int.from_bytes(fp[3:7], 'little'):08x}"
+
+
+def check_fingerprint(hdr, expected: bytes):
+    """Raise ValueError when a stream carries a fingerprint other than this codec's.  Streams without one (made by
+    the reference itself, or by an older version of this library) are not checked."""
+    got = bytes(hdr[5]) if len(hdr) > 5 else b""
+    if len(got) == 0 or not expected:
+        return
+    if len(got) != 7 or got[0] != 2:
+        raise ValueError("unknown fingerprint in header slot 5")
+    if got != expected:
+        raise ValueError(f"stream was coded with {describe_fingerprint(got)}, this codec has {describe_fingerprint(expected)}: "
+                         "the CDF tables would differ and the decode would be garbage")
+
+
+def image_checksum(hdr):
+    """crc32 of the original uint8 RGB planes (header slot 6), or None."""
+    c = bytes(hdr[6]) if len(hdr) > 6 else b""
+    if len(c) == 0:
+        return None
+    if len(c) != 4:
+        raise ValueError("malformed image checksum in header slot 6")
+    return int.from_bytes(c, "little")
 
 
 def image_size_from_header(num_scales: int, h_last: int, w_last: int, pad_int: int):
@@ -53,9 +90,10 @@ def stream_size(bsl):
 
 
 def assemble(num_scales: int, sub_len: int, h_last: int, w_last: int, pad_int: int, rgb: np.ndarray,
-             blob, off: np.ndarray, minmax: np.ndarray):
+             blob, off: np.ndarray, minmax: np.ndarray, fp: bytes = b"", checksum: bool = False):
     """(blob, off, minmax) of a batch -> list of bytestream_lists
-    [[hdr(3B), minmax(12B), pad(2B), x00 raw RGB, tag, b'' x4], 9 streams per scale S-1..0]."""
+    [[hdr(3B), minmax(12B), pad(2B), x00 raw RGB, tag, fingerprint, crc32(rgb), b'' x2], 9 streams per scale S-1..0].
+    Slots 0-3 are the reference's (LLICTI_nets.py:346-354, which leaves slots 4-8 empty and never reads them back)."""
     n = rgb.shape[0]
     S = num_scales
     st = 2 ** S
@@ -66,7 +104,9 @@ def assemble(num_scales: int, sub_len: int, h_last: int, w_last: int, pad_int: i
                np.asarray(minmax[i], dtype=np.int16).tobytes(),
                np.array([pad_int & 0xFFFF], dtype=np.uint16).tobytes(),
                np.ascontiguousarray(rgb[i, :, 0::st, 0::st]).tobytes(),
-               mode_tag(sub_len), b"", b"", b"", b""]
+               mode_tag(sub_len), bytes(fp),
+               (zlib.crc32(np.ascontiguousarray(rgb[i]).data) & 0xFFFFFFFF).to_bytes(4, "little") if checksum else b"",
+               b"", b""]
         rows = [hdr]
         for r in range(S):
             base = i * 9 * S + r * 9
@@ -75,9 +115,10 @@ def assemble(num_scales: int, sub_len: int, h_last: int, w_last: int, pad_int: i
     return out
 
 
-def parse(num_scales: int, sub_len: int, bsls: Sequence):
+def parse(num_scales: int, sub_len: int, bsls: Sequence, fp: bytes = b""):
     """list of bytestream_lists -> (blob u8, off u64 [n*9S+1], minmax i16 [n,6], x00 u8
-    [n,3,h,w], n, H, W).  Raises ValueError on inconsistent headers."""
+    [n,3,h,w], n, H, W).  Raises ValueError on inconsistent headers, and when a stream's fingerprint
+    (header slot 5) differs from `fp`."""
     S = num_scales
     n = len(bsls)
     if n == 0:
@@ -93,6 +134,7 @@ def parse(num_scales: int, sub_len: int, bsls: Sequence):
         got = parse_mode_tag(hdr[4] if len(hdr) > 4 else b"")
         if got != sub_len:
             raise ValueError(f"stream coded with sub_len={got}, codec configured with {sub_len}")
+        check_fingerprint(hdr, fp)
         mm[i] = np.frombuffer(hdr[1], dtype=np.int16)
         pad_int = int(np.frombuffer(hdr[2], dtype=np.uint16)[0])
         hw = image_size_from_header(S, h_last, w_last, pad_int)

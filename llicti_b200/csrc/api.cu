@@ -19,6 +19,15 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int device_sm_count(llicti_ctx *ctx, int *out) {
+    if (!ctx->sm_count) {
+        LLICTI_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->cfg.device));
+        LLICTI_CUDA(cudaDeviceGetAttribute(&ctx->regs_per_sm, cudaDevAttrMaxRegistersPerMultiprocessor, ctx->cfg.device));
+    }
+    *out = ctx->sm_count;
+    return LLICTI_OK;
+}
+
 int num_substreams(int64_t n, int sub_len) {
     if (sub_len <= 0) return 1;
     int64_t s = std::max<int64_t>(1, (n + sub_len - 1) / sub_len);
@@ -309,18 +318,29 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
     ctx->blob_cap = n * (size_t)g.max_stream_bytes;
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_blob, ctx->blob_cap));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_x00, n * 3 * (size_t)g.Hs[S - 1] * g.Ws[S - 1]));
-    ctx->items_cap = (int64_t)n * decode_items_per_image(p);
-    LLICTI_CUDA(cudaMalloc(&ctx->d_items, wb * (size_t)ctx->items_cap * decode_item_bytes()));
-    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)decode_flag_words(wb * ctx->items_cap) * sizeof(uint32_t)));
-    LLICTI_CUDA(cudaMalloc(&ctx->d_chain_state_raw, n * 9 * 64));
-    ctx->wave_ws = wb == 3;
-    ctx->sym_cap = ((int64_t)g.Hs[0] * g.Ws[0] + 63) / 64 * 64;
-    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_syms, wb * n * 3 * (size_t)ctx->sym_cap * sizeof(int16_t)));
+    // window items, their flags and the compact symbol arrays exist only for the windowed decode schedules
+    // (torchac-compatible streams, or decode_impl = 2); the group schedule of the substream container needs none
+    const bool windows = ctx->cfg.decode_impl == 2 || (ctx->cfg.decode_impl == 0 && ctx->cfg.sub_len == 0);
+    ctx->wave_ws = false;
+    if (windows) {
+        ctx->items_cap = (int64_t)n * decode_items_per_image(p);
+        LLICTI_CUDA(cudaMalloc(&ctx->d_items, wb * (size_t)ctx->items_cap * decode_item_bytes()));
+        LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)decode_flag_words(wb * ctx->items_cap) * sizeof(uint32_t)));
+        LLICTI_CUDA(cudaMalloc(&ctx->d_chain_state_raw, n * 9 * 64));
+        ctx->wave_ws = wb == 3;
+        ctx->sym_cap = ((int64_t)g.Hs[0] * g.Ws[0] + 63) / 64 * 64;
+        LLICTI_CUDA(cudaMalloc((void **)&ctx->d_syms, wb * n * 3 * (size_t)ctx->sym_cap * sizeof(int16_t)));
+    }
     ctx->ws_images = max_images; ctx->ws_H = H; ctx->ws_W = W;
     return LLICTI_OK;
 }
 
 int64_t llicti_launch_count(const llicti_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int llicti_status(llicti_ctx *ctx, void *stream) {
+    LLICTI_REQUIRE(ctx, "null context");
+    return read_status(ctx, (cudaStream_t)stream);
+}
 
 int llicti_profile(llicti_ctx *ctx, int enable) {
     LLICTI_REQUIRE(ctx, "null context");
@@ -449,6 +469,7 @@ int llicti_encode_host(llicti_ctx *ctx, const uint8_t *rgb, int n, int H, int W,
     LLICTI_REQUIRE(rgb && out && stream_off && minmax, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int ns = ctx->plan.n_streams;
+    LLICTI_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int32_t), st));     // a flag left by an earlier *_dev call is not this call's
     LLICTI_CUDA(cudaMemcpyAsync(ctx->d_rgb, rgb, (size_t)n * 3 * H * W, cudaMemcpyHostToDevice, st));
     if ((rc = llicti_encode_dev(ctx, ctx->d_rgb, n, H, W, ctx->d_blob, ctx->blob_cap, ctx->d_stream_off, ctx->d_minmax16, st)))
         return rc;
@@ -543,7 +564,10 @@ static int decode_dev_launches(llicti_ctx *ctx, const uint8_t *blob_dev, const u
     const llicti_geom &g = p.g;
     const int S = g.num_scales;
     if ((rc = launch_minmax32(ctx, minmax_dev, ctx->d_minmax, n, st))) return rc;
-    if ((rc = launch_index_streams(ctx, p, n, blob_dev, stream_off_dev, ctx->d_suboff, ctx->d_sublen, st))) return rc;
+    // no valid encoding of n images exceeds n * max_stream_bytes (the encoder's own capacity): offsets beyond it are malformed
+    if ((rc = launch_index_streams(ctx, p, n, blob_dev, (uint64_t)n * (uint64_t)g.max_stream_bytes, stream_off_dev, ctx->d_suboff,
+                                   ctx->d_sublen, st)))
+        return rc;
     if ((rc = launch_x00_from_header(ctx, p, x00_rgb_dev, n, ctx->d_planes[S - 1], st))) return rc;
     for (int s = S - 1; s >= 0; --s) {
         if (wave_eligible(ctx, p, s, n)) {       // the three bands concurrently, two strips of rows apart
@@ -574,6 +598,13 @@ int llicti_decode_host(llicti_ctx *ctx, const uint8_t *blob, const uint64_t *str
     const uint64_t total = stream_off[(size_t)n * ns];
     LLICTI_REQUIRE(total <= ctx->blob_cap, "bitstream of %llu bytes exceeds the reserved %llu", (unsigned long long)total,
                    (unsigned long long)ctx->blob_cap);
+    if (stream_off[0] != 0) { set_error("malformed stream offsets: the first offset is not 0"); return LLICTI_E_STREAM; }
+    for (size_t i = 0; i < (size_t)n * ns; ++i)
+        if (stream_off[i] > stream_off[i + 1]) {
+            set_error("malformed stream offsets: offset %zu decreases", i + 1);
+            return LLICTI_E_STREAM;
+        }
+    LLICTI_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int32_t), st));
     LLICTI_CUDA(cudaMemcpyAsync(ctx->d_blob, blob, total, cudaMemcpyHostToDevice, st));
     LLICTI_CUDA(cudaMemcpyAsync(ctx->d_stream_off, stream_off, ((size_t)n * ns + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     LLICTI_CUDA(cudaMemcpyAsync(ctx->d_minmax16, minmax, (size_t)n * 6 * sizeof(int16_t), cudaMemcpyHostToDevice, st));

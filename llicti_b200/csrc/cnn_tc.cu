@@ -589,20 +589,18 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
     const long long ntiles = (long long)n * nrows * tg.tpr;
     LLICTI_REQUIRE(ntiles < (1ll << 31), "batch too large for one CNN launch");
     tg.ntiles = (int)ntiles;
-    static int sm_count = 0;
-    static size_t attr_smem = 0;
-    if (!sm_count) {
-        int dev = 0;
-        LLICTI_CUDA(cudaGetDevice(&dev));
-        LLICTI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    int sm_count = 0;
+    {
+        const int rc = device_sm_count(ctx, &sm_count);
+        if (rc) return rc;
     }
     size_t mx = 0;
     for (auto &b : tw->band) mx = std::max(mx, b.smem_bytes);
-    if (mx > attr_smem) {
+    if (mx > ctx->tc_attr_smem) {
         LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
         LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
         LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        attr_smem = mx;
+        ctx->tc_attr_smem = mx;
     }
     // persistent grid: one CTA per SM, an even number (one sub-network pair per CTA), no more than the work
     const int ctas = std::min(sm_count / 2 * 2, tg.ntiles * 2);

@@ -17,6 +17,7 @@ constexpr int kParamCh = 12 * kM;  // 60 output channels of the interpolator CNN
 constexpr int kMaxStreams = 9 * LLICTI_MAX_SCALES;
 
 void set_error(const char *fmt, ...);
+int device_sm_count(llicti_ctx *ctx, int *out);
 
 #define LLICTI_CUDA(call)                                                                    \
     do {                                                                                     \
@@ -136,6 +137,13 @@ struct llicti_ctx {
     bool dec_key_seen = false;
     int64_t dec_graph_launches = 0;
     int32_t *d_status = nullptr;       // device-side error flag
+
+    // properties of the context's device and of the kernels on it (filled on first use; per context, not per
+    // process: two contexts of one process may sit on two devices)
+    int sm_count = 0, regs_per_sm = 0;
+    int pipe_resident = 0;             // one-warp CTAs of decode_band_pipe_kernel per SM
+    int prod_resident = 0, cons_regs = 0, prod_regs = 0;   // wavefront kernels
+    size_t tc_attr_smem = 0;           // dynamic shared memory opted in for the tcgen05 CNN kernels
 };
 
 namespace llicti {
@@ -200,8 +208,8 @@ int launch_encode_flat(llicti_ctx *ctx, const uint32_t *bounds, int n_sym, int S
 int launch_compact(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *scratch, int64_t scratch_stride,
                    const uint32_t *sublen, uint64_t *stream_bytes, uint64_t *stream_off, uint8_t *out,
                    size_t out_cap, cudaStream_t st);
-int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *blob, const uint64_t *stream_off,
-                         uint64_t *suboff, uint32_t *sublen, cudaStream_t st);
+int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *blob, uint64_t blob_bytes,
+                         const uint64_t *stream_off, uint64_t *suboff, uint32_t *sublen, cudaStream_t st);
 int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, const float *params, int16_t *planes,
                        const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
                        const uint32_t *sublen, cudaStream_t st);

@@ -592,7 +592,7 @@ gather_kernel(const StreamDesc *__restrict__ sd, int n_streams, int total_sub, i
 // Decode side: parse the per-stream containers into absolute substream offsets / lengths.
 __global__ void __launch_bounds__(256)
 index_streams_kernel(const StreamDesc *__restrict__ sd, int n_streams, int total_sub, int sub_mode,
-                     const uint8_t *__restrict__ blob, const uint64_t *__restrict__ stream_off,
+                     const uint8_t *__restrict__ blob, uint64_t blob_bytes, int n_images, const uint64_t *__restrict__ stream_off,
                      uint64_t *__restrict__ suboff, uint32_t *__restrict__ sublen, int32_t *__restrict__ status) {
     const int k = blockIdx.x, img = blockIdx.y;
     const StreamDesc d = sd[k];
@@ -600,6 +600,14 @@ index_streams_kernel(const StreamDesc *__restrict__ sd, int n_streams, int total
     const uint64_t o1 = stream_off[(size_t)img * n_streams + k + 1];
     uint64_t *so = suboff + (size_t)img * total_sub + d.sub_first;
     uint32_t *sl = sublen + (size_t)img * total_sub + d.sub_first;
+    // the offsets come from the caller: they must start at 0, never decrease and end inside the blob, or every
+    // substream of this stream reads as empty (zeros past the end, like torchac) and the call reports LLICTI_E_STREAM
+    const uint64_t total = stream_off[(size_t)n_images * n_streams];
+    if (!(o0 <= o1 && o1 <= total && total <= blob_bytes && o1 - o0 <= 0xFFFFFFFFull) || stream_off[0] != 0) {
+        if (threadIdx.x == 0) atomicExch(status, LLICTI_E_STREAM);
+        for (int j = threadIdx.x; j < d.S; j += blockDim.x) { so[j] = 0; sl[j] = 0; }
+        return;
+    }
     if (!sub_mode) {
         if (threadIdx.x == 0) { so[0] = o0; sl[0] = (uint32_t)(o1 - o0); }
         return;
@@ -810,12 +818,12 @@ int launch_compact(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *scratch
     return LLICTI_OK;
 }
 
-int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *blob, const uint64_t *stream_off,
+int launch_index_streams(llicti_ctx *ctx, const Plan &p, int n, const uint8_t *blob, uint64_t blob_bytes, const uint64_t *stream_off,
                          uint64_t *suboff, uint32_t *sublen, cudaStream_t st) {
     ProfScope prof_(ctx, KC_INDEX, st);
     const int total_sub = (int)p.g.substreams;
     dim3 grid(p.n_streams, n);
-    index_streams_kernel<<<grid, 256, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, ctx->cfg.sub_len > 0, blob,
+    index_streams_kernel<<<grid, 256, 0, st>>>(ctx->d_sd, p.n_streams, total_sub, ctx->cfg.sub_len > 0, blob, blob_bytes, n,
                                                stream_off, suboff, sublen, ctx->d_status);
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());

@@ -976,6 +976,137 @@ decode_band_warp_kernel(const float *__restrict__ params, int16_t *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// Group schedule (interleaved-substream container, the throughput configs): a group of G lanes owns one
+// chain position stream j of a band -- substream j of the Y, Co and Cg streams -- and decodes the three
+// samples of position i = j + t S in turn, for t = 0, 1, ...  No windows, no items, no producer kernel: the
+// lanes of the group evaluate G exact table entries q(base + l * stride) around the predicted value, the
+// candidate is the last one with low + ((span * q) >> 16) <= value (torchac's search key without the
+// division), and a miss walks / gallops from the window that missed.  The coder state is replicated in the
+// lanes of the group.  Thousands of chains are in flight (one per ~sub_len symbols), so the instruction
+// count per symbol is what matters here: G entries instead of the 32 of a window row, and the decoded
+// samples go straight into the planes (with the replicate padding of the short phases).
+// Neighbouring groups work on neighbouring positions (substream j codes symbols j, j + S, ...), so the
+// parameter planes are read in full sectors.
+// ------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128)
+decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__ planes, const int32_t *__restrict__ minmax,
+                         DecodeGeom dg, NumericsProfile np, const uint8_t *__restrict__ blob,
+                         const uint64_t *__restrict__ suboff, const uint32_t *__restrict__ sublen, int total_sub, int n) {
+    static_assert(G == 2 || G == 4 || G == 8 || G == 16, "group size");
+    const int lane = threadIdx.x & 31, sub = lane & (G - 1);
+    const int gshift = lane - sub;
+    constexpr uint32_t gm = (1u << G) - 1u;
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool valid = gid < (long long)n * dg.S;
+    // whole warps without work leave; otherwise every lane stays for the warp-wide ballots and shuffles
+    if (!__any_sync(kFull, valid)) return;
+    const int img = valid ? (int)(gid / dg.S) : 0, j = valid ? (int)(gid - (long long)img * dg.S) : 0;
+    const size_t P = (size_t)dg.Hs * dg.Ws;
+    const float *pp = params + (size_t)img * kParamCh * P;
+    int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1)) * P;
+    const int32_t *mm = minmax + img * 4;
+    const int lo[3] = {-127, mm[0], mm[1]};
+    const int hi[3] = {128, mm[2], mm[3]};
+    AcDecoderW dec[3];
+    CdfGrid grid[3];
+#pragma unroll
+    for (int clr = 0; clr < 3; ++clr) {
+        const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
+        dec[clr].init(blob + suboff[e], valid ? sublen[e] : 0u);
+        grid[clr] = make_grid(lo[clr], hi[clr]);
+    }
+    const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
+    const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
+    const int n_steps = valid ? (dg.n_sym - j + dg.S - 1) / dg.S : 0;
+    const int max_steps = dg.max_steps;          // warp-uniform trip count
+    unsigned long long rounds = 0;
+    for (int t = 0; t < max_steps; ++t) {
+        const bool live = t < n_steps;
+        const int i = j + t * dg.S;
+        const int r = live ? i / dg.crop_w : 0, c = live ? i - r * dg.crop_w : 0;
+        const size_t pidx = (size_t)r * dg.Ws + c;
+        int yv[3] = {0, 0, 0};
+#pragma unroll
+        for (int clr = 0; clr < 3; ++clr) {
+            const CdfGrid &g = grid[clr];
+            const int last = g.Lp - 1;
+            GmmChannel ch;
+            if (live) {
+                load_channel(pp, P, pidx, clr, yv[0], yv[1], np, ch);
+            } else {
+#pragma unroll
+                for (int m = 0; m < kM; ++m) { ch.sigma[m] = 1.f; ch.mu[m] = 0.f; ch.w[m] = 0.2f; ch.rinv[m] = 1.f; }
+                ch.fast = 1;
+            }
+            float mean = 0.f;
+#pragma unroll
+            for (int m = 0; m < kM; ++m) mean = fmaf(ch.w[m], ch.mu[m], mean);
+            const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
+            const uint32_t low = dec[clr].low, sm1 = dec[clr].high - dec[clr].low;
+            const uint64_t value = dec[clr].value;
+            // search state: q(s_lo) <= target is known (or s_lo = 0), q(s_hi) > target is known (s_hi = last: 2^16)
+            int s_lo = 0, s_hi = last, base = min(max(kc - (G / 2 - 1), 0), max(last - (G - 1), 0)), stride = 1, round = 0;
+            bool done = !live, miss_down = false;
+            uint32_t c_low = 0, c_high = 0x10000u;
+            int sym = 0;
+            for (;;) {
+                const int k = base + sub * stride;
+                uint32_t q = 0x10000u;
+                if (!done && k < last) q = cdf_q(ch, g, k, np);
+                const uint64_t nl = (uint64_t)low + (((uint64_t)sm1 * q + q) >> 16);
+                const unsigned le = __ballot_sync(kFull, nl <= value);
+                const int cnt = __popc((le >> gshift) & gm);
+                const int i_lo = max(cnt - 1, 0), i_hi = min(i_lo + 1, G - 1);
+                const uint32_t q_lo = __shfl_sync(kFull, q, i_lo, G), q_hi = __shfl_sync(kFull, q, i_hi, G);
+                if (!done) {
+                    ++round;
+                    if (cnt == 0) {
+                        if (base == 0 && stride == 1) {        // below q(0): torchac's search returns symbol 0
+                            sym = 0; c_low = q_lo; c_high = q_hi; done = true;
+                        } else {
+                            s_hi = max(base, 1);
+                            miss_down = true;
+                        }
+                    } else if (cnt == G) {
+                        s_lo = base + (G - 1) * stride;
+                        miss_down = false;
+                    } else {
+                        s_lo = base + (cnt - 1) * stride;
+                        s_hi = min(base + cnt * stride, last);
+                        miss_down = false;
+                        if (stride == 1) { sym = s_lo; c_low = q_lo; c_high = q_hi; done = true; }
+                    }
+                    if (!done) {
+                        // next probes: the G - 1 entries next to the window that missed, then four times as far, then
+                        // whatever is left in equal steps; always inside [s_lo, s_hi]
+                        const int full = max((s_hi - s_lo + G - 2) / (G - 1), 1);
+                        stride = min(full, round == 1 ? 1 : round == 2 ? 4 : full);
+                        base = miss_down ? max(s_hi - (G - 1) * stride, s_lo) : s_lo;
+                    }
+                }
+                if (__all_sync(kFull, done)) break;
+            }
+            if (live) {
+                if (t + 1 < n_steps) dec[clr].consume(c_low, c_high);      // torchac does not update after the last symbol
+                yv[clr] = sym + lo[clr];
+                rounds += (unsigned long long)(round - 1);
+            }
+        }
+        if (live && sub < 3) {
+            const int16_t v = (int16_t)(sub == 0 ? yv[0] : sub == 1 ? yv[1] : yv[2]);
+            int16_t *dst = yb + (size_t)sub * P + pidx;
+            dst[0] = v;
+            const bool last_c = rep_w && c == dg.crop_w - 1, last_r = rep_h && r == dg.crop_h - 1;
+            if (last_c) dst[1] = v;
+            if (last_r) dst[dg.Ws] = v;
+            if (last_c && last_r) dst[dg.Ws + 1] = v;
+        }
+    }
+    if (sub == 0 && rounds) atomicAdd(&g_decode_stats[0], rounds);       // search rounds beyond the first (window misses)
+}
+
+// ------------------------------------------------------------------------------------------
 // Launcher
 // ------------------------------------------------------------------------------------------
 static int stream_index(const Plan &p, int scale, int band, int clr) {
@@ -1039,11 +1170,23 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
         LLICTI_CUDA(cudaGetLastError());
         return LLICTI_OK;
     }
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        LLICTI_CUDA(cudaGetDevice(&dev));
-        LLICTI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (ctx->cfg.sub_len > 0 && ctx->cfg.decode_impl == 0) {
+        ProfScope prof_(ctx, KC_DECODE, st);
+        const int G = std::max(env_int("LLICTI_GROUP_LANES", 4), 2);
+        const long long threads = (long long)n * dg.S * G;
+        const int blocks = (int)((threads + 127) / 128);
+        if (G >= 16) decode_band_group_kernel<16><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
+        else if (G >= 8) decode_band_group_kernel<8><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
+        else if (G >= 4) decode_band_group_kernel<4><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
+        else decode_band_group_kernel<2><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
+        ctx->launches += 1;
+        LLICTI_CUDA(cudaGetLastError());
+        return LLICTI_OK;
+    }
+    int sm_count = 0;
+    {
+        const int rc = device_sm_count(ctx, &sm_count);
+        if (rc) return rc;
     }
     uint4 *items = reinterpret_cast<uint4 *>(ctx->d_items);
     int16_t *syms = ctx->d_syms;
@@ -1056,7 +1199,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
     // to half of the SMs, the other half produces
     const int cons_auto = (3 * n + sm_count / 2 - 1) / (sm_count / 2);
     const int cons_per_sm = std::min(std::max(env_int("LLICTI_PIPE_CONS_PER_SM", cons_auto), 1), kConsPerSmMax);
-    static int pipe_resident = 0;       // one-warp CTAs of the piped kernel that fit on one SM
+    int &pipe_resident = ctx->pipe_resident;       // one-warp CTAs of the piped kernel that fit on one SM
     if (!pipe_resident)
         LLICTI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pipe_resident, decode_band_pipe_kernel, 32, 0));
     const int ctas_per_sm = std::min(std::min(std::max(env_int("LLICTI_PIPE_CTAS_PER_SM", 12), cons_per_sm + 1), 24), pipe_resident);
@@ -1177,21 +1320,28 @@ bool wave_eligible(const llicti_ctx *ctx, const Plan &p, int scale, int n) {
     if (ctx->cfg.decode_impl != 0 || ctx->cfg.cnn_impl != LLICTI_CNN_TCGEN05 || ctx->cfg.sub_len != 0) return false;
     if (!ctx->wave_ws || !ctx->concurrent_kernels || env_int("LLICTI_NO_WAVE", 0) || env_int("LLICTI_NO_PIPE", 0)) return false;
     if (wave_strips(p.g.Hs[scale]) < 2) return false;
+    // A strip is decoded in whole 32-symbol items, so band b may stop up to ceil(31 / crop_w) rows short of the strip's last
+    // row; the three-row lag between the bands covers ONE missing row (launch_decode_scale_wave), i.e. rows of >= 32 symbols.
+    for (int b = 0; b < 3; ++b)
+        if (p.g.crop_w[scale][b] < 32) return false;
     return 9 * n <= kConsPerSmMax * 64;
 }
 
 int wave_bands_in_workspace(const llicti_config &cfg, int max_images) {
+    // (the encoder's d_params holds one band; only the wavefront decode keeps three in flight)
     return (cfg.decode_impl == 0 && cfg.cnn_impl == LLICTI_CNN_TCGEN05 && cfg.sub_len == 0 && 9 * max_images <= kConsPerSmMax * 64) ? 3 : 1;
 }
 
 int launch_decode_scale_wave(llicti_ctx *ctx, const Plan &p, int scale, int16_t *planes, const int32_t *minmax, int n,
                              const uint8_t *blob, const uint64_t *suboff, const uint32_t *sublen, cudaStream_t st) {
-    static int sm_count = 0, prod_resident = 0, regs_per_sm = 0, cons_regs = 0, prod_regs = 0;
-    if (!sm_count) {
-        int dev = 0;
-        LLICTI_CUDA(cudaGetDevice(&dev));
-        LLICTI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        LLICTI_CUDA(cudaDeviceGetAttribute(&regs_per_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+    int sm_count = 0;
+    {
+        const int rc = device_sm_count(ctx, &sm_count);
+        if (rc) return rc;
+    }
+    const int regs_per_sm = ctx->regs_per_sm;
+    int &prod_resident = ctx->prod_resident, &cons_regs = ctx->cons_regs, &prod_regs = ctx->prod_regs;
+    if (!prod_resident) {
         LLICTI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&prod_resident, wave_produce_kernel, 128, 0));
         cudaFuncAttributes fa;
         LLICTI_CUDA(cudaFuncGetAttributes(&fa, wave_consume_kernel));

@@ -163,6 +163,7 @@ class LLICTI(nn.Module):
         codec = self._codec()
         rgb = torch.round(x.to(codec.device) * 255).to(torch.uint8).contiguous()
         blob, off, mm = codec.encode_dev(rgb)
+        codec.check_status()
         off_h = off.cpu().numpy().astype(np.uint64)
         blob_h = blob[:int(off_h[-1])].cpu().numpy()
         bsl = codec.to_bytestream_lists(rgb.cpu().numpy(), blob_h, off_h, mm.cpu().numpy())[0]

@@ -1,6 +1,7 @@
 """Rate bookkeeping of the eval loop: bits per pixel per (scale, band, channel) stream
 (mirrors graphs/losses/rate_dist.py:125-135 and the 'te' table of loggers/rate.py)."""
 import logging
+from datetime import datetime
 
 import numpy as np
 
@@ -47,12 +48,35 @@ class RateLogger:
 
     def display(self, lr=0.0, typ="te"):
         rate = self.mean()
-        assert rate.shape[1] == 9, "expected 3 bands x 3 colour channels per scale"
-        total = float(rate.sum())
-        self.logger.info("  {} rate: {:.3f} bpp = {:.3f} bpsp".format(typ, total, total / 3))
-        self.logger.info("    hdr : {:.3f}".format(float(rate[0].sum())))
-        for i in range(1, rate.shape[0]):
-            scl = rate.shape[0] - 1 - i
-            cells = "  ".join("b{}: {:.3f}+{:.3f}+{:.3f}".format(b, *rate[i][3 * b:3 * b + 3]) for b in range(3))
-            self.logger.info("    scl{}: {:.3f}  ({})".format(scl, float(rate[i].sum()), cells))
-        return total, 0.0
+        self.logger.info(self.format_table(self.current_epoch, rate, lr, typ))
+        return float(rate.sum()), 0.0
+
+    # first line / continuation-line prefixes per table type, as the reference prints them
+    _HEAD = {"tr": "  Train Epoch: {:3d}  Rates: scl", "te": "   Test Epoch: {:3d}  Rates: hdr ",
+             "va": "  Valid Epoch: {:3d}  Rates: scl", "it": "Train Itera: {:3d}  Rates: scl"}
+    _CONT = {"tr": " " * 35 + "scl", "te": " " * 35 + "scl", "va": " " * 35 + "scl", "it": " " * 33 + "scl"}
+
+    @classmethod
+    def format_table(cls, epoch, rate, lr=0.0, typ="te", now=None):
+        """The reference's table text (loggers/rate.py:120-168, text_log_list): one line per row of `rate`
+        ([rows][9] bits per pixel, 3 bands x (Y, Co, Cg)); for typ 'te' row 0 is the header row ("hdr ->", "hd=")
+        and row s > 0 is printed as scale s-1."""
+        rate = np.asarray(rate, dtype=np.float64)
+        assert rate.ndim == 2 and rate.shape[1] == 9, "expected 3 bands x 3 colour channels per row"
+        te = typ == "te"
+        lines, total = [], 0.0
+        for s in range(rate.shape[0]):
+            label = "-> " if te and s == 0 else "{:d}-> ".format(s - 1 if te else s)
+            cells, row_sum = "", 0.0
+            for b in range(3):
+                y, co, cg = rate[s][3 * b:3 * b + 3]
+                band_sum = y + co + cg
+                cells += "{:.2f}+{:.2f}+{:.2f}(b{:d}={:.3f}) ".format(y, co, cg, b, band_sum)
+                row_sum += band_sum
+            tail = "(hd={:.3f}) ".format(row_sum) if te and s == 0 else "(s{:d}={:.3f}) ".format(s - 1 if te else s, row_sum)
+            total += row_sum
+            prefix = cls._HEAD[typ].format(epoch) if s == 0 else cls._CONT[typ]
+            lines.append(prefix + label + cells + tail)
+        stamp = (now or datetime.now()).strftime("%H:%M:%S")
+        end = "(({:.3f})) ".format(total) + ("  (lr: {:.6f}) ({})".format(lr, stamp) if typ in ("tr", "it") else " ({})".format(stamp))
+        return "\n".join(lines) + end

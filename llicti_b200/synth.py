@@ -101,3 +101,43 @@ def synthetic_image(H: int, W: int, index: int = 0, noise: float = 2.0) -> np.nd
         img[:, y0:y1, x0:x1] += rng.uniform(-40, 40, size=(3, 1, 1)).astype(np.float32)
     img += rng.standard_normal(img.shape).astype(np.float32) * np.float32(noise)
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def synthetic_batch_torch(n: int, H: int, W: int, first_index: int, device, noise: float = 2.0):
+    """n DISTINCT synthetic images (image k is seeded by first_index + k) as a uint8 [n,3,H,W] tensor on `device`,
+    built with torch ops from the same recipe as synthetic_image (random 2-D cosines with 1/f amplitudes, chroma
+    fields, three rectangles, Gaussian noise).  Large batches (4K images, 50k-image sweeps) take milliseconds per image
+    on a GPU instead of seconds per image on the host; the pixels are not bit-identical to synthetic_image's (other
+    cosine / noise generators), which only matters to tests that pin inputs -- those use synthetic_image."""
+    import torch
+    dev = torch.device(device)
+    yy = (torch.arange(H, device=dev, dtype=torch.float32) / H)[:, None]
+    xx = (torch.arange(W, device=dev, dtype=torch.float32) / W)[None, :]
+    out = torch.empty((n, 3, H, W), dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev)
+    two_pi = float(2 * np.pi)
+    for k in range(n):
+        rng = np.random.default_rng(1337 + first_index + k)
+
+        def field_(ncomp, amp):
+            f = torch.zeros((H, W), dtype=torch.float32, device=dev)
+            for _ in range(ncomp):
+                fx, fy = rng.uniform(0.2, 24.0, size=2)
+                ph = rng.uniform(0, 2 * np.pi)
+                a = amp / np.sqrt(fx * fx + fy * fy)
+                # cos(u + v) = cos u cos v - sin u sin v: two 1-D tables and one outer product per component
+                u = two_pi * float(fx) * xx + float(ph)
+                v = two_pi * float(fy) * yy
+                f.add_(float(a) * (torch.cos(v) * torch.cos(u) - torch.sin(v) * torch.sin(u)))
+            return f
+
+        lum = 128 + field_(32, 90.0)
+        img = torch.stack([lum + field_(8, 25.0), lum + field_(8, 15.0), lum + field_(8, 25.0)])
+        for _ in range(3):
+            x0, y0 = int(rng.integers(0, W)), int(rng.integers(0, H))
+            x1, y1 = int(rng.integers(x0, W + 1)), int(rng.integers(y0, H + 1))
+            img[:, y0:y1, x0:x1] += torch.as_tensor(rng.uniform(-40, 40, size=(3, 1, 1)).astype(np.float32), device=dev)
+        gen.manual_seed(1337 + first_index + k)
+        img += torch.randn(img.shape, generator=gen, device=dev, dtype=torch.float32) * float(noise)
+        out[k] = torch.clamp(torch.round(img), 0, 255).to(torch.uint8)
+    return out

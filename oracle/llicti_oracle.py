@@ -564,8 +564,9 @@ class OracleCodec:
         return bytes([1]) + int(self.sub_len).to_bytes(4, "little")
 
     # -- decompress (LLICTI_nets.py:161-179, 415-509) -----------------------------
-    def decompress(self, bsl) -> np.ndarray:
-        """bytestream_list -> uint8 RGB [3,H,W]."""
+    def decompress(self, bsl, dump: StageDump = None) -> np.ndarray:
+        """bytestream_list -> uint8 RGB [3,H,W].  `dump` receives the decoder's own network outputs, tables and
+        symbols (diagnose_round_trip compares them with the encoder's)."""
         S, M = self.S, self.M
         hdr = bsl[0]
         ns, h_last, w_last = (int(v) for v in np.frombuffer(hdr[0], dtype=np.uint8))
@@ -595,11 +596,16 @@ class OracleCodec:
             for b in range(3):
                 params = self.net.params(b, pl)
                 ch, cw = crop_shape(b, Hs, Ws, padH, padW)
+                if dump is not None:
+                    dump.params[(scl, b)] = params.copy()
                 for clr in range(3):
                     y_band = pl[3 * (b + 1):3 * (b + 2)]
                     table = self._table(params, clr, y_band, minmax)
                     t = np.ascontiguousarray(table[:ch, :cw]).reshape(ch * cw, -1)
                     sym = self._decode_stream(t, row[3 * b + clr]).reshape(ch, cw)
+                    if dump is not None:
+                        dump.tables[(scl, b, clr)] = t
+                        dump.symbols[(scl, b, clr)] = sym.reshape(-1).copy()
                     val = (sym.astype(np.int32) - self._shift(minmax, clr)).astype(np.int16)
                     val = np.pad(val, ((0, Hs - ch), (0, Ws - cw)), mode="edge")       # :512-530
                     pl[3 * (b + 1) + clr] = val
@@ -610,6 +616,36 @@ class OracleCodec:
         full[0] += 127                                                                # :174
         rgb = ycocg_r_to_rgb(full)
         return rgb.astype(np.uint8)
+
+
+def diagnose_round_trip(codec: "OracleCodec", rgb: np.ndarray) -> str:
+    """Compress and decompress `rgb` once more with stage dumps on both sides and say where the decoder first
+    departs from the encoder, in coding order: the network outputs of a (scale, band), the integer table of a
+    (scale, band, channel), or the decoded symbols.  The two sides run the same functions on the same inputs, so a
+    difference in `params` or `tables` means a floating-point library call (conv2d, erfc, sum) did not reproduce
+    itself inside one process."""
+    enc, dec = StageDump(), StageDump()
+    bsl = codec.compress(rgb, enc)
+    rec = codec.decompress(bsl, dec)
+    S = codec.S
+    for scl in range(S - 1, -1, -1):
+        for b in range(3):
+            pe, pd = enc.params[(scl, b)], dec.params[(scl, b)]
+            if not np.array_equal(pe, pd):
+                bad = np.argwhere(pe != pd)
+                return (f"network outputs differ at scale {scl} band {b}: {len(bad)} of {pe.size} values, first at "
+                        f"(channel, row, col) = {tuple(int(v) for v in bad[0])} (max abs difference {float(np.abs(pe - pd).max()):.3e}); "
+                        f"torch threads {torch.get_num_threads()}")
+            for clr in range(3):
+                te, td = enc.tables[(scl, b, clr)], dec.tables[(scl, b, clr)]
+                if not np.array_equal(te, td):
+                    bad = np.argwhere(te != td)
+                    return (f"integer CDF tables differ at scale {scl} band {b} channel {clr} although the network outputs "
+                            f"agree: {len(bad)} of {te.size} entries, first at (position, entry) = {tuple(int(v) for v in bad[0])}; "
+                            f"torch threads {torch.get_num_threads()}")
+                if not np.array_equal(enc.symbols[(scl, b, clr)], dec.symbols[(scl, b, clr)]):
+                    return f"tables agree but the coder returned other symbols at scale {scl} band {b} channel {clr}"
+    return "this repetition round-tripped" if np.array_equal(rec, rgb) else "stages agree but the pixels differ (inverse transform)"
 
 
 def _interleave(pl: np.ndarray) -> np.ndarray:

@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     from llicti_b200 import _lib as L
     hdr = open(os.path.join(ROOT, "include", "llicti.h")).read()
     declared = set(re.findall(r"LLICTI_API[^;(]*?\b(llicti_\w+)\s*\(", hdr))
-    assert len(declared) >= 21
+    assert len(declared) >= 22 and "llicti_status" in declared
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     for name in declared:
         assert hasattr(built_lib, name), name
@@ -231,7 +231,68 @@ def test_product_sources_do_not_import_the_oracle():
                     offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
     bench = open(os.path.join(root, "bench.py")).read()
-    body = bench[bench.index("def run_b200("):bench.index("# ---- CPU baseline")]
+    body = bench[bench.index("# B200 arm"):bench.index("def main(")]
     assert not re.search(r"^\s*(from|import)\s+oracle\b", body, re.M), "bench.py's product arm imports the oracle"
+    assert "cpu_oracle_pass(" not in body, "bench.py's product arm runs the CPU oracle in-process (it belongs in the reference arm's process)"
     main = open(os.path.join(root, "main.py")).read()
     assert not re.search(r"^\s*(from|import)\s+oracle\b", main, re.M)
+
+
+def test_container_fingerprint_and_checksum():
+    """A stream records what its decoder must share with the encoder (CNN implementation, numerics profile, weights)
+    and the checksum of its image; a codec with another fingerprint refuses it.  Streams without a fingerprint
+    (the reference's own header row leaves slots 4-8 empty) are accepted."""
+    from llicti_b200 import container
+    rng = np.random.default_rng(3)
+    S, H, W = 2, 20, 24
+    rgb = rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)
+    off = np.arange(9 * S + 1, dtype=np.uint64) * 3
+    blob = rng.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    mm = np.array([[0, -5, -7, 255, 9, 11]], dtype=np.int16)
+    fp = container.fingerprint(1, 0, 0xDEADBEEF)
+    bsl = container.assemble(S, 0, 5, 6, 0, rgb, blob, off, mm, fp=fp, checksum=True)[0]
+    assert bsl[0][5] == fp and len(bsl[0][6]) == 4 and bsl[0][7:] == [b"", b""]
+    import zlib
+    assert container.image_checksum(bsl[0]) == zlib.crc32(rgb[0].tobytes())
+    container.parse(S, 0, [bsl], fp=fp)                                       # same codec: fine
+    with pytest.raises(ValueError, match="cnn_impl=1.*cnn_impl=0"):
+        container.parse(S, 0, [bsl], fp=container.fingerprint(0, 0, 0xDEADBEEF))
+    with pytest.raises(ValueError, match="weights crc32"):
+        container.parse(S, 0, [bsl], fp=container.fingerprint(1, 0, 0x12345678))
+    plain = container.assemble(S, 0, 5, 6, 0, rgb, blob, off, mm)[0]          # the reference's header row: nothing to check
+    assert plain[0][4:] == [b""] * 5 and container.image_checksum(plain[0]) is None
+    container.parse(S, 0, [plain], fp=fp)
+    bad = [list(r) for r in bsl]
+    bad[0][5] = b"\x07abc"
+    with pytest.raises(ValueError):
+        container.parse(S, 0, [bad], fp=fp)
+
+
+def test_rate_table_text_is_the_references():
+    """RateLogger.display prints the reference's table (loggers/rate.py:120-168): the expected strings below were
+    produced by the unmodified reference's text_log_list on the same numbers (tools: see the test body)."""
+    from datetime import datetime
+    from llicti_b200.rate import RateLogger
+    rate = (np.arange(3 * 9, dtype=np.float64).reshape(3, 9) + 1) / 8
+    now = datetime(2020, 1, 2, 3, 4, 5)
+    te = RateLogger.format_table(7, rate, 0.0, "te", now)
+    assert te == ("   Test Epoch:   7  Rates: hdr -> 0.12+0.25+0.38(b0=0.750) 0.50+0.62+0.75(b1=1.875) 0.88+1.00+1.12(b2=3.000) (hd=5.625) \n"
+                  "                                   scl0-> 1.25+1.38+1.50(b0=4.125) 1.62+1.75+1.88(b1=5.250) 2.00+2.12+2.25(b2=6.375) (s0=15.750) \n"
+                  "                                   scl1-> 2.38+2.50+2.62(b0=7.500) 2.75+2.88+3.00(b1=8.625) 3.12+3.25+3.38(b2=9.750) (s1=25.875) "
+                  "((47.250))  (03:04:05)")
+    va = RateLogger.format_table(7, rate[:1], 0.0, "va", now)
+    assert va == "  Valid Epoch:   7  Rates: scl0-> 0.12+0.25+0.38(b0=0.750) 0.50+0.62+0.75(b1=1.875) 0.88+1.00+1.12(b2=3.000) (s0=5.625) ((5.625))  (03:04:05)"
+    if os.path.exists("/root/reference/loggers/rate.py"):                      # build container: against the reference itself
+        import importlib.util
+        import types
+        spec = importlib.util.spec_from_file_location("ref_rate", "/root/reference/loggers/rate.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref = mod.RateLogger()
+        lines = []
+        ref.logger = types.SimpleNamespace(info=lines.append)
+        ref._get_time_now_str = lambda: now.strftime("%H:%M:%S")
+        for typ in ("te", "tr", "va", "it"):
+            lines.clear()
+            ref.text_log_list(7, rate, 0.001, typ)
+            assert lines[0] == RateLogger.format_table(7, rate, 0.001, typ, now), typ

@@ -39,6 +39,12 @@ def test_main_eval_model(tmp_path, cfg_name, ocfg):
     log = (tmp_path / exp / "logs" / "exp_debug.log").read_text()
     assert log.count("(Check: Decoded img matches original)") == 2, log[-2000:]
     assert "Checkpoint loaded successfully" in log
+    # the shipped configs run the product CNN (tcgen05), and its kernel class really launched
+    import re
+    assert "cnn_impl=1 (tcgen05" in log, log[-2000:]
+    m = re.search(r"cnn\[tcgen05\]=(\d+)", log)
+    assert m and int(m.group(1)) >= 2 * 2 * 3 * len(ocfg.dwtlevels), log[-2000:]
+    assert "Test Epoch:" in log and "Rates: hdr ->" in log and "(hd=" in log       # the reference's rate table text
     assert (ckdir / "checkpoint.pth.tar").exists()
 
 

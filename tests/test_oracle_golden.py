@@ -98,3 +98,26 @@ def test_oracle_round_trip_modes(sub_len):
     img = O.synthetic_image(40, 56, 9)
     codec = O.OracleCodec(cfg, sd, sub_len=sub_len)
     assert np.array_equal(codec.decompress(codec.compress(img)), img)
+
+
+@pytest.mark.parametrize("threads", [1, 8, 16, 32, 64])
+def test_oracle_round_trips_in_the_product_process_state(threads):
+    """The oracle must reproduce itself (compress -> decompress) in a process that has loaded the product package
+    and done torch CPU work at another thread count first (round 1: bench.py lost its cpu_baseline leg on one host
+    to an oracle that did not), whatever the thread count; diagnose_round_trip names the stage if it does not."""
+    import torch
+    import llicti_b200  # noqa: F401  (the product package, as in bench.py's B200 arm)
+    from oracle import llicti_oracle as O
+    x = torch.randn(512, 512)
+    (x @ x).sum().item()                                   # warms the intra-op pool at the default thread count
+    before = torch.get_num_threads()
+    try:
+        torch.set_num_threads(threads)
+        for cfg, (H, W) in ((O.OracleConfig(dwtlevels=(0, 1), chs=60), (64, 96)), (O.OracleConfig(), (53, 77))):
+            codec = O.OracleCodec(cfg, O.synthetic_state_dict(cfg))
+            img = O.synthetic_image(H, W, 11)
+            rec = codec.decompress(codec.compress(img))
+            assert np.array_equal(rec, img), O.diagnose_round_trip(codec, img)
+            assert O.diagnose_round_trip(codec, img) == "this repetition round-tripped"
+    finally:
+        torch.set_num_threads(before)
