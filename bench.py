@@ -8,10 +8,10 @@ Workloads are BASELINE.json's configs:
 
   c0  configs[0]  llicti_A, 24 x 768x512, torchac-compatible streams (the reference's own CPU-runnable case)
   c1  configs[1]  llicti_B, the same 24 images, torchac-compatible byte-exact mode
-  c2  configs[2]  llicti_A, 100 x 2040x1356 in 4 batches of 25, interleaved-substream coder      <- default at N = 1
-  c3  configs[3]  llicti_A, 512 x 3840x2160 sharded over the N GPUs (512 / N distinct images per rank, batches of 16)
+  c2  configs[2]  llicti_A, 100 x 2040x1356 in 2 batches of 50, interleaved-substream coder      <- default at N = 1
+  c3  configs[3]  llicti_A, 512 x 3840x2160 sharded over the N GPUs (512 / N distinct images per rank, batches of 32)
                                                                                                 <- default at N > 1
-  c4  configs[4]  llicti_A, 50,000 x 512x512 sharded over the N GPUs (batches of 256)
+  c4  configs[4]  llicti_A, 50,000 x 512x512 sharded over the N GPUs (batches of 512)
 
 Every rank generates ITS OWN images (seeded by global image index); step k codes batch k mod (resident batches).
 Rank 0 prints ONE JSON line on stdout:
@@ -49,14 +49,14 @@ WORKLOADS = {
                cfg="llicti_A.json", batch=24, H=512, W=768, sub_len=0, total=24, shard=False),
     "c1": dict(desc="configs[1]: llicti_B eval_model, 24 synthetic 768x512 RGB images, torchac-compatible byte-exact mode",
                cfg="llicti_B.json", batch=24, H=512, W=768, sub_len=0, total=24, shard=False),
-    "c2": dict(desc="configs[2]: llicti_A, 100 synthetic 2040x1356 images in 4 batches of 25, interleaved-substream coder",
-               cfg="llicti_A.json", batch=25, H=1356, W=2040, sub_len=2048, total=100, shard=False),
-    "c3": dict(desc="configs[3]: llicti_A, 512 synthetic 3840x2160 images sharded over the GPUs, batches of 16, "
+    "c2": dict(desc="configs[2]: llicti_A, 100 synthetic 2040x1356 images in 2 batches of 50, interleaved-substream coder",
+               cfg="llicti_A.json", batch=50, H=1356, W=2040, sub_len=2048, total=100, shard=False),
+    "c3": dict(desc="configs[3]: llicti_A, 512 synthetic 3840x2160 images sharded over the GPUs, batches of 32, "
                     "interleaved-substream coder",
-               cfg="llicti_A.json", batch=16, H=2160, W=3840, sub_len=2048, total=512, shard=True),
-    "c4": dict(desc="configs[4]: llicti_A, 50,000 synthetic 512x512 images sharded over the GPUs, batches of 256, "
+               cfg="llicti_A.json", batch=32, H=2160, W=3840, sub_len=2048, total=512, shard=True),
+    "c4": dict(desc="configs[4]: llicti_A, 50,000 synthetic 512x512 images sharded over the GPUs, batches of 512, "
                     "interleaved-substream coder",
-               cfg="llicti_A.json", batch=256, H=512, W=512, sub_len=2048, total=50000, shard=True),
+               cfg="llicti_A.json", batch=512, H=512, W=512, sub_len=2048, total=50000, shard=True),
 }
 METRIC = "encode+decode round-trip megapixels/s (compress then decompres of every image)"
 MAC_PER_POS = {88: (53152, 61600, 78496), 60: (29520, 35280, 46800)}
@@ -110,31 +110,48 @@ def load_cfg(name):
 # =============================================================================================
 # reference arm / cpu_baseline: the CPU oracle, one image per step
 # =============================================================================================
-def cpu_oracle_pass(cfg_json, H, W, steps, warmup, seed0=0):
-    """Time the CPU oracle (compress + decompress of one image per step).  Every image must round-trip;
-    a mismatch is diagnosed (which stream's table differs between encode and decode) before raising."""
+def cpu_oracle_pass(cfg_name, cfg_json, H, W, steps, warmup, seed0=0):
+    """Time the reference's CPU path (compress + decompres of one image per step): the UNMODIFIED reference from
+    oracle/_ref when it travelled with the repo (kind "reference": its own LLICTI.compress / LLICTI.decompres, called as
+    LLICTIAgent.eval_model calls them), else the oracle's restatement (kind "port").  Every image must round-trip; a
+    mismatch is diagnosed (which stream's table differs between encode and decode) before raising."""
     from oracle import llicti_oracle as O
+    from oracle import make_ref
     torch.set_num_threads(os.cpu_count() or 1)
     ocfg = O.OracleConfig.from_dict(cfg_json)
-    codec = O.OracleCodec(ocfg, O.synthetic_state_dict(ocfg), sub_len=0)
+    sd = O.synthetic_state_dict(ocfg)
+    codec = O.OracleCodec(ocfg, sd, sub_len=0)
+    model = None if os.environ.get("LLICTI_BENCH_PORT") else make_ref.load_reference_model(cfg_name, sd)
+    kind = "reference" if model is not None else "port"
     times = []
     for it in range(warmup + steps):
         img = O.synthetic_image(H, W, seed0 + it)
-        t0 = time.perf_counter()
-        bsl = codec.compress(img)
-        t1 = time.perf_counter()
-        rec = codec.decompress(bsl)
-        t2 = time.perf_counter()
-        if not np.array_equal(rec, img):
-            raise RuntimeError(f"CPU oracle round trip of image {seed0 + it} is not lossless: " + O.diagnose_round_trip(codec, img))
-        log(f"[cpu oracle] step {it}: enc {t1 - t0:.2f}s dec {t2 - t1:.2f}s")
+        if model is not None:
+            x = torch.from_numpy(img.astype(np.float32) / np.float32(255.0))[None]      # what the reference's ToTensor() loader yields
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                bsl, _ = model.compress(x.clone())
+                t1 = time.perf_counter()
+                rec_f = model.decompres(bsl, torch.device("cpu"))
+                t2 = time.perf_counter()
+            ok = ((x - rec_f) * 255).abs().max().item() < 0.5                             # eval_model's own check (llicti_agent.py:151)
+        else:
+            t0 = time.perf_counter()
+            bsl = codec.compress(img)
+            t1 = time.perf_counter()
+            rec = codec.decompress(bsl)
+            t2 = time.perf_counter()
+            ok = np.array_equal(rec, img)
+        if not ok:
+            raise RuntimeError(f"CPU {kind} round trip of image {seed0 + it} is not lossless: " + O.diagnose_round_trip(codec, img))
+        log(f"[cpu {kind}] step {it}: enc {t1 - t0:.2f}s dec {t2 - t1:.2f}s")
         if it >= warmup:
             times.append((t1 - t0, t2 - t1))
     enc = sum(t[0] for t in times)
     dec = sum(t[1] for t in times)
     px = H * W * len(times) / 1e6
     return {"value": px / (enc + dec), "encode_mpps": px / enc, "decode_mpps": px / dec,
-            "ms_per_step": 1e3 * (enc + dec) / len(times), "cores": torch.get_num_threads()}
+            "ms_per_step": 1e3 * (enc + dec) / len(times), "cores": torch.get_num_threads(), "kind": kind}
 
 
 def reference_sample_shape(wl):
@@ -150,15 +167,16 @@ def run_reference(args, rank, world):
     wl = WORKLOADS[args.workload]
     cfg = load_cfg(wl["cfg"])
     sh, sw = reference_sample_shape(wl)
-    r = cpu_oracle_pass(cfg, sh, sw, args.steps, args.warmup)
+    r = cpu_oracle_pass(wl["cfg"], cfg, sh, sw, args.steps, args.warmup)
     sample = (f"{args.steps} step(s) of 1 synthetic {sw}x{sh} image each, compress+decompres, {r['cores']} torch threads, "
-              f"model config {wl['cfg']}")
+              f"model config {wl['cfg']}; " + ("the unmodified reference (oracle/_ref: its sources + stand-ins for compressai / "
+              "torchac / easydict)" if r["kind"] == "reference" else "the oracle's restatement of the reference (oracle/_ref absent)"))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "model_config": wl["cfg"], "sample": sample},
             "encode_mpps": r["encode_mpps"], "decode_mpps": r["decode_mpps"],
-            "cpu_baseline": {"value": r["value"], "unit": "MP/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": r["value"], "unit": "MP/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
             "e2e": {"value": r["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

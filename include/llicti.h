@@ -51,7 +51,10 @@ enum {
     LLICTI_E_CUDA = -2,     /* a CUDA runtime call failed                 */
     LLICTI_E_NOMEM = -3,    /* workspace / output capacity too small      */
     LLICTI_E_STREAM = -4,   /* malformed bitstream                        */
-    LLICTI_E_NODEVICE = -5  /* no usable CUDA device (no CPU fallback)    */
+    LLICTI_E_NODEVICE = -5, /* no usable CUDA device (no CPU fallback)    */
+    LLICTI_E_TIMEOUT = -6   /* kernels that hand work to each other inside one decode (torchac-compatible streams) were not
+                               resident together and gave up; the context has switched to the schedule without such
+                               hand-overs: llicti_decode_host retries by itself, llicti_decode_dev must be called again */
 };
 
 /* Floating-point conventions of the GMM-CDF stage (see DESIGN.md "numerics profile"). */
@@ -180,6 +183,15 @@ LLICTI_API int llicti_encode_host(llicti_ctx *ctx, const uint8_t *rgb, int n, in
                        size_t out_cap, uint64_t *stream_off, int16_t *minmax, void *stream);
 LLICTI_API int llicti_encode_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, uint8_t *out_dev,
                       size_t out_cap, uint64_t *stream_off_dev, int16_t *minmax_dev, void *stream);
+
+/* LLICTI.forward for a batch (LLICTI_nets.py:101-123, 318-342, 802-811, 827-935; entropy_layer_nets.py:160-183,
+ * 121-139): the rate-estimation path of validate() / training -- no coding, -log2 of the probability mass of every
+ * sample.  Float lifting of :40-49 (NOT the integer transform of compress), un-padded lazyDWT (H and W must be
+ * multiples of 2^num_scales), the same CNN kernels, then the point likelihood.
+ *   fplanes_dev[s]  float [n][12][Hs][Ws]  scratch / by-product: the fp32 phase planes of scale s
+ *   sinfo_dev[s]    float [n][9][Hs][Ws]   self-information in bits, index 3*band + clr (what forward returns) */
+LLICTI_API int llicti_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W,
+                       float *const *fplanes_dev, float *const *sinfo_dev, void *stream);
 
 /* LLICTI.decompres for a batch (LLICTI_nets.py:161-179, 415-509).
  *   blob / stream_off  as produced by encode

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libllicti_b200.so")
 
 MAX_SCALES = 8
-OK, E_ARG, E_CUDA, E_NOMEM, E_STREAM, E_NODEVICE = 0, -1, -2, -3, -4, -5
+OK, E_ARG, E_CUDA, E_NOMEM, E_STREAM, E_NODEVICE, E_TIMEOUT = 0, -1, -2, -3, -4, -5, -6
 NUM_TORCH_CUDA, NUM_TORCH_CPU = 0, 1
 CNN_FP32, CNN_TCGEN05 = 0, 1
 KERNEL_CLASSES = ("split", "cnn", "bounds", "encode", "compact", "index", "decode", "merge", "window")
@@ -75,6 +75,8 @@ _PROTOS = {
                                      C.c_int, C.c_void_p, C.c_void_p]),
     "llicti_decode_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_void_p, C.c_void_p]),
+    "llicti_forward_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.c_void_p]),
     "llicti_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llicti_launch_count": (C.c_int64, [C.c_void_p]),
     "llicti_profile": (C.c_int, [C.c_void_p, C.c_int]),

@@ -223,6 +223,22 @@ class Codec:
                                            n, H, W, out.data_ptr(), self._stream()))
         return out
 
+    # -- rate estimation (LLICTI.forward) ----------------------------------------------------------
+    def forward_dev(self, rgb: torch.Tensor):
+        """rgb uint8 [n,3,H,W] CUDA tensor, H and W multiples of 2^S -> list over scales of float32 [n,9,Hs,Ws]
+        self-informations in bits (index 3*band + clr), as LLICTI.forward returns them."""
+        assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
+        n, _, H, W = rgb.shape
+        self.reserve(n, H, W)
+        g = self.geometry(H, W)
+        S = self.cfg.num_scales
+        fpl = [torch.empty((n, 12, g.Hs[s], g.Ws[s]), dtype=torch.float32, device=self.device) for s in range(S)]
+        out = [torch.empty((n, 9, g.Hs[s], g.Ws[s]), dtype=torch.float32, device=self.device) for s in range(S)]
+        fp = (C.c_void_p * S)(*[t.data_ptr() for t in fpl])
+        op = (C.c_void_p * S)(*[t.data_ptr() for t in out])
+        L.check(self.lib.llicti_forward_dev(self._ctx, rgb.data_ptr(), n, H, W, fp, op, self._stream()))
+        return out
+
     # -- bytestream_list assembly (LLICTI_nets.py:346-354, 409-411) ----------------------------
     def to_bytestream_lists(self, rgb: np.ndarray, blob: np.ndarray, off: np.ndarray, mm: np.ndarray):
         S = self.cfg.num_scales

@@ -200,7 +200,9 @@ static int read_status(llicti_ctx *ctx, cudaStream_t st) {
         int32_t zero = 0;
         cudaMemcpyAsync(ctx->d_status, &zero, sizeof(zero), cudaMemcpyHostToDevice, st);
         cudaStreamSynchronize(st);
-        set_error(s == LLICTI_E_NOMEM ? "device-side capacity overflow while coding" : "malformed bitstream container");
+        set_error(s == LLICTI_E_NOMEM ? "device-side capacity overflow while coding"
+                  : s == LLICTI_E_TIMEOUT ? "decode kernels that hand work to each other were not resident together and gave up"
+                                          : "malformed bitstream container");
     }
     return s;
 }
@@ -265,6 +267,7 @@ int llicti_create(const llicti_config *cfg, const llicti_weights *w, llicti_ctx 
         }
         ctx->side_stream = s2; ctx->ev_fork = e1; ctx->ev_join = e2;
         if (rc == LLICTI_OK) rc = probe_concurrent_kernels(ctx, &ctx->concurrent_kernels);
+        if (rc == LLICTI_OK) rc = apply_decode_test_knobs();
     }
     if (rc == LLICTI_OK) {
         cudaError_t e = cudaMalloc((void **)&ctx->d_status, sizeof(int32_t));
@@ -318,12 +321,12 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
     ctx->blob_cap = n * (size_t)g.max_stream_bytes;
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_blob, ctx->blob_cap));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_x00, n * 3 * (size_t)g.Hs[S - 1] * g.Ws[S - 1]));
-    // window items, their flags and the compact symbol arrays exist only for the windowed decode schedules
-    // (torchac-compatible streams, or decode_impl = 2); the group schedule of the substream container needs none
-    const bool windows = ctx->cfg.decode_impl == 2 || (ctx->cfg.decode_impl == 0 && ctx->cfg.sub_len == 0);
+    // window items, their flags and the compact symbol arrays serve the windowed decode schedules: every band of
+    // torchac-compatible streams, and the bands of a substream container with too few chains for the group schedule
+    const bool windows = ctx->cfg.decode_impl != 1;
     ctx->wave_ws = false;
     if (windows) {
-        ctx->items_cap = (int64_t)n * decode_items_per_image(p);
+        ctx->items_cap = std::max<int64_t>(decode_items_capacity(ctx->cfg, p, max_images), 1);
         LLICTI_CUDA(cudaMalloc(&ctx->d_items, wb * (size_t)ctx->items_cap * decode_item_bytes()));
         LLICTI_CUDA(cudaMalloc((void **)&ctx->d_item_flags, (size_t)decode_flag_words(wb * ctx->items_cap) * sizeof(uint32_t)));
         LLICTI_CUDA(cudaMalloc(&ctx->d_chain_state_raw, n * 9 * 64));
@@ -339,7 +342,12 @@ int64_t llicti_launch_count(const llicti_ctx *ctx) { return ctx ? ctx->launches 
 
 int llicti_status(llicti_ctx *ctx, void *stream) {
     LLICTI_REQUIRE(ctx, "null context");
-    return read_status(ctx, (cudaStream_t)stream);
+    const int rc = read_status(ctx, (cudaStream_t)stream);
+    if (rc == LLICTI_E_TIMEOUT && !ctx->no_coresidency) {      // the next decode takes the schedule without hand-overs
+        ctx->no_coresidency = true;
+        drop_decode_graph(ctx);
+    }
+    return rc;
 }
 
 int llicti_profile(llicti_ctx *ctx, int enable) {
@@ -462,6 +470,30 @@ int llicti_encode_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int
     return launch_minmax16(ctx, ctx->d_minmax, minmax_dev, n, st);
 }
 
+// LLICTI.forward for a batch: float lifting + un-padded pyramid, then per scale and band the CNN and the point
+// likelihood of every sample.  Uses the workspace's int16 planes and parameter buffer.
+int llicti_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, float *const *fplanes_dev,
+                       float *const *sinfo_dev, void *stream) {
+    int rc = check_batch(ctx, n, H, W);
+    if (rc) return rc;
+    LLICTI_REQUIRE(rgb_dev && fplanes_dev && sinfo_dev, "null argument");
+    const Plan &p = ctx->plan;
+    const llicti_geom &g = p.g;
+    LLICTI_REQUIRE(H % (1 << g.num_scales) == 0 && W % (1 << g.num_scales) == 0,
+                   "forward() needs H and W to be multiples of 2^num_scales = %d (the reference's un-padded lazyDWT, "
+                   "LLICTI_nets.py:218-241, concatenates phases of equal size; validate() pads its images, "
+                   "agents/llicti_agent.py:105-116)", 1 << g.num_scales);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s = 0; s < g.num_scales; ++s) LLICTI_REQUIRE(fplanes_dev[s] && sinfo_dev[s], "null plane pointer");
+    if ((rc = launch_color_split_float(ctx, p, rgb_dev, n, fplanes_dev, ctx->d_planes, st))) return rc;
+    for (int s = 0; s < g.num_scales; ++s)
+        for (int b = 0; b < 3; ++b) {
+            if ((rc = cnn(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st))) return rc;
+            if ((rc = launch_self_info(ctx, ctx->d_params, fplanes_dev[s], b, n, g.Hs[s] * g.Ws[s], sinfo_dev[s], st))) return rc;
+        }
+    return LLICTI_OK;
+}
+
 int llicti_encode_host(llicti_ctx *ctx, const uint8_t *rgb, int n, int H, int W, uint8_t *out, size_t out_cap,
                        uint64_t *stream_off, int16_t *minmax, void *stream) {
     int rc = check_batch(ctx, n, H, W);
@@ -512,6 +544,7 @@ int llicti_decode_dev(llicti_ctx *ctx, const uint8_t *blob_dev, const uint64_t *
         for (const char *c = v ? v : "-"; *c; ++c) h = (h ^ (unsigned char)*c) * 1099511628211ull;
         h = (h ^ 0xFFu) * 1099511628211ull;
     }
+    h = (h ^ (ctx->no_coresidency ? 0x55u : 0xAAu)) * 1099511628211ull;
     const long long kd[4] = {n, H, W, (long long)h};
     bool same = ctx->dec_key_seen;
     for (int i = 0; i < 5; ++i) same = same && kp[i] == ctx->dec_key_ptr[i];
@@ -584,7 +617,10 @@ static int decode_dev_launches(llicti_ctx *ctx, const uint8_t *blob_dev, const u
         }
         if (s > 0 && (rc = launch_interleave(ctx, p, s, ctx->d_planes[s], ctx->d_planes[s - 1], n, st))) return rc;
     }
-    return launch_merge_color(ctx, p, ctx->d_planes[0], n, rgb_out_dev, st);
+    if ((rc = launch_merge_color(ctx, p, ctx->d_planes[0], n, rgb_out_dev, st))) return rc;
+    // schedules whose kernels wait on one another end by reporting an abandoned wait (LLICTI_E_TIMEOUT)
+    if (ctx->cfg.sub_len == 0 && ctx->cfg.decode_impl != 1 && !ctx->no_coresidency) return launch_abort_check(ctx, st);
+    return LLICTI_OK;
 }
 
 int llicti_decode_host(llicti_ctx *ctx, const uint8_t *blob, const uint64_t *stream_off, const int16_t *minmax,
@@ -611,8 +647,20 @@ int llicti_decode_host(llicti_ctx *ctx, const uint8_t *blob, const uint64_t *str
     LLICTI_CUDA(cudaMemcpyAsync(ctx->d_x00, x00_rgb, (size_t)n * 3 * p.g.Hs[S - 1] * p.g.Ws[S - 1], cudaMemcpyHostToDevice, st));
     if ((rc = llicti_decode_dev(ctx, ctx->d_blob, ctx->d_stream_off, ctx->d_minmax16, ctx->d_x00, n, H, W, ctx->d_rgb, st)))
         return rc;
+    rc = read_status(ctx, st);
+    if (rc == LLICTI_E_TIMEOUT && !ctx->no_coresidency) {
+        // the producer / consumer kernels were not resident together: decode again with the schedule whose kernels
+        // never wait on each other, and stay with it
+        ctx->no_coresidency = true;
+        drop_decode_graph(ctx);
+        if ((rc = llicti_decode_dev(ctx, ctx->d_blob, ctx->d_stream_off, ctx->d_minmax16, ctx->d_x00, n, H, W, ctx->d_rgb, st)))
+            return rc;
+        rc = read_status(ctx, st);
+    }
+    if (rc) return rc;
     LLICTI_CUDA(cudaMemcpyAsync(rgb_out, ctx->d_rgb, (size_t)n * 3 * H * W, cudaMemcpyDeviceToHost, st));
-    return read_status(ctx, st);
+    LLICTI_CUDA(cudaStreamSynchronize(st));
+    return LLICTI_OK;
 }
 
 }  // extern "C"

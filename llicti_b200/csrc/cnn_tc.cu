@@ -292,8 +292,8 @@ __device__ __forceinline__ void build_a_row(const uint16_t *sSeg, uint8_t *sA, i
 }
 
 // Barrier slots in shared memory.
-enum { B_W = 0, B_AFULL = 1, B_AEMPTY = 3, B_D0FULL = 5, B_DFREE = 7, B_H0FULL = 9, B_D1FULL = 11, B_H1FULL = 13,
-       B_D2FULL = 15, B_COUNT = 17 };
+enum { B_W = 0, B_AFULL = 1, B_AEMPTY = 3, B_D0FULL = 5 /* [slot][sub-network] */, B_DFREE = 9, B_H0FULL = 11, B_D1FULL = 13,
+       B_H1FULL = 15, B_D2FULL = 17, B_COUNT = 19 };
 
 template <int BAND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -334,7 +334,8 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar(B_AFULL + s), 2 * TC_M);
             mbar_init(bar(B_AEMPTY + s), 1);
-            mbar_init(bar(B_D0FULL + s), 1);
+            mbar_init(bar(B_D0FULL + 2 * s), 1);
+            mbar_init(bar(B_D0FULL + 2 * s + 1), 1);
             mbar_init(bar(B_DFREE + s), 2 * TC_M);
             mbar_init(bar(B_H0FULL + s), TC_M);
             mbar_init(bar(B_D1FULL + s), 1);
@@ -374,7 +375,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             mbar_expect_tx(bar(B_W), (uint32_t)tg.pair_bytes);
             tma_bulk_g2s(smem_u32(sW0), packed + (size_t)pair * tg.pair_bytes, (uint32_t)tg.pair_bytes, bar(B_W));
             mbar_wait(bar(B_W), 0);
-            const uint32_t idesc0 = umma_idesc(2 * NP), idesc1 = umma_idesc(NP), idesc2 = umma_idesc(16);
+            const uint32_t idesc1 = umma_idesc(NP), idesc2 = umma_idesc(16);
             const uint32_t w0_lbo = (uint32_t)(2 * NP) * 16, w1_lbo = (uint32_t)NP * 16, w2_lbo = 16 * 16;
             const uint32_t w1_bytes = (uint32_t)(NP / 8) * NP * 16, w2_bytes = (uint32_t)(NP / 8) * 16 * 16;
             auto issue_l0 = [&](int it) {
@@ -384,11 +385,18 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
                 tc_fence_after();
                 const uint32_t d0 = tmem + (uint32_t)(s * TC_SLOT_COLS);
                 const uint32_t a0 = smem_u32(sA) + s * a_stage;
+                // Layer 0 of the two sub-networks as two MMA groups with a commit each: sub-network 0's epilogue starts
+                // while sub-network 1's layer 0 still runs, and from then on the two run half a phase apart -- one reads
+                // its accumulators out of TMEM (the scarce resource: 64 B/clk against 212 KB per tile) while the other waits
+                // for its next layer's MMAs, instead of both reading, then both waiting.
 #pragma unroll
-                for (int ks = 0; ks < K0p / 16; ++ks)
-                    umma_bf16(d0, umma_desc(a0 + ks * 2 * a_lbo, a_lbo, 128),
-                              umma_desc(smem_u32(sW0) + ks * 2 * w0_lbo, w0_lbo, 128), idesc0, ks > 0);
-                umma_commit(bar(B_D0FULL + s));
+                for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                    for (int ks = 0; ks < K0p / 16; ++ks)
+                        umma_bf16(d0 + (uint32_t)(g * NP), umma_desc(a0 + ks * 2 * a_lbo, a_lbo, 128),
+                                  umma_desc(smem_u32(sW0) + ks * 2 * w0_lbo + (uint32_t)(g * NP) * 16, w0_lbo, 128), idesc1, ks > 0);
+                    umma_commit(bar(B_D0FULL + 2 * s + g));
+                }
                 umma_commit(bar(B_AEMPTY + s));
             };
             if (my_tiles > 0) issue_l0(0);
@@ -428,7 +436,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             const int tile = tile0 + it * tile_stride;
             const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + row;   // this thread's position: plane row, column
             // ---- layer 0 -> H0 ----
-            mbar_wait(bar(B_D0FULL + s), (it >> 1) & 1);
+            mbar_wait(bar(B_D0FULL + 2 * s + g), (it >> 1) & 1);
             tc_fence_after();
             if (NP == 96) epilogue_hidden<96>(dbase + (uint32_t)(g * NP), h, a_lbo);
             else epilogue_hidden<64>(dbase + (uint32_t)(g * NP), h, a_lbo);

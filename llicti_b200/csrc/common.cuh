@@ -125,6 +125,7 @@ struct llicti_ctx {
     int64_t sym_cap = 0;
     void *d_chain_state_raw = nullptr;
     void *side_stream = nullptr, *ev_fork = nullptr, *ev_join = nullptr;   // second stream of the wavefront decode (consumer kernel)
+    bool no_coresidency = false;       // a decode gave up waiting (LLICTI_E_TIMEOUT): only schedules without kernel-to-kernel hand-overs from now on
     bool concurrent_kernels = false;   // two kernels on two streams really overlap (false under kernel-serialising profilers)
     bool wave_ws = false;              // workspace holds three bands' worth of decode buffers (wavefront schedule)
     uint32_t *d_item_flags = nullptr;  // [items_cap] readiness flags of the piped decode schedule
@@ -174,6 +175,10 @@ struct ProfScope {
 // kernels_color.cu
 int launch_color_split(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n, int16_t *const *planes,
                        int32_t *minmax, cudaStream_t st);
+int launch_color_split_float(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n, float *const *fplanes,
+                             int16_t *const *planes, cudaStream_t st);
+int launch_self_info(llicti_ctx *ctx, const float *params, const float *fplanes, int band, int n, int P, float *sinfo,
+                     cudaStream_t st);
 int launch_merge_color(llicti_ctx *ctx, const Plan &p, const int16_t *planes0, int n, uint8_t *rgb,
                        cudaStream_t st);
 int launch_x00_from_header(llicti_ctx *ctx, const Plan &p, const uint8_t *x00_rgb, int n, int16_t *planes_last,
@@ -214,6 +219,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
                        const int32_t *minmax, int n, const uint8_t *blob, const uint64_t *suboff,
                        const uint32_t *sublen, cudaStream_t st);
 int64_t decode_items_per_image(const Plan &p);
+int64_t decode_items_capacity(const llicti_config &cfg, const Plan &p, int max_images);
 size_t decode_item_bytes();
 bool wave_eligible(const llicti_ctx *ctx, const llicti::Plan &p, int scale, int n);
 int wave_bands_in_workspace(const llicti_config &cfg, int max_images);
@@ -221,6 +227,8 @@ int probe_concurrent_kernels(llicti_ctx *ctx, bool *ok);
 int launch_decode_scale_wave(llicti_ctx *ctx, const llicti::Plan &p, int scale, int16_t *planes, const int32_t *minmax, int n,
                              const uint8_t *blob, const uint64_t *suboff, const uint32_t *sublen, cudaStream_t st);
 int64_t decode_flag_words(int64_t items_cap);
+int launch_abort_check(llicti_ctx *ctx, cudaStream_t st);
+int apply_decode_test_knobs();
 int read_decode_stats(uint64_t *out, int reset);
 int launch_selftest_fdiv(llicti_ctx *ctx, long long n_pairs, uint64_t seed, unsigned long long *mismatches_dev, cudaStream_t st);
 int launch_decode_table(llicti_ctx *ctx, const int16_t *table, int n_sym, int Lp, int S, const uint8_t *in,

@@ -65,16 +65,17 @@ split_rgb_kernel(const uint8_t *__restrict__ rgb, int H, int W, int Hs, int Ws, 
     }
 }
 
-// Scale s+1 from the x00 planes of scale s (both int16).
+// Scale s+1 from the x00 planes of scale s (int16 for the coder, fp32 for the rate-estimation path).
+template <typename T>
 __global__ void __launch_bounds__(256)
-split_x00_kernel(const int16_t *__restrict__ prev, int Hp, int Wp, int Hs, int Ws, int H11, int W11,
-                 int16_t *__restrict__ planes) {
+split_x00_kernel(const T *__restrict__ prev, int Hp, int Wp, int Hs, int Ws, int H11, int W11,
+                 T *__restrict__ planes) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     const int img = blockIdx.z;
     if (c >= Ws) return;
-    const int16_t *base = prev + (size_t)img * 12 * Hp * Wp;   // channels 0..2 = x00 of the finer scale
-    int16_t *out = planes + (size_t)img * 12 * Hs * Ws + (size_t)r * Ws + c;
+    const T *base = prev + (size_t)img * 12 * Hp * Wp;   // channels 0..2 = x00 of the finer scale
+    T *out = planes + (size_t)img * 12 * Hs * Ws + (size_t)r * Ws + c;
     const size_t ps = (size_t)Hs * Ws, pp = (size_t)Hp * Wp;
     const int r1 = 2 * min(r, H11 - 1) + 1, c1 = 2 * min(c, W11 - 1) + 1;
     const int rr[4] = {2 * r, r1, 2 * r, r1};
@@ -178,9 +179,70 @@ int launch_color_split(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n
     ctx->launches += 2;
     for (int s = 1; s < g.num_scales; ++s) {
         dim3 grid((g.Ws[s] + 255) / 256, g.Hs[s], n);
-        split_x00_kernel<<<grid, 256, 0, st>>>(planes[s - 1], g.Hs[s - 1], g.Ws[s - 1], g.Hs[s], g.Ws[s],
+        split_x00_kernel<int16_t><<<grid, 256, 0, st>>>(planes[s - 1], g.Hs[s - 1], g.Ws[s - 1], g.Hs[s], g.Ws[s],
                                                 g.Hs[s - 1] / 2, g.Ws[s - 1] / 2, planes[s]);
         ctx->launches += 1;
+    }
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+// ---- rate-estimation path (LLICTI.forward): the FLOAT lifting of LLICTI_nets.py:40-49 --------------------
+// x = k / 255 (ToTensor: IEEE division on the host), Co = R - B, t = B + round(Co * 255 / 2) / 255,
+// Cg = G - t, Y = t + round(Cg * 255 / 2) / 255, Y -= 127/255 (:110), every step in fp32 with round-half-even --
+// operation for operation what the reference's tensor expressions evaluate.  Not the integer transform of the
+// coder (that one floors): odd differences land on other integers, and a product like 1.4999999 rounds down.
+// One thread per scale-0 position; writes the fp32 planes the likelihood reads and the int16 planes
+// (value * 255, an integer up to fp32 noise) the CNN kernels read.  H and W are multiples of 2^S: no padding.
+__global__ void __launch_bounds__(256)
+split_rgb_float_kernel(const uint8_t *__restrict__ rgb, int H, int W, int Hs, int Ws, NumericsProfile np,
+                       float *__restrict__ fplanes, int16_t *__restrict__ planes) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;
+    if (c >= Ws) return;
+    const uint8_t *base = rgb + (size_t)img * 3 * H * W;
+    const size_t ps = (size_t)Hs * Ws;
+    float *fo = fplanes + (size_t)img * 12 * ps + (size_t)r * Ws + c;
+    int16_t *io = planes + (size_t)img * 12 * ps + (size_t)r * Ws + c;
+    const int rr[4] = {2 * r, 2 * r + 1, 2 * r, 2 * r + 1};   // x00, x11, x01, x10
+    const int cc[4] = {2 * c, 2 * c + 1, 2 * c + 1, 2 * c};
+    const float mean_y = (float)(127.0 / 255.0);
+    auto div255 = [&](float v) { return np.div255_recip ? __fmul_rn(v, 1.0f / 255.0f) : __fdiv_rn(v, 255.0f); };
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        const size_t o = (size_t)rr[ph] * W + cc[ph];
+        const float R = __fdiv_rn((float)base[o], 255.0f), G = __fdiv_rn((float)base[o + (size_t)H * W], 255.0f),
+                    B = __fdiv_rn((float)base[o + 2 * (size_t)H * W], 255.0f);
+        const float co = __fsub_rn(R, B);
+        const float t = __fadd_rn(B, div255(rintf(__fmul_rn(__fmul_rn(co, 255.0f), 0.5f))));
+        const float cg = __fsub_rn(G, t);
+        const float y = __fsub_rn(__fadd_rn(t, div255(rintf(__fmul_rn(__fmul_rn(cg, 255.0f), 0.5f)))), mean_y);
+        const float v[3] = {y, co, cg};
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            fo[(ph * 3 + ch) * ps] = v[ch];
+            io[(ph * 3 + ch) * ps] = (int16_t)__float2int_rn(__fmul_rn(v[ch], 255.0f));
+        }
+    }
+}
+
+int launch_color_split_float(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n, float *const *fplanes,
+                             int16_t *const *planes, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_SPLIT, st);
+    const llicti_geom &g = p.g;
+    {
+        dim3 grid((g.Ws[0] + 255) / 256, g.Hs[0], n);
+        split_rgb_float_kernel<<<grid, 256, 0, st>>>(rgb, g.H, g.W, g.Hs[0], g.Ws[0], ctx->num, fplanes[0], planes[0]);
+    }
+    ctx->launches += 1;
+    for (int s = 1; s < g.num_scales; ++s) {
+        dim3 grid((g.Ws[s] + 255) / 256, g.Hs[s], n);
+        split_x00_kernel<float><<<grid, 256, 0, st>>>(fplanes[s - 1], g.Hs[s - 1], g.Ws[s - 1], g.Hs[s], g.Ws[s],
+                                                       g.Hs[s - 1] / 2, g.Ws[s - 1] / 2, fplanes[s]);
+        split_x00_kernel<int16_t><<<grid, 256, 0, st>>>(planes[s - 1], g.Hs[s - 1], g.Ws[s - 1], g.Hs[s], g.Ws[s],
+                                                         g.Hs[s - 1] / 2, g.Ws[s - 1] / 2, planes[s]);
+        ctx->launches += 2;
     }
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;

@@ -90,29 +90,50 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
 // array starts as sentinels and the consumer's store is the publication (data = flag).
 // Waits inside the piped grid are bounded: a wait that outlives any legitimate kernel run time (a
 // programming error, or a grid that is not co-resident) traps instead of hanging the GPU.
-constexpr uint32_t kMaxPolls = 1u << 25;      // x >= 100 ns per poll: several seconds
+// The kernels of the piped and wavefront schedules wait for one another (consumers for items, producers for
+// decoded symbols), which only makes progress while both sides are resident.  CUDA does not promise that -- another
+// process on the GPU, a tool that serialises launches, a smaller part -- so no wait is unbounded and none traps: a
+// wait that outlives g_max_polls raises g_abort, every waiter sees the flag and leaves, the launch sequence ends
+// with abort_to_status_kernel (status = LLICTI_E_TIMEOUT), and the host re-runs the decode with the split
+// schedule, whose kernels never wait on each other (api.cu: llicti_decode_host).
+__device__ uint32_t g_max_polls = 1u << 25;    // x >= 100 ns per poll: several seconds (LLICTI_TEST_POLL_LIMIT shortens it in tests)
+__device__ int g_abort = 0;
+__device__ int g_test_starve = 0;              // LLICTI_TEST_STARVE: producers leave at once (a producer kernel that never runs)
+
+__device__ __forceinline__ bool aborted() { return *(volatile int *)&g_abort != 0; }
+__device__ __forceinline__ bool give_up(uint32_t polls) {
+    if ((polls & 1023u) == 1023u && aborted()) return true;
+    if (polls > *(volatile uint32_t *)&g_max_polls) { atomicExch(&g_abort, 1); return true; }
+    return false;
+}
+
+__global__ void abort_to_status_kernel(int32_t *status) {
+    if (g_abort) { atomicExch(status, LLICTI_E_TIMEOUT); g_abort = 0; }
+}
 
 template <bool kPipe>
 __device__ __forceinline__ int read_symbol(const int16_t *p) {
     if (!kPipe) return (int)*p;
     int v = ld_relaxed_s16(p);
     for (uint32_t polls = 0; v == (int)kSentinel; ++polls) {       // not decoded yet
-        if (polls > kMaxPolls) __trap();
+        if (give_up(polls)) return 0;                             // the launch is being abandoned: any value will do
         __nanosleep(200);
         v = ld_relaxed_s16(p);
     }
     return v;
 }
 
-__device__ __forceinline__ void wait_flag(const uint32_t *flag, unsigned long long &polls, long long &waited) {
-    if (ld_relaxed_u32(flag) != 0u) return;
+// false: the wait was abandoned (g_abort)
+__device__ __forceinline__ bool wait_flag(const uint32_t *flag, unsigned long long &polls, long long &waited) {
+    if (ld_relaxed_u32(flag) != 0u) return true;
     const long long t0 = clock64();
     for (uint32_t spins = 0; ld_relaxed_u32(flag) == 0u; ++spins) {
-        if (spins > kMaxPolls * 4u) __trap();
+        if (give_up(spins >> 2)) return false;
         ++polls;
         if (LLICTI_WAIT_SLEEP) __nanosleep(LLICTI_WAIT_SLEEP);
     }
     waited += clock64() - t0;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -145,7 +166,7 @@ __device__ __forceinline__ void produce_item(const float *__restrict__ pp, const
             const long long i_last = (long long)j + (min((long long)tb * 32 + 31, steps - 1)) * dg.S;
             const int16_t *p = syms + (size_t)(clr - 1) * sym_cap + i_last;
             for (uint32_t polls = 0; ld_relaxed_s16(p) == (int)kSentinel; ++polls) {
-                if (polls > kMaxPolls) __trap();
+                if (give_up(polls)) break;
                 __nanosleep(500);
             }
         }
@@ -495,7 +516,7 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
     }
     long long i = j + (long long)it_begin * 32 * S;
 
-    if (kPipe) wait_flag(flags + it_begin, polls, waited);
+    if (kPipe && !wait_flag(flags + it_begin, polls, waited)) return;      // abandoned launch (g_abort)
     const long long first_wait = waited;
     const uint4 *src = items + lane;
     const uint4 *first = src + (size_t)it_begin * kItemU4;
@@ -580,7 +601,7 @@ __device__ __forceinline__ void consume_chain(const ChainCtx &cx, int n_sym, con
         __syncwarp();
         i += 32ll * S;
         if (!have_next) {
-            wait_flag(flags + it + 1, polls, waited);
+            if (!wait_flag(flags + it + 1, polls, waited)) return;          // abandoned launch (g_abort)
             const uint4 *nx = src + (size_t)(it + 1) * kItemU4;
             n0 = load_chunk<kPipe>(nx); n1 = load_chunk<kPipe>(nx + 32); n2 = load_chunk<kPipe>(nx + 64); n3 = load_chunk<kPipe>(nx + 96);
             base_nxt = load_base<kPipe>(items + (size_t)(it + 1) * kItemU4, lane);
@@ -726,7 +747,7 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
         if (chain < 0) {
             uint32_t role;
             for (uint32_t spins = 0; (role = ld_relaxed_u32(&ctl[256 + smid])) == 0u; ++spins) {
-                if (spins > kMaxPolls) __trap();
+                if (give_up(spins)) break;
                 __nanosleep(100);
             }
             if (role == 2u) producer_id = (int)atomicAdd(&ctl[513], 1u);
@@ -747,6 +768,7 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
         return;
     }
     if (producer_id < 0) return;       // on a consumer SM without a ticket
+    if (g_test_starve) return;
 
     const int r5 = producer_id % 5;    // Y : Co : Cg producers start 1 : 2 : 2, then help the other channels
     const int clr0 = r5 == 0 ? 0 : r5 <= 2 ? 1 : 2;
@@ -757,7 +779,7 @@ decode_band_pipe_kernel(const float *__restrict__ params, int16_t *syms, size_t 
             uint32_t w = 0;
             if (lane == 0) w = atomicAdd(&ctl[514 + clr], 1u);
             w = __shfl_sync(kFull, w, 0);
-            if (w >= total) break;
+            if (w >= total || aborted()) break;
             const int tb = (int)(w / (uint32_t)n);
             const int img = (int)(w - (uint32_t)tb * (uint32_t)n);
             const int ch = img * 3 + clr;
@@ -856,7 +878,7 @@ wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
 #pragma unroll
     for (int b = 0; b < 3; ++b)
         if (wa.b[b].it1 > wa.b[b].it0) act[n_act++] = b;
-    if (n_act == 0) return;
+    if (n_act == 0 || g_test_starve) return;
     int lo[3];
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -890,7 +912,7 @@ wave_produce_kernel(WaveArgs wa, const int32_t *__restrict__ minmax, NumericsPro
                 uint32_t w = 0;
                 if (lane == 0) w = atomicAdd(&ctl[514 + q], 1u);
                 w = __shfl_sync(kFull, w, 0);
-                if (w >= total) break;
+                if (w >= total || aborted()) break;
                 const int tb = wb.it0 + (int)(w / (uint32_t)n);
                 const int img = (int)(w % (uint32_t)n);
                 const size_t ch = (size_t)img * 3 + clr;
@@ -988,16 +1010,51 @@ decode_band_warp_kernel(const float *__restrict__ params, int16_t *__restrict__ 
 // Neighbouring groups work on neighbouring positions (substream j codes symbols j, j + S, ...), so the
 // parameter planes are read in full sectors.
 // ------------------------------------------------------------------------------------------
+// The 60 network outputs of a position arrive in shared memory two steps ahead of their use (cp.async, no
+// registers held): the parameter planes were written by the CNN launch before and are far larger than L2, so every
+// position is an HBM access of ~1 us that must not sit on the serial chain of the coder.
+constexpr int kGroupStages = 3;
+__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// GMM channel `clr` of a position from its 60 staged network outputs, with the mean coupling (LLICTI_nets.py:385-392).
+__device__ __forceinline__ void staged_channel(const float *__restrict__ sp, int clr, int y0, int y1, const NumericsProfile &np,
+                                               GmmChannel &c) {
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        c.sigma[m] = sp[clr * kM + m];
+        c.mu[m] = sp[(3 + clr) * kM + m];
+        c.w[m] = sp[(6 + clr) * kM + m];
+    }
+    if (clr == 1) {
+        const float f0 = div255((float)y0, np);
+#pragma unroll
+        for (int m = 0; m < kM; ++m) c.mu[m] = __fadd_rn(c.mu[m], __fmul_rn(sp[9 * kM + m], f0));
+    } else if (clr == 2) {
+        const float f0 = div255((float)y0, np), f1 = div255((float)y1, np);
+#pragma unroll
+        for (int m = 0; m < kM; ++m)
+            c.mu[m] = __fadd_rn(c.mu[m], __fadd_rn(__fmul_rn(sp[10 * kM + m], f0), __fmul_rn(sp[11 * kM + m], f1)));
+    }
+    gmm_prepare(c, np);
+}
+
 template <int G>
 __global__ void __launch_bounds__(128)
 decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__ planes, const int32_t *__restrict__ minmax,
                          DecodeGeom dg, NumericsProfile np, const uint8_t *__restrict__ blob,
                          const uint64_t *__restrict__ suboff, const uint32_t *__restrict__ sublen, int total_sub, int n) {
     static_assert(G == 2 || G == 4 || G == 8 || G == 16, "group size");
+    __shared__ float stage[kGroupStages][128 / G][kParamCh];
     const int lane = threadIdx.x & 31, sub = lane & (G - 1);
     const int gshift = lane - sub;
     constexpr uint32_t gm = (1u << G) - 1u;
     const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gib = threadIdx.x / G;                 // group within the block
     const bool valid = gid < (long long)n * dg.S;
     // whole warps without work leave; otherwise every lane stays for the warp-wide ballots and shuffles
     if (!__any_sync(kFull, valid)) return;
@@ -1006,103 +1063,131 @@ decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__
     const float *pp = params + (size_t)img * kParamCh * P;
     int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1)) * P;
     const int32_t *mm = minmax + img * 4;
-    const int lo[3] = {-127, mm[0], mm[1]};
-    const int hi[3] = {128, mm[2], mm[3]};
-    AcDecoderW dec[3];
-    CdfGrid grid[3];
-#pragma unroll
-    for (int clr = 0; clr < 3; ++clr) {
-        const size_t e = (size_t)img * total_sub + dg.sub_first[clr] + j;
-        dec[clr].init(blob + suboff[e], valid ? sublen[e] : 0u);
-        grid[clr] = make_grid(lo[clr], hi[clr]);
+    const int mn_co = mm[0], mn_cg = mm[1], mx_co = mm[2], mx_cg = mm[3];
+    // The decoder of the channel being decoded is always `d`: the three are rotated after every symbol, so the body
+    // below exists once in the code (a tenth of the unrolled form's instruction footprint).
+    AcDecoderW d, d_next, d_last;
+    {
+        const size_t e0 = (size_t)img * total_sub + j;
+        d.init(blob + suboff[e0 + dg.sub_first[0]], valid ? sublen[e0 + dg.sub_first[0]] : 0u);
+        d_next.init(blob + suboff[e0 + dg.sub_first[1]], valid ? sublen[e0 + dg.sub_first[1]] : 0u);
+        d_last.init(blob + suboff[e0 + dg.sub_first[2]], valid ? sublen[e0 + dg.sub_first[2]] : 0u);
     }
     const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
     const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
     const int n_steps = valid ? (dg.n_sym - j + dg.S - 1) / dg.S : 0;
     const int max_steps = dg.max_steps;          // warp-uniform trip count
-    unsigned long long rounds = 0;
-    for (int t = 0; t < max_steps; ++t) {
-        const bool live = t < n_steps;
-        const int i = j + t * dg.S;
-        const int r = live ? i / dg.crop_w : 0, c = live ? i - r * dg.crop_w : 0;
-        const size_t pidx = (size_t)r * dg.Ws + c;
-        int yv[3] = {0, 0, 0};
-#pragma unroll
-        for (int clr = 0; clr < 3; ++clr) {
-            const CdfGrid &g = grid[clr];
-            const int last = g.Lp - 1;
-            GmmChannel ch;
-            if (live) {
-                load_channel(pp, P, pidx, clr, yv[0], yv[1], np, ch);
-            } else {
-#pragma unroll
-                for (int m = 0; m < kM; ++m) { ch.sigma[m] = 1.f; ch.mu[m] = 0.f; ch.w[m] = 0.2f; ch.rinv[m] = 1.f; }
-                ch.fast = 1;
-            }
-            float mean = 0.f;
-#pragma unroll
-            for (int m = 0; m < kM; ++m) mean = fmaf(ch.w[m], ch.mu[m], mean);
-            const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
-            const uint32_t low = dec[clr].low, sm1 = dec[clr].high - dec[clr].low;
-            const uint64_t value = dec[clr].value;
-            // search state: q(s_lo) <= target is known (or s_lo = 0), q(s_hi) > target is known (s_hi = last: 2^16)
-            int s_lo = 0, s_hi = last, base = min(max(kc - (G / 2 - 1), 0), max(last - (G - 1), 0)), stride = 1, round = 0;
-            bool done = !live, miss_down = false;
-            uint32_t c_low = 0, c_high = 0x10000u;
-            int sym = 0;
-            for (;;) {
-                const int k = base + sub * stride;
-                uint32_t q = 0x10000u;
-                if (!done && k < last) q = cdf_q(ch, g, k, np);
-                const uint64_t nl = (uint64_t)low + (((uint64_t)sm1 * q + q) >> 16);
-                const unsigned le = __ballot_sync(kFull, nl <= value);
-                const int cnt = __popc((le >> gshift) & gm);
-                const int i_lo = max(cnt - 1, 0), i_hi = min(i_lo + 1, G - 1);
-                const uint32_t q_lo = __shfl_sync(kFull, q, i_lo, G), q_hi = __shfl_sync(kFull, q, i_hi, G);
-                if (!done) {
-                    ++round;
-                    if (cnt == 0) {
-                        if (base == 0 && stride == 1) {        // below q(0): torchac's search returns symbol 0
-                            sym = 0; c_low = q_lo; c_high = q_hi; done = true;
-                        } else {
-                            s_hi = max(base, 1);
-                            miss_down = true;
-                        }
-                    } else if (cnt == G) {
-                        s_lo = base + (G - 1) * stride;
-                        miss_down = false;
-                    } else {
-                        s_lo = base + (cnt - 1) * stride;
-                        s_hi = min(base + cnt * stride, last);
-                        miss_down = false;
-                        if (stride == 1) { sym = s_lo; c_low = q_lo; c_high = q_hi; done = true; }
-                    }
-                    if (!done) {
-                        // next probes: the G - 1 entries next to the window that missed, then four times as far, then
-                        // whatever is left in equal steps; always inside [s_lo, s_hi]
-                        const int full = max((s_hi - s_lo + G - 2) / (G - 1), 1);
-                        stride = min(full, round == 1 ? 1 : round == 2 ? 4 : full);
-                        base = miss_down ? max(s_hi - (G - 1) * stride, s_lo) : s_lo;
-                    }
-                }
-                if (__all_sync(kFull, done)) break;
-            }
-            if (live) {
-                if (t + 1 < n_steps) dec[clr].consume(c_low, c_high);      // torchac does not update after the last symbol
-                yv[clr] = sym + lo[clr];
-                rounds += (unsigned long long)(round - 1);
-            }
+    auto prefetch = [&](int t) {                 // the group's lanes share the 60 loads of step t's position
+        if (t < n_steps) {
+            const int i = j + t * dg.S;
+            const int r = i / dg.crop_w, c = i - r * dg.crop_w;
+            const float *src = pp + (size_t)r * dg.Ws + c;
+            float *dst = stage[t % kGroupStages][gib];
+            for (int ch = sub; ch < kParamCh; ch += G) cp_async_f32(dst + ch, src + (size_t)ch * P);
         }
-        if (live && sub < 3) {
-            const int16_t v = (int16_t)(sub == 0 ? yv[0] : sub == 1 ? yv[1] : yv[2]);
-            int16_t *dst = yb + (size_t)sub * P + pidx;
+        cp_async_commit();
+    };
+    prefetch(0);
+    prefetch(1);
+    unsigned long long rounds = 0;
+    int t = 0, clr = 0, y0 = 0, y1 = 0, r = 0, c = 0;
+    bool live = false;
+    const float *sp = stage[0][gib];
+#pragma unroll 1
+    for (;;) {
+        if (clr == 0) {
+            if (t >= max_steps) break;
+            cp_async_wait<1>();                      // step t has landed (step t+1 may be in flight)
+            __syncwarp();                            // ... for every lane of the group; and step t-1's reads are done
+            prefetch(t + 2);
+            live = t < n_steps;
+            const int i = j + t * dg.S;
+            r = live ? i / dg.crop_w : 0;
+            c = live ? i - r * dg.crop_w : 0;
+            sp = stage[t % kGroupStages][gib];
+        }
+        const int lo_c = clr == 0 ? -127 : clr == 1 ? mn_co : mn_cg;
+        const CdfGrid g = make_grid(lo_c, clr == 0 ? 128 : clr == 1 ? mx_co : mx_cg);
+        const int last = g.Lp - 1;
+        GmmChannel ch;
+        if (live) {
+            staged_channel(sp, clr, y0, y1, np, ch);
+        } else {
+#pragma unroll
+            for (int m = 0; m < kM; ++m) { ch.sigma[m] = 1.f; ch.mu[m] = 0.f; ch.w[m] = 0.2f; ch.rinv[m] = 1.f; }
+            ch.fast = 1;
+        }
+        float mean = 0.f;
+#pragma unroll
+        for (int m = 0; m < kM; ++m) mean = fmaf(ch.w[m], ch.mu[m], mean);
+        const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
+        const uint32_t low = d.low, sm1 = d.high - d.low;
+        const uint64_t value = d.value;
+        // search state: q(s_lo) <= target is known (or s_lo = 0), q(s_hi) > target is known (s_hi = last: 2^16)
+        int s_lo = 0, s_hi = last, base = min(max(kc - (G / 2 - 1), 0), max(last - (G - 1), 0)), stride = 1, round = 0;
+        bool done = !live, miss_down = false;
+        uint32_t c_low = 0, c_high = 0x10000u;
+        int sym = 0;
+#pragma unroll 1
+        for (;;) {
+            const int k = base + sub * stride;
+            uint32_t q = 0x10000u;
+            if (!done && k < last) q = cdf_q(ch, g, k, np);
+            const uint64_t nl = (uint64_t)low + (((uint64_t)sm1 * q + q) >> 16);
+            const unsigned le = __ballot_sync(kFull, nl <= value);
+            const int cnt = __popc((le >> gshift) & gm);
+            const int i_lo = max(cnt - 1, 0), i_hi = min(i_lo + 1, G - 1);
+            const uint32_t q_lo = __shfl_sync(kFull, q, i_lo, G), q_hi = __shfl_sync(kFull, q, i_hi, G);
+            if (!done) {
+                ++round;
+                if (cnt == 0) {
+                    if (base == 0 && stride == 1) {        // below q(0): torchac's search returns symbol 0
+                        sym = 0; c_low = q_lo; c_high = q_hi; done = true;
+                    } else {
+                        s_hi = max(base, 1);
+                        miss_down = true;
+                    }
+                } else if (cnt == G) {
+                    s_lo = base + (G - 1) * stride;
+                    miss_down = false;
+                } else {
+                    s_lo = base + (cnt - 1) * stride;
+                    s_hi = min(base + cnt * stride, last);
+                    miss_down = false;
+                    if (stride == 1) { sym = s_lo; c_low = q_lo; c_high = q_hi; done = true; }
+                }
+                if (!done) {
+                    // next probes: the entries next to the window that missed, then four times as far, then whatever is
+                    // left of [s_lo, s_hi] in G equal steps (probe 0 repeats s_lo, the others lie strictly inside: every
+                    // round narrows the interval, also for G = 2)
+                    const int full = max((s_hi - s_lo + G - 1) / G, 1);
+                    stride = min(full, round == 1 ? 1 : round == 2 ? 4 : full);
+                    base = miss_down ? max(s_hi - (G - 1) * stride, s_lo) : s_lo;
+                }
+            }
+            if (__all_sync(kFull, done)) break;
+        }
+        if (live) {
+            if (t + 1 < n_steps) d.consume(c_low, c_high);      // torchac does not update after the last symbol
+            rounds += (unsigned long long)(round - 1);
+        }
+        const int yv = sym + lo_c;
+        if (live && sub == 0) {                                  // the sample goes straight into the planes, with the replicate padding
+            const int16_t v = (int16_t)yv;
+            int16_t *dst = yb + (size_t)clr * P + (size_t)r * dg.Ws + c;
             dst[0] = v;
             const bool last_c = rep_w && c == dg.crop_w - 1, last_r = rep_h && r == dg.crop_h - 1;
             if (last_c) dst[1] = v;
             if (last_r) dst[dg.Ws] = v;
             if (last_c && last_r) dst[dg.Ws + 1] = v;
         }
+        // rotate: the next channel's decoder becomes `d`
+        { const AcDecoderW tmp = d; d = d_next; d_next = d_last; d_last = tmp; }
+        if (clr == 0) { y0 = yv; clr = 1; }
+        else if (clr == 1) { y1 = yv; clr = 2; }
+        else { clr = 0; ++t; }
     }
+    cp_async_wait<0>();
     if (sub == 0 && rounds) atomicAdd(&g_decode_stats[0], rounds);       // search rounds beyond the first (window misses)
 }
 
@@ -1126,6 +1211,26 @@ static DecodeGeom make_decode_geom(const Plan &p, int scale, int band) {
     return dg;
 }
 
+// Turns a raised g_abort into the context's status flag (and clears it); last launch of every decode that used a
+// schedule with kernel-to-kernel hand-overs.
+int launch_abort_check(llicti_ctx *ctx, cudaStream_t st) {
+    abort_to_status_kernel<<<1, 1, 0, st>>>(ctx->d_status);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+// Test hooks, read once per context creation: LLICTI_TEST_POLL_LIMIT shortens the bounded waits, LLICTI_TEST_STARVE
+// makes every producer leave at once (what a producer kernel that cannot become resident looks like to the consumers).
+int apply_decode_test_knobs() {
+    const char *pl = getenv("LLICTI_TEST_POLL_LIMIT"), *sv = getenv("LLICTI_TEST_STARVE");
+    const uint32_t polls = pl && *pl ? (uint32_t)atoll(pl) : (1u << 25);
+    const int starve = sv && *sv ? atoi(sv) : 0;
+    LLICTI_CUDA(cudaMemcpyToSymbol(g_max_polls, &polls, sizeof(polls)));
+    LLICTI_CUDA(cudaMemcpyToSymbol(g_test_starve, &starve, sizeof(starve)));
+    return LLICTI_OK;
+}
+
 size_t decode_item_bytes() { return (size_t)kItemU4 * sizeof(uint4); }
 
 // Window items one image needs for its largest band.
@@ -1139,6 +1244,31 @@ int64_t decode_items_per_image(const Plan &p) {
             m = std::max<int64_t>(m, 3ll * dg.S * dg.items_per_chain);
         }
     return m;
+}
+
+static int env_int(const char *name, int dflt);
+static int group_lanes() { return std::max(env_int("LLICTI_GROUP_LANES", 8), 2); }
+static long long group_min_warps() { return env_int("LLICTI_GROUP_MIN_WARPS", 592); }      // one warp per scheduler of a B200
+
+// Does band (scale, b) of a batch of n images take the group schedule?  (Substream container, default decoder, enough
+// chains to occupy the machine.)
+static bool group_scheduled(const llicti_config &cfg, const DecodeGeom &dg, int n) {
+    return cfg.sub_len > 0 && cfg.decode_impl == 0 && (long long)n * dg.S * group_lanes() / 32 >= group_min_warps();
+}
+
+// Window items the workspace must hold for batches of up to max_images images: the largest band that can reach a
+// windowed schedule (torchac-compatible streams: every band; substream container: the bands with too few chains for
+// the group schedule at some batch size n <= max_images).
+int64_t decode_items_capacity(const llicti_config &cfg, const Plan &p, int max_images) {
+    int64_t cap = 0;
+    for (int s = 0; s < p.g.num_scales; ++s)
+        for (int b = 0; b < 3; ++b) {
+            const DecodeGeom dg = make_decode_geom(p, s, b);
+            int n_win = max_images;                                  // largest batch that still takes windows for this band
+            while (n_win > 0 && group_scheduled(cfg, dg, n_win)) --n_win;
+            cap = std::max<int64_t>(cap, 3ll * n_win * dg.S * dg.items_per_chain);
+        }
+    return cap;
 }
 
 int read_decode_stats(uint64_t *out, int reset) {
@@ -1170,9 +1300,12 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
         LLICTI_CUDA(cudaGetLastError());
         return LLICTI_OK;
     }
-    if (ctx->cfg.sub_len > 0 && ctx->cfg.decode_impl == 0) {
+    // Group schedule where the launch has enough chains to occupy the machine (its serial chain per symbol is long: the
+    // whole CDF evaluation); with few chains -- the coarse scales -- the windows are produced by all SMs in parallel and
+    // the serial part is the short chain kernel.
+    const int G = group_lanes();
+    if (group_scheduled(ctx->cfg, dg, n)) {
         ProfScope prof_(ctx, KC_DECODE, st);
-        const int G = std::max(env_int("LLICTI_GROUP_LANES", 4), 2);
         const long long threads = (long long)n * dg.S * G;
         const int blocks = (int)((threads + 127) / 128);
         if (G >= 16) decode_band_group_kernel<16><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
@@ -1204,7 +1337,7 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
         LLICTI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pipe_resident, decode_band_pipe_kernel, 32, 0));
     const int ctas_per_sm = std::min(std::min(std::max(env_int("LLICTI_PIPE_CTAS_PER_SM", 12), cons_per_sm + 1), 24), pipe_resident);
     const int cons_sms = (3 * n + cons_per_sm - 1) / cons_per_sm;
-    const bool piped = dg.S == 1 && ctas_per_sm > cons_per_sm && cons_sms <= sm_count / 2 && 3 * n <= kConsPerSmMax * (sm_count / 2) && sm_count <= 256 &&
+    const bool piped = !ctx->no_coresidency && dg.S == 1 && ctas_per_sm > cons_per_sm && cons_sms <= sm_count / 2 && 3 * n <= kConsPerSmMax * (sm_count / 2) && sm_count <= 256 &&
                        !env_int("LLICTI_NO_PIPE", 0);
     if (piped) {
         ProfScope prof_(ctx, KC_DECODE, st);
@@ -1318,7 +1451,7 @@ static int wave_strips(int Hs) {      // strips of >= 32 rows, at most 8 (measur
 // consumer warp each, and a workspace reserved with three bands' worth of buffers.)
 bool wave_eligible(const llicti_ctx *ctx, const Plan &p, int scale, int n) {
     if (ctx->cfg.decode_impl != 0 || ctx->cfg.cnn_impl != LLICTI_CNN_TCGEN05 || ctx->cfg.sub_len != 0) return false;
-    if (!ctx->wave_ws || !ctx->concurrent_kernels || env_int("LLICTI_NO_WAVE", 0) || env_int("LLICTI_NO_PIPE", 0)) return false;
+    if (!ctx->wave_ws || !ctx->concurrent_kernels || ctx->no_coresidency || env_int("LLICTI_NO_WAVE", 0) || env_int("LLICTI_NO_PIPE", 0)) return false;
     if (wave_strips(p.g.Hs[scale]) < 2) return false;
     // A strip is decoded in whole 32-symbol items, so band b may stop up to ceil(31 / crop_w) rows short of the strip's last
     // row; the three-row lag between the bands covers ONE missing row (launch_decode_scale_wave), i.e. rows of >= 32 symbols.

@@ -149,9 +149,15 @@ class LLICTI(nn.Module):
         return c
 
     # -- reference interface ----------------------------------------------------------------------
+    @torch.no_grad()
     def forward(self, x):
-        raise NotImplementedError("the training / rate-estimation forward pass is outside the B200 hot path "
-                                  "(SURVEY.md section 8f)")
+        """x float32 [B,3,H,W] in [0,1] (uint8/255), H and W multiples of 2^num_scales -> list[num_scales] of
+        float32 [B,9,Hs,Ws] self-informations (reference :101-123): the rate-estimation path of validate().  Inference
+        only: the values carry no autograd graph (training is outside the B200 path)."""
+        assert x.dim() == 4 and x.shape[1] == 3, "expected [B,3,H,W]"
+        codec = self._codec()
+        rgb = torch.round(x.to(codec.device) * 255).to(torch.uint8).contiguous()
+        return codec.forward_dev(rgb)
 
     @torch.no_grad()
     def compress(self, x: torch.Tensor):

@@ -333,8 +333,12 @@ class OracleNet:
     def params(self, band: int, planes_int: np.ndarray) -> np.ndarray:
         """planes_int int16 [12,Hs,Ws] (only phases 0..band are read) -> fp32 [12*M,Hs,Ws].
         The network sees value/255 in fp32 (LLICTI_nets.py:143-144)."""
-        pre = f"entropymodel.entmdls_scale_band.0.{band}."
         y = torch.from_numpy(planes_int[None].astype(np.int16)) / 255  # int16 / 255 -> fp32 true division
+        return self.params_float(band, y)[0].numpy()
+
+    def params_float(self, band: int, y: torch.Tensor) -> torch.Tensor:
+        """y fp32 [B, >= 3 (band + 1), Hs, Ws] -> fp32 [B, 12 M, Hs, Ws] (get_params, LLICTI_nets.py:822-825)."""
+        pre = f"entropymodel.entmdls_scale_band.0.{band}."
         acc = None
         for name, phase, pad in self.branches[band]:
             inp = F.pad(y[:, 3 * phase:3 * phase + 3], pad=pad, mode="replicate")
@@ -342,8 +346,7 @@ class OracleNet:
             acc = o if acc is None else acc + o
         h = torch.relu(acc)
         h = torch.relu(F.conv2d(h, self.sd[pre + "layers1toL.0.weight"], self.sd[pre + "layers1toL.0.bias"], groups=4))
-        p = F.conv2d(h, self.sd[pre + "layers1toL.2.weight"], self.sd[pre + "layers1toL.2.bias"], groups=4)
-        return p[0].numpy()
+        return F.conv2d(h, self.sd[pre + "layers1toL.2.weight"], self.sd[pre + "layers1toL.2.bias"], groups=4)
 
 
 # --------------------------------------------------------------------------
@@ -616,6 +619,66 @@ class OracleCodec:
         full[0] += 127                                                                # :174
         rgb = ycocg_r_to_rgb(full)
         return rgb.astype(np.uint8)
+
+
+# --------------------------------------------------------------------------
+# Rate estimation: LLICTI.forward (LLICTI_nets.py:101-123) -> LLICTIEntropyLayer.forward (:318-342)
+# -> LLICTIEntropyModel4.forward / get_self_infos (:802-811, :827-935) -> GaussianConditionalLosslessGMM.forward
+# (entropy_layer_nets.py:160-183) with _likelihood_fk (:121-139).  The training / validation path: no coding,
+# -log2 of the probability mass of every sample.
+# --------------------------------------------------------------------------
+LIKELIHOOD_BOUND = 1e-9          # compressai GaussianConditional(likelihood_bound=1e-9), applied at entropy_layer_nets.py:181-182
+
+
+def float_ycocg_r(x: torch.Tensor) -> torch.Tensor:
+    """LLICTI_nets.py:40-49 with RNDFACTOR = 255 (lif_prec_bits = 8): the lifting steps in fp32 on values k/255,
+    rounding half to even.  NOT the integer transform compress() uses (:62-74 floors): training sees this one."""
+    R, G, B = x[:, 0:1], x[:, 1:2], x[:, 2:3]
+    Co = R - B
+    t = B + torch.round(Co * 255 / 2) / 255
+    Cg = G - t
+    Y = t + torch.round(Cg * 255 / 2) / 255
+    return torch.cat((Y, Co, Cg), dim=1)
+
+
+def forward_self_informations(cfg: OracleConfig, net: "OracleNet", rgb: np.ndarray) -> List[np.ndarray]:
+    """rgb uint8 [3,H,W], H and W multiples of 2^S (the un-padded lazyDWT needs equal phase sizes; the reference
+    trains on such patches and pads validation images, agents/llicti_agent.py:105-116) -> per scale fp32
+    [9,Hs,Ws]: -log2 p of band b, channel clr at index 3 b + clr."""
+    S, M = len(cfg.dwtlevels), cfg.num_mixtures
+    assert rgb.shape[1] % 2 ** S == 0 and rgb.shape[2] % 2 ** S == 0
+    x = torch.from_numpy(rgb.astype(np.float32) / np.float32(255.0))[None]          # ToTensor()
+    x = float_ycocg_r(x)
+    x[:, 0] = x[:, 0] - (2 ** 7 - 1) / (2 ** 8 - 1)                                  # :110, mean_y_ycocg :26
+    out = []
+    half = float(0.5 / 255.0)
+    for lev in cfg.dwtlevels:                                                        # lazyDWT(pad=False), :218-241
+        st, of = 2 ** (lev + 1), 2 ** lev
+        y = torch.cat((x[:, :, 0::st, 0::st], x[:, :, of::st, of::st], x[:, :, 0::st, of::st], x[:, :, of::st, 0::st]), dim=1)
+        B_, _, H, W = y.shape
+        infos = []
+        for b in range(3):
+            params = net.params_float(b, y[:, 0:3 * (b + 1)])
+            yt = y[:, 3 * (b + 1):3 * (b + 2)]
+            stdev, mean, wts = params[:, 0:3 * M], params[:, 3 * M:6 * M].clone(), params[:, 6 * M:9 * M]
+            a, bb, d = params[:, 9 * M:10 * M], params[:, 10 * M:11 * M], params[:, 11 * M:12 * M]
+            mean[:, M:2 * M] = mean[:, M:2 * M] + a * yt[:, 0:1]                     # :858-860
+            mean[:, 2 * M:3 * M] = mean[:, 2 * M:3 * M] + bb * yt[:, 0:1] + d * yt[:, 1:2]
+            # GaussianConditionalLosslessGMM.forward: channels-last, inputs repeated per mixture
+            inp = yt.permute(0, 2, 3, 1).repeat_interleave(M, dim=3)
+            sc = torch.max(stdev.permute(0, 2, 3, 1), torch.tensor([SCALE_BOUND]))
+            values = torch.abs(inp - mean.permute(0, 2, 3, 1))
+            const = float(-(2 ** -0.5))
+            upper = 0.5 * torch.erfc(const * ((half - values) / sc))
+            lower = 0.5 * torch.erfc(const * ((-half - values) / sc))
+            lik_m = (upper - lower).view(B_, H, W, 3, M)
+            w = torch.max(wts.permute(0, 2, 3, 1).view(B_, H, W, 3, M), torch.tensor([WEIGHT_BOUND]))
+            w = w / torch.sum(w, dim=4, keepdim=True)
+            lik = torch.sum(w * lik_m, dim=4).permute(0, 3, 1, 2)
+            lik = torch.max(lik, torch.tensor([LIKELIHOOD_BOUND]))
+            infos.append(-torch.log2(lik))
+        out.append(torch.cat(infos, dim=1)[0].numpy())
+    return out
 
 
 def diagnose_round_trip(codec: "OracleCodec", rgb: np.ndarray) -> str:

@@ -11,6 +11,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE = os.path.abspath(os.path.join(_HERE, "..", ".."))
+while not os.path.exists(os.path.join(_ORACLE, "torchac_port.c")) and os.path.dirname(_ORACLE) != _ORACLE:
+    _ORACLE = os.path.dirname(_ORACLE)          # the copy under oracle/_ref/shims sits one level deeper
 
 
 def _lib():

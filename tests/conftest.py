@@ -26,6 +26,10 @@ GOLDEN_CASES = ["a_photo_33x47", "a_photo_53x77", "a_photo_64x96", "a_const_40x7
                 "a_checker_35x32", "b_photo_64x96", "b_photo_37x53"]
 
 
+TRAINED_CASES = ["t_photo_64x96", "t_photo_53x77"]     # weights trained by the reference's own mode: train (ckpt_A_trained.npz)
+FORWARD_CASES = ["fwd_a_photo_64x96", "fwd_a_noise_32x64", "fwd_a_checker_32x32", "fwd_b_photo_64x96", "fwd_b_photo_36x52"]
+
+
 def load_golden(name):
     import numpy as np
     return np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -33,4 +37,12 @@ def load_golden(name):
 
 def oracle_config_for(name):
     from oracle import llicti_oracle as O
-    return O.OracleConfig() if name.startswith("a_") else O.OracleConfig(dwtlevels=(0, 1), chs=60)
+    return O.OracleConfig() if name.startswith(("a_", "fwd_a_", "t_")) else O.OracleConfig(dwtlevels=(0, 1), chs=60)
+
+
+def trained_state_dict():
+    """llicti_A weights short-trained by the unmodified reference's `mode: train` on synthetic patches
+    (tools/train_reference_ckpt.py); the reference's shipped checkpoint is absent."""
+    import numpy as np
+    with np.load(os.path.join(GOLDEN, "ckpt_A_trained.npz")) as z:
+        return {k: z[k] for k in z.files}

@@ -55,6 +55,8 @@ def ref_config(name):
 def make_image(kind, H, W, idx):
     if kind == "photo":
         return O.synthetic_image(H, W, idx)
+    if kind == "photo_lownoise":
+        return O.synthetic_image(H, W, idx, noise=0.7)
     if kind == "const":
         img = np.empty((3, H, W), dtype=np.uint8)
         img[0], img[1], img[2] = 200, 31, 97
@@ -80,14 +82,29 @@ CASES = [
     ("b_photo_37x53", "llicti_B.json", "photo", 37, 53),
 ]
 
+# the same pipeline with weights TRAINED by the reference's own `mode: train` (tools/train_reference_ckpt.py ->
+# tests/golden/ckpt_A_trained.npz): spreads down to the 0.11-level clamp where the content allows, i.e. the regime in
+# which rounding of the predicted means moves the rate (the hand-wired stand-in weights keep spreads at 1.5-10 levels)
+TRAINED_CASES = [
+    ("t_photo_64x96", "llicti_A.json", "photo_lownoise", 64, 96),
+    ("t_photo_53x77", "llicti_A.json", "photo", 53, 77),
+]
+
+
+def trained_state_dict():
+    with np.load(os.path.join(HERE, "ckpt_A_trained.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
 SUB = 7    # stride of the position subsample stored for the float parameter arrays
 TSUB = 37  # stride of the row subsample stored for the integer CDF tables
 
 
-def run_case(name, cfg_name, kind, H, W, idx):
+def run_case(name, cfg_name, kind, H, W, idx, sd=None):
     cfg = ref_config(cfg_name)
     ocfg = O.OracleConfig.from_dict(cfg)
-    sd = O.synthetic_state_dict(ocfg, seed=1337)
+    if sd is None:
+        sd = O.synthetic_state_dict(ocfg, seed=1337)
     torch.manual_seed(0)
     model = LLICTI(cfg).eval()
     missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
@@ -169,6 +186,41 @@ def run_case(name, cfg_name, kind, H, W, idx):
           f"minmax={minmax} -> OK (reference == oracle, lossless)")
 
 
+FORWARD_CASES = [
+    # name, config, kind, H, W, image index  (H and W multiples of 2^S: the un-padded lazyDWT of forward())
+    ("fwd_a_photo_64x96", "llicti_A.json", "photo", 64, 96, 2),
+    ("fwd_a_noise_32x64", "llicti_A.json", "noise", 32, 64, 4),
+    ("fwd_a_checker_32x32", "llicti_A.json", "checker", 32, 32, 5),
+    ("fwd_b_photo_64x96", "llicti_B.json", "photo", 64, 96, 6),
+    ("fwd_b_photo_36x52", "llicti_B.json", "photo", 36, 52, 7),
+]
+
+
+def run_forward_case(name, cfg_name, kind, H, W, idx):
+    """LLICTI.forward (the rate-estimation path of validate / training) of the unmodified reference:
+    self-informations per scale, stored whole (they are small), and checked bit-exactly against the oracle's
+    restatement (oracle.forward_self_informations)."""
+    cfg = ref_config(cfg_name)
+    ocfg = O.OracleConfig.from_dict(cfg)
+    sd = O.synthetic_state_dict(ocfg, seed=1337)
+    torch.manual_seed(0)
+    model = LLICTI(cfg).eval()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    rgb = make_image(kind, H, W, idx)
+    x = torch.from_numpy(rgb.astype(np.float32) / np.float32(255.0))[None]
+    with torch.no_grad():
+        ref = model.forward(x.clone())
+    mine = O.forward_self_informations(ocfg, O.OracleNet(ocfg, sd), rgb)
+    out = {"rgb": rgb, "config": np.array(cfg_name)}
+    for s, (r, q) in enumerate(zip(ref, mine)):
+        assert np.array_equal(r[0].numpy(), q), f"{name}: self-informations of scale {s} differ between reference and oracle"
+        out[f"sinfo_{s}"] = q
+    bits = sum(float(q.sum(dtype=np.float64)) for q in mine)
+    out["total_bits"] = np.array(bits)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {H}x{W} {cfg_name} estimated {bits / (H * W):.3f} bpp -> OK (reference forward == oracle)")
+
+
 def canary():
     """Bit patterns of the two host-dependent float primitives (vector erfc, reduction
     order); tests skip the bit-exact float checks when the running host disagrees."""
@@ -184,7 +236,15 @@ def canary():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     canary()
-    for i, c in enumerate(CASES):
-        run_case(*c, idx=i)
+    if "--only-forward" not in sys.argv and "--only-trained" not in sys.argv:
+        for i, c in enumerate(CASES):
+            run_case(*c, idx=i)
+    if "--only-forward" not in sys.argv:
+        for i, c in enumerate(TRAINED_CASES):
+            run_case(*c, idx=20 + i, sd=trained_state_dict())
+    if "--only-trained" in sys.argv:
+        sys.exit(0)
+    for c in FORWARD_CASES:
+        run_forward_case(*c)
     sz = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print("fixtures total bytes:", sz)

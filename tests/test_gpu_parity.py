@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, load_golden, oracle_config_for
+from conftest import FORWARD_CASES, GOLDEN_CASES, TRAINED_CASES, load_golden, oracle_config_for, trained_state_dict
 from oracle import llicti_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -541,7 +541,7 @@ def test_decode_graph_replay(L, sub_len, H, W, monkeypatch):
 
 
 # ------------------------------------------------------------------ round 2 additions
-@pytest.mark.parametrize("H,W", [(200, 20), (300, 40), (1024, 50), (257, 33), (128, 62), (128, 66)])
+@pytest.mark.parametrize("H,W", [(200, 20), (300, 40), (1000, 50), (257, 33), (128, 62), (128, 66)])
 @pytest.mark.parametrize("cfgname", ["A", "B"])
 def test_narrow_images_torchac_streams_tcgen05(L, H, W, cfgname):
     """Narrow, tall images through the default path for torchac-compatible streams (tcgen05 CNN, sub_len = 0).  The
@@ -656,3 +656,145 @@ def test_two_contexts_do_not_share_device_state(L):
         codecs.append(make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=sub_len, cnn_impl=L.CNN_TCGEN05))
     for c in codecs + codecs[::-1]:
         assert np.array_equal(c.decompress_images(c.compress_images(img[None]))[0], img)
+
+
+# ------------------------------------------------------------------ forward() / rate estimation
+@pytest.mark.parametrize("cnn_impl", [0, 1], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("name", FORWARD_CASES)
+def test_forward_self_informations_against_reference_golden(L, name, cnn_impl):
+    """LLICTI.forward on the GPU against the unmodified reference's outputs (golden fixtures): the float lifting and
+    the un-padded pyramid are exact fp32 restatements, the CNN is the compress path's kernel, the likelihood is
+    erfc / log2 in fp32.  Stated tolerance: per sample 2e-3 bits absolute + 1e-3 relative with the fp32 CNN,
+    total bits within 0.02 %; with the tcgen05 CNN (bf16 operands) per sample 0.35 bits + 5 %, total within 0.5 %."""
+    g = load_golden(name)
+    ocfg = oracle_config_for(name)
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), cnn_impl=cnn_impl, numerics=L.NUM_TORCH_CPU)
+    rgb = torch.from_numpy(g["rgb"][None].copy()).cuda()
+    out = codec.forward_dev(rgb)
+    assert len(out) == len(ocfg.dwtlevels)
+    bits = 0.0
+    for s, t in enumerate(out):
+        q, ref = t[0].cpu().numpy(), g[f"sinfo_{s}"]
+        assert q.shape == ref.shape
+        if cnn_impl == 0:
+            np.testing.assert_allclose(q, ref, rtol=1e-3, atol=2e-3, err_msg=f"scale {s}")
+        else:
+            np.testing.assert_allclose(q, ref, rtol=5e-2, atol=0.35, err_msg=f"scale {s}")
+        bits += float(q.sum(dtype=np.float64))
+    ref_bits = float(g["total_bits"])
+    assert abs(bits - ref_bits) <= (2e-4 if cnn_impl == 0 else 5e-3) * ref_bits, (bits, ref_bits)
+    codec.close()
+
+
+def test_forward_through_the_model_interface(L):
+    """model.forward(x) -> list[num_scales] of [B,9,Hs,Ws], batch of 2, against the oracle; sizes that are not
+    multiples of 2^S are rejected like the reference's torch.cat of unequal phases would be."""
+    import json
+    import os
+    from conftest import ROOT
+    from llicti_b200 import LLICTI
+    from llicti_b200._lib import LlictiError
+    cfg = json.load(open(os.path.join(ROOT, "configs", "llicti_A.json")))
+    model = LLICTI(cfg, cnn_impl=0, numerics=L.NUM_TORCH_CPU).to("cuda")
+    ocfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(ocfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    imgs = np.stack([O.synthetic_image(96, 64, 20 + i) for i in range(2)])
+    x = (torch.from_numpy(imgs).float() / 255).cuda()
+    out = model(x)
+    assert [tuple(t.shape) for t in out] == [(2, 9, 48 >> s, 32 >> s) for s in range(5)]
+    net = O.OracleNet(ocfg, sd)
+    for i in range(2):
+        ref = O.forward_self_informations(ocfg, net, imgs[i])
+        for s in range(5):
+            np.testing.assert_allclose(out[s][i].cpu().numpy(), ref[s], rtol=1e-3, atol=2e-3)
+    with pytest.raises(LlictiError, match="multiples of 2"):
+        model(x[:, :, :90])
+
+
+@pytest.mark.parametrize("H,W,cfgname", [(128, 192, "B"), (96, 160, "B"), (160, 224, "A")], ids=["wavefront", "piped", "cfgA"])
+def test_starved_decode_falls_back_instead_of_trapping(L, monkeypatch, H, W, cfgname):
+    """The piped / wavefront schedules of torchac-compatible streams rely on kernels that hand work to each other
+    being resident together, which CUDA does not promise.  With every producer made to leave at once (what a producer
+    kernel that never becomes resident looks like) the consumers' bounded waits give up, the decode reports
+    LLICTI_E_TIMEOUT instead of trapping the context, and the host entry point retries with the split schedule:
+    same pixels, context alive, and it stays on the safe schedule."""
+    from llicti_b200._lib import LlictiError, E_TIMEOUT
+    monkeypatch.setenv("LLICTI_TEST_POLL_LIMIT", "20000")
+    monkeypatch.setenv("LLICTI_TEST_STARVE", "1")
+    ocfg = O.OracleConfig() if cfgname == "A" else O.OracleConfig(dwtlevels=(0, 1), chs=60)
+    sd = O.synthetic_state_dict(ocfg)
+    codec = make_codec(L, ocfg, sd, sub_len=0, cnn_impl=L.CNN_TCGEN05)          # the knobs are read at context creation
+    imgs = np.stack([O.synthetic_image(H, W, 80 + i) for i in range(3)])
+    bsls = codec.compress_images(imgs)
+    assert np.array_equal(codec.decompress_images(bsls), imgs)                   # gave up, retried, decoded
+    n0 = codec.launches
+    assert np.array_equal(codec.decompress_images(bsls), imgs)                   # stays on the schedule without hand-overs
+    safe_launches = codec.launches - n0
+    codec.close()
+    # device entry point: the flag is reported by llicti_status, the next call decodes
+    codec = make_codec(L, ocfg, sd, sub_len=0, cnn_impl=L.CNN_TCGEN05)
+    st = 2 ** len(ocfg.dwtlevels)
+    rgb_d = torch.from_numpy(imgs).cuda()
+    x00_d = torch.from_numpy(np.ascontiguousarray(imgs[:, :, ::st, ::st])).cuda()
+    enc = codec.encode_dev(rgb_d)
+    out = codec.decode_dev(*enc, x00_d, 3, H, W)
+    with pytest.raises(LlictiError) as ei:
+        codec.check_status()
+    assert ei.value.code == E_TIMEOUT
+    out = codec.decode_dev(*enc, x00_d, 3, H, W, out)
+    codec.check_status()
+    assert torch.equal(out, rgb_d)
+    codec.close()
+    monkeypatch.delenv("LLICTI_TEST_STARVE")
+    monkeypatch.delenv("LLICTI_TEST_POLL_LIMIT")
+    codec = make_codec(L, ocfg, sd, sub_len=0, cnn_impl=L.CNN_TCGEN05)          # resets the hooks
+    n0 = codec.launches
+    assert np.array_equal(codec.decompress_images(bsls), imgs)
+    assert codec.launches - n0 != safe_launches                                  # the concurrent schedule again
+    codec.close()
+
+
+# ------------------------------------------------------------------ the 0.5 % criterion on the PRODUCT CNN with trained weights
+@pytest.mark.parametrize("cnn_impl", [0, 1], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("name", TRAINED_CASES)
+def test_rate_with_trained_weights_against_reference_golden(L, name, cnn_impl):
+    """bpp within 0.5 % of the reference's own streams with weights trained by the reference's training loop, for the
+    fp32 CNN and for the tcgen05 CNN (bf16 operands: the predicted means carry ~1e-3 relative error, which matters
+    where the trained spreads approach the 0.11-level clamp).  Tiny images: +/- 8 bytes of flush slack on 45 streams."""
+    g = load_golden(name)
+    ocfg = oracle_config_for(name)
+    codec = make_codec(L, ocfg, trained_state_dict(), sub_len=0, cnn_impl=cnn_impl)
+    bsl = codec.compress_images(g["rgb"][None])[0]
+    for j in range(5):
+        assert bsl[0][j] == g[f"stream_0_{j}"].tobytes()
+    mine = sum(len(b) for r in bsl for b in r) - 11            # fingerprint + checksum slots, see above
+    ref = int(g["total_bytes"])
+    assert abs(mine - ref) <= 0.005 * ref + 8, (mine, ref)
+    assert np.array_equal(codec.decompress_images([bsl])[0], g["rgb"])
+    codec.close()
+
+
+def test_rate_with_trained_weights_kodak_shape_tcgen05(L):
+    """The same criterion at 768x512 against the oracle (one image, a few seconds of CPU): torchac-compatible streams of
+    the tcgen05 path within 0.5 % of the reference algorithm's bytes, the substream container within 0.5 % more, and a
+    per-scale table of the deltas printed for DESIGN.md."""
+    ocfg = O.OracleConfig()
+    sd = trained_state_dict()
+    img = O.synthetic_image(512, 768, 321, noise=0.7)
+    o_bsl = O.OracleCodec(ocfg, sd).compress(img)
+    ref = sum(len(b) for r in o_bsl[1:] for b in r)
+    out = {}
+    for tag, cnn_impl, sub_len in (("fp32", 0, 0), ("tcgen05", 1, 0), ("tcgen05-substreams", 1, 2048)):
+        codec = make_codec(L, ocfg, sd, sub_len=sub_len, cnn_impl=cnn_impl)
+        bsl = codec.compress_images(img[None])[0]
+        assert np.array_equal(codec.decompress_images([bsl])[0], img)
+        out[tag] = sum(len(b) for r in bsl[1:] for b in r)
+        per_scale = [sum(len(b) for b in r) for r in bsl[1:]]
+        ref_scale = [sum(len(b) for b in r) for r in o_bsl[1:]]
+        print(f"{tag}: {out[tag]} bytes vs reference algorithm {ref} ({100.0 * (out[tag] - ref) / ref:+.3f} %), per scale (coarse to fine) "
+              + ", ".join(f"{100.0 * (a - b) / b:+.2f}%" for a, b in zip(per_scale, ref_scale)))
+        codec.close()
+    assert abs(out["fp32"] - ref) <= 0.001 * ref
+    assert abs(out["tcgen05"] - ref) <= 0.005 * ref, out
+    assert out["tcgen05-substreams"] <= 1.005 * out["tcgen05"], out

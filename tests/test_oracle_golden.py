@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, load_golden, oracle_config_for
+from conftest import FORWARD_CASES, GOLDEN_CASES, TRAINED_CASES, load_golden, oracle_config_for, trained_state_dict
 from oracle import llicti_oracle as O
 
 
@@ -121,3 +121,55 @@ def test_oracle_round_trips_in_the_product_process_state(threads):
             assert O.diagnose_round_trip(codec, img) == "this repetition round-tripped"
     finally:
         torch.set_num_threads(before)
+
+
+@pytest.mark.parametrize("name", FORWARD_CASES)
+def test_forward_self_informations_against_the_reference(name):
+    """oracle.forward_self_informations restates LLICTI.forward (the rate-estimation path of validate / training);
+    the fixtures are the unmodified reference's outputs (tests/golden/make_golden.py checks equality bit for bit on
+    the host that makes them).  Bit-exact where this host's erfc / reduction order is the golden host's, and within
+    a tight tolerance in bits everywhere."""
+    g = load_golden(name)
+    cfg = oracle_config_for(name)
+    sd = O.synthetic_state_dict(cfg)
+    mine = O.forward_self_informations(cfg, O.OracleNet(cfg, sd), g["rgb"])
+    assert len(mine) == len(cfg.dwtlevels)
+    exact = host_matches_canary()
+    for s, q in enumerate(mine):
+        ref = g[f"sinfo_{s}"]
+        assert q.shape == ref.shape and q.shape[0] == 9
+        if exact:
+            assert np.array_equal(q, ref), f"scale {s}"
+        np.testing.assert_allclose(q, ref, rtol=2e-4, atol=2e-4)
+    bits = sum(float(q.sum(dtype=np.float64)) for q in mine)
+    assert abs(bits - float(g["total_bits"])) <= 1e-5 * float(g["total_bits"])
+
+
+@pytest.mark.parametrize("name", TRAINED_CASES)
+def test_trained_checkpoint_cases_against_the_reference(name):
+    """The same stage-by-stage comparison with weights trained by the reference's own training loop (sharper
+    spreads than the hand-wired stand-ins): integer stages and header bit-exact, network outputs close, and on a
+    host with the golden host's float behaviour every table digest and byte stream identical."""
+    g = load_golden(name)
+    cfg = oracle_config_for(name)
+    sd = trained_state_dict()
+    assert sum(v.size for v in sd.values()) == 196596                      # the reference's parameter count (exp_debug.log:101)
+    d = O.StageDump()
+    codec = O.OracleCodec(cfg, sd)
+    bsl = codec.compress(g["rgb"], d)
+    assert np.array_equal(d.ycocg, g["ycocg"]) and d.pad_int == int(g["pad_int"])
+    for s in range(len(cfg.dwtlevels)):
+        assert np.array_equal(d.planes[s], g[f"planes_{s}"])
+    for j in range(9):
+        assert bsl[0][j] == g[f"stream_0_{j}"].tobytes()
+    for (s, b), p in d.params.items():
+        np.testing.assert_allclose(p.reshape(60, -1)[:, ::7], g[f"params_{s}_{b}_sub"], rtol=1e-4, atol=1e-5)
+    total = sum(len(x) for r in bsl for x in r)
+    assert abs(total - int(g["total_bytes"])) <= 0.002 * int(g["total_bytes"]) + 2
+    if host_matches_canary():
+        for (s, b, c), t in d.tables.items():
+            assert digest(t) == str(g[f"table_{s}_{b}_{c}_digest"])
+        for i in range(1, len(bsl)):
+            for j in range(9):
+                assert bsl[i][j] == g[f"stream_{i}_{j}"].tobytes(), f"stream {i},{j}"
+    assert np.array_equal(codec.decompress(bsl), g["rgb"])
