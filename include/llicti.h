@@ -208,6 +208,11 @@ LLICTI_API int llicti_decode_dev(llicti_ctx *ctx, const uint8_t *blob_dev, const
                       const int16_t *minmax_dev, const uint8_t *x00_rgb_dev, int n, int H, int W,
                       uint8_t *rgb_out_dev, void *stream);
 
+/* Arithmetic type of the CNN's operands in this context: 0 fp32 (LLICTI_CNN_FP32), 1 bf16, 2 fp16 (LLICTI_CNN_TCGEN05;
+ * fp16 when the weights prove that no hidden activation can leave fp16's range, bf16 otherwise; accumulation is fp32
+ * either way).  Part of a stream's fingerprint: encoder and decoder must agree on it. */
+LLICTI_API int llicti_cnn_operands(const llicti_ctx *ctx);
+
 /* Device-side error flag of the asynchronous *_dev entry points (an encoder that ran out of output
  * capacity: LLICTI_E_NOMEM; a malformed container or stream offsets: LLICTI_E_STREAM).  Waits for
  * `stream`, returns the flag (0 = none) and clears it.  The *_host entry points do this themselves. */

@@ -77,6 +77,7 @@ _PROTOS = {
                                     C.c_int, C.c_void_p, C.c_void_p]),
     "llicti_forward_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.c_void_p]),
+    "llicti_cnn_operands": (C.c_int, [C.c_void_p]),
     "llicti_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llicti_launch_count": (C.c_int64, [C.c_void_p]),
     "llicti_profile": (C.c_int, [C.c_void_p, C.c_int]),

@@ -92,7 +92,7 @@ class LLICTIAgent(BaseAgent):
         codec = self.model._codec()
         cc = self.model.codec_config
         self.logger.info(" B200 path: cnn_impl={} ({}), sub_len={} ({}), stream fingerprint {}".format(
-            cc.cnn_impl, "tcgen05 tensor cores, bf16 operands" if cc.cnn_impl == 1 else "fp32 CUDA cores",
+            cc.cnn_impl, "tcgen05 tensor cores, {} operands".format("fp16" if codec.cnn_operands == 2 else "bf16") if cc.cnn_impl == 1 else "fp32 CUDA cores",
             cc.sub_len, "interleaved substreams" if cc.sub_len > 0 else "torchac-compatible streams",
             codec.fingerprint.hex()))
         codec.profile(True)          # per-kernel-class launch groups of this run, logged below

@@ -102,7 +102,10 @@ class Codec:
         for a in keep:                     # fixed order: l0 (w, b) x 6 branches, then per band l1 w, b, l2 w, b
             crc = zlib.crc32(a.data, crc)
         self.weights_crc = crc & 0xFFFFFFFF
-        self.fingerprint = container.fingerprint(cfg.cnn_impl, cfg.numerics, self.weights_crc)
+        # what the CDFs depend on besides the weights: the CNN's arithmetic (0 fp32, 1 tcgen05 / bf16 operands,
+        # 2 tcgen05 / fp16 operands) and the numerics profile of the CDF stage
+        self.cnn_operands = int(self.lib.llicti_cnn_operands(self._ctx))
+        self.fingerprint = container.fingerprint(self.cnn_operands, cfg.numerics, self.weights_crc)
         del keep
 
     def close(self):

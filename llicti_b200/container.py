@@ -7,33 +7,43 @@ from typing import Sequence
 import numpy as np
 
 
+CONTAINER_VERSION = 2     # 2: substreams of sub_len symbols at the finest scale, sub_len / 2 at the coarser ones (1: sub_len everywhere)
+
+
 def mode_tag(sub_len: int) -> bytes:
     """Header slot 4 (b'' in the reference): b'' = torchac-compatible streams, otherwise
-    [1, sub_len as u32 LE] = interleaved-substream container."""
+    [container version, sub_len as u32 LE] = interleaved-substream container."""
     if sub_len <= 0:
         return b""
-    return bytes([1]) + int(sub_len).to_bytes(4, "little")
+    return bytes([CONTAINER_VERSION]) + int(sub_len).to_bytes(4, "little")
 
 
 def parse_mode_tag(tag: bytes) -> int:
     if len(tag) == 0:
         return 0
-    if len(tag) != 5 or tag[0] != 1:
+    if len(tag) == 5 and tag[0] == 1:
+        raise ValueError("substream container version 1 (one substream length for every scale) is no longer read")
+    if len(tag) != 5 or tag[0] != CONTAINER_VERSION:
         raise ValueError("unknown container tag in header slot 4")
     return int.from_bytes(tag[1:5], "little")
 
 
-def fingerprint(cnn_impl: int, numerics: int, weights_crc: int) -> bytes:
+CNN_ARITHMETIC = {0: "fp32", 1: "tcgen05/bf16", 2: "tcgen05/fp16"}       # llicti_cnn_operands()
+
+
+def fingerprint(cnn_operands: int, numerics: int, weights_crc: int) -> bytes:
     """Header slot 5 (b'' in the reference): what the decoder must share with the encoder for the CDFs to agree --
-    [2, cnn_impl, numerics, crc32 of the fp32 weights as u32 LE].  Streams are decodable only by a codec with the same
-    fingerprint: the tcgen05 CNN (bf16 operands) and the fp32 CNN give different network outputs, hence different tables."""
-    return bytes([2, cnn_impl & 0xFF, numerics & 0xFF]) + int(weights_crc & 0xFFFFFFFF).to_bytes(4, "little")
+    [2, CNN arithmetic (0 fp32, 1 tcgen05 with bf16 operands, 2 tcgen05 with fp16 operands), numerics profile of the
+    CDF stage, crc32 of the fp32 weights as u32 LE].  Streams are decodable only by a codec with the same fingerprint:
+    other operand types give other network outputs, hence other tables."""
+    return bytes([2, cnn_operands & 0xFF, numerics & 0xFF]) + int(weights_crc & 0xFFFFFFFF).to_bytes(4, "little")
 
 
 def describe_fingerprint(fp: bytes) -> str:
     if len(fp) != 7 or fp[0] != 2:
         return "unknown fingerprint"
-    return f"cnn_impl={fp[1]}, numerics={fp[2]}, weights crc32={int.from_bytes(fp[3:7], 'little'):08x}"
+    return (f"cnn={CNN_ARITHMETIC.get(fp[1], fp[1])}, numerics={fp[2]}, "
+            f"weights crc32={int.from_bytes(fp[3:7], 'little'):08x}")
 
 
 def check_fingerprint(hdr, expected: bytes):

@@ -52,7 +52,10 @@ int make_plan(const llicti_config &cfg, int H, int W, Plan *out) {
         for (int b = 0; b < 3; ++b) {
             g.crop_h[s][b] = (b == 0 || b == 2) ? g.Hs[s] - g.padH[s] : g.Hs[s];
             g.crop_w[s][b] = (b == 0 || b == 1) ? g.Ws[s] - g.padW[s] : g.Ws[s];
-            g.num_sub[s][b] = num_substreams((int64_t)g.crop_h[s][b] * g.crop_w[s][b], cfg.sub_len);
+            // container version 2: substreams (= serial decoder chains) of sub_len symbols at the finest scale, half of that
+            // at the coarser ones, which have a quarter and less of the symbols and would otherwise have too few chains
+            g.num_sub[s][b] = num_substreams((int64_t)g.crop_h[s][b] * g.crop_w[s][b],
+                                             cfg.sub_len > 0 && s > 0 ? std::max(cfg.sub_len / 2, 1) : cfg.sub_len);
         }
         g.positions += (int64_t)g.Hs[s] * g.Ws[s];
         p.plane_elems[s] = 12ll * g.Hs[s] * g.Ws[s];
@@ -339,6 +342,11 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
 }
 
 int64_t llicti_launch_count(const llicti_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int llicti_cnn_operands(const llicti_ctx *ctx) {
+    if (!ctx) return -1;
+    return ctx->cfg.cnn_impl == LLICTI_CNN_TCGEN05 ? tc_operand_type(ctx) : 0;
+}
 
 int llicti_status(llicti_ctx *ctx, void *stream) {
     LLICTI_REQUIRE(ctx, "null context");

@@ -30,6 +30,8 @@
 // (no split-K, no atomics), so compress and decompres compute bit-identical parameters whatever
 // the batch size, tile position or launch.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -131,8 +133,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = n.
+// Operands are fp16 when the packer has shown that no activation can overflow it (11-bit significands: an eighth of
+// bf16's rounding error on the predicted means, which matters against spreads near the 0.11-level clamp), bf16 otherwise.
+template <bool F16>
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    return (1u << 4) | (F16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -167,11 +172,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ReLU + bf16 of 16 accumulator columns -> two 16-byte operand chunks.
+template <bool F16>
 __device__ __forceinline__ void relu_pack16(const uint32_t *r, uint8_t *dst_chunk0, uint32_t chunk_stride) {
     uint32_t w[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e)     // one instruction per column pair: round to bf16 with ReLU (element 2e in the low half)
-        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(__uint_as_float(r[2 * e + 1])), "f"(__uint_as_float(r[2 * e])));
+    for (int e = 0; e < 8; ++e) {   // one instruction per column pair: round to the operand type with ReLU (element 2e in the low half)
+        if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(__uint_as_float(r[2 * e + 1])), "f"(__uint_as_float(r[2 * e])));
+        else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(__uint_as_float(r[2 * e + 1])), "f"(__uint_as_float(r[2 * e])));
+    }
     *reinterpret_cast<uint4 *>(dst_chunk0) = make_uint4(w[0], w[1], w[2], w[3]);
     *reinterpret_cast<uint4 *>(dst_chunk0 + chunk_stride) = make_uint4(w[4], w[5], w[6], w[7]);
 }
@@ -179,14 +187,14 @@ __device__ __forceinline__ void relu_pack16(const uint32_t *r, uint8_t *dst_chun
 // One hidden layer's epilogue for one sub-network: all NP accumulator columns of this thread's row
 // are fetched with back-to-back TMEM loads and ONE wait (the loads overlap each other and the
 // conversion of 8 independent column pairs per 16-byte chunk pipelines), then ReLU + bf16 + store.
-template <int NP>
+template <int NP, bool F16>
 __device__ __forceinline__ void epilogue_hidden(uint32_t taddr, uint8_t *h_row, uint32_t chunk_stride) {
     uint32_t r[NP];
 #pragma unroll
     for (int c = 0; c < NP / 32; ++c) TMEM_LD_X32(taddr + (uint32_t)(c * 32), (r + c * 32));
     tmem_ld_wait();
 #pragma unroll
-    for (int c16 = 0; c16 < NP / 16; ++c16) relu_pack16(r + c16 * 16, h_row + (size_t)(c16 * 2) * chunk_stride, chunk_stride);
+    for (int c16 = 0; c16 < NP / 16; ++c16) relu_pack16<F16>(r + c16 * 16, h_row + (size_t)(c16 * 2) * chunk_stride, chunk_stride);
 }
 
 // Compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{}).
@@ -242,12 +250,14 @@ constexpr int TC_SEG_PITCH = 136;      // staged samples per segment (132 used),
 // bf16 bits of a small integer (|v| <= 255, exact): the sample enters as unsigned 16 bits; xor 0x8000 makes it
 // v + 32768, which or-ed into the mantissa of 2^23 gives the float 2^23 + 32768 + v; subtracting the offset
 // leaves float(v), whose low 16 bits are zero.
-__device__ __forceinline__ uint16_t bf16_of_sample(uint16_t u) {
+template <bool F16>
+__device__ __forceinline__ uint16_t operand_of_sample(uint16_t u) {
     const float f = __uint_as_float(0x4B008000u ^ (uint32_t)u) - 8421376.0f;
+    if (F16) return __half_as_ushort(__float2half_rn(f));          // |v| <= 255: exact in fp16 as well
     return (uint16_t)(__float_as_uint(f) >> 16);
 }
 
-template <int BAND, int HALF>
+template <int BAND, int HALF, bool F16>
 __device__ __forceinline__ void stage_segments(const int16_t *__restrict__ planes, const TcGeom &tg, int img, int i, int j0,
                                                uint16_t *sSeg, int t) {
     constexpr int NSEG = band_nseg(BAND);
@@ -261,16 +271,16 @@ __device__ __forceinline__ void stage_segments(const int16_t *__restrict__ plane
         constexpr int sg = 2 * decltype(s_)::value + HALF;
         constexpr SegTc seg = band_seg(BAND, sg);
         const uint16_t *src = pl + (size_t)(seg.phase * 3 + seg.chan) * tg.P + rowoff[seg.dy + 2];
-        sSeg[sg * TC_SEG_PITCH + t] = bf16_of_sample(src[c_main]);
-        if (t < 4) sSeg[sg * TC_SEG_PITCH + 128 + t] = bf16_of_sample(src[c_extra]);
+        sSeg[sg * TC_SEG_PITCH + t] = operand_of_sample<F16>(src[c_main]);
+        if (t < 4) sSeg[sg * TC_SEG_PITCH + 128 + t] = operand_of_sample<F16>(src[c_extra]);
     });
 }
 
-template <int BAND, int HALF>
+template <int BAND, int HALF, bool F16>
 __device__ __forceinline__ void build_a_row(const uint16_t *sSeg, uint8_t *sA, int row) {
     constexpr int K0 = band_k0(BAND);
     constexpr int K0p = (K0 + 2 + 15) / 16 * 16;
-    constexpr uint32_t kOne = 0x3F80u;   // bf16 1.0
+    constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;   // 1.0 in the operand type
     const uint16_t *my = sSeg + row + 2;
     static_for<K0p / 16>([&](auto kc_) {                       // ... and build alternate 16-byte chunks of every row
         constexpr int kc = 2 * decltype(kc_)::value + HALF;
@@ -295,7 +305,7 @@ __device__ __forceinline__ void build_a_row(const uint16_t *sSeg, uint8_t *sA, i
 enum { B_W = 0, B_AFULL = 1, B_AEMPTY = 3, B_D0FULL = 5 /* [slot][sub-network] */, B_DFREE = 9, B_H0FULL = 11, B_D1FULL = 13,
        B_H1FULL = 15, B_D2FULL = 17, B_COUNT = 19 };
 
-template <int BAND>
+template <int BAND, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__restrict__ packed, float *__restrict__ params) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -361,11 +371,11 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             const int rowid = tile / tg.tpr, jb = tile - rowid * tg.tpr;       // (image, plane row), column block
             const int img = rowid / tg.nrows, i = tg.row0 + rowid - img * tg.nrows;
             asm volatile("bar.sync 1, 256;" ::: "memory");                      // everyone is done reading the previous segments
-            if (half == 0) stage_segments<BAND, 0>(planes, tg, img, i, jb * TC_M, sSeg, row);
-            else stage_segments<BAND, 1>(planes, tg, img, i, jb * TC_M, sSeg, row);
+            if (half == 0) stage_segments<BAND, 0, F16>(planes, tg, img, i, jb * TC_M, sSeg, row);
+            else stage_segments<BAND, 1, F16>(planes, tg, img, i, jb * TC_M, sSeg, row);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0) build_a_row<BAND, 0>(sSeg, sA + s * a_stage, row);
-            else build_a_row<BAND, 1>(sSeg, sA + s * a_stage, row);
+            if (half == 0) build_a_row<BAND, 0, F16>(sSeg, sA + s * a_stage, row);
+            else build_a_row<BAND, 1, F16>(sSeg, sA + s * a_stage, row);
             fence_async_smem();
             mbar_arrive(bar(B_AFULL + s));
         }
@@ -375,7 +385,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             mbar_expect_tx(bar(B_W), (uint32_t)tg.pair_bytes);
             tma_bulk_g2s(smem_u32(sW0), packed + (size_t)pair * tg.pair_bytes, (uint32_t)tg.pair_bytes, bar(B_W));
             mbar_wait(bar(B_W), 0);
-            const uint32_t idesc1 = umma_idesc(NP), idesc2 = umma_idesc(16);
+            const uint32_t idesc1 = umma_idesc<F16>(NP), idesc2 = umma_idesc<F16>(16);
             const uint32_t w0_lbo = (uint32_t)(2 * NP) * 16, w1_lbo = (uint32_t)NP * 16, w2_lbo = 16 * 16;
             const uint32_t w1_bytes = (uint32_t)(NP / 8) * NP * 16, w2_bytes = (uint32_t)(NP / 8) * 16 * 16;
             auto issue_l0 = [&](int it) {
@@ -438,16 +448,16 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             // ---- layer 0 -> H0 ----
             mbar_wait(bar(B_D0FULL + 2 * s + g), (it >> 1) & 1);
             tc_fence_after();
-            if (NP == 96) epilogue_hidden<96>(dbase + (uint32_t)(g * NP), h, a_lbo);
-            else epilogue_hidden<64>(dbase + (uint32_t)(g * NP), h, a_lbo);
+            if (NP == 96) epilogue_hidden<96, F16>(dbase + (uint32_t)(g * NP), h, a_lbo);
+            else epilogue_hidden<64, F16>(dbase + (uint32_t)(g * NP), h, a_lbo);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar(B_H0FULL + g));
             // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
             mbar_wait(bar(B_D1FULL + g), it & 1);
             tc_fence_after();
-            if (NP == 96) epilogue_hidden<96>(dbase + (uint32_t)(g * NP), h, a_lbo);
-            else epilogue_hidden<64>(dbase + (uint32_t)(g * NP), h, a_lbo);
+            if (NP == 96) epilogue_hidden<96, F16>(dbase + (uint32_t)(g * NP), h, a_lbo);
+            else epilogue_hidden<64, F16>(dbase + (uint32_t)(g * NP), h, a_lbo);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar(B_H1FULL + g));
@@ -484,7 +494,81 @@ struct TcBand {
 };
 struct TcWeights {
     TcBand band[3];
+    bool f16 = false;            // operand type of all three bands: fp16 when provably overflow-free, else bf16
 };
+
+// Upper bounds of the hidden activations from the weights alone (inputs are integers of magnitude <= 255 against
+// layer-0 weights / 255, so |pre-activation| <= L1 norm of the unit's weights + |bias|): fp16 operands are used only
+// if neither hidden layer can leave fp16's range.
+static bool fits_fp16(const llicti_weights &w, int G) {
+    const int Ch = 4 * G;
+    const float kLimit = 6.0e4f;
+    static const int kh[6] = {4, 3, 4, 4, 3, 4}, kw[6] = {4, 4, 3, 3, 4, 4}, band_of[6] = {0, 1, 1, 2, 2, 2};
+    for (int band = 0; band < 3; ++band) {
+        std::vector<double> h0(Ch, 0.0);
+        for (int br = 0; br < 6; ++br) {
+            if (band_of[br] != band) continue;
+            const int taps = 3 * kh[br] * kw[br];
+            for (int ch = 0; ch < Ch; ++ch) {
+                double a = 0;
+                for (int t = 0; t < taps; ++t) a += fabs((double)w.l0_w[br][(size_t)ch * taps + t]);
+                h0[ch] += a + fabs((double)w.l0_b[br][ch]);
+            }
+        }
+        double h1max = 0, h0max = 0;
+        for (int g = 0; g < 4; ++g)
+            for (int o = 0; o < G; ++o) {
+                double a = fabs((double)w.l1_b[band][g * G + o]);
+                for (int i = 0; i < G; ++i) a += fabs((double)w.l1_w[band][(size_t)(g * G + o) * G + i]) * h0[g * G + i];
+                h1max = std::max(h1max, a);
+            }
+        for (int ch = 0; ch < Ch; ++ch) h0max = std::max(h0max, h0[ch]);
+        if (!(h0max < kLimit && h1max < kLimit)) return false;
+    }
+    return true;
+}
+
+static uint16_t f2h(float f) {    // fp32 -> fp16, round to nearest even, subnormals and overflow to infinity handled
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    const int32_t exp = (int32_t)((u >> 23) & 0xFF) - 127 + 15;
+    uint32_t man = u & 0x7FFFFFu;
+    if (((u >> 23) & 0xFF) == 0xFF) return (uint16_t)(sign | 0x7C00u | (man ? 0x200u : 0u));
+    if (exp >= 31) return (uint16_t)(sign | 0x7C00u);
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        const int shift = 14 - exp;                       // 14 .. 24
+        uint32_t h = man >> shift;
+        const uint32_t rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1u))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)exp << 10) | (man >> 13);
+    const uint32_t rem = man & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;   // may carry into the exponent: still correct
+    return (uint16_t)(sign | h);
+}
+static float h2f(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, u;
+    if (exp == 0) {
+        if (man == 0) { u = sign; }
+        else {
+            int e = -1;
+            do { ++e; man <<= 1; } while (!(man & 0x400u));
+            u = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) {
+        u = sign | 0x7F800000u | (man << 13);
+    } else {
+        u = sign | ((exp - 15 + 127) << 23) | (man << 13);
+    }
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
 
 static uint16_t f2bf(float f) {   // round to nearest even
     uint32_t u;
@@ -504,6 +588,13 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
     const int NP = (G + 2 + 15) / 16 * 16;   // 88 -> 96, 60 -> 64 (two bias slots included)
     LLICTI_REQUIRE(G + 2 <= NP, "no room for the bias slots");
     TcWeights *tw = new TcWeights();
+    {
+        const char *force = getenv("LLICTI_TC_OPERANDS");          // "bf16" / "fp16": A/B and tests
+        tw->f16 = force && *force ? strcmp(force, "fp16") == 0 : fits_fp16(w, G);
+    }
+    const bool f16 = tw->f16;
+    auto cv = [f16](float v) { return f16 ? f2h(v) : f2bf(v); };
+    auto back = [f16](uint16_t v) { return f16 ? h2f(v) : bf2f(v); };
     for (int band = 0; band < 3; ++band) {
         const int K0 = band_k0(band), K0p = (K0 + 2 + 15) / 16 * 16;
         LLICTI_REQUIRE(K0 == ctx->taps[band].K0, "tap tables disagree for band %d", band);
@@ -528,18 +619,18 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
         }
         auto put = [](uint16_t *base, int rows, int n, int kk, uint16_t v) { base[((size_t)(kk / 8) * rows + n) * 8 + kk % 8] = v; };
         auto put_bias = [&](uint16_t *base, int rows, int n, int kk, float b) {   // hi + lo pair in slots kk, kk + 1
-            const uint16_t hi = f2bf(b);
+            const uint16_t hi = cv(b);
             put(base, rows, n, kk, hi);
-            put(base, rows, n, kk + 1, f2bf(b - bf2f(hi)));
+            put(base, rows, n, kk + 1, cv(b - back(hi)));
         };
-        const uint16_t one = f2bf(1.0f);
+        const uint16_t one = cv(1.0f);
         for (int pr = 0; pr < 2; ++pr) {
             uint8_t *base = host.data() + (size_t)pr * pair_bytes;
             uint16_t *p0 = reinterpret_cast<uint16_t *>(base);            // [K0p/8][2NP][8]
             for (int gl = 0; gl < 2; ++gl) {
                 const int g = 2 * pr + gl;
                 for (int n = 0; n < G; ++n) {
-                    for (int kk = 0; kk < K0; ++kk) put(p0, 2 * NP, gl * NP + n, kk, f2bf(w0[(size_t)kk * Ch + g * G + n]));
+                    for (int kk = 0; kk < K0; ++kk) put(p0, 2 * NP, gl * NP + n, kk, cv(w0[(size_t)kk * Ch + g * G + n]));
                     put_bias(p0, 2 * NP, gl * NP + n, K0, b0[g * G + n]);
                 }
                 // hidden units G, G+1 reproduce the constant one (the next layer's bias slots)
@@ -547,14 +638,14 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
                 put(p0, 2 * NP, gl * NP + G + 1, K0, one);
                 uint16_t *p1 = reinterpret_cast<uint16_t *>(base + w0_bytes) + (size_t)gl * (NP / 8) * NP * 8;   // [NP/8][NP][8]
                 for (int n = 0; n < G; ++n) {
-                    for (int in = 0; in < G; ++in) put(p1, NP, n, in, f2bf(w.l1_w[band][(size_t)(g * G + n) * G + in]));
+                    for (int in = 0; in < G; ++in) put(p1, NP, n, in, cv(w.l1_w[band][(size_t)(g * G + n) * G + in]));
                     put_bias(p1, NP, n, G, w.l1_b[band][g * G + n]);
                 }
                 put(p1, NP, G, G, one);
                 put(p1, NP, G + 1, G, one);
                 uint16_t *p2 = reinterpret_cast<uint16_t *>(base + w0_bytes + w1_bytes) + (size_t)gl * (NP / 8) * 16 * 8;   // [NP/8][16][8]
                 for (int n = 0; n < 15; ++n) {
-                    for (int in = 0; in < G; ++in) put(p2, 16, n, in, f2bf(w.l2_w[band][(size_t)(g * 15 + n) * G + in]));
+                    for (int in = 0; in < G; ++in) put(p2, 16, n, in, cv(w.l2_w[band][(size_t)(g * 15 + n) * G + in]));
                     put_bias(p2, 16, n, G, w.l2_b[band][g * 15 + n]);
                 }
             }
@@ -569,6 +660,11 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
     }
     ctx->tc_weights = tw;
     return LLICTI_OK;
+}
+
+int tc_operand_type(const llicti_ctx *ctx) {       // 1 bf16, 2 fp16
+    const TcWeights *tw = static_cast<const TcWeights *>(ctx->tc_weights);
+    return tw && tw->f16 ? 2 : 1;
 }
 
 void tc_free_weights(llicti_ctx *ctx) {
@@ -605,16 +701,23 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
     size_t mx = 0;
     for (auto &b : tw->band) mx = std::max(mx, b.smem_bytes);
     if (mx > ctx->tc_attr_smem) {
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
         ctx->tc_attr_smem = mx;
     }
     // persistent grid: one CTA per SM, an even number (one sub-network pair per CTA), no more than the work
     const int ctas = std::min(sm_count / 2 * 2, tg.ntiles * 2);
-    if (band == 0) cnn_tc_kernel<0><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params);
-    else if (band == 1) cnn_tc_kernel<1><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params);
-    else cnn_tc_kernel<2><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params);
+#define LLICTI_TC_LAUNCH(B) \
+    do { if (tw->f16) cnn_tc_kernel<B, true><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); \
+         else cnn_tc_kernel<B, false><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); } while (0)
+    if (band == 0) LLICTI_TC_LAUNCH(0);
+    else if (band == 1) LLICTI_TC_LAUNCH(1);
+    else LLICTI_TC_LAUNCH(2);
+#undef LLICTI_TC_LAUNCH
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;

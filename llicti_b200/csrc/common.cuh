@@ -195,6 +195,7 @@ int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int
 // cnn_tc.cu
 int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w);
 void tc_free_weights(llicti_ctx *ctx);
+int tc_operand_type(const llicti_ctx *ctx);
 int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
                   cudaStream_t st, int row0 = 0, int nrows = -1);
 

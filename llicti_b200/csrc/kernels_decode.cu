@@ -1043,7 +1043,76 @@ __device__ __forceinline__ void staged_channel(const float *__restrict__ sp, int
     gmm_prepare(c, np);
 }
 
+// Cheap stand-in for the mixture CDF, used only to GUESS where the symbol is (the decoder then verifies the guess with
+// exact table entries, so a wrong guess costs time, never correctness): the normal CDF as
+// 1 / (1 + exp(-2 c (z + 0.044715 z^3))), c = sqrt(2 / pi) -- absolute error < 3e-4 -- with MUFU.EX2 and MUFU.RCP: ten
+// instructions per mixture against ~70 for the exact erfcf term.  On the synthetic images it puts the symbol exactly in
+// 99.7 % of the cases and within one symbol in all of them (tools: see DESIGN.md), where a window centred on the
+// mixture mean holds it in 70-96 %.  Returns the approximate table entry q~(k) as a float.
+__device__ __forceinline__ float approx_q(const GmmChannel &c, const CdfGrid &g, int k) {
+    if (k <= 0) return 0.f;
+    if (k >= g.Lp - 1) return 65536.f;
+    const float p = ((float)(g.min_val + k) - 0.5f) * (1.0f / 255.0f);
+    float acc = 0.f;
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        const float z = (p - c.mu[m]) * c.rinv[m];
+        const float y = z * fmaf(z * z, 0.044715f, 1.0f);
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * -2.3022082f));        // exp(-2 c y) = 2^(-2 c log2(e) y)
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        acc = fmaf(c.w[m], r, acc);
+    }
+    return fmaf(acc, g.scale, (float)k);
+}
+
+// First probes of the approximate search, relative to the index of the mixture mean: geometric spacing, so that one
+// round brackets the (usual) near symbols tightly and the (rare) far ones at all.
+template <int G> __device__ __forceinline__ int first_probe_offset(int l);
+template <> __device__ __forceinline__ int first_probe_offset<2>(int l) { return l == 0 ? -2 : 3; }
+template <> __device__ __forceinline__ int first_probe_offset<4>(int l) { return l == 0 ? -12 : l == 1 ? -2 : l == 2 ? 3 : 13; }
+template <> __device__ __forceinline__ int first_probe_offset<8>(int l) {
+    return l == 0 ? -40 : l == 1 ? -13 : l == 2 ? -4 : l == 3 ? -1 : l == 4 ? 2 : l == 5 ? 5 : l == 6 ? 14 : 41;
+}
+template <> __device__ __forceinline__ int first_probe_offset<16>(int l) { return 3 * (l - 8) + 1; }
+
+// The same, shared out over the lanes of a group of G >= 8: lane m < 5 prepares mixture m (clamps, coupling, the
+// weight's division, the refined reciprocal of the spread), then the 20 prepared values are exchanged by shuffles --
+// a third of the instructions of every lane preparing all five mixtures.  Bit-identical to gmm_prepare (same operations
+// on the same operands; the weight normaliser is summed by every lane in the profile's order).
 template <int G>
+__device__ __forceinline__ void staged_channel_shared(const float *__restrict__ sp, int clr, int y0, int y1, const NumericsProfile &np,
+                                                      int sub, GmmChannel &c) {
+    static_assert(G >= 8, "needs five lanes per group");
+    const int m = min(sub, kM - 1);
+    const float sb = (float)(0.11 / 255.0);
+    float wall[kM];
+#pragma unroll
+    for (int k = 0; k < kM; ++k) wall[k] = fmaxf(sp[(6 + clr) * kM + k], 1e-6f);
+    const float den = __fadd_rn(sum5(wall, np), 1e-9f);
+    float sg = fmaxf(sp[clr * kM + m], sb), mu = sp[(3 + clr) * kM + m];
+    if (clr == 1) {
+        mu = __fadd_rn(mu, __fmul_rn(sp[9 * kM + m], div255((float)y0, np)));
+    } else if (clr == 2) {
+        mu = __fadd_rn(mu, __fadd_rn(__fmul_rn(sp[10 * kM + m], div255((float)y0, np)), __fmul_rn(sp[11 * kM + m], div255((float)y1, np))));
+    }
+    const float w = __fdiv_rn(fmaxf(sp[(6 + clr) * kM + m], 1e-6f), den);
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(sg));
+    const float rinv = __fmaf_rn(r0, __fmaf_rn(-sg, r0, 1.0f), r0);
+    const bool fast = (fabsf(mu) <= 1024.0f) & (sg >= 9.5367431640625e-07f) & (sg <= 1048576.0f);
+#pragma unroll
+    for (int k = 0; k < kM; ++k) {
+        c.sigma[k] = __shfl_sync(kFull, sg, k, G);
+        c.mu[k] = __shfl_sync(kFull, mu, k, G);
+        c.w[k] = __shfl_sync(kFull, w, k, G);
+        c.rinv[k] = __shfl_sync(kFull, rinv, k, G);
+    }
+    const unsigned slow = __ballot_sync(kFull, !fast && sub < kM);        // a group's lanes 0..4 vote for their mixtures
+    c.fast = ((slow >> ((threadIdx.x & 31) - sub)) & ((1u << G) - 1u)) == 0u;
+}
+
+template <int G, bool kLocate>
 __global__ void __launch_bounds__(128)
 decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__ planes, const int32_t *__restrict__ minmax,
                          DecodeGeom dg, NumericsProfile np, const uint8_t *__restrict__ blob,
@@ -1064,6 +1133,7 @@ decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__
     int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1)) * P;
     const int32_t *mm = minmax + img * 4;
     const int mn_co = mm[0], mn_cg = mm[1], mx_co = mm[2], mx_cg = mm[3];
+    const CdfGrid gY = make_grid(-127, 128), gCo = make_grid(mn_co, mx_co), gCg = make_grid(mn_cg, mx_cg);
     // The decoder of the channel being decoded is always `d`: the three are rotated after every symbol, so the body
     // below exists once in the code (a tenth of the unrolled form's instruction footprint).
     AcDecoderW d, d_next, d_last;
@@ -1107,12 +1177,20 @@ decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__
             sp = stage[t % kGroupStages][gib];
         }
         const int lo_c = clr == 0 ? -127 : clr == 1 ? mn_co : mn_cg;
-        const CdfGrid g = make_grid(lo_c, clr == 0 ? 128 : clr == 1 ? mx_co : mx_cg);
+        CdfGrid g;                                           // (the grids' end points cost two fp64 divisions: made once, above)
+        g.min_val = lo_c;
+        g.Lp = clr == 0 ? gY.Lp : clr == 1 ? gCo.Lp : gCg.Lp;
+        g.p_first = clr == 0 ? gY.p_first : clr == 1 ? gCo.p_first : gCg.p_first;
+        g.p_last = clr == 0 ? gY.p_last : clr == 1 ? gCo.p_last : gCg.p_last;
+        g.scale = clr == 0 ? gY.scale : clr == 1 ? gCo.scale : gCg.scale;
         const int last = g.Lp - 1;
         GmmChannel ch;
-        if (live) {
+        if (G >= 8) {                                        // (warp-wide shuffles inside: every lane, live or not)
+            if constexpr (G >= 8) staged_channel_shared<G>(sp, clr, y0, y1, np, sub, ch);
+        } else if (live) {
             staged_channel(sp, clr, y0, y1, np, ch);
-        } else {
+        }
+        if (!live) {
 #pragma unroll
             for (int m = 0; m < kM; ++m) { ch.sigma[m] = 1.f; ch.mu[m] = 0.f; ch.w[m] = 0.2f; ch.rinv[m] = 1.f; }
             ch.fast = 1;
@@ -1123,8 +1201,38 @@ decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__
         const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
         const uint32_t low = d.low, sm1 = d.high - d.low;
         const uint64_t value = d.value;
-        // search state: q(s_lo) <= target is known (or s_lo = 0), q(s_hi) > target is known (s_hi = last: 2^16)
-        int s_lo = 0, s_hi = last, base = min(max(kc - (G / 2 - 1), 0), max(last - (G - 1), 0)), stride = 1, round = 0;
+        // ---- guess: largest k with q~(k) <= target, by a (G+1)-ary search of the group's lanes over the approximate table ----
+        int guess = kc;
+        if (kLocate) {
+            // torchac's search key ((value - low + 1) 2^16 - 1) / span, in fp32 (7 digits: a guess is all it feeds)
+            const float tf = __fdividef(((float)(d.value - d.low) + 1.0f) * 65536.0f, (float)sm1 + 1.0f);
+            int a = 0, bnd = last;                           // the answer lies in [a, bnd)
+            bool located = !live;
+            {
+                const int k = kc + first_probe_offset<G>(sub);
+                const bool le = k <= 0 || (k < last && approx_q(ch, g, k) <= tf);
+                const int cnt = __popc((__ballot_sync(kFull, le) >> gshift) & gm);
+                const int k_lo = __shfl_sync(kFull, k, max(cnt - 1, 0), G), k_hi = __shfl_sync(kFull, k, min(cnt, G - 1), G);
+                if (cnt > 0) a = min(max(k_lo, 0), last - 1);
+                if (cnt < G) bnd = max(min(k_hi, last), a + 1);
+            }
+#pragma unroll 1
+            for (;;) {
+                located = located || bnd - a <= 1;
+                if (__all_sync(kFull, located)) break;
+                const int step = max((bnd - a + G) / (G + 1), 1);
+                const int k = a + (sub + 1) * step;
+                const bool le = !located && k < bnd && approx_q(ch, g, k) <= tf;
+                const int cnt = __popc((__ballot_sync(kFull, le) >> gshift) & gm);
+                if (!located) {
+                    bnd = min(bnd, a + (cnt + 1) * step);
+                    a += cnt * step;
+                }
+            }
+            guess = a;
+        }
+        // ---- verify with exact entries.  q(s_lo) <= target is known (or s_lo = 0), q(s_hi) > target is known (s_hi = last: 2^16)
+        int s_lo = 0, s_hi = last, base = min(max(guess - (G / 2 - 1), 0), max(last - (G - 1), 0)), stride = 1, round = 0;
         bool done = !live, miss_down = false;
         uint32_t c_low = 0, c_high = 0x10000u;
         int sym = 0;
@@ -1247,7 +1355,7 @@ int64_t decode_items_per_image(const Plan &p) {
 }
 
 static int env_int(const char *name, int dflt);
-static int group_lanes() { return std::max(env_int("LLICTI_GROUP_LANES", 8), 2); }
+static int group_lanes() { return std::max(env_int("LLICTI_GROUP_LANES", 4), 2); }
 static long long group_min_warps() { return env_int("LLICTI_GROUP_MIN_WARPS", 592); }      // one warp per scheduler of a B200
 
 // Does band (scale, b) of a batch of n images take the group schedule?  (Substream container, default decoder, enough
@@ -1308,10 +1416,13 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
         ProfScope prof_(ctx, KC_DECODE, st);
         const long long threads = (long long)n * dg.S * G;
         const int blocks = (int)((threads + 127) / 128);
-        if (G >= 16) decode_band_group_kernel<16><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
-        else if (G >= 8) decode_band_group_kernel<8><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
-        else if (G >= 4) decode_band_group_kernel<4><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
-        else decode_band_group_kernel<2><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n);
+        const bool locate = env_int("LLICTI_GROUP_LOCATE", 1) != 0;
+#define LLICTI_GROUP_LAUNCH(GG, LL) decode_band_group_kernel<GG, LL><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n)
+        if (G >= 16) { if (locate) LLICTI_GROUP_LAUNCH(16, true); else LLICTI_GROUP_LAUNCH(16, false); }
+        else if (G >= 8) { if (locate) LLICTI_GROUP_LAUNCH(8, true); else LLICTI_GROUP_LAUNCH(8, false); }
+        else if (G >= 4) { if (locate) LLICTI_GROUP_LAUNCH(4, true); else LLICTI_GROUP_LAUNCH(4, false); }
+        else { if (locate) LLICTI_GROUP_LAUNCH(2, true); else LLICTI_GROUP_LAUNCH(2, false); }
+#undef LLICTI_GROUP_LAUNCH
         ctx->launches += 1;
         LLICTI_CUDA(cudaGetLastError());
         return LLICTI_OK;

@@ -423,6 +423,13 @@ def couple_means(params: np.ndarray, clr: int, y_band: np.ndarray, M: int) -> np
 # --------------------------------------------------------------------------
 # Interleaved-substream container (new in this repo; not in the reference)
 # --------------------------------------------------------------------------
+def scale_sub_len(sub_len: int, scl: int) -> int:
+    """Target symbols per substream at scale `scl`: sub_len at the finest scale, half of it at the coarser ones.  (A
+    substream is one serial decoder chain: the coarser scales have a quarter and less of the symbols, and with chains
+    of the same length they would have too few chains to fill a GPU.  Container version 2.)"""
+    return sub_len if scl == 0 else max(sub_len // 2, 1)
+
+
 def num_substreams(n: int, sub_len: int) -> int:
     """Number of interleaved substreams of a stream with n symbols: about one per
     sub_len symbols, a multiple of 32 once there are more than 32 (one warp each)."""
@@ -496,20 +503,20 @@ class OracleCodec:
         lo, hi = self._ranges(minmax, clr)
         return gmm_cdf_table(sigma, mu, w, lo, hi, self.sum_order)
 
-    def _encode_stream(self, table: np.ndarray, sym: np.ndarray) -> bytes:
+    def _encode_stream(self, table: np.ndarray, sym: np.ndarray, scl: int) -> bytes:
         n = sym.shape[0]
         if self.sub_len <= 0:
             return ac_encode_table(table, sym)
-        S = num_substreams(n, self.sub_len)
+        S = num_substreams(n, scale_sub_len(self.sub_len, scl))
         return pack_substreams([ac_encode_table(table[j::S], sym[j::S]) for j in range(S)])
 
-    def _decode_stream(self, table: np.ndarray, blob: bytes) -> np.ndarray:
+    def _decode_stream(self, table: np.ndarray, blob: bytes, scl: int) -> np.ndarray:
         n = table.shape[0]
         if self.sub_len <= 0:
             return ac_decode_table(table, blob)
         parts = unpack_substreams(blob)
         S = len(parts)
-        assert S == num_substreams(n, self.sub_len)
+        assert S == num_substreams(n, scale_sub_len(self.sub_len, scl))
         out = np.empty(n, dtype=np.int16)
         for j in range(S):
             out[j::S] = ac_decode_table(table[j::S], parts[j])
@@ -555,16 +562,17 @@ class OracleCodec:
                     if dump is not None:
                         dump.tables[(scl, b, clr)] = t
                         dump.symbols[(scl, b, clr)] = s
-                    row.append(self._encode_stream(t, s))
+                    row.append(self._encode_stream(t, s, scl))
             out.append(row)
         return out
 
     def _mode_tag(self) -> bytes:
         """Header slot 4 is b'' in the reference (LLICTI_nets.py:351-354); this repo uses it
-        to flag the substream container: b'' = torchac-compatible, else [1, sub_len as u32 LE]."""
+        to flag the substream container: b'' = torchac-compatible, else [2, sub_len as u32 LE] (2 = container
+        version: substreams of sub_len symbols at scale 0, sub_len / 2 at the coarser scales)."""
         if self.sub_len <= 0:
             return b""
-        return bytes([1]) + int(self.sub_len).to_bytes(4, "little")
+        return bytes([2]) + int(self.sub_len).to_bytes(4, "little")
 
     # -- decompress (LLICTI_nets.py:161-179, 415-509) -----------------------------
     def decompress(self, bsl, dump: StageDump = None) -> np.ndarray:
@@ -605,7 +613,7 @@ class OracleCodec:
                     y_band = pl[3 * (b + 1):3 * (b + 2)]
                     table = self._table(params, clr, y_band, minmax)
                     t = np.ascontiguousarray(table[:ch, :cw]).reshape(ch * cw, -1)
-                    sym = self._decode_stream(t, row[3 * b + clr]).reshape(ch, cw)
+                    sym = self._decode_stream(t, row[3 * b + clr], scl).reshape(ch, cw)
                     if dump is not None:
                         dump.tables[(scl, b, clr)] = t
                         dump.symbols[(scl, b, clr)] = sym.reshape(-1).copy()

@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     from llicti_b200 import _lib as L
     hdr = open(os.path.join(ROOT, "include", "llicti.h")).read()
     declared = set(re.findall(r"LLICTI_API[^;(]*?\b(llicti_\w+)\s*\(", hdr))
-    assert len(declared) >= 22 and "llicti_status" in declared
+    assert len(declared) >= 24 and {"llicti_status", "llicti_forward_dev", "llicti_cnn_operands"} <= declared
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     for name in declared:
         assert hasattr(built_lib, name), name
@@ -70,7 +70,7 @@ def test_substream_counts_match_oracle(built_lib, sub_len):
     for s in range(5):
         for b in range(3):
             n = g.crop_h[s][b] * g.crop_w[s][b]
-            assert g.num_sub[s][b] == O.num_substreams(n, sub_len)
+            assert g.num_sub[s][b] == O.num_substreams(n, O.scale_sub_len(sub_len, s))
             tot += 3 * g.num_sub[s][b]
     assert g.substreams == tot
 
@@ -255,7 +255,7 @@ def test_container_fingerprint_and_checksum():
     import zlib
     assert container.image_checksum(bsl[0]) == zlib.crc32(rgb[0].tobytes())
     container.parse(S, 0, [bsl], fp=fp)                                       # same codec: fine
-    with pytest.raises(ValueError, match="cnn_impl=1.*cnn_impl=0"):
+    with pytest.raises(ValueError, match="cnn=tcgen05/bf16.*cnn=fp32"):
         container.parse(S, 0, [bsl], fp=container.fingerprint(0, 0, 0xDEADBEEF))
     with pytest.raises(ValueError, match="weights crc32"):
         container.parse(S, 0, [bsl], fp=container.fingerprint(1, 0, 0x12345678))
