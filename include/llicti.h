@@ -184,6 +184,29 @@ LLICTI_API int llicti_encode_host(llicti_ctx *ctx, const uint8_t *rgb, int n, in
 LLICTI_API int llicti_encode_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, uint8_t *out_dev,
                       size_t out_cap, uint64_t *stream_off_dev, int16_t *minmax_dev, void *stream);
 
+/* The same two calls for a batch of images of DIFFERENT sizes, described per image (host pointers).  Images are coded
+ * independently (the reference's eval loop walks them with batch size 1, agents/llicti_agent.py:129-149), so the
+ * library groups the descriptors by size, reserves the workspace per group and runs each group through the uniform
+ * path above; results land in the caller's per-image buffers.  Streams of an image do not depend on its neighbours. */
+typedef struct {
+    const uint8_t *rgb;      /* in : uint8 [3][H][W] planar                                              */
+    int32_t H, W;
+    uint8_t *out;            /* out: the image's 9*num_scales streams back to back                      */
+    size_t out_cap;          /*      capacity of out (llicti_geom.max_stream_bytes is always enough)     */
+    uint64_t *stream_off;    /* out: uint64 [9*num_scales + 1] byte offsets into out (first 0, last = total) */
+    int16_t *minmax;         /* out: int16 [6] header words                                             */
+} llicti_encode_item;
+typedef struct {
+    const uint8_t *blob;          /* in : the image's streams back to back                               */
+    const uint64_t *stream_off;   /* in : uint64 [9*num_scales + 1] offsets into blob                    */
+    const int16_t *minmax;        /* in : int16 [6]                                                      */
+    const uint8_t *x00_rgb;       /* in : uint8 [3][h_last][w_last] raw coarsest band                    */
+    int32_t H, W;
+    uint8_t *rgb_out;             /* out: uint8 [3][H][W]                                                */
+} llicti_decode_item;
+LLICTI_API int llicti_encode_batch_host(llicti_ctx *ctx, const llicti_encode_item *items, int n, void *stream);
+LLICTI_API int llicti_decode_batch_host(llicti_ctx *ctx, const llicti_decode_item *items, int n, void *stream);
+
 /* LLICTI.forward for a batch (LLICTI_nets.py:101-123, 318-342, 802-811, 827-935; entropy_layer_nets.py:160-183,
  * 121-139): the rate-estimation path of validate() / training -- no coding, -log2 of the probability mass of every
  * sample.  Float lifting of :40-49 (NOT the integer transform of compress), un-padded lazyDWT (H and W must be

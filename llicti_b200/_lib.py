@@ -39,6 +39,16 @@ class Geom(C.Structure):
                 ("max_stream_bytes", C.c_int64)]
 
 
+class EncodeItem(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("out", C.c_void_p), ("out_cap", C.c_size_t),
+                ("stream_off", C.c_void_p), ("minmax", C.c_void_p)]
+
+
+class DecodeItem(C.Structure):
+    _fields_ = [("blob", C.c_void_p), ("stream_off", C.c_void_p), ("minmax", C.c_void_p), ("x00_rgb", C.c_void_p),
+                ("H", C.c_int32), ("W", C.c_int32), ("rgb_out", C.c_void_p)]
+
+
 class LlictiError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libllicti_b200 error {code}: {msg}")
@@ -78,6 +88,8 @@ _PROTOS = {
     "llicti_forward_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.c_void_p]),
     "llicti_cnn_operands": (C.c_int, [C.c_void_p]),
+    "llicti_encode_batch_host": (C.c_int, [C.c_void_p, C.POINTER(EncodeItem), C.c_int, C.c_void_p]),
+    "llicti_decode_batch_host": (C.c_int, [C.c_void_p, C.POINTER(DecodeItem), C.c_int, C.c_void_p]),
     "llicti_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llicti_launch_count": (C.c_int64, [C.c_void_p]),
     "llicti_profile": (C.c_int, [C.c_void_p, C.c_int]),

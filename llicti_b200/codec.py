@@ -226,6 +226,51 @@ class Codec:
                                            n, H, W, out.data_ptr(), self._stream()))
         return out
 
+    # -- batches of mixed sizes (llicti_encode_batch_host / llicti_decode_batch_host) ------------------
+    def compress_mixed(self, images: Sequence[np.ndarray]):
+        """images: uint8 [3,H_i,W_i] arrays of any sizes -> list of bytestream_lists, in order (one C call: the
+        library groups the descriptors by size)."""
+        n = len(images)
+        ns = 9 * self.cfg.num_scales
+        items = (L.EncodeItem * n)()
+        keep = []
+        for i, img in enumerate(images):
+            img = np.ascontiguousarray(img, dtype=np.uint8)
+            assert img.ndim == 3 and img.shape[0] == 3
+            g = self.geometry(img.shape[1], img.shape[2])
+            out = np.empty(int(g.max_stream_bytes), dtype=np.uint8)
+            off = np.empty(ns + 1, dtype=np.uint64)
+            mm = np.empty(6, dtype=np.int16)
+            keep.append((img, out, off, mm, g))
+            items[i] = L.EncodeItem(img.ctypes.data, img.shape[1], img.shape[2], out.ctypes.data, out.nbytes, off.ctypes.data, mm.ctypes.data)
+        L.check(self.lib.llicti_encode_batch_host(self._ctx, items, n, self._stream()))
+        self._reserved = (0, 0, 0)          # the library re-reserved per size group
+        S = self.cfg.num_scales
+        res = []
+        for img, out, off, mm, g in keep:
+            res.append(container.assemble(S, self.cfg.sub_len, g.Hs[S - 1], g.Ws[S - 1], g.pad_int, img[None], out[:int(off[-1])], off,
+                                          mm[None], fp=self.fingerprint, checksum=True)[0])
+        return res
+
+    def decompress_mixed(self, bsls: Sequence) -> List[np.ndarray]:
+        """list of bytestream_lists of any image sizes -> list of uint8 [3,H_i,W_i] arrays, in order."""
+        n = len(bsls)
+        items = (L.DecodeItem * n)()
+        keep = []
+        for i, bsl in enumerate(bsls):
+            blob, off, mm, x00, _, H, W = self.from_bytestream_lists([bsl])
+            blob, off, mm, x00 = (np.ascontiguousarray(a) for a in (blob, off, mm, x00))
+            out = np.empty((3, H, W), dtype=np.uint8)
+            keep.append((blob, off, mm, x00, out))
+            items[i] = L.DecodeItem(blob.ctypes.data, off.ctypes.data, mm.ctypes.data, x00.ctypes.data, H, W, out.ctypes.data)
+        L.check(self.lib.llicti_decode_batch_host(self._ctx, items, n, self._stream()))
+        self._reserved = (0, 0, 0)
+        for i, bsl in enumerate(bsls):
+            want = container.image_checksum(bsl[0])
+            if want is not None and (zlib.crc32(keep[i][4].data) & 0xFFFFFFFF) != want:
+                raise ValueError(f"image {i}: the decoded pixels fail the stream's checksum")
+        return [k[4] for k in keep]
+
     # -- rate estimation (LLICTI.forward) ----------------------------------------------------------
     def forward_dev(self, rgb: torch.Tensor):
         """rgb uint8 [n,3,H,W] CUDA tensor, H and W multiples of 2^S -> list over scales of float32 [n,9,Hs,Ws]

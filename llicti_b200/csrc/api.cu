@@ -219,6 +219,26 @@ static int cnn(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, 
 
 }  // namespace llicti
 
+// ---- batches of mixed sizes ------------------------------------------------------------------
+// Indices of `n` descriptors grouped by (H, W), first-seen order of the sizes, original order inside a group.
+template <class Item>
+static std::vector<std::vector<int>> group_by_size(const Item *items, int n) {
+    std::vector<std::vector<int>> groups;
+    for (int i = 0; i < n; ++i) {
+        size_t g = 0;
+        for (; g < groups.size(); ++g)
+            if (items[groups[g][0]].H == items[i].H && items[groups[g][0]].W == items[i].W) break;
+        if (g == groups.size()) groups.emplace_back();
+        groups[g].push_back(i);
+    }
+    return groups;
+}
+
+static int reserve_for(llicti_ctx *ctx, int n, int H, int W) {
+    if (ctx->ws_images >= n && ctx->ws_H == H && ctx->ws_W == W) return LLICTI_OK;
+    return llicti_reserve(ctx, std::max(n, ctx->ws_H == H && ctx->ws_W == W ? ctx->ws_images : 0), H, W);
+}
+
 using namespace llicti;
 
 extern "C" {
@@ -668,6 +688,86 @@ int llicti_decode_host(llicti_ctx *ctx, const uint8_t *blob, const uint64_t *str
     if (rc) return rc;
     LLICTI_CUDA(cudaMemcpyAsync(rgb_out, ctx->d_rgb, (size_t)n * 3 * H * W, cudaMemcpyDeviceToHost, st));
     LLICTI_CUDA(cudaStreamSynchronize(st));
+    return LLICTI_OK;
+}
+
+int llicti_encode_batch_host(llicti_ctx *ctx, const llicti_encode_item *items, int n, void *stream) {
+    LLICTI_REQUIRE(ctx && items && n >= 1, "bad argument");
+    for (int i = 0; i < n; ++i)
+        LLICTI_REQUIRE(items[i].rgb && items[i].out && items[i].stream_off && items[i].minmax, "null pointer in item %d", i);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<uint64_t> off;
+    for (const std::vector<int> &grp : group_by_size(items, n)) {
+        const int m = (int)grp.size(), H = items[grp[0]].H, W = items[grp[0]].W;
+        int rc = reserve_for(ctx, m, H, W);
+        if (rc) return rc;
+        const int ns = ctx->plan.n_streams;
+        const size_t img_bytes = (size_t)3 * H * W;
+        LLICTI_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int32_t), st));
+        for (int k = 0; k < m; ++k)
+            LLICTI_CUDA(cudaMemcpyAsync(ctx->d_rgb + (size_t)k * img_bytes, items[grp[k]].rgb, img_bytes, cudaMemcpyHostToDevice, st));
+        if ((rc = llicti_encode_dev(ctx, ctx->d_rgb, m, H, W, ctx->d_blob, ctx->blob_cap, ctx->d_stream_off, ctx->d_minmax16, st))) return rc;
+        off.resize((size_t)m * ns + 1);
+        LLICTI_CUDA(cudaMemcpyAsync(off.data(), ctx->d_stream_off, off.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if ((rc = read_status(ctx, st))) return rc;
+        for (int k = 0; k < m; ++k) {
+            const llicti_encode_item &it = items[grp[k]];
+            const uint64_t b0 = off[(size_t)k * ns], b1 = off[(size_t)(k + 1) * ns];
+            if (b1 - b0 > it.out_cap) {
+                set_error("item %d needs %llu bytes, capacity is %llu", grp[k], (unsigned long long)(b1 - b0), (unsigned long long)it.out_cap);
+                return LLICTI_E_NOMEM;
+            }
+            for (int j = 0; j <= ns; ++j) it.stream_off[j] = off[(size_t)k * ns + j] - b0;
+            LLICTI_CUDA(cudaMemcpyAsync(it.out, ctx->d_blob + b0, b1 - b0, cudaMemcpyDeviceToHost, st));
+            LLICTI_CUDA(cudaMemcpyAsync(it.minmax, ctx->d_minmax16 + (size_t)k * 6, 6 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+        }
+        LLICTI_CUDA(cudaStreamSynchronize(st));
+    }
+    return LLICTI_OK;
+}
+
+int llicti_decode_batch_host(llicti_ctx *ctx, const llicti_decode_item *items, int n, void *stream) {
+    LLICTI_REQUIRE(ctx && items && n >= 1, "bad argument");
+    for (int i = 0; i < n; ++i)
+        LLICTI_REQUIRE(items[i].blob && items[i].stream_off && items[i].minmax && items[i].x00_rgb && items[i].rgb_out,
+                       "null pointer in item %d", i);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<uint64_t> off;
+    std::vector<uint8_t> blob, x00;
+    std::vector<int16_t> mm;
+    std::vector<uint8_t> rgb;
+    for (const std::vector<int> &grp : group_by_size(items, n)) {
+        const int m = (int)grp.size(), H = items[grp[0]].H, W = items[grp[0]].W;
+        int rc = reserve_for(ctx, m, H, W);
+        if (rc) return rc;
+        const Plan &p = ctx->plan;
+        const int ns = p.n_streams, S = p.g.num_scales;
+        const size_t x00_bytes = (size_t)3 * p.g.Hs[S - 1] * p.g.Ws[S - 1], img_bytes = (size_t)3 * H * W;
+        // the uniform entry point takes one blob with running offsets: lay the group's streams end to end
+        off.assign((size_t)m * ns + 1, 0);
+        uint64_t pos = 0;
+        for (int k = 0; k < m; ++k) {
+            const llicti_decode_item &it = items[grp[k]];
+            for (int j = 0; j < ns; ++j) {
+                if (it.stream_off[j] > it.stream_off[j + 1]) { set_error("item %d: stream offsets decrease", grp[k]); return LLICTI_E_STREAM; }
+                off[(size_t)k * ns + j] = pos + (it.stream_off[j] - it.stream_off[0]);
+            }
+            pos += it.stream_off[ns] - it.stream_off[0];
+        }
+        off[(size_t)m * ns] = pos;
+        blob.resize(std::max<uint64_t>(pos, 1));
+        x00.resize((size_t)m * x00_bytes);
+        mm.resize((size_t)m * 6);
+        for (int k = 0; k < m; ++k) {
+            const llicti_decode_item &it = items[grp[k]];
+            memcpy(blob.data() + off[(size_t)k * ns], it.blob + it.stream_off[0], it.stream_off[ns] - it.stream_off[0]);
+            memcpy(x00.data() + (size_t)k * x00_bytes, it.x00_rgb, x00_bytes);
+            memcpy(mm.data() + (size_t)k * 6, it.minmax, 6 * sizeof(int16_t));
+        }
+        rgb.resize((size_t)m * img_bytes);
+        if ((rc = llicti_decode_host(ctx, blob.data(), off.data(), mm.data(), x00.data(), m, H, W, rgb.data(), st))) return rc;
+        for (int k = 0; k < m; ++k) memcpy(items[grp[k]].rgb_out, rgb.data() + (size_t)k * img_bytes, img_bytes);
+    }
     return LLICTI_OK;
 }
 

@@ -1043,6 +1043,21 @@ __device__ __forceinline__ void staged_channel(const float *__restrict__ sp, int
     gmm_prepare(c, np);
 }
 
+// One decoded symbol's interval update on the look-ahead bit source, with the closed-form renormalisation (one clz, one
+// shift; next_state above) instead of AcDecoderW::consume's two-stage loop: the same registers afterwards.
+__device__ __forceinline__ void consume_closed_form(AcDecoderW &d, uint32_t c_low, uint32_t c_high) {
+    if (d.br.avail < 32) {                                  // BitReaderW::take's refill, so that 32 bits can be peeked
+        d.br.buf |= (uint64_t)d.br.a0 << (32 - d.br.avail);
+        d.br.avail += 32;
+        d.br.a0 = d.br.a1;
+        d.br.a1 = d.br.fetch(d.br.idx++);
+    }
+    const NextState ns = next_state(d.low, d.high, d.value, (uint32_t)(d.br.buf >> 32), c_low, c_high);
+    d.low = ns.low; d.high = ns.high; d.value = ns.value;
+    d.br.buf <<= ns.sh;
+    d.br.avail -= ns.sh;
+}
+
 // Cheap stand-in for the mixture CDF, used only to GUESS where the symbol is (the decoder then verifies the guess with
 // exact table entries, so a wrong guess costs time, never correctness): the normal CDF as
 // 1 / (1 + exp(-2 c (z + 0.044715 z^3))), c = sqrt(2 / pi) -- absolute error < 3e-4 -- with MUFU.EX2 and MUFU.RCP: ten
@@ -1199,8 +1214,7 @@ decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__
 #pragma unroll
         for (int m = 0; m < kM; ++m) mean = fmaf(ch.w[m], ch.mu[m], mean);
         const int kc = __float2int_rn(mean * 255.0f) - g.min_val;
-        const uint32_t low = d.low, sm1 = d.high - d.low;
-        const uint64_t value = d.value;
+        const uint32_t low = d.low, sm1 = d.high - d.low, span = sm1 + 1u, value32 = d.value;
         // ---- guess: largest k with q~(k) <= target, by a (G+1)-ary search of the group's lanes over the approximate table ----
         int guess = kc;
         if (kLocate) {
@@ -1241,8 +1255,12 @@ decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__
             const int k = base + sub * stride;
             uint32_t q = 0x10000u;
             if (!done && k < last) q = cdf_q(ch, g, k, np);
-            const uint64_t nl = (uint64_t)low + (((uint64_t)sm1 * q + q) >> 16);
-            const unsigned le = __ballot_sync(kFull, nl <= value);
+            // candidate test low + ((span * q) >> 16) <= value in 32 bits: the high word of span * (q << 16); the full range
+            // (span = 2^32, seen as 0: a stream's first symbols) gives q << 16 itself, and q = 2^16 (the alphabet's end, or a
+            // probe beyond it) gives high + 1 > value
+            const uint32_t q16 = q << 16;
+            const uint32_t nl = low + (span == 0u ? q16 : __umulhi(span, q16));
+            const unsigned le = __ballot_sync(kFull, q != 0x10000u && nl <= value32);
             const int cnt = __popc((le >> gshift) & gm);
             const int i_lo = max(cnt - 1, 0), i_hi = min(i_lo + 1, G - 1);
             const uint32_t q_lo = __shfl_sync(kFull, q, i_lo, G), q_hi = __shfl_sync(kFull, q, i_hi, G);
@@ -1276,7 +1294,7 @@ decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__
             if (__all_sync(kFull, done)) break;
         }
         if (live) {
-            if (t + 1 < n_steps) d.consume(c_low, c_high);      // torchac does not update after the last symbol
+            if (t + 1 < n_steps) consume_closed_form(d, c_low, c_high);      // torchac does not update after the last symbol
             rounds += (unsigned long long)(round - 1);
         }
         const int yv = sym + lo_c;

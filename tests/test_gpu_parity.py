@@ -809,3 +809,31 @@ def test_rate_with_trained_weights_kodak_shape_tcgen05(L):
     # 0.5 % of the reference's bytes.  (sub_len 4096 at this image size: a 768x512 stream is ~100 k symbols; the bench
     # shapes are 7-21 times larger and use 2048.)
     assert abs(out["tcgen05-substreams"] - ref) <= 0.005 * ref, out
+
+
+@pytest.mark.parametrize("sub_len", [0, 256])
+def test_mixed_size_batch_entry_points(L, sub_len):
+    """llicti_encode_batch_host / llicti_decode_batch_host: one call for images of different sizes, described per
+    image.  Every image's streams equal the ones the uniform path makes for it alone, in the
+    caller's order, and decode back to the pixels."""
+    ocfg = O.OracleConfig(dwtlevels=(0, 1), chs=60)
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=sub_len, cnn_impl=L.CNN_TCGEN05)
+    sizes = [(64, 96), (53, 77), (64, 96), (128, 192), (53, 77), (37, 41)]
+    imgs = [O.synthetic_image(h, w, 90 + i) for i, (h, w) in enumerate(sizes)]
+    bsls = codec.compress_mixed(imgs)
+    assert len(bsls) == len(imgs)
+    for img, bsl in zip(imgs, bsls):
+        alone = codec.compress_images(img[None])[0]
+        assert bsl == alone, img.shape
+    recs = codec.decompress_mixed(bsls)
+    for img, rec in zip(imgs, recs):
+        assert rec.shape == img.shape and np.array_equal(rec, img)
+    # a corrupt item is reported, the context survives
+    from llicti_b200._lib import LlictiError
+    bad = [list(r) for r in bsls[3]]
+    bad[0] = list(bad[0])
+    bad[0][6] = b"\x00\x00\x00\x00"
+    with pytest.raises(ValueError, match="checksum"):
+        codec.decompress_mixed([bsls[0], bad])
+    assert np.array_equal(codec.decompress_mixed(bsls[:2])[1], imgs[1])
+    codec.close()
