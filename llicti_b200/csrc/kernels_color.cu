@@ -65,6 +65,65 @@ split_rgb_kernel(const uint8_t *__restrict__ rgb, int H, int W, int Hs, int Ws, 
     }
 }
 
+// The same for even H and W % 8 == 0 (every BASELINE shape), vectorised: a thread owns four consecutive positions of
+// a scale-0 row, i.e. eight pixels of two image rows: six 8-byte loads (three channels, two rows) and twelve 8-byte
+// stores (four int16 samples per plane) instead of 12 byte loads and 12 two-byte stores per position.
+__global__ void __launch_bounds__(256)
+split_rgb_vec_kernel(const uint8_t *__restrict__ rgb, int H, int W, int Hs, int Ws, int16_t *__restrict__ planes,
+                     int32_t *__restrict__ minmax) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;      // group of four positions
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;
+    int mnCo = 1 << 20, mnCg = 1 << 20, mxCo = -(1 << 20), mxCg = -(1 << 20);
+    if (c4 * 4 < Ws) {
+        const size_t hw = (size_t)H * W, ps = (size_t)Hs * Ws;
+        const uint8_t *base = rgb + (size_t)img * 3 * hw + (size_t)(2 * r) * W + 8 * c4;
+        uint2 px[2][3];                                          // [image row parity][channel]: eight pixels each
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) px[rr][ch] = __ldg(reinterpret_cast<const uint2 *>(base + (size_t)ch * hw + (size_t)rr * W));
+        int16_t *out = planes + (size_t)img * 12 * ps + (size_t)r * Ws + 4 * c4;
+        // phase order x00, x11, x01, x10 = (row 0, even col), (row 1, odd col), (row 0, odd col), (row 1, even col)
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            const int rr = (ph == 1 || ph == 3) ? 1 : 0, odd = (ph == 1 || ph == 2) ? 1 : 0;
+            short y4[4], co4[4], cg4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int byte = 2 * k + odd;                    // pixel within the eight
+                const uint32_t wr = byte < 4 ? px[rr][0].x : px[rr][0].y, wg = byte < 4 ? px[rr][1].x : px[rr][1].y,
+                               wb = byte < 4 ? px[rr][2].x : px[rr][2].y;
+                const int sh = 8 * (byte & 3);
+                int y, co, cg;
+                rgb_to_ycocg((wr >> sh) & 0xFF, (wg >> sh) & 0xFF, (wb >> sh) & 0xFF, y, co, cg);
+                y4[k] = (short)(y - 127); co4[k] = (short)co; cg4[k] = (short)cg;
+                mnCo = min(mnCo, co); mxCo = max(mxCo, co);
+                mnCg = min(mnCg, cg); mxCg = max(mxCg, cg);
+            }
+            auto pack = [](const short *v) {
+                return make_uint2((uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16), (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16));
+            };
+            *reinterpret_cast<uint2 *>(out + (size_t)(ph * 3 + 0) * ps) = pack(y4);
+            *reinterpret_cast<uint2 *>(out + (size_t)(ph * 3 + 1) * ps) = pack(co4);
+            *reinterpret_cast<uint2 *>(out + (size_t)(ph * 3 + 2) * ps) = pack(cg4);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnCo = min(mnCo, __shfl_xor_sync(0xffffffffu, mnCo, o));
+        mnCg = min(mnCg, __shfl_xor_sync(0xffffffffu, mnCg, o));
+        mxCo = max(mxCo, __shfl_xor_sync(0xffffffffu, mxCo, o));
+        mxCg = max(mxCg, __shfl_xor_sync(0xffffffffu, mxCg, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mnCo <= mxCo) {
+        atomicMin(minmax + img * 4 + 0, mnCo);
+        atomicMin(minmax + img * 4 + 1, mnCg);
+        atomicMax(minmax + img * 4 + 2, mxCo);
+        atomicMax(minmax + img * 4 + 3, mxCg);
+    }
+}
+
 // Scale s+1 from the x00 planes of scale s (int16 for the coder, fp32 for the rate-estimation path).
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -172,7 +231,12 @@ int launch_color_split(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb, int n
     ProfScope prof_(ctx, KC_SPLIT, st);
     const llicti_geom &g = p.g;
     init_minmax_kernel<<<(n + 127) / 128, 128, 0, st>>>(minmax, n);
-    {
+    const bool aligned = (reinterpret_cast<uintptr_t>(rgb) % 8 == 0) && (reinterpret_cast<uintptr_t>(planes[0]) % 8 == 0);
+    if (g.H % 2 == 0 && g.W % 8 == 0 && aligned) {
+        const int groups = g.Ws[0] / 4, threads = groups >= 256 ? 256 : 64;
+        dim3 grid((groups + threads - 1) / threads, g.Hs[0], n);
+        split_rgb_vec_kernel<<<grid, threads, 0, st>>>(rgb, g.H, g.W, g.Hs[0], g.Ws[0], planes[0], minmax);
+    } else {
         dim3 grid((g.Ws[0] + 255) / 256, g.Hs[0], n);
         split_rgb_kernel<<<grid, 256, 0, st>>>(rgb, g.H, g.W, g.Hs[0], g.Ws[0], g.H / 2, g.W / 2, planes[0], minmax);
     }
@@ -248,9 +312,52 @@ int launch_color_split_float(llicti_ctx *ctx, const Plan &p, const uint8_t *rgb,
     return LLICTI_OK;
 }
 
+// Vectorised form for even H and W % 8 == 0: a thread owns eight consecutive pixels of an image row -- four samples of
+// each of the two phases that alternate along the row, three channels: six 8-byte loads, three 8-byte stores.
+__global__ void __launch_bounds__(256)
+merge_rgb_vec_kernel(const int16_t *__restrict__ from, int Hs, int Ws, uint8_t *__restrict__ rgb, int H, int W) {
+    const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;
+    if (c8 * 8 >= W) return;
+    const size_t ps = (size_t)Hs * Ws, hw = (size_t)H * W;
+    const int ph_even = (r & 1) ? 3 : 0, ph_odd = (r & 1) ? 1 : 2;          // phase of the even / odd columns of this row
+    const int16_t *src = from + (size_t)img * 12 * ps + (size_t)(r >> 1) * Ws + 4 * c8;
+    uint2 ev[3], od[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        ev[ch] = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)(ph_even * 3 + ch) * ps));
+        od[ch] = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)(ph_odd * 3 + ch) * ps));
+    }
+    uint32_t outw[3][2] = {};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int j = k >> 1;                                               // sample within the four
+        const uint2 *v = (k & 1) ? od : ev;
+        auto pick = [&](const uint2 &q) { const uint32_t w = j < 2 ? q.x : q.y; return (int)(short)((j & 1) ? (w >> 16) : (w & 0xFFFF)); };
+        int R, G, B;
+        ycocg_to_rgb(pick(v[0]) + 127, pick(v[1]), pick(v[2]), R, G, B);
+        outw[0][k >> 2] |= (uint32_t)(R & 0xFF) << (8 * (k & 3));
+        outw[1][k >> 2] |= (uint32_t)(G & 0xFF) << (8 * (k & 3));
+        outw[2][k >> 2] |= (uint32_t)(B & 0xFF) << (8 * (k & 3));
+    }
+    uint8_t *dst = rgb + (size_t)img * 3 * hw + (size_t)r * W + 8 * c8;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) *reinterpret_cast<uint2 *>(dst + (size_t)ch * hw) = make_uint2(outw[ch][0], outw[ch][1]);
+}
+
 int launch_merge_color(llicti_ctx *ctx, const Plan &p, const int16_t *planes0, int n, uint8_t *rgb, cudaStream_t st) {
     ProfScope prof_(ctx, KC_MERGE, st);
     const llicti_geom &g = p.g;
+    const bool aligned = (reinterpret_cast<uintptr_t>(rgb) % 8 == 0) && (reinterpret_cast<uintptr_t>(planes0) % 8 == 0);
+    if (g.H % 2 == 0 && g.W % 8 == 0 && aligned) {
+        const int groups = g.W / 8, threads = groups >= 256 ? 256 : 64;
+        dim3 grid((groups + threads - 1) / threads, g.H, n);
+        merge_rgb_vec_kernel<<<grid, threads, 0, st>>>(planes0, g.Hs[0], g.Ws[0], rgb, g.H, g.W);
+        ctx->launches += 1;
+        LLICTI_CUDA(cudaGetLastError());
+        return LLICTI_OK;
+    }
     dim3 grid((g.W + 255) / 256, g.H, n);
     merge_rgb_kernel<<<grid, 256, 0, st>>>(planes0, g.Hs[0], g.Ws[0], rgb, g.H, g.W);
     ctx->launches += 1;
