@@ -14,11 +14,17 @@
 //                L2  D2_g[128 x 16] = H1_g * W2_g^T
 //              L0 of tile t+1 is issued before L1/L2 of tile t, so the tensor pipe works on the
 //              next tile while the epilogue warps turn D0/D1 of this one into operands;
-//   warps 0-7  epilogue (four warps per sub-network): TMEM -> registers -> ReLU -> bf16 -> shared (K-major operand of the next
-//              layer); layer 2 -> fp32 params in global memory.
+//   warps 0-7  epilogue (four warps per sub-network): TMEM -> registers -> ReLU -> bf16 pairs -> TMEM (tcgen05.st): the hidden
+//              activations are the next layer's A operand straight from tensor memory (tcgen05.mma with A in TMEM), so they
+//              never pass through shared memory; layer 2 -> fp32 params in global memory.
 //
-// Two tiles are in flight in TMEM (2 x (2NP + 32) <= 448 columns).  Biases ride in two spare K
-// slots as a bf16 hi + lo pair against constant-one activation columns (which the previous
+// TMEM map (columns): [0, 2NP) and [2NP, 4NP) accumulators D0/D1 of the two tiles in flight, [4NP, 5NP) the bf16 hidden
+// activations of the two sub-networks (NP/2 columns each, two values per column), [5NP, 5NP + 32) D2: 512 for NP = 96.
+// Why TMEM and not shared memory: the shared-memory port (128 B/clk) was the kernel's limit -- per tile the MMAs read
+// 218 KB of operands from it, the epilogues stored 98 KB of activations into it and the im2col warps another ~100 KB
+// (~3.3 k cycles against 1.44 k tensor cycles; tools/tmem_probe.cu: TMEM itself reads at 944 B/clk).  With the
+// activations in TMEM the 98 KB of stores and the 96 KB of A-operand reads of layers 1 and 2 are gone.
+// Biases ride in two spare K slots as a bf16 hi + lo pair against constant-one activation columns (which the previous
 // layer's weights regenerate), so the epilogues are pure ReLU + pack.  The 4*chs-wide
 // activations never touch HBM.
 //
@@ -45,7 +51,8 @@ namespace llicti {
 constexpr int TC_M = 128;            // positions per tile = UMMA_M
 constexpr int TC_THREADS = 544;      // 8 epilogue warps (4 per sub-network), 8 im2col warps, 1 MMA warp
 constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_SLOT_COLS = 256;    // TMEM columns per tile slot: [0, 2NP) D0/D1, [2NP, 2NP+32) D2
+// TMEM columns: tile slot s holds D0/D1 of both sub-networks at [s * 2NP, (s + 1) * 2NP); hidden activations of sub-network g
+// at 4NP + g * NP/2 (bf16 pairs); D2 of sub-network g at 5NP + 16 g.
 
 struct TcGeom {
     int Hs, Ws, P;          // plane size
@@ -147,6 +154,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same with the A operand in tensor memory: 128 lanes = rows, 8 columns of bf16 pairs per K = 16 step.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -170,31 +185,53 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                    "=r"(r[31])                                                                          \
                  : "r"(taddr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#define TMEM_ST_X16(taddr, r)                                                                           \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                        \
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"            \
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory")
+#define TMEM_ST_X32(taddr, r)                                                                           \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                        \
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "            \
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"    \
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),      \
+                   "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),    \
+                   "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory")
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// ReLU + bf16 of 16 accumulator columns -> two 16-byte operand chunks.
+// One hidden layer's epilogue for one sub-network: all NP accumulator columns of this thread's row are fetched with
+// back-to-back TMEM loads and ONE wait, turned into NP/2 operand pairs -- one cvt per column pair: round to the operand type
+// with ReLU, element 2e in the low half -- and stored into the NP/2 TMEM columns the next layer's MMAs read as their A operand.
 template <bool F16>
-__device__ __forceinline__ void relu_pack16(const uint32_t *r, uint8_t *dst_chunk0, uint32_t chunk_stride) {
-    uint32_t w[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {   // one instruction per column pair: round to the operand type with ReLU (element 2e in the low half)
-        if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(__uint_as_float(r[2 * e + 1])), "f"(__uint_as_float(r[2 * e])));
-        else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(__uint_as_float(r[2 * e + 1])), "f"(__uint_as_float(r[2 * e])));
-    }
-    *reinterpret_cast<uint4 *>(dst_chunk0) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4 *>(dst_chunk0 + chunk_stride) = make_uint4(w[4], w[5], w[6], w[7]);
+__device__ __forceinline__ uint32_t relu_pair(uint32_t lo, uint32_t hi) {
+    uint32_t w;
+    if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+    return w;
 }
-
-// One hidden layer's epilogue for one sub-network: all NP accumulator columns of this thread's row
-// are fetched with back-to-back TMEM loads and ONE wait (the loads overlap each other and the
-// conversion of 8 independent column pairs per 16-byte chunk pipelines), then ReLU + bf16 + store.
+// (The third load of NP = 96 is issued once the first 32 columns are converted: at most 80 accumulator / operand registers
+// are live, which keeps the kernel inside the 96 registers a 17-warp CTA leaves per thread.)
 template <int NP, bool F16>
-__device__ __forceinline__ void epilogue_hidden(uint32_t taddr, uint8_t *h_row, uint32_t chunk_stride) {
-    uint32_t r[NP];
-#pragma unroll
-    for (int c = 0; c < NP / 32; ++c) TMEM_LD_X32(taddr + (uint32_t)(c * 32), (r + c * 32));
+__device__ __forceinline__ void epilogue_hidden(uint32_t d_addr, uint32_t h_addr) {
+    uint32_t ra[32], rb[32], w[32];
+    TMEM_LD_X32(d_addr, ra);
+    TMEM_LD_X32(d_addr + 32u, rb);
     tmem_ld_wait();
 #pragma unroll
-    for (int c16 = 0; c16 < NP / 16; ++c16) relu_pack16<F16>(r + c16 * 16, h_row + (size_t)(c16 * 2) * chunk_stride, chunk_stride);
+    for (int e = 0; e < 16; ++e) w[e] = relu_pair<F16>(ra[2 * e], ra[2 * e + 1]);
+    if (NP == 96) TMEM_LD_X32(d_addr + 64u, ra);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) w[16 + e] = relu_pair<F16>(rb[2 * e], rb[2 * e + 1]);
+    TMEM_ST_X32(h_addr, w);
+    if (NP == 96) {
+        tmem_ld_wait();
+        uint32_t w2[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) w2[e] = relu_pair<F16>(ra[2 * e], ra[2 * e + 1]);
+        TMEM_ST_X16(h_addr + 32u, w2);
+    }
+    tmem_st_wait();
 }
 
 // Compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{}).
@@ -325,11 +362,9 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     uint8_t *sW2 = smem + tg.off_w2;                             // 2 x [NP/8][16][16 B]
     uint8_t *sA = smem + ((tg.pair_bytes + 127) & ~127);         // 2 stages x [K0p/8][128][16 B]
     constexpr uint32_t a_stage = (K0p / 8) * TC_M * 16;
-    const uint32_t h_bytes = (uint32_t)(NP / 8) * TC_M * 16;
-    uint8_t *sH = sA + 2 * a_stage;                              // 2 sub-networks x [NP/8][128][16 B]
-    uint16_t *sSeg = reinterpret_cast<uint16_t *>(sH + 2 * h_bytes);   // staged row segments, [NSEG][TC_SEG_PITCH] bf16
+    uint16_t *sSeg = reinterpret_cast<uint16_t *>(sA + 2 * a_stage);   // staged row segments, [NSEG][TC_SEG_PITCH] bf16
     constexpr uint32_t seg_bytes = (band_nseg(BAND) * TC_SEG_PITCH * 2 + 15) / 16 * 16;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sH + 2 * h_bytes + seg_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + 2 * a_stage + seg_bytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int idx) { return bar0 + 8u * (uint32_t)idx; };
@@ -393,7 +428,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
                 mbar_wait(bar(B_AFULL + s), (it >> 1) & 1);
                 mbar_wait(bar(B_DFREE + s), ((it >> 1) & 1) ^ 1);     // epilogues of tile it-2 have drained this slot
                 tc_fence_after();
-                const uint32_t d0 = tmem + (uint32_t)(s * TC_SLOT_COLS);
+                const uint32_t d0 = tmem + (uint32_t)(s * 2 * NP);
                 const uint32_t a0 = smem_u32(sA) + s * a_stage;
                 // Layer 0 of the two sub-networks as two MMA groups with a commit each: sub-network 0's epilogue starts
                 // while sub-network 1's layer 0 still runs, and from then on the two run half a phase apart -- one reads
@@ -413,23 +448,21 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             for (int it = 0; it < my_tiles; ++it) {
                 if (it + 1 < my_tiles) issue_l0(it + 1);
                 const int s = it & 1;
-                const uint32_t dbase = tmem + (uint32_t)(s * TC_SLOT_COLS);
-                for (int g = 0; g < 2; ++g) {       // layer 1 of sub-network g, into D0_g's columns
+                const uint32_t dbase = tmem + (uint32_t)(s * 2 * NP);
+                for (int g = 0; g < 2; ++g) {       // layer 1 of sub-network g, into D0_g's columns; A = H0_g in TMEM
                     mbar_wait(bar(B_H0FULL + g), it & 1);
                     tc_fence_after();
-                    const uint32_t h = smem_u32(sH) + g * h_bytes, w1 = smem_u32(sW1) + g * w1_bytes;
+                    const uint32_t h = tmem + (uint32_t)(4 * NP + g * (NP / 2)), w1 = smem_u32(sW1) + g * w1_bytes;
                     for (int ks = 0; ks < NP / 16; ++ks)
-                        umma_bf16(dbase + (uint32_t)(g * NP), umma_desc(h + ks * 2 * a_lbo, a_lbo, 128),
-                                  umma_desc(w1 + ks * 2 * w1_lbo, w1_lbo, 128), idesc1, ks > 0);
+                        umma_bf16_ts(dbase + (uint32_t)(g * NP), h + (uint32_t)(ks * 8), umma_desc(w1 + ks * 2 * w1_lbo, w1_lbo, 128), idesc1, ks > 0);
                     umma_commit(bar(B_D1FULL + g));
                 }
-                for (int g = 0; g < 2; ++g) {       // layer 2
+                for (int g = 0; g < 2; ++g) {       // layer 2; A = H1_g in TMEM (over H0_g: the layer-1 MMAs that read it are complete)
                     mbar_wait(bar(B_H1FULL + g), it & 1);
                     tc_fence_after();
-                    const uint32_t h = smem_u32(sH) + g * h_bytes, w2 = smem_u32(sW2) + g * w2_bytes;
+                    const uint32_t h = tmem + (uint32_t)(4 * NP + g * (NP / 2)), w2 = smem_u32(sW2) + g * w2_bytes;
                     for (int ks = 0; ks < NP / 16; ++ks)
-                        umma_bf16(dbase + (uint32_t)(2 * NP + g * 16), umma_desc(h + ks * 2 * a_lbo, a_lbo, 128),
-                                  umma_desc(w2 + ks * 2 * w2_lbo, w2_lbo, 128), idesc2, ks > 0);
+                        umma_bf16_ts(tmem + (uint32_t)(5 * NP + g * 16), h + (uint32_t)(ks * 8), umma_desc(w2 + ks * 2 * w2_lbo, w2_lbo, 128), idesc2, ks > 0);
                     umma_commit(bar(B_D2FULL + g));
                 }
             }
@@ -439,26 +472,25 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         // (a warp reaches the TMEM lanes 32 * (warp % 4) .. +31, so each quadrant of rows has one warp per sub-network)
         const int row = tid & (TC_M - 1), g = tid >> 7;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        uint8_t *h = sH + g * h_bytes + row * 16;
+        const uint32_t hcol = tmem + lane_base + (uint32_t)(4 * NP + g * (NP / 2));
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
-            const uint32_t dbase = tmem + lane_base + (uint32_t)(s * TC_SLOT_COLS);
+            const uint32_t dbase = tmem + lane_base + (uint32_t)(s * 2 * NP);
             const int tile = tile0 + it * tile_stride;
             const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + row;   // this thread's position: plane row, column
-            // ---- layer 0 -> H0 ----
+            // ---- layer 0 -> H0 (the layer-2 MMAs of the previous tile, which read these columns, completed before its
+            //      D2FULL, which this warp has waited for) ----
             mbar_wait(bar(B_D0FULL + 2 * s + g), (it >> 1) & 1);
             tc_fence_after();
-            if (NP == 96) epilogue_hidden<96, F16>(dbase + (uint32_t)(g * NP), h, a_lbo);
-            else epilogue_hidden<64, F16>(dbase + (uint32_t)(g * NP), h, a_lbo);
-            fence_async_smem();
+            if (NP == 96) epilogue_hidden<96, F16>(dbase + (uint32_t)(g * NP), hcol);
+            else epilogue_hidden<64, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
             mbar_arrive(bar(B_H0FULL + g));
             // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
             mbar_wait(bar(B_D1FULL + g), it & 1);
             tc_fence_after();
-            if (NP == 96) epilogue_hidden<96, F16>(dbase + (uint32_t)(g * NP), h, a_lbo);
-            else epilogue_hidden<64, F16>(dbase + (uint32_t)(g * NP), h, a_lbo);
-            fence_async_smem();
+            if (NP == 96) epilogue_hidden<96, F16>(dbase + (uint32_t)(g * NP), hcol);
+            else epilogue_hidden<64, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
             mbar_arrive(bar(B_H1FULL + g));
             mbar_arrive(bar(B_DFREE + s));      // D0/D1 columns of this slot may be overwritten by tile it+2
@@ -466,7 +498,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             mbar_wait(bar(B_D2FULL + g), it & 1);
             tc_fence_after();
             uint32_t r[16];
-            TMEM_LD_X16(dbase + (uint32_t)(2 * NP + g * 16), r);
+            TMEM_LD_X16(tmem + lane_base + (uint32_t)(5 * NP + g * 16), r);
             tmem_ld_wait();
             if (jcol < tg.Ws) {
                 const int img = rowid / tg.nrows, p = (tg.row0 + rowid - img * tg.nrows) * tg.Ws + jcol;
@@ -655,7 +687,7 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
         LLICTI_CUDA(cudaMemcpy(tb.packed, host.data(), host.size(), cudaMemcpyHostToDevice));
         tb.g.K0 = K0; tb.g.K0p = K0p; tb.g.G = G; tb.g.NP = NP; tb.g.pair_bytes = pair_bytes;
         tb.g.off_w1 = w0_bytes; tb.g.off_w2 = w0_bytes + w1_bytes;
-        tb.smem_bytes = (size_t)((pair_bytes + 127) & ~127) + 2 * (size_t)(K0p / 8) * TC_M * 16 + 2 * (size_t)(NP / 8) * TC_M * 16 +
+        tb.smem_bytes = (size_t)((pair_bytes + 127) & ~127) + 2 * (size_t)(K0p / 8) * TC_M * 16 +
                         (size_t)(band_nseg(band) * TC_SEG_PITCH * 2 + 15) / 16 * 16 + B_COUNT * 8 + 16;
     }
     ctx->tc_weights = tw;

@@ -1318,6 +1318,226 @@ decode_band_group_kernel(const float *__restrict__ params, int16_t *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// Lane schedule (default for the interleaved-substream container): ONE lane per coded substream.
+//
+// The group schedule above spends G lanes on one symbol -- every lane prepares the same mixture, runs the same
+// approximate search and evaluates an exact table entry of which at most two are used: ~4000 thread-instructions per
+// symbol at G = 4, and the launch is issue-bound (62 % issue utilisation at 4 warps per scheduler).  Here a lane does the
+// minimum a decoded symbol needs: prepare ITS channel's mixture, find the symbol by a safeguarded Newton iteration on
+// the cheap logistic stand-in of the CDF (scalar: no ballots or shuffles), then evaluate the two exact entries q(s),
+// q(s + 1) that prove the symbol and are its interval (the same two entries the encoder evaluates).
+// The parallelism the group's lanes gave comes back from the colour channels: substream j of the Y, Co and Cg streams
+// are three lanes of one warp running one and two steps apart -- lane Y decodes position t while lane Co decodes t - 1
+// with the Y sample it was handed by a shuffle and lane Cg decodes t - 2 -- so 3 x n x S lanes are in flight instead of
+// n x S groups.  A warp holds 10 chains: lanes 0-9 Y, 10-19 Co, 20-29 Cg (neighbouring lanes = neighbouring positions,
+// so parameter loads and sample stores touch whole sectors); lanes 30, 31 idle.
+// A wrong guess costs time, never correctness: the exact pair test decides, and a miss widens the search with exact
+// entries (neighbours first, then four apart, then thirds of what is left).
+// ------------------------------------------------------------------------------------------
+constexpr int kLaneChains = 10;
+constexpr int kLaneStages = 3;
+constexpr int kLaneParams = 5 * kM;     // 15 mixture parameters + up to 10 coupling coefficients
+#ifndef LLICTI_LANE_MARGIN
+#define LLICTI_LANE_MARGIN 0.2f
+#endif
+constexpr float kLaneMargin = LLICTI_LANE_MARGIN;
+
+// Stand-in table entry q~(k) and its slope per index step (see approx_q), 1 <= k <= Lp - 2.
+__device__ __forceinline__ void approx_q_slope(const GmmChannel &c, const CdfGrid &g, int k, float &q, float &dq) {
+    const float p = ((float)(g.min_val + k) - 0.5f) * (1.0f / 255.0f);
+    float acc = 0.f, dacc = 0.f;
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        const float z = (p - c.mu[m]) * c.rinv[m];
+        const float z2 = z * z;
+        const float y = z * fmaf(z2, 0.044715f, 1.0f);
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * -2.3022082f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        acc = fmaf(c.w[m], r, acc);
+        // d/dz 1 / (1 + exp(-2 c (z + a z^3))) = r (1 - r) 2 c (1 + 3 a z^2)
+        const float s = fmaf(-r, r, r) * fmaf(z2, 0.21406557f, 1.5957691f);
+        dacc = fmaf(c.w[m] * c.rinv[m], s, dacc);
+    }
+    q = fmaf(acc, g.scale, (float)k);
+    dq = fmaf(dacc, g.scale * (1.0f / 255.0f), 1.0f);
+}
+
+__global__ void __launch_bounds__(128, 3)
+decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ planes, const int32_t *__restrict__ minmax,
+                        DecodeGeom dg, NumericsProfile np, const uint8_t *__restrict__ blob,
+                        const uint64_t *__restrict__ suboff, const uint32_t *__restrict__ sublen, int total_sub, int n, int guess_skew) {
+    __shared__ float stage[kLaneStages][kLaneParams][128];
+    const int lane = threadIdx.x & 31;
+    const int clr = lane / kLaneChains;                       // 3: idle lane
+    const long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long gid = wg * kLaneChains + (lane - clr * kLaneChains);
+    const bool valid = clr < 3 && gid < (long long)n * dg.S;
+    if (!__any_sync(kFull, valid)) return;
+    const int img = valid ? (int)(gid / dg.S) : 0, j = valid ? (int)(gid - (long long)img * dg.S) : 0;
+    const size_t P = (size_t)dg.Hs * dg.Ws;
+    const int cl = min(clr, 2);
+    const float *pp = params + (size_t)img * kParamCh * P;
+    int16_t *yb = planes + (size_t)img * 12 * P + (size_t)(3 * (dg.band + 1) + cl) * P;
+    const int32_t *mm = minmax + img * 4;
+    const CdfGrid g = cl == 0 ? make_grid(-127, 128) : cl == 1 ? make_grid(mm[0], mm[2]) : make_grid(mm[1], mm[3]);
+    const int last = g.Lp - 1;
+    AcDecoderW d;
+    {
+        const size_t e = (size_t)img * total_sub + j + dg.sub_first[cl];
+        d.init(blob + suboff[e], valid ? sublen[e] : 0u);
+    }
+    const bool rep_w = dg.padW && (dg.band == 0 || dg.band == 1);
+    const bool rep_h = dg.padH && (dg.band == 0 || dg.band == 2);
+    const int n_steps = valid ? (dg.n_sym - j + dg.S - 1) / dg.S : 0;
+    // network-output planes that feed this lane's channel: sigma, mu, weight (five mixtures each), then its coupling
+    // coefficients (Co: one set, Cg: two); staged parameter k sits at stage[.][k][thread]
+    const float *p_sigma = pp + (size_t)(cl * kM) * P, *p_mu = pp + (size_t)((3 + cl) * kM) * P, *p_w = pp + (size_t)((6 + cl) * kM) * P;
+    const float *p_cpl = pp + (size_t)((cl == 1 ? 9 : 10) * kM) * P;
+    auto prefetch = [&](int tau) {                            // parameters consumed in iteration tau (this lane's step tau - clr)
+        const int t = tau - cl;
+        if (t >= 0 && t < n_steps) {
+            const int i = j + t * dg.S;
+            const int r = i / dg.crop_w, c = i - r * dg.crop_w;
+            const size_t off = (size_t)r * dg.Ws + c;
+            float *dst = &stage[tau % kLaneStages][0][threadIdx.x];
+#pragma unroll
+            for (int m = 0; m < kM; ++m) {
+                cp_async_f32(dst + m * 128, p_sigma + off + (size_t)m * P);
+                cp_async_f32(dst + (kM + m) * 128, p_mu + off + (size_t)m * P);
+                cp_async_f32(dst + (2 * kM + m) * 128, p_w + off + (size_t)m * P);
+            }
+            if (cl >= 1) {
+#pragma unroll
+                for (int m = 0; m < kM; ++m) cp_async_f32(dst + (3 * kM + m) * 128, p_cpl + off + (size_t)m * P);
+            }
+            if (cl == 2) {
+#pragma unroll
+                for (int m = 0; m < kM; ++m) cp_async_f32(dst + (4 * kM + m) * 128, p_cpl + off + (size_t)(kM + m) * P);
+            }
+        }
+        cp_async_commit();
+    };
+    prefetch(0);
+    prefetch(1);
+    unsigned long long extra_rounds = 0, newton_its = 0;
+    int in0 = 0, in1 = 0;                                     // decoded Y (and Co) sample of this lane's position
+    const int iters = dg.max_steps + 2;                       // warp-uniform
+#pragma unroll 1
+    for (int tau = 0; tau < iters; ++tau) {
+        cp_async_wait<1>();                                   // this iteration's parameters have landed (own copies only: no barrier)
+        prefetch(tau + 2);
+        const int t = tau - cl;
+        const bool live = t >= 0 && t < n_steps;
+        int yv = 0;
+        if (live) {
+            const float *sp = &stage[tau % kLaneStages][0][threadIdx.x];
+            GmmChannel ch;
+#pragma unroll
+            for (int m = 0; m < kM; ++m) {
+                ch.sigma[m] = sp[m * 128];
+                ch.mu[m] = sp[(kM + m) * 128];
+                ch.w[m] = sp[(2 * kM + m) * 128];
+            }
+            if (cl == 1) {                                    // mean coupling (LLICTI_nets.py:385-392), as staged_channel
+                const float f0 = div255((float)in0, np);
+#pragma unroll
+                for (int m = 0; m < kM; ++m) ch.mu[m] = __fadd_rn(ch.mu[m], __fmul_rn(sp[(3 * kM + m) * 128], f0));
+            } else if (cl == 2) {
+                const float f0 = div255((float)in0, np), f1 = div255((float)in1, np);
+#pragma unroll
+                for (int m = 0; m < kM; ++m)
+                    ch.mu[m] = __fadd_rn(ch.mu[m], __fadd_rn(__fmul_rn(sp[(3 * kM + m) * 128], f0), __fmul_rn(sp[(4 * kM + m) * 128], f1)));
+            }
+            gmm_prepare(ch, np);
+            const uint32_t low = d.low, sm1 = d.high - d.low, span = sm1 + 1u, value32 = d.value;
+            // ---- guess: floor of the root of q~(x) = target, by Newton steps kept inside a bracket [a, b) -------------
+            int guess = 0;
+            if (last >= 2) {
+                float mean = 0.f;
+#pragma unroll
+                for (int m = 0; m < kM; ++m) mean = fmaf(ch.w[m], ch.mu[m], mean);
+                // torchac's search key ((value - low + 1) 2^16 - 1) / span, in fp32 (a guess is all it feeds)
+                const float tf = __fdividef(((float)(value32 - low) + 1.0f) * 65536.0f, (float)sm1 + 1.0f);
+                int a = 0, b = last, k = __float2int_rn(mean * 255.0f) - g.min_val;
+#pragma unroll 1
+                for (int it = 0;; ++it) {
+                    if (b - a <= 1) { guess = a; break; }
+                    k = min(max(k, a + 1), b - 1);
+                    float q, dq;
+                    approx_q_slope(ch, g, k, q, dq);
+                    const float res = tf - q, dx = __fdividef(res, dq);
+                    ++newton_its;
+                    // The estimated root k + dx decides as long as it is not within kLaneMargin of the bound the bracket has not
+                    // confirmed; otherwise the neighbouring entry is evaluated too (1.8 % of the guesses were one off without this).
+                    if (res >= 0.f) {
+                        a = k;
+                        if (dx < 1.0f - kLaneMargin || b == k + 1) { guess = k; break; }          // root in [k, k + 1)
+                    } else {
+                        b = k;
+                        if (dx >= -1.0f + kLaneMargin || a == k - 1) { guess = k - 1; break; }    // root in (k - 1, k)
+                    }
+                    const int kn = k + (int)floorf(fminf(fmaxf(res >= 0.f ? dx + kLaneMargin : dx, -70000.f), 70000.f));
+                    k = (kn <= a || kn >= b || it >= 6) ? (a + b) >> 1 : kn;
+                }
+            }
+            if (guess_skew) guess = min(max(guess + (int)((unsigned)(tau * 7 + lane) % (unsigned)(2 * guess_skew + 1)) - guess_skew, 0), last - 1);   // tests: wrong guesses
+            // ---- prove: exact entries.  Invariant: entry s_lo passes the candidate test (or s_lo = 0: torchac's search
+            // returns symbol 0 below q(0)), entry s_hi fails it (s_hi = last: 2^16); done when they are neighbours and
+            // q(s_lo) has been evaluated.
+            int s_lo = 0, s_hi = last, ka = guess, kb = guess + 1, round = 0, dir = 0;
+            uint32_t q_lo = 0u, q_hi = 0x10000u;
+            bool lo_known = false;
+#pragma unroll 1
+            for (;;) {
+                const uint32_t qa = cdf_q(ch, g, ka, np);
+                const uint32_t qb = kb < last ? cdf_q(ch, g, kb, np) : 0x10000u;
+                // candidate test low + ((span * q) >> 16) <= value in 32 bits: the high word of span * (q << 16); the full
+                // range (span = 2^32, seen as 0) gives q << 16 itself
+                const uint32_t qa16 = qa << 16, qb16 = qb << 16;
+                const bool va = ka == 0 || low + (span == 0u ? qa16 : __umulhi(span, qa16)) <= value32;
+                const bool vb = kb < last && low + (span == 0u ? qb16 : __umulhi(span, qb16)) <= value32;
+                if (!va) { s_hi = ka; q_hi = qa; dir = -1; }
+                else if (!vb) { s_lo = ka; q_lo = qa; lo_known = true; s_hi = kb; q_hi = qb; }
+                else { s_lo = kb; q_lo = qb; lo_known = true; dir = 1; }
+                ++round;
+                if (s_hi - s_lo == 1 && lo_known) break;
+                const int lo_min = lo_known ? s_lo + 1 : s_lo, hi_max = s_hi - 1;     // entries still worth evaluating (lo_min <= hi_max)
+                const int step = round == 1 ? 1 : round == 2 ? 4 : max((s_hi - s_lo) / 3, 1);
+                if (dir < 0) { kb = max(s_hi - step, lo_min); ka = max(kb - step, lo_min); }
+                else { ka = min(s_lo + step, hi_max); kb = min(ka + step, hi_max); }
+                if (ka == kb) {
+                    if (kb < hi_max) ++kb;
+                    else if (ka > lo_min) --ka;
+                    else kb = ka + 1;                                               // = s_hi: re-evaluated (or the alphabet's end)
+                }
+            }
+            extra_rounds += (unsigned long long)(round - 1);
+            if (t + 1 < n_steps) consume_closed_form(d, q_lo, q_hi);                // torchac does not update after the last symbol
+            yv = s_lo + g.min_val;
+            {                                                                       // the sample goes straight into the planes, with the replicate padding
+                const int i = j + t * dg.S;
+                const int r = i / dg.crop_w, c = i - r * dg.crop_w;
+                const int16_t v = (int16_t)yv;
+                int16_t *dst = yb + (size_t)r * dg.Ws + c;
+                dst[0] = v;
+                const bool last_c = rep_w && c == dg.crop_w - 1, last_r = rep_h && r == dg.crop_h - 1;
+                if (last_c) dst[1] = v;
+                if (last_r) dst[dg.Ws] = v;
+                if (last_c && last_r) dst[dg.Ws + 1] = v;
+            }
+        }
+        // hand the samples on: Co receives Y's, Cg receives Co's pair (the Y sample Co was working with and Co's own)
+        const int from_dec = __shfl_up_sync(kFull, yv, kLaneChains), from_in0 = __shfl_up_sync(kFull, in0, kLaneChains);
+        if (cl == 1) in0 = from_dec;
+        else if (cl == 2) { in0 = from_in0; in1 = from_dec; }
+    }
+    cp_async_wait<0>();
+    if (extra_rounds) atomicAdd(&g_decode_stats[0], extra_rounds);       // exact rounds beyond the first (wrong guesses)
+    if (newton_its) atomicAdd(&g_decode_stats[1], newton_its);          // stand-in evaluations of the guess
+}
+
+// ------------------------------------------------------------------------------------------
 // Launcher
 // ------------------------------------------------------------------------------------------
 static int stream_index(const Plan &p, int scale, int band, int clr) {
@@ -1378,8 +1598,12 @@ static long long group_min_warps() { return env_int("LLICTI_GROUP_MIN_WARPS", 59
 
 // Does band (scale, b) of a batch of n images take the group schedule?  (Substream container, default decoder, enough
 // chains to occupy the machine.)
+static bool lane_schedule() { return env_int("LLICTI_DECODE_LANES", 1) != 0; }                // 0: the group schedule (A/B, tests)
+static long long lane_min_warps() { return env_int("LLICTI_LANE_MIN_WARPS", 148); }
 static bool group_scheduled(const llicti_config &cfg, const DecodeGeom &dg, int n) {
-    return cfg.sub_len > 0 && cfg.decode_impl == 0 && (long long)n * dg.S * group_lanes() / 32 >= group_min_warps();
+    if (cfg.sub_len <= 0 || cfg.decode_impl != 0) return false;
+    if (lane_schedule()) return ((long long)n * dg.S + kLaneChains - 1) / kLaneChains >= lane_min_warps();
+    return (long long)n * dg.S * group_lanes() / 32 >= group_min_warps();
 }
 
 // Window items the workspace must hold for batches of up to max_images images: the largest band that can reach a
@@ -1430,6 +1654,16 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
     // whole CDF evaluation); with few chains -- the coarse scales -- the windows are produced by all SMs in parallel and
     // the serial part is the short chain kernel.
     const int G = group_lanes();
+    if (group_scheduled(ctx->cfg, dg, n) && lane_schedule()) {
+        ProfScope prof_(ctx, KC_DECODE, st);
+        const long long warps = ((long long)n * dg.S + kLaneChains - 1) / kLaneChains;
+        const int blocks = (int)((warps + 3) / 4);
+        decode_band_lane_kernel<<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n,
+                                                        env_int("LLICTI_TEST_GUESS_SKEW", 0));
+        ctx->launches += 1;
+        LLICTI_CUDA(cudaGetLastError());
+        return LLICTI_OK;
+    }
     if (group_scheduled(ctx->cfg, dg, n)) {
         ProfScope prof_(ctx, KC_DECODE, st);
         const long long threads = (long long)n * dg.S * G;

@@ -562,6 +562,8 @@ def test_group_decoder_every_group_size(L, lanes, sub_len, monkeypatch):
     """The group schedule of the substream container: every group size decodes every edge image, including the ones
     whose symbols sit far from the predicted value (noise, checkerboard: the search walks and gallops) and alphabets
     smaller than a group."""
+    monkeypatch.setenv("LLICTI_DECODE_LANES", "0")
+    monkeypatch.setenv("LLICTI_GROUP_MIN_WARPS", "1")          # the group kernel also for these small launches
     monkeypatch.setenv("LLICTI_GROUP_LANES", str(lanes))
     ocfg = O.OracleConfig()
     codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=sub_len, cnn_impl=L.CNN_TCGEN05)
@@ -573,6 +575,44 @@ def test_group_decoder_every_group_size(L, lanes, sub_len, monkeypatch):
     imgs[2] = np.random.default_rng(1).integers(0, 256, size=imgs[2].shape, dtype=np.uint8)
     assert np.array_equal(codec.decompress_images(codec.compress_images(imgs)), imgs)
     codec.close()
+
+
+@pytest.mark.parametrize("skew", [0, 1, 3, 41])
+@pytest.mark.parametrize("sub_len", [64, 300, 2048])
+def test_lane_decoder_reads_every_edge_image(L, skew, sub_len, monkeypatch):
+    """The lane schedule (one lane per substream, Y / Co / Cg of a chain one step apart in three lanes of a warp; default
+    for the substream container): every edge image, alphabets of one and two symbols, noise and a batch whose chains do
+    not fill the last warp.  `skew` pushes every guess of the Newton search off by up to that many symbols, so the
+    exact search's neighbour / four-apart / thirds rounds all run: a wrong guess may cost time, never correctness."""
+    monkeypatch.setenv("LLICTI_DECODE_LANES", "1")
+    monkeypatch.setenv("LLICTI_LANE_MIN_WARPS", "1")
+    monkeypatch.setenv("LLICTI_TEST_GUESS_SKEW", str(skew))
+    ocfg = O.OracleConfig()
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg), sub_len=sub_len, cnn_impl=L.CNN_TCGEN05)
+    for name, make in EDGE_IMAGES.items():
+        img = make()
+        bsl = codec.compress_images(img[None])
+        assert np.array_equal(codec.decompress_images(bsl)[0], img), (name, skew, sub_len)
+    imgs = np.stack([O.synthetic_image(181, 250, 30 + i) for i in range(5)])
+    imgs[2] = np.random.default_rng(1).integers(0, 256, size=imgs[2].shape, dtype=np.uint8)
+    assert np.array_equal(codec.decompress_images(codec.compress_images(imgs)), imgs)
+    codec.close()
+
+
+def test_lane_group_and_window_decoders_read_the_same_streams(L, monkeypatch):
+    ocfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(ocfg)
+    imgs = np.stack([O.synthetic_image(150, 212, i) for i in range(3)])
+    enc = make_codec(L, ocfg, sd, sub_len=256, cnn_impl=L.CNN_TCGEN05)
+    bsls = enc.compress_images(imgs)
+    enc.close()
+    for env in ({"LLICTI_DECODE_LANES": "1", "LLICTI_LANE_MIN_WARPS": "1"}, {"LLICTI_DECODE_LANES": "0", "LLICTI_GROUP_MIN_WARPS": "1"},
+                {"LLICTI_DECODE_LANES": "1", "LLICTI_LANE_MIN_WARPS": "1000000"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        dec = make_codec(L, ocfg, sd, sub_len=256, cnn_impl=L.CNN_TCGEN05)
+        assert np.array_equal(dec.decompress_images(bsls), imgs), env
+        dec.close()
 
 
 def test_group_and_window_decoders_read_the_same_streams(L):
