@@ -6,8 +6,9 @@
 // bf16 weights (<= 92 KB) arrive once by a TMA bulk copy and stay in shared memory while the CTA
 // walks over 128-position tiles.  Nine warps, three roles:
 //
-//   warps 8-15 im2col producers (two threads per tile row): row t of the A tile = the receptive field of position t, gathered
-//              from the int16 planes with replicate padding (integers, exact in bf16), two stages;
+//   warps 8-15 producers: stage the tile's receptive field (row segments of the int16 planes, replicate padding, integers: exact
+//              in bf16) pixel-major in shared memory, two stages; the layer-0 MMAs read it through shifted descriptors
+//              (implicit im2col, see "layer-0 operand" below) -- no A tile is ever built;
 //   warp  16   one elected lane issues every tcgen05.mma:
 //                L0  D0[128 x 2NP]  = A[128 x K0p] * W0^T          (both sub-networks at once)
 //                L1  D1_g[128 x NP] = H0_g * W1_g^T                (into D0_g's TMEM columns)
@@ -121,6 +122,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
         if (spins > (1u << 26)) __trap();
 }
+__device__ __forceinline__ bool elect_one() {      // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -143,7 +149,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // Operands are fp16 when the packer has shown that no activation can overflow it (11-bit significands: an eighth of
 // bf16's rounding error on the predicted means, which matters against spreads near the 0.11-level clamp), bf16 otherwise.
 template <bool F16>
-__device__ __forceinline__ uint32_t umma_idesc(int n) {
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
     return (1u << 4) | (F16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
@@ -240,15 +246,18 @@ __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>
 template <int N, class F>
 __device__ __forceinline__ void static_for(F &&f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
 
-// ---- im2col ----------------------------------------------------------------------------------------
-// A tile = up to 128 consecutive positions (i, j0 .. j0+127) of one plane row.  Its receptive
-// field is a handful of 132-sample row segments (columns j0-2 .. j0+129 of rows i+dy of the
-// planes the band reads), which the 128 producer threads first stage in shared memory as bf16
-// -- every sample is loaded from global memory (coalesced) and converted ONCE, with the
-// reference's replicate padding applied by clamping -- and then each thread gathers its own A row
-// from the staged segments with constant offsets.
+// ---- layer-0 operand: implicit im2col --------------------------------------------------------------
+// A tile = up to 128 consecutive positions (i, j0 .. j0+127) of one plane row.  Its receptive field is a handful of row
+// segments (phase, channel, dy): columns j0+DXLO .. of rows i+dy of the planes the band reads.  The producer warps stage them
+// PIXEL-MAJOR: chunk c holds, for every staged pixel x, the eight "slots" 8c .. 8c+7 -- a slot is one segment, the constant
+// one (two slots: the bias rides on them as a hi + lo pair) or zero -- as one 16-byte K-chunk, [chunk][pixel][8 values].
+// In the MMA's un-swizzled K-major layout row r of an operand starts 16 bytes after row r-1, so a descriptor that starts at
+// pixel d of chunk c IS the im2col column block "slots of chunk c at horizontal tap d" for all 128 positions: the conv's
+// shifted reads are descriptor start addresses, nothing is gathered or copied.  One K = 16 MMA takes taps (d, d+1) of a
+// chunk (leading-dimension offset = one pixel = 16 bytes).  Layer-0 depth: chunks x 4 taps x 8 slots = 64 / 96 / 160 for the
+// three bands (48 / 72 / 120 real taps + bias; the rest meets zero weights).  Every sample is loaded from global memory
+// (coalesced along x) and converted ONCE, with the reference's replicate padding applied by clamping.
 struct SegTc { int phase, chan, dy; };
-__host__ __device__ constexpr int branch_rows_lo(const BranchTc &b) { return -b.padt; }
 __host__ __device__ constexpr int band_phase_lo(int band, int phase) {       // smallest dy used on this phase, 99 if unused
     int lo = 99;
     for (int b = 0; b < band_branches(band); ++b)
@@ -276,95 +285,107 @@ __host__ __device__ constexpr SegTc band_seg(int band, int s) {
     }
     return SegTc{0, 0, 0};
 }
-__host__ __device__ constexpr int band_seg_index(int band, int phase, int chan, int dy) {
-    int base = 0;
-    for (int ph = 0; ph < phase; ++ph) base += 3 * (band_phase_hi(band, ph) - band_phase_lo(band, ph) + 1);
-    const int rows = band_phase_hi(band, phase) - band_phase_lo(band, phase) + 1;
-    return base + chan * rows + (dy - band_phase_lo(band, phase));
-}
-constexpr int TC_SEG_PITCH = 136;      // staged samples per segment (132 used), bf16
+__host__ __device__ constexpr int band_dxlo(int band) { return band == 2 ? -2 : -1; }          // leftmost horizontal tap
+__host__ __device__ constexpr int band_nchunk(int band) { return (band_nseg(band) + 2 + 7) / 8; }   // + the two constant-one slots
+__host__ __device__ constexpr int band_k0p(int band) { return band_nchunk(band) * 32; }        // chunks x 4 taps x 8 slots
+constexpr int TC_NDX = 4;              // horizontal taps dxlo .. dxlo + 3
+constexpr int TC_TPX = 132;            // staged pixels per chunk (128 + 3 used)
+constexpr int TC_CHUNK_BYTES = TC_TPX * 16;
 
 // bf16 bits of a small integer (|v| <= 255, exact): the sample enters as unsigned 16 bits; xor 0x8000 makes it
 // v + 32768, which or-ed into the mantissa of 2^23 gives the float 2^23 + 32768 + v; subtracting the offset
 // leaves float(v), whose low 16 bits are zero.
 template <bool F16>
-__device__ __forceinline__ uint16_t operand_of_sample(uint16_t u) {
-    const float f = __uint_as_float(0x4B008000u ^ (uint32_t)u) - 8421376.0f;
-    if (F16) return __half_as_ushort(__float2half_rn(f));          // |v| <= 255: exact in fp16 as well
-    return (uint16_t)(__float_as_uint(f) >> 16);
+__device__ __forceinline__ uint32_t operand_of_sample(uint32_t u) {
+    const float f = __uint_as_float(0x4B008000u ^ u) - 8421376.0f;
+    if (F16) return (uint32_t)__half_as_ushort(__float2half_rn(f));          // |v| <= 255: exact in fp16 as well
+    return __float_as_uint(f) >> 16;
 }
 
-template <int BAND, int HALF, bool F16>
-__device__ __forceinline__ void stage_segments(const int16_t *__restrict__ planes, const TcGeom &tg, int img, int i, int j0,
-                                               uint16_t *sSeg, int t) {
-    constexpr int NSEG = band_nseg(BAND);
+// The producers' work on one tile is cut in items = (chunk, staged pixel): eight 2-byte loads (one per slot), conversion, one
+// 16-byte store.  Producer thread pt owns items pt, pt + 256, ...; the raw samples of the NEXT tile are fetched into
+// registers before this tile's are converted and stored, so the global-memory latency is off the tile-to-tile path.
+constexpr int TC_PRODUCERS = 256;
+template <int BAND> struct TileItems { static constexpr int kItems = band_nchunk(BAND) * TC_TPX, kRounds = (kItems + TC_PRODUCERS - 1) / TC_PRODUCERS; };
+
+// Slot table of the three bands: source plane (phase * 3 + channel) and vertical tap of every slot, looked up with the
+// item's chunk -- no branch on the chunk: branches that load into the same registers would wait for each other's loads.
+__constant__ uint8_t c_slot_plane[3][40];
+__constant__ int8_t c_slot_dy[3][40];
+
+template <int BAND>
+__device__ __forceinline__ void load_items(const int16_t *__restrict__ planes, const TcGeom &tg, int img, int i, int j0, int pt,
+                                           uint32_t (&raw)[TileItems<BAND>::kRounds][8]) {
     const uint16_t *pl = reinterpret_cast<const uint16_t *>(planes) + (size_t)img * 12 * tg.P;
-    const int c_main = min(max(j0 - 2 + t, 0), tg.Ws - 1);           // replicate padding
-    const int c_extra = min(max(j0 + 126 + t, 0), tg.Ws - 1);        // threads 0..3: columns j0+126 .. j0+129
-    int rowoff[5];
 #pragma unroll
-    for (int d = 0; d < 5; ++d) rowoff[d] = min(max(i + d - 2, 0), tg.Hs - 1) * tg.Ws;
-    static_for<(NSEG + 1 - HALF) / 2>([&](auto s_) {          // the two producer groups stage alternate segments
-        constexpr int sg = 2 * decltype(s_)::value + HALF;
-        constexpr SegTc seg = band_seg(BAND, sg);
-        const uint16_t *src = pl + (size_t)(seg.phase * 3 + seg.chan) * tg.P + rowoff[seg.dy + 2];
-        sSeg[sg * TC_SEG_PITCH + t] = operand_of_sample<F16>(src[c_main]);
-        if (t < 4) sSeg[sg * TC_SEG_PITCH + 128 + t] = operand_of_sample<F16>(src[c_extra]);
-    });
+    for (int rd = 0; rd < TileItems<BAND>::kRounds; ++rd) {
+        const int item = min(pt + rd * TC_PRODUCERS, TileItems<BAND>::kItems - 1);      // (a thread past the end repeats the last item)
+        const int c = item / TC_TPX, x = item - c * TC_TPX;
+        const int col = min(max(j0 + band_dxlo(BAND) + x, 0), tg.Ws - 1);           // replicate padding
+        const uint16_t *src = pl + col;
+        // (each sample stays in a register of its own until store_items: nothing here waits for a load; slots past the
+        // segments read a valid sample that store_items replaces by its constant)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int plane = c_slot_plane[BAND][c * 8 + e], row = min(max(i + (int)c_slot_dy[BAND][c * 8 + e], 0), tg.Hs - 1);
+            raw[rd][e] = src[plane * tg.P + row * tg.Ws];
+        }
+    }
 }
 
-template <int BAND, int HALF, bool F16>
-__device__ __forceinline__ void build_a_row(const uint16_t *sSeg, uint8_t *sA, int row) {
-    constexpr int K0 = band_k0(BAND);
-    constexpr int K0p = (K0 + 2 + 15) / 16 * 16;
+template <int BAND, bool F16>
+__device__ __forceinline__ void store_items(uint8_t *sT, int pt, const uint32_t (&raw)[TileItems<BAND>::kRounds][8]) {
+    constexpr int NSEG = band_nseg(BAND), NCH = band_nchunk(BAND);
     constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;   // 1.0 in the operand type
-    const uint16_t *my = sSeg + row + 2;
-    static_for<K0p / 16>([&](auto kc_) {                       // ... and build alternate 16-byte chunks of every row
-        constexpr int kc = 2 * decltype(kc_)::value + HALF;
+#pragma unroll
+    for (int rd = 0; rd < TileItems<BAND>::kRounds; ++rd) {
+        const int item = pt + rd * TC_PRODUCERS;
+        if (item >= TileItems<BAND>::kItems) continue;
+        const int c = item / TC_TPX;
         uint32_t w[4];
-        static_for<4>([&](auto e2_) {
-            constexpr int e2 = decltype(e2_)::value;
-            uint32_t v[2] = {0u, 0u};
-            static_for<2>([&](auto h_) {
-                constexpr int h = decltype(h_)::value;
-                constexpr int k = kc * 8 + e2 * 2 + h;
-                constexpr TapTc t = band_tap(BAND, k);
-                if constexpr (t.valid != 0) v[h] = my[band_seg_index(BAND, t.phase, t.chan, t.dy) * TC_SEG_PITCH + t.dx];
-                else if constexpr (k == K0 || k == K0 + 1) v[h] = kOne;   // the two bias slots
-            });
-            w[e2] = v[0] | (v[1] << 16);
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2)
+            w[e2] = operand_of_sample<F16>(raw[rd][2 * e2]) | (operand_of_sample<F16>(raw[rd][2 * e2 + 1]) << 16);
+        // slots past the segments: the two constant ones, then zeros (a loaded zero sample converts to zero as well)
+        static_for<NCH>([&](auto c_) {
+            constexpr int cc = decltype(c_)::value;
+            if (c == cc) {
+                static_for<8>([&](auto e_) {
+                    constexpr int e = decltype(e_)::value, slot = cc * 8 + e;
+                    if constexpr (slot >= NSEG) {
+                        constexpr uint32_t val = (slot == NSEG || slot == NSEG + 1) ? kOne : 0u;
+                        w[e >> 1] = (e & 1) ? ((w[e >> 1] & 0xFFFFu) | (val << 16)) : ((w[e >> 1] & 0xFFFF0000u) | val);
+                    }
+                });
+            }
         });
-        *reinterpret_cast<uint4 *>(sA + (size_t)kc * (TC_M * 16) + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    });
+        *reinterpret_cast<uint4 *>(sT + (size_t)item * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 }
 
 // Barrier slots in shared memory.
 enum { B_W = 0, B_AFULL = 1, B_AEMPTY = 3, B_D0FULL = 5 /* [slot][sub-network] */, B_DFREE = 9, B_H0FULL = 11, B_D1FULL = 13,
        B_H1FULL = 15, B_D2FULL = 17, B_COUNT = 19 };
 
-template <int BAND, bool F16>
+template <int BAND, bool F16, int NP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__restrict__ packed, float *__restrict__ params) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int K0 = band_k0(BAND);
-    constexpr int K0p = (K0 + 2 + 15) / 16 * 16;
+    constexpr int NCH = band_nchunk(BAND);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int pair = blockIdx.x & 1;                 // sub-networks 2*pair, 2*pair + 1
     const int tile0 = blockIdx.x >> 1;
     const int tile_stride = gridDim.x >> 1;
-    const int NP = tg.NP;
     const int my_tiles = tile0 < tg.ntiles ? (tg.ntiles - tile0 + tile_stride - 1) / tile_stride : 0;
 
     // ---- shared memory carve-up -------------------------------------------------------------
     uint8_t *sW0 = smem;                                         // [K0p/8][2NP][16 B]
     uint8_t *sW1 = smem + tg.off_w1;                             // 2 x [NP/8][NP][16 B]
     uint8_t *sW2 = smem + tg.off_w2;                             // 2 x [NP/8][16][16 B]
-    uint8_t *sA = smem + ((tg.pair_bytes + 127) & ~127);         // 2 stages x [K0p/8][128][16 B]
-    constexpr uint32_t a_stage = (K0p / 8) * TC_M * 16;
-    uint16_t *sSeg = reinterpret_cast<uint16_t *>(sA + 2 * a_stage);   // staged row segments, [NSEG][TC_SEG_PITCH] bf16
-    constexpr uint32_t seg_bytes = (band_nseg(BAND) * TC_SEG_PITCH * 2 + 15) / 16 * 16;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + 2 * a_stage + seg_bytes);
+    uint8_t *sT = smem + ((tg.pair_bytes + 127) & ~127);         // 2 stages x [NCH][TC_TPX][16 B]: the staged receptive field
+    constexpr uint32_t t_stage = NCH * TC_CHUNK_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sT + 2 * t_stage);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int idx) { return bar0 + 8u * (uint32_t)idx; };
@@ -377,7 +398,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     if (tid == 0) {
         mbar_init(bar(B_W), 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(B_AFULL + s), 2 * TC_M);
+            mbar_init(bar(B_AFULL + s), TC_PRODUCERS);
             mbar_init(bar(B_AEMPTY + s), 1);
             mbar_init(bar(B_D0FULL + 2 * s), 1);
             mbar_init(bar(B_D0FULL + 2 * s + 1), 1);
@@ -394,77 +415,105 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const uint32_t a_lbo = TC_M * 16;
-
     if (warp >= 8 && warp < 16) {
-        // ================= im2col producers: two threads per tile row =================
-        const int row = (tid - 256) & (TC_M - 1), half = (tid - 256) >> 7;
+        // ================= producers: stage the receptive field of every tile, pixel-major =================
+        const int pt = tid - 256;
+        uint32_t raw[TileItems<BAND>::kRounds][8];
+        auto tile_coords = [&](int it, int &img, int &i, int &j0) {
+            const int tile = tile0 + it * tile_stride;
+            const int rowid = tile / tg.tpr, jb = tile - rowid * tg.tpr;       // (image, plane row), column block
+            img = rowid / tg.nrows; i = tg.row0 + rowid - img * tg.nrows; j0 = jb * TC_M;
+        };
+        if (my_tiles > 0) {
+            int img, i, j0;
+            tile_coords(0, img, i, j0);
+            load_items<BAND>(planes, tg, img, i, j0, pt, raw);
+        }
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
             mbar_wait(bar(B_AEMPTY + s), ((it >> 1) & 1) ^ 1);     // MMAs that read this stage are complete
-            const int tile = tile0 + it * tile_stride;
-            const int rowid = tile / tg.tpr, jb = tile - rowid * tg.tpr;       // (image, plane row), column block
-            const int img = rowid / tg.nrows, i = tg.row0 + rowid - img * tg.nrows;
-            asm volatile("bar.sync 1, 256;" ::: "memory");                      // everyone is done reading the previous segments
-            if (half == 0) stage_segments<BAND, 0, F16>(planes, tg, img, i, jb * TC_M, sSeg, row);
-            else stage_segments<BAND, 1, F16>(planes, tg, img, i, jb * TC_M, sSeg, row);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0) build_a_row<BAND, 0, F16>(sSeg, sA + s * a_stage, row);
-            else build_a_row<BAND, 1, F16>(sSeg, sA + s * a_stage, row);
+            store_items<BAND, F16>(sT + s * t_stage, pt, raw);
             fence_async_smem();
             mbar_arrive(bar(B_AFULL + s));
+            if (it + 1 < my_tiles) {                               // the next tile's samples travel while this one is multiplied
+                int img, i, j0;
+                tile_coords(it + 1, img, i, j0);
+                load_items<BAND>(planes, tg, img, i, j0, pt, raw);
+            }
         }
     } else if (warp == 16) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp runs this code (so every address below is warp-uniform and lives in uniform registers); one elected
+        // lane issues the TMA copy, the MMAs and the commits.  Descriptors are a 64-bit base plus a compile-time multiple of
+        // 16 bytes: the issue stream is a couple of uniform adds per MMA -- with the descriptors rebuilt per MMA by one
+        // divergent lane (9-15 instructions each) the issuer, not the tensor pipe, set the pace of the short layer-2 MMAs.
+        const bool leader = elect_one();
+        if (leader) {
             mbar_expect_tx(bar(B_W), (uint32_t)tg.pair_bytes);
             tma_bulk_g2s(smem_u32(sW0), packed + (size_t)pair * tg.pair_bytes, (uint32_t)tg.pair_bytes, bar(B_W));
-            mbar_wait(bar(B_W), 0);
-            const uint32_t idesc1 = umma_idesc<F16>(NP), idesc2 = umma_idesc<F16>(16);
-            const uint32_t w0_lbo = (uint32_t)(2 * NP) * 16, w1_lbo = (uint32_t)NP * 16, w2_lbo = 16 * 16;
-            const uint32_t w1_bytes = (uint32_t)(NP / 8) * NP * 16, w2_bytes = (uint32_t)(NP / 8) * 16 * 16;
-            auto issue_l0 = [&](int it) {
-                const int s = it & 1;
-                mbar_wait(bar(B_AFULL + s), (it >> 1) & 1);
-                mbar_wait(bar(B_DFREE + s), ((it >> 1) & 1) ^ 1);     // epilogues of tile it-2 have drained this slot
-                tc_fence_after();
-                const uint32_t d0 = tmem + (uint32_t)(s * 2 * NP);
-                const uint32_t a0 = smem_u32(sA) + s * a_stage;
-                // Layer 0 of the two sub-networks as two MMA groups with a commit each: sub-network 0's epilogue starts
-                // while sub-network 1's layer 0 still runs, and from then on the two run half a phase apart -- one reads
-                // its accumulators out of TMEM (the scarce resource: 64 B/clk against 212 KB per tile) while the other waits
-                // for its next layer's MMAs, instead of both reading, then both waiting.
+        }
+        mbar_wait(bar(B_W), 0);
+        constexpr uint32_t idesc1 = umma_idesc<F16>(NP), idesc2 = umma_idesc<F16>(16);
+        constexpr uint32_t w0_lbo = (uint32_t)(2 * NP) * 16, w1_lbo = (uint32_t)NP * 16, w2_lbo = 16 * 16;
+        constexpr uint32_t w1_bytes = (uint32_t)(NP / 8) * NP * 16, w2_bytes = (uint32_t)(NP / 8) * 16 * 16;
+        const uint64_t a_desc0 = umma_desc(smem_u32(sT), 16, 128);             // stage 0, chunk 0, tap 0
+        const uint64_t w0_desc0 = umma_desc(smem_u32(sW0), w0_lbo, 128), w1_desc0 = umma_desc(smem_u32(sW1), w1_lbo, 128),
+                       w2_desc0 = umma_desc(smem_u32(sW2), w2_lbo, 128);
+        const uint32_t hbase = tmem + (uint32_t)(4 * NP);
+        auto issue_l0 = [&](int it) {
+            const int s = it & 1;
+            mbar_wait(bar(B_AFULL + s), (it >> 1) & 1);
+            mbar_wait(bar(B_DFREE + s), ((it >> 1) & 1) ^ 1);     // epilogues of tile it-2 have drained this slot
+            tc_fence_after();
+            const uint32_t d0 = tmem + (uint32_t)(s * 2 * NP);
+            const uint64_t a0 = a_desc0 + (uint64_t)((uint32_t)s * (t_stage >> 4));
+            // Layer 0 of the two sub-networks as two MMA groups with a commit each: sub-network 0's epilogue starts
+            // while sub-network 1's layer 0 still runs, and from then on the two run half a phase apart.
+            // K step ks = (chunk ks / 2, taps 2 (ks % 2) and 2 (ks % 2) + 1): the A descriptor starts at that pixel of the
+            // chunk, rows (positions) are 16 bytes apart, the two taps of the step one pixel (16 bytes) apart.
+            if (leader) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
 #pragma unroll
-                    for (int ks = 0; ks < K0p / 16; ++ks)
-                        umma_bf16(d0 + (uint32_t)(g * NP), umma_desc(a0 + ks * 2 * a_lbo, a_lbo, 128),
-                                  umma_desc(smem_u32(sW0) + ks * 2 * w0_lbo + (uint32_t)(g * NP) * 16, w0_lbo, 128), idesc1, ks > 0);
+                    for (int ks = 0; ks < 2 * NCH; ++ks)
+                        umma_bf16(d0 + (uint32_t)(g * NP), a0 + (uint64_t)(((ks >> 1) * TC_CHUNK_BYTES + (ks & 1) * 32) >> 4),
+                                  w0_desc0 + (uint64_t)((ks * 2 * w0_lbo + (uint32_t)(g * NP) * 16) >> 4), idesc1, ks > 0);
                     umma_commit(bar(B_D0FULL + 2 * s + g));
                 }
                 umma_commit(bar(B_AEMPTY + s));
-            };
-            if (my_tiles > 0) issue_l0(0);
-            for (int it = 0; it < my_tiles; ++it) {
-                if (it + 1 < my_tiles) issue_l0(it + 1);
-                const int s = it & 1;
-                const uint32_t dbase = tmem + (uint32_t)(s * 2 * NP);
-                for (int g = 0; g < 2; ++g) {       // layer 1 of sub-network g, into D0_g's columns; A = H0_g in TMEM
-                    mbar_wait(bar(B_H0FULL + g), it & 1);
-                    tc_fence_after();
-                    const uint32_t h = tmem + (uint32_t)(4 * NP + g * (NP / 2)), w1 = smem_u32(sW1) + g * w1_bytes;
+            }
+            __syncwarp();
+        };
+        if (my_tiles > 0) issue_l0(0);
+        for (int it = 0; it < my_tiles; ++it) {
+            if (it + 1 < my_tiles) issue_l0(it + 1);
+            const int s = it & 1;
+            const uint32_t dbase = tmem + (uint32_t)(s * 2 * NP);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {       // layer 1 of sub-network g, into D0_g's columns; A = H0_g in TMEM
+                mbar_wait(bar(B_H0FULL + g), it & 1);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
                     for (int ks = 0; ks < NP / 16; ++ks)
-                        umma_bf16_ts(dbase + (uint32_t)(g * NP), h + (uint32_t)(ks * 8), umma_desc(w1 + ks * 2 * w1_lbo, w1_lbo, 128), idesc1, ks > 0);
+                        umma_bf16_ts(dbase + (uint32_t)(g * NP), hbase + (uint32_t)(g * (NP / 2) + ks * 8),
+                                     w1_desc0 + (uint64_t)((g * w1_bytes + ks * 2 * w1_lbo) >> 4), idesc1, ks > 0);
                     umma_commit(bar(B_D1FULL + g));
                 }
-                for (int g = 0; g < 2; ++g) {       // layer 2; A = H1_g in TMEM (over H0_g: the layer-1 MMAs that read it are complete)
-                    mbar_wait(bar(B_H1FULL + g), it & 1);
-                    tc_fence_after();
-                    const uint32_t h = tmem + (uint32_t)(4 * NP + g * (NP / 2)), w2 = smem_u32(sW2) + g * w2_bytes;
+                __syncwarp();
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {       // layer 2; A = H1_g in TMEM (over H0_g: the layer-1 MMAs that read it are complete)
+                mbar_wait(bar(B_H1FULL + g), it & 1);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
                     for (int ks = 0; ks < NP / 16; ++ks)
-                        umma_bf16_ts(tmem + (uint32_t)(5 * NP + g * 16), h + (uint32_t)(ks * 8), umma_desc(w2 + ks * 2 * w2_lbo, w2_lbo, 128), idesc2, ks > 0);
+                        umma_bf16_ts(tmem + (uint32_t)(5 * NP + g * 16), hbase + (uint32_t)(g * (NP / 2) + ks * 8),
+                                     w2_desc0 + (uint64_t)((g * w2_bytes + ks * 2 * w2_lbo) >> 4), idesc2, ks > 0);
                     umma_commit(bar(B_D2FULL + g));
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -482,15 +531,13 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             //      D2FULL, which this warp has waited for) ----
             mbar_wait(bar(B_D0FULL + 2 * s + g), (it >> 1) & 1);
             tc_fence_after();
-            if (NP == 96) epilogue_hidden<96, F16>(dbase + (uint32_t)(g * NP), hcol);
-            else epilogue_hidden<64, F16>(dbase + (uint32_t)(g * NP), hcol);
+            epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
             mbar_arrive(bar(B_H0FULL + g));
             // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
             mbar_wait(bar(B_D1FULL + g), it & 1);
             tc_fence_after();
-            if (NP == 96) epilogue_hidden<96, F16>(dbase + (uint32_t)(g * NP), hcol);
-            else epilogue_hidden<64, F16>(dbase + (uint32_t)(g * NP), hcol);
+            epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
             mbar_arrive(bar(B_H1FULL + g));
             mbar_arrive(bar(B_DFREE + s));      // D0/D1 columns of this slot may be overwritten by tile it+2
@@ -627,34 +674,60 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
     const bool f16 = tw->f16;
     auto cv = [f16](float v) { return f16 ? f2h(v) : f2bf(v); };
     auto back = [f16](uint16_t v) { return f16 ? h2f(v) : bf2f(v); };
+    {
+        uint8_t plane[3][40] = {};
+        int8_t dy[3][40] = {};
+        for (int band = 0; band < 3; ++band)
+            for (int slot = 0; slot < band_nseg(band); ++slot) {
+                const SegTc sg = band_seg(band, slot);
+                plane[band][slot] = (uint8_t)(sg.phase * 3 + sg.chan);
+                dy[band][slot] = (int8_t)sg.dy;
+            }
+        LLICTI_CUDA(cudaMemcpyToSymbol(c_slot_plane, plane, sizeof(plane)));
+        LLICTI_CUDA(cudaMemcpyToSymbol(c_slot_dy, dy, sizeof(dy)));
+    }
     for (int band = 0; band < 3; ++band) {
-        const int K0 = band_k0(band), K0p = (K0 + 2 + 15) / 16 * 16;
+        const int K0 = band_k0(band), K0p = band_k0p(band), NSEG = band_nseg(band);
         LLICTI_REQUIRE(K0 == ctx->taps[band].K0, "tap tables disagree for band %d", band);
         const int w0_bytes = (K0p / 8) * (2 * NP) * 16, w1_bytes = 2 * (NP / 8) * NP * 16, w2_bytes = 2 * (NP / 8) * 16 * 16;
         const int pair_bytes = w0_bytes + w1_bytes + w2_bytes;
         std::vector<uint8_t> host((size_t)2 * pair_bytes, 0);
-        // layer-0 weights in the kernel's k order (branch, c, dy, dx), scaled by 1/255 (the kernel
-        // feeds integer sample values, the reference feeds value/255)
-        std::vector<float> w0((size_t)K0 * Ch, 0.f), b0(Ch, 0.f);
-        int k = 0, brn = 0;
-        for (int b = 0; b < band_branches(band); ++b) {
-            const BranchTc bd = band_branch(band, b);
-            int br = 0;   // index into llicti_weights.l0_*: 00_11 | 00_01, 11_01 | 00_10, 11_10, 01_10
-            br = (band == 0 ? 0 : band == 1 ? 1 : 3) + b;
-            for (int c = 0; c < 3; ++c)
-                for (int dy = 0; dy < bd.kh; ++dy)
-                    for (int dx = 0; dx < bd.kw; ++dx, ++k)
-                        for (int ch = 0; ch < Ch; ++ch)
-                            w0[(size_t)k * Ch + ch] = w.l0_w[br][(((size_t)ch * 3 + c) * bd.kh + dy) * bd.kw + dx] / 255.0f;
-            for (int ch = 0; ch < Ch; ++ch) b0[ch] += w.l0_b[br][ch];
-            ++brn;
+        // layer-0 weights in the kernel's k order -- k = (4 chunk + tap) * 8 + slot, slot 8 chunk + e = segment (phase, channel,
+        // dy), tap d = horizontal offset dxlo + d -- scaled by 1/255 (the kernel feeds integer sample values, the reference
+        // feeds value/255); (segment, tap) pairs outside the branch's kernel keep a zero weight
+        std::vector<float> w0((size_t)K0p * Ch, 0.f), b0(Ch, 0.f);
+        int taps_placed = 0;
+        for (int slot = 0; slot < NSEG; ++slot) {
+            const SegTc sg = band_seg(band, slot);
+            for (int b = 0; b < band_branches(band); ++b) {
+                const BranchTc bd = band_branch(band, b);
+                if (bd.phase != sg.phase) continue;
+                const int br = (band == 0 ? 0 : band == 1 ? 1 : 3) + b;   // index into llicti_weights.l0_*: 00_11 | 00_01, 11_01 | 00_10, 11_10, 01_10
+                const int ky = sg.dy + bd.padt;
+                LLICTI_REQUIRE(ky >= 0 && ky < bd.kh, "segment table disagrees with the branch geometry");
+                for (int d = 0; d < TC_NDX; ++d) {
+                    const int kx = band_dxlo(band) + d + bd.padl;
+                    if (kx < 0 || kx >= bd.kw) continue;
+                    const int kk = (4 * (slot / 8) + d) * 8 + slot % 8;
+                    for (int ch = 0; ch < Ch; ++ch)
+                        w0[(size_t)kk * Ch + ch] = w.l0_w[br][(((size_t)ch * 3 + sg.chan) * bd.kh + ky) * bd.kw + kx] / 255.0f;
+                    ++taps_placed;
+                }
+            }
         }
+        LLICTI_REQUIRE(taps_placed == K0, "band %d: %d of %d layer-0 taps placed", band, taps_placed, K0);
+        for (int b = 0; b < band_branches(band); ++b) {
+            const int br = (band == 0 ? 0 : band == 1 ? 1 : 3) + b;
+            for (int ch = 0; ch < Ch; ++ch) b0[ch] += w.l0_b[br][ch];
+        }
+        const int k_one_hi = (4 * (NSEG / 8)) * 8 + NSEG % 8, k_one_lo = (4 * ((NSEG + 1) / 8)) * 8 + (NSEG + 1) % 8;   // the constant-one slots at tap 0
         auto put = [](uint16_t *base, int rows, int n, int kk, uint16_t v) { base[((size_t)(kk / 8) * rows + n) * 8 + kk % 8] = v; };
-        auto put_bias = [&](uint16_t *base, int rows, int n, int kk, float b) {   // hi + lo pair in slots kk, kk + 1
+        auto put_bias2 = [&](uint16_t *base, int rows, int n, int k_hi, int k_lo, float b) {   // hi + lo pair against two constant-one inputs
             const uint16_t hi = cv(b);
-            put(base, rows, n, kk, hi);
-            put(base, rows, n, kk + 1, cv(b - back(hi)));
+            put(base, rows, n, k_hi, hi);
+            put(base, rows, n, k_lo, cv(b - back(hi)));
         };
+        auto put_bias = [&](uint16_t *base, int rows, int n, int kk, float b) { put_bias2(base, rows, n, kk, kk + 1, b); };
         const uint16_t one = cv(1.0f);
         for (int pr = 0; pr < 2; ++pr) {
             uint8_t *base = host.data() + (size_t)pr * pair_bytes;
@@ -662,12 +735,12 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
             for (int gl = 0; gl < 2; ++gl) {
                 const int g = 2 * pr + gl;
                 for (int n = 0; n < G; ++n) {
-                    for (int kk = 0; kk < K0; ++kk) put(p0, 2 * NP, gl * NP + n, kk, cv(w0[(size_t)kk * Ch + g * G + n]));
-                    put_bias(p0, 2 * NP, gl * NP + n, K0, b0[g * G + n]);
+                    for (int kk = 0; kk < K0p; ++kk) put(p0, 2 * NP, gl * NP + n, kk, cv(w0[(size_t)kk * Ch + g * G + n]));
+                    put_bias2(p0, 2 * NP, gl * NP + n, k_one_hi, k_one_lo, b0[g * G + n]);
                 }
                 // hidden units G, G+1 reproduce the constant one (the next layer's bias slots)
-                put(p0, 2 * NP, gl * NP + G, K0, one);
-                put(p0, 2 * NP, gl * NP + G + 1, K0, one);
+                put(p0, 2 * NP, gl * NP + G, k_one_hi, one);
+                put(p0, 2 * NP, gl * NP + G + 1, k_one_hi, one);
                 uint16_t *p1 = reinterpret_cast<uint16_t *>(base + w0_bytes) + (size_t)gl * (NP / 8) * NP * 8;   // [NP/8][NP][8]
                 for (int n = 0; n < G; ++n) {
                     for (int in = 0; in < G; ++in) put(p1, NP, n, in, cv(w.l1_w[band][(size_t)(g * G + n) * G + in]));
@@ -687,8 +760,7 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
         LLICTI_CUDA(cudaMemcpy(tb.packed, host.data(), host.size(), cudaMemcpyHostToDevice));
         tb.g.K0 = K0; tb.g.K0p = K0p; tb.g.G = G; tb.g.NP = NP; tb.g.pair_bytes = pair_bytes;
         tb.g.off_w1 = w0_bytes; tb.g.off_w2 = w0_bytes + w1_bytes;
-        tb.smem_bytes = (size_t)((pair_bytes + 127) & ~127) + 2 * (size_t)(K0p / 8) * TC_M * 16 +
-                        (size_t)(band_nseg(band) * TC_SEG_PITCH * 2 + 15) / 16 * 16 + B_COUNT * 8 + 16;
+        tb.smem_bytes = (size_t)((pair_bytes + 127) & ~127) + 2 * (size_t)band_nchunk(band) * TC_CHUNK_BYTES + B_COUNT * 8 + 16;
     }
     ctx->tc_weights = tw;
     return LLICTI_OK;
@@ -733,23 +805,26 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
     size_t mx = 0;
     for (auto &b : tw->band) mx = std::max(mx, b.smem_bytes);
     if (mx > ctx->tc_attr_smem) {
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+#define LLICTI_TC_ATTR(B, F, N) LLICTI_CUDA(cudaFuncSetAttribute(cnn_tc_kernel<B, F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx))
+        LLICTI_TC_ATTR(0, false, 96); LLICTI_TC_ATTR(1, false, 96); LLICTI_TC_ATTR(2, false, 96);
+        LLICTI_TC_ATTR(0, true, 96); LLICTI_TC_ATTR(1, true, 96); LLICTI_TC_ATTR(2, true, 96);
+        LLICTI_TC_ATTR(0, false, 64); LLICTI_TC_ATTR(1, false, 64); LLICTI_TC_ATTR(2, false, 64);
+        LLICTI_TC_ATTR(0, true, 64); LLICTI_TC_ATTR(1, true, 64); LLICTI_TC_ATTR(2, true, 64);
+#undef LLICTI_TC_ATTR
         ctx->tc_attr_smem = mx;
     }
     // persistent grid: one CTA per SM, an even number (one sub-network pair per CTA), no more than the work
     const int ctas = std::min(sm_count / 2 * 2, tg.ntiles * 2);
-#define LLICTI_TC_LAUNCH(B) \
-    do { if (tw->f16) cnn_tc_kernel<B, true><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); \
-         else cnn_tc_kernel<B, false><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); } while (0)
+    LLICTI_REQUIRE(tg.NP == 96 || tg.NP == 64, "tcgen05 CNN is built for chs = 88 and 60");
+#define LLICTI_TC_LAUNCH2(B, F) \
+    do { if (tg.NP == 96) cnn_tc_kernel<B, F, 96><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); \
+         else cnn_tc_kernel<B, F, 64><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); } while (0)
+#define LLICTI_TC_LAUNCH(B) do { if (tw->f16) LLICTI_TC_LAUNCH2(B, true); else LLICTI_TC_LAUNCH2(B, false); } while (0)
     if (band == 0) LLICTI_TC_LAUNCH(0);
     else if (band == 1) LLICTI_TC_LAUNCH(1);
     else LLICTI_TC_LAUNCH(2);
 #undef LLICTI_TC_LAUNCH
+#undef LLICTI_TC_LAUNCH2
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;
