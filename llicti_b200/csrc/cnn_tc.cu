@@ -460,61 +460,69 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         const uint64_t w0_desc0 = umma_desc(smem_u32(sW0), w0_lbo, 128), w1_desc0 = umma_desc(smem_u32(sW1), w1_lbo, 128),
                        w2_desc0 = umma_desc(smem_u32(sW2), w2_lbo, 128);
         const uint32_t hbase = tmem + (uint32_t)(4 * NP);
-        auto issue_l0 = [&](int it) {
+        // Issue order.  What bounds the tile rate is the serial chain of a tile and sub-network g -- D0 -> epilogue -> layer 1 ->
+        // epilogue -> layer 2, TMEM holding the hidden activations of ONE tile per sub-network -- so the long layer 0 of the tiles
+        // ahead is cut in its two sub-network halves and slotted between the chain's short MMA groups, software-pipelined:
+        //     L1 g0 (t) | L0 g1 (t+1) | L1 g1 (t) | L2 g0 (t) | L0 g0 (t+2) | L2 g1 (t)
+        // A chain group never queues behind more than half a layer 0 on the in-order tensor pipe, and every accumulator slot
+        // is provably free when its layer 0 is issued: L0 g (t+2) overwrites D1 g (t), whose epilogue finished before the
+        // H1FULL g (t) this warp has already waited for (no extra barrier).
+        auto l0_half = [&](int it, auto g_) {
+            constexpr int g = decltype(g_)::value;
             const int s = it & 1;
-            mbar_wait(bar(B_AFULL + s), (it >> 1) & 1);
-            mbar_wait(bar(B_DFREE + s), ((it >> 1) & 1) ^ 1);     // epilogues of tile it-2 have drained this slot
+            if (g == 0) mbar_wait(bar(B_AFULL + s), (it >> 1) & 1);        // the producers have staged tile `it`
             tc_fence_after();
-            const uint32_t d0 = tmem + (uint32_t)(s * 2 * NP);
+            const uint32_t d0 = tmem + (uint32_t)(s * 2 * NP + g * NP);
             const uint64_t a0 = a_desc0 + (uint64_t)((uint32_t)s * (t_stage >> 4));
-            // Layer 0 of the two sub-networks as two MMA groups with a commit each: sub-network 0's epilogue starts
-            // while sub-network 1's layer 0 still runs, and from then on the two run half a phase apart.
             // K step ks = (chunk ks / 2, taps 2 (ks % 2) and 2 (ks % 2) + 1): the A descriptor starts at that pixel of the
             // chunk, rows (positions) are 16 bytes apart, the two taps of the step one pixel (16 bytes) apart.
             if (leader) {
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-#pragma unroll
-                    for (int ks = 0; ks < 2 * NCH; ++ks)
-                        umma_bf16(d0 + (uint32_t)(g * NP), a0 + (uint64_t)(((ks >> 1) * TC_CHUNK_BYTES + (ks & 1) * 32) >> 4),
-                                  w0_desc0 + (uint64_t)((ks * 2 * w0_lbo + (uint32_t)(g * NP) * 16) >> 4), idesc1, ks > 0);
-                    umma_commit(bar(B_D0FULL + 2 * s + g));
-                }
-                umma_commit(bar(B_AEMPTY + s));
+                for (int ks = 0; ks < 2 * NCH; ++ks)
+                    umma_bf16(d0, a0 + (uint64_t)(((ks >> 1) * TC_CHUNK_BYTES + (ks & 1) * 32) >> 4),
+                              w0_desc0 + (uint64_t)((ks * 2 * w0_lbo + (uint32_t)(g * NP) * 16) >> 4), idesc1, ks > 0);
+                umma_commit(bar(B_D0FULL + 2 * s + g));
+                if (g == 1) umma_commit(bar(B_AEMPTY + s));               // both halves have read the staged tile
             }
             __syncwarp();
         };
-        if (my_tiles > 0) issue_l0(0);
+        auto l1_group = [&](int it, auto g_) {       // layer 1 of sub-network g, into D0_g's columns; A = H0_g in TMEM
+            constexpr int g = decltype(g_)::value;
+            mbar_wait(bar(B_H0FULL + g), it & 1);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < NP / 16; ++ks)
+                    umma_bf16_ts(tmem + (uint32_t)((it & 1) * 2 * NP + g * NP), hbase + (uint32_t)(g * (NP / 2) + ks * 8),
+                                 w1_desc0 + (uint64_t)((g * w1_bytes + ks * 2 * w1_lbo) >> 4), idesc1, ks > 0);
+                umma_commit(bar(B_D1FULL + g));
+            }
+            __syncwarp();
+        };
+        auto l2_group = [&](int it, auto g_) {       // layer 2; A = H1_g in TMEM (over H0_g: the layer-1 MMAs that read it are complete)
+            constexpr int g = decltype(g_)::value;
+            mbar_wait(bar(B_H1FULL + g), it & 1);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < NP / 16; ++ks)
+                    umma_bf16_ts(tmem + (uint32_t)(5 * NP + g * 16), hbase + (uint32_t)(g * (NP / 2) + ks * 8),
+                                 w2_desc0 + (uint64_t)((g * w2_bytes + ks * 2 * w2_lbo) >> 4), idesc2, ks > 0);
+                umma_commit(bar(B_D2FULL + g));
+            }
+            __syncwarp();
+        };
+        constexpr std::integral_constant<int, 0> G0{};
+        constexpr std::integral_constant<int, 1> G1{};
+        if (my_tiles > 0) { l0_half(0, G0); l0_half(0, G1); }
+        if (my_tiles > 1) l0_half(1, G0);
         for (int it = 0; it < my_tiles; ++it) {
-            if (it + 1 < my_tiles) issue_l0(it + 1);
-            const int s = it & 1;
-            const uint32_t dbase = tmem + (uint32_t)(s * 2 * NP);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {       // layer 1 of sub-network g, into D0_g's columns; A = H0_g in TMEM
-                mbar_wait(bar(B_H0FULL + g), it & 1);
-                tc_fence_after();
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < NP / 16; ++ks)
-                        umma_bf16_ts(dbase + (uint32_t)(g * NP), hbase + (uint32_t)(g * (NP / 2) + ks * 8),
-                                     w1_desc0 + (uint64_t)((g * w1_bytes + ks * 2 * w1_lbo) >> 4), idesc1, ks > 0);
-                    umma_commit(bar(B_D1FULL + g));
-                }
-                __syncwarp();
-            }
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {       // layer 2; A = H1_g in TMEM (over H0_g: the layer-1 MMAs that read it are complete)
-                mbar_wait(bar(B_H1FULL + g), it & 1);
-                tc_fence_after();
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < NP / 16; ++ks)
-                        umma_bf16_ts(tmem + (uint32_t)(5 * NP + g * 16), hbase + (uint32_t)(g * (NP / 2) + ks * 8),
-                                     w2_desc0 + (uint64_t)((g * w2_bytes + ks * 2 * w2_lbo) >> 4), idesc2, ks > 0);
-                    umma_commit(bar(B_D2FULL + g));
-                }
-                __syncwarp();
-            }
+            l1_group(it, G0);
+            if (it + 1 < my_tiles) l0_half(it + 1, G1);
+            l1_group(it, G1);
+            l2_group(it, G0);
+            if (it + 2 < my_tiles) l0_half(it + 2, G0);
+            l2_group(it, G1);
         }
     } else {
         // ================= epilogue warps: warps 0-3 sub-network 0, warps 4-7 sub-network 1 =================
@@ -522,28 +530,10 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         const int row = tid & (TC_M - 1), g = tid >> 7;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t hcol = tmem + lane_base + (uint32_t)(4 * NP + g * (NP / 2));
-        for (int it = 0; it < my_tiles; ++it) {
-            const int s = it & 1;
-            const uint32_t dbase = tmem + lane_base + (uint32_t)(s * 2 * NP);
+        // layer 2 of tile `it` -> params (fp32).  Runs one step late (after the NEXT tile's first epilogue), off the chain.
+        auto store_params = [&](int it) {
             const int tile = tile0 + it * tile_stride;
             const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + row;   // this thread's position: plane row, column
-            // ---- layer 0 -> H0 (the layer-2 MMAs of the previous tile, which read these columns, completed before its
-            //      D2FULL, which this warp has waited for) ----
-            mbar_wait(bar(B_D0FULL + 2 * s + g), (it >> 1) & 1);
-            tc_fence_after();
-            epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
-            tc_fence_before();
-            mbar_arrive(bar(B_H0FULL + g));
-            // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
-            mbar_wait(bar(B_D1FULL + g), it & 1);
-            tc_fence_after();
-            epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
-            tc_fence_before();
-            mbar_arrive(bar(B_H1FULL + g));
-            mbar_arrive(bar(B_DFREE + s));      // D0/D1 columns of this slot may be overwritten by tile it+2
-            // ---- layer 2 -> params (fp32) ----
-            mbar_wait(bar(B_D2FULL + g), it & 1);
-            tc_fence_after();
             uint32_t r[16];
             TMEM_LD_X16(tmem + lane_base + (uint32_t)(5 * NP + g * 16), r);
             tmem_ld_wait();
@@ -553,8 +543,31 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
 #pragma unroll
                 for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
             }
+        };
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it & 1;
+            const uint32_t dbase = tmem + lane_base + (uint32_t)(s * 2 * NP);
+            // ---- layer 0 -> H0.  The layer-2 MMAs of the previous tile read these TMEM columns: they must be complete. ----
+            if (it > 0) mbar_wait(bar(B_D2FULL + g), (it - 1) & 1);
+            mbar_wait(bar(B_D0FULL + 2 * s + g), (it >> 1) & 1);
+            tc_fence_after();
+            epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
+            mbar_arrive(bar(B_H0FULL + g));
+            if (it > 0) store_params(it - 1);       // (D2 of the previous tile: its MMAs completed before the wait above)
+            // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
+            mbar_wait(bar(B_D1FULL + g), it & 1);
+            tc_fence_after();
+            epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
+            tc_fence_before();
+            mbar_arrive(bar(B_H1FULL + g));         // also: D1 of this slot has been read (the issuer's licence to overwrite it)
         }
+        if (my_tiles > 0) {
+            mbar_wait(bar(B_D2FULL + g), (my_tiles - 1) & 1);
+            tc_fence_after();
+            store_params(my_tiles - 1);
+        }
+        tc_fence_before();
     }
 
     tc_fence_before();

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round 2, call m: CNN software-pipelined issue order: cnn parity, bench, ncu of the CNN.
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "cnn or full_size or trained" > gpurun_out/pytest_m.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_m.log
+timeout 300 python bench.py --workload c2 --steps 3 --warmup 2 --no-cpu --no-per-config > gpurun_out/m_c2.json 2> gpurun_out/m_c2.err
+echo "bench rc=$?"; python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/m_c2.json').read().strip().splitlines()[-1])
+    print(round(d['value'],1), 'enc', round(d['encode_mpps']), 'dec', round(d['decode_mpps']), {k:round(v,2) for k,v in d['kernel_ms_per_step'].items()}, 'bpp', round(d['bpp'],4), 'cnn TF', round(d['cnn_tflops'],1))
+except Exception as e: print('failed', e)
+PY
+NCU="ncu --set full --clock-control none --import-source on"
+C2="python bench.py --workload c2 --images 8 --steps 1 --warmup 1 --no-cpu --no-per-config"
+$NCU --kernel-name-base demangled -k "regex:cnn_tc_kernel<\(int\)2" -s 4 -c 1 -o gpurun_out/r02_cnn_c2_m $C2 > gpurun_out/ncu_cnn_m.log 2>&1; echo "ncu cnn rc=$?"
