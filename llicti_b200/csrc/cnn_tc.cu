@@ -109,6 +109,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One arrival for the whole (converged) warp, after every lane's preceding accesses.
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -365,11 +370,15 @@ __device__ __forceinline__ void store_items(uint8_t *sT, int pt, const uint32_t 
 
 // Barrier slots in shared memory.
 enum { B_W = 0, B_AFULL = 1, B_AEMPTY = 3, B_D0FULL = 5 /* [slot][sub-network] */, B_DFREE = 9, B_H0FULL = 11, B_D1FULL = 13,
-       B_H1FULL = 15, B_D2FULL = 17, B_COUNT = 19 };
+       B_H1FULL = 15, B_D2FULL = 17, B_D2FREE = 19, B_COUNT = 21 };
+
+// LLICTI_TC_DEBUG=1: cycles CTA 0 spends per phase (epilogue warp 0 of each sub-network, the MMA issuer), printed per launch.
+__device__ unsigned long long g_tc_dbg[24];
+#define TC_T(slot) do { if (dbg) { const long long now_ = clock64(); if (dbg_on) acc[slot] += (unsigned long long)(now_ - t_last); t_last = now_; } } while (0)
 
 template <int BAND, bool F16, int NP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__restrict__ packed, float *__restrict__ params) {
+cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__restrict__ packed, float *__restrict__ params, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NCH = band_nchunk(BAND);
     const int tid = threadIdx.x;
@@ -398,15 +407,16 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     if (tid == 0) {
         mbar_init(bar(B_W), 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(B_AFULL + s), TC_PRODUCERS);
+            mbar_init(bar(B_AFULL + s), TC_PRODUCERS / 32);       // one arrival per warp (128 same-address arrivals serialise)
             mbar_init(bar(B_AEMPTY + s), 1);
             mbar_init(bar(B_D0FULL + 2 * s), 1);
             mbar_init(bar(B_D0FULL + 2 * s + 1), 1);
             mbar_init(bar(B_DFREE + s), 2 * TC_M);
-            mbar_init(bar(B_H0FULL + s), TC_M);
+            mbar_init(bar(B_H0FULL + s), TC_M / 32);
             mbar_init(bar(B_D1FULL + s), 1);
-            mbar_init(bar(B_H1FULL + s), TC_M);
+            mbar_init(bar(B_H1FULL + s), TC_M / 32);
             mbar_init(bar(B_D2FULL + s), 1);
+            mbar_init(bar(B_D2FREE + s), TC_M / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -429,18 +439,42 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             tile_coords(0, img, i, j0);
             load_items<BAND>(planes, tg, img, i, j0, pt, raw);
         }
+        // The producer warps also write the network outputs (layer 2 -> fp32 params): warp 8 + w reads the TMEM lane quadrant
+        // w % 4 of sub-network w / 4's D2 two tiles after staging -- ~170 instructions per tile that used to sit on the
+        // epilogue warps' serial chain (every instruction of a lone warp costs 5-6 cycles there).
+        const int og = (pt >> 5) >> 2, orow = ((pt >> 5) & 3) * 32 + lane;
+        const uint32_t d2_addr = tmem + ((uint32_t)(((pt >> 5) & 3) * 32) << 16) + (uint32_t)(5 * NP + og * 16);
+        auto store_params = [&](int k) {
+            const int tile = tile0 + k * tile_stride;
+            const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + orow;   // this thread's position: plane row, column
+            const int img = rowid / tg.nrows, p = (tg.row0 + rowid - img * tg.nrows) * tg.Ws + jcol;
+            float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + og) * 15) * tg.P + p;
+            mbar_wait(bar(B_D2FULL + og), k & 1);
+            tc_fence_after();
+            uint32_t r[16];
+            TMEM_LD_X16(d2_addr, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive_warp(bar(B_D2FREE + og), lane);        // layer 2 of the next tile may overwrite D2
+            if (jcol < tg.Ws) {
+#pragma unroll
+                for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
+            }
+        };
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
             mbar_wait(bar(B_AEMPTY + s), ((it >> 1) & 1) ^ 1);     // MMAs that read this stage are complete
             store_items<BAND, F16>(sT + s * t_stage, pt, raw);
             fence_async_smem();
-            mbar_arrive(bar(B_AFULL + s));
+            mbar_arrive_warp(bar(B_AFULL + s), lane);
             if (it + 1 < my_tiles) {                               // the next tile's samples travel while this one is multiplied
                 int img, i, j0;
                 tile_coords(it + 1, img, i, j0);
                 load_items<BAND>(planes, tg, img, i, j0, pt, raw);
             }
+            if (it >= 2) store_params(it - 2);
         }
+        for (int k = max(my_tiles - 2, 0); k < my_tiles; ++k) store_params(k);
     } else if (warp == 16) {
         // ================= MMA issuer =================
         // The whole warp runs this code (so every address below is warp-uniform and lives in uniform registers); one elected
@@ -502,6 +536,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         auto l2_group = [&](int it, auto g_) {       // layer 2; A = H1_g in TMEM (over H0_g: the layer-1 MMAs that read it are complete)
             constexpr int g = decltype(g_)::value;
             mbar_wait(bar(B_H1FULL + g), it & 1);
+            if (it > 0) mbar_wait(bar(B_D2FREE + g), (it - 1) & 1);     // the output warps have read D2 of the previous tile
             tc_fence_after();
             if (leader) {
 #pragma unroll
@@ -514,59 +549,56 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         };
         constexpr std::integral_constant<int, 0> G0{};
         constexpr std::integral_constant<int, 1> G1{};
+        unsigned long long acc[8] = {};
+        long long t_last = 0;
+        const bool dbg_on = dbg && blockIdx.x == 0 && leader;
         if (my_tiles > 0) { l0_half(0, G0); l0_half(0, G1); }
         if (my_tiles > 1) l0_half(1, G0);
+        TC_T(7);
         for (int it = 0; it < my_tiles; ++it) {
-            l1_group(it, G0);
+            l1_group(it, G0); TC_T(0);
             if (it + 1 < my_tiles) l0_half(it + 1, G1);
-            l1_group(it, G1);
-            l2_group(it, G0);
+            TC_T(1);
+            l1_group(it, G1); TC_T(2);
+            l2_group(it, G0); TC_T(3);
             if (it + 2 < my_tiles) l0_half(it + 2, G0);
-            l2_group(it, G1);
+            TC_T(4);
+            l2_group(it, G1); TC_T(5);
         }
+        if (dbg_on) { for (int k = 0; k < 6; ++k) g_tc_dbg[16 + k] = acc[k]; g_tc_dbg[22] = (unsigned long long)my_tiles; }
     } else {
         // ================= epilogue warps: warps 0-3 sub-network 0, warps 4-7 sub-network 1 =================
         // (a warp reaches the TMEM lanes 32 * (warp % 4) .. +31, so each quadrant of rows has one warp per sub-network)
         const int row = tid & (TC_M - 1), g = tid >> 7;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t hcol = tmem + lane_base + (uint32_t)(4 * NP + g * (NP / 2));
-        // layer 2 of tile `it` -> params (fp32).  Runs one step late (after the NEXT tile's first epilogue), off the chain.
-        auto store_params = [&](int it) {
-            const int tile = tile0 + it * tile_stride;
-            const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + row;   // this thread's position: plane row, column
-            uint32_t r[16];
-            TMEM_LD_X16(tmem + lane_base + (uint32_t)(5 * NP + g * 16), r);
-            tmem_ld_wait();
-            if (jcol < tg.Ws) {
-                const int img = rowid / tg.nrows, p = (tg.row0 + rowid - img * tg.nrows) * tg.Ws + jcol;
-                float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + g) * 15) * tg.P + p;
-#pragma unroll
-                for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
-            }
-        };
+        unsigned long long acc[8] = {};
+        long long t_last = 0;
+        const bool dbg_on = dbg && blockIdx.x == 0 && (tid & 127) == 0;
+        TC_T(7);
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
             const uint32_t dbase = tmem + lane_base + (uint32_t)(s * 2 * NP);
             // ---- layer 0 -> H0.  The layer-2 MMAs of the previous tile read these TMEM columns: they must be complete. ----
             if (it > 0) mbar_wait(bar(B_D2FULL + g), (it - 1) & 1);
+            TC_T(0);
             mbar_wait(bar(B_D0FULL + 2 * s + g), (it >> 1) & 1);
+            TC_T(1);
             tc_fence_after();
             epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
-            mbar_arrive(bar(B_H0FULL + g));
-            if (it > 0) store_params(it - 1);       // (D2 of the previous tile: its MMAs completed before the wait above)
+            mbar_arrive_warp(bar(B_H0FULL + g), lane);
+            TC_T(2);
             // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
             mbar_wait(bar(B_D1FULL + g), it & 1);
+            TC_T(4);
             tc_fence_after();
             epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
-            mbar_arrive(bar(B_H1FULL + g));         // also: D1 of this slot has been read (the issuer's licence to overwrite it)
+            mbar_arrive_warp(bar(B_H1FULL + g), lane);         // also: D1 of this slot has been read (the issuer's licence to overwrite it)
+            TC_T(5);
         }
-        if (my_tiles > 0) {
-            mbar_wait(bar(B_D2FULL + g), (my_tiles - 1) & 1);
-            tc_fence_after();
-            store_params(my_tiles - 1);
-        }
+        if (dbg_on) for (int k = 0; k < 7; ++k) g_tc_dbg[g * 8 + k] = acc[k];
         tc_fence_before();
     }
 
@@ -829,9 +861,10 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
     // persistent grid: one CTA per SM, an even number (one sub-network pair per CTA), no more than the work
     const int ctas = std::min(sm_count / 2 * 2, tg.ntiles * 2);
     LLICTI_REQUIRE(tg.NP == 96 || tg.NP == 64, "tcgen05 CNN is built for chs = 88 and 60");
+    static const int dbg = [] { const char *e = getenv("LLICTI_TC_DEBUG"); return e && *e ? atoi(e) : 0; }();
 #define LLICTI_TC_LAUNCH2(B, F) \
-    do { if (tg.NP == 96) cnn_tc_kernel<B, F, 96><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); \
-         else cnn_tc_kernel<B, F, 64><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); } while (0)
+    do { if (tg.NP == 96) cnn_tc_kernel<B, F, 96><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params, dbg); \
+         else cnn_tc_kernel<B, F, 64><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params, dbg); } while (0)
 #define LLICTI_TC_LAUNCH(B) do { if (tw->f16) LLICTI_TC_LAUNCH2(B, true); else LLICTI_TC_LAUNCH2(B, false); } while (0)
     if (band == 0) LLICTI_TC_LAUNCH(0);
     else if (band == 1) LLICTI_TC_LAUNCH(1);
@@ -840,6 +873,16 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
 #undef LLICTI_TC_LAUNCH2
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
+    if (dbg) {
+        unsigned long long h[24];
+        LLICTI_CUDA(cudaStreamSynchronize(st));
+        LLICTI_CUDA(cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h)));
+        const double t = h[22] ? (double)h[22] : 1.0;
+        fprintf(stderr, "[tc] band %d n %d %dx%d tiles/CTA %.0f | epilogue g0: waitD2 %.0f waitD0 %.0f epi0 %.0f ldD2 %.0f store %.0f waitD1 %.0f epi1 %.0f | g1: %.0f %.0f %.0f %.0f %.0f %.0f %.0f | "
+                "issuer: L1g0 %.0f L0g1 %.0f L1g1 %.0f L2g0 %.0f L0g0 %.0f L2g1 %.0f cycles per tile\n", band, n, Hs, Ws, t,
+                h[0] / t, h[1] / t, h[2] / t, h[6] / t, h[3] / t, h[4] / t, h[5] / t, h[8] / t, h[9] / t, h[10] / t, h[14] / t, h[11] / t, h[12] / t, h[13] / t,
+                h[16] / t, h[17] / t, h[18] / t, h[19] / t, h[20] / t, h[21] / t);
+    }
     return LLICTI_OK;
 }
 
