@@ -109,11 +109,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// One arrival for the whole (converged) warp, after every lane's preceding accesses.
-__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar, int lane) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
-}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -125,7 +120,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a barrier that never completes (a programming error) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();
+        if (spins > (1u << 22)) __trap();
 }
 __device__ __forceinline__ bool elect_one() {      // one lane of the (converged) warp
     uint32_t pred;
@@ -297,88 +292,72 @@ constexpr int TC_NDX = 4;              // horizontal taps dxlo .. dxlo + 3
 constexpr int TC_TPX = 132;            // staged pixels per chunk (128 + 3 used)
 constexpr int TC_CHUNK_BYTES = TC_TPX * 16;
 
-// bf16 bits of a small integer (|v| <= 255, exact): the sample enters as unsigned 16 bits; xor 0x8000 makes it
-// v + 32768, which or-ed into the mantissa of 2^23 gives the float 2^23 + 32768 + v; subtracting the offset
-// leaves float(v), whose low 16 bits are zero.
+// Operand pair (element 0 in the low half) of two small integers (|v| <= 255: exact in bf16 and fp16).  A sample enters as
+// unsigned 16 bits; xor 0x8000 makes it v + 32768, which or-ed into the mantissa of 2^23 gives the float 2^23 + 32768 + v;
+// subtracting the offset leaves float(v); one cvt packs the pair.
 template <bool F16>
-__device__ __forceinline__ uint32_t operand_of_sample(uint32_t u) {
-    const float f = __uint_as_float(0x4B008000u ^ u) - 8421376.0f;
-    if (F16) return (uint32_t)__half_as_ushort(__float2half_rn(f));          // |v| <= 255: exact in fp16 as well
-    return __float_as_uint(f) >> 16;
+__device__ __forceinline__ uint32_t operand_pair(uint32_t u0, uint32_t u1) {
+    const float f0 = __uint_as_float(0x4B008000u ^ u0) - 8421376.0f, f1 = __uint_as_float(0x4B008000u ^ u1) - 8421376.0f;
+    uint32_t w;
+    if (F16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(f1), "f"(f0));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(f1), "f"(f0));
+    return w;
 }
 
-// The producers' work on one tile is cut in items = (chunk, staged pixel): eight 2-byte loads (one per slot), conversion, one
-// 16-byte store.  Producer thread pt owns items pt, pt + 256, ...; the raw samples of the NEXT tile are fetched into
+// Producer thread x < TC_TPX owns staged pixel x of every chunk: 8 NCH two-byte loads with compile-time plane / row
+// offsets (three instructions each), conversion, NCH 16-byte stores.  The raw samples of the NEXT tile are fetched into
 // registers before this tile's are converted and stored, so the global-memory latency is off the tile-to-tile path.
-constexpr int TC_PRODUCERS = 256;
-template <int BAND> struct TileItems { static constexpr int kItems = band_nchunk(BAND) * TC_TPX, kRounds = (kItems + TC_PRODUCERS - 1) / TC_PRODUCERS; };
-
-// Slot table of the three bands: source plane (phase * 3 + channel) and vertical tap of every slot, looked up with the
-// item's chunk -- no branch on the chunk: branches that load into the same registers would wait for each other's loads.
-__constant__ uint8_t c_slot_plane[3][40];
-__constant__ int8_t c_slot_dy[3][40];
+constexpr int TC_PRODUCERS = 256;      // producer threads (the first TC_TPX of them stage; all of them keep the barrier phases)
 
 template <int BAND>
-__device__ __forceinline__ void load_items(const int16_t *__restrict__ planes, const TcGeom &tg, int img, int i, int j0, int pt,
-                                           uint32_t (&raw)[TileItems<BAND>::kRounds][8]) {
-    const uint16_t *pl = reinterpret_cast<const uint16_t *>(planes) + (size_t)img * 12 * tg.P;
+__device__ __forceinline__ void load_items(const int16_t *__restrict__ planes, const TcGeom &tg, int img, int i, int j0, int x,
+                                           uint32_t (&raw)[band_nchunk(BAND)][8]) {
+    constexpr int NSEG = band_nseg(BAND), NCH = band_nchunk(BAND);
+    const int col = min(max(j0 + band_dxlo(BAND) + x, 0), tg.Ws - 1);           // replicate padding
+    const uint16_t *src = reinterpret_cast<const uint16_t *>(planes) + (size_t)img * 12 * tg.P + col;
+    int rowoff[5];
 #pragma unroll
-    for (int rd = 0; rd < TileItems<BAND>::kRounds; ++rd) {
-        const int item = min(pt + rd * TC_PRODUCERS, TileItems<BAND>::kItems - 1);      // (a thread past the end repeats the last item)
-        const int c = item / TC_TPX, x = item - c * TC_TPX;
-        const int col = min(max(j0 + band_dxlo(BAND) + x, 0), tg.Ws - 1);           // replicate padding
-        const uint16_t *src = pl + col;
-        // (each sample stays in a register of its own until store_items: nothing here waits for a load; slots past the
-        // segments read a valid sample that store_items replaces by its constant)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int plane = c_slot_plane[BAND][c * 8 + e], row = min(max(i + (int)c_slot_dy[BAND][c * 8 + e], 0), tg.Hs - 1);
-            raw[rd][e] = src[plane * tg.P + row * tg.Ws];
-        }
-    }
+    for (int d = 0; d < 5; ++d) rowoff[d] = min(max(i + d - 2, 0), tg.Hs - 1) * tg.Ws;
+    // (each sample stays in a register of its own until store_items: nothing here waits for a load)
+    static_for<NCH>([&](auto c_) {
+        constexpr int c = decltype(c_)::value;
+        static_for<8>([&](auto e_) {
+            constexpr int e = decltype(e_)::value, slot = c * 8 + e;
+            if constexpr (slot < NSEG) {
+                constexpr SegTc seg = band_seg(BAND, slot);
+                raw[c][e] = src[(size_t)(seg.phase * 3 + seg.chan) * tg.P + rowoff[seg.dy + 2]];
+            } else {
+                raw[c][e] = 0u;
+            }
+        });
+    });
 }
 
 template <int BAND, bool F16>
-__device__ __forceinline__ void store_items(uint8_t *sT, int pt, const uint32_t (&raw)[TileItems<BAND>::kRounds][8]) {
+__device__ __forceinline__ void store_items(uint8_t *sT, int x, const uint32_t (&raw)[band_nchunk(BAND)][8]) {
     constexpr int NSEG = band_nseg(BAND), NCH = band_nchunk(BAND);
     constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;   // 1.0 in the operand type
-#pragma unroll
-    for (int rd = 0; rd < TileItems<BAND>::kRounds; ++rd) {
-        const int item = pt + rd * TC_PRODUCERS;
-        if (item >= TileItems<BAND>::kItems) continue;
-        const int c = item / TC_TPX;
+    static_for<NCH>([&](auto c_) {
+        constexpr int c = decltype(c_)::value;
         uint32_t w[4];
-#pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2)
-            w[e2] = operand_of_sample<F16>(raw[rd][2 * e2]) | (operand_of_sample<F16>(raw[rd][2 * e2 + 1]) << 16);
-        // slots past the segments: the two constant ones, then zeros (a loaded zero sample converts to zero as well)
-        static_for<NCH>([&](auto c_) {
-            constexpr int cc = decltype(c_)::value;
-            if (c == cc) {
-                static_for<8>([&](auto e_) {
-                    constexpr int e = decltype(e_)::value, slot = cc * 8 + e;
-                    if constexpr (slot >= NSEG) {
-                        constexpr uint32_t val = (slot == NSEG || slot == NSEG + 1) ? kOne : 0u;
-                        w[e >> 1] = (e & 1) ? ((w[e >> 1] & 0xFFFFu) | (val << 16)) : ((w[e >> 1] & 0xFFFF0000u) | val);
-                    }
-                });
-            }
+        static_for<4>([&](auto e2_) {
+            constexpr int e2 = decltype(e2_)::value, s0 = c * 8 + 2 * e2, s1 = s0 + 1;
+            // slots past the segments: the two constant ones, then zeros
+            if constexpr (s1 < NSEG) w[e2] = operand_pair<F16>(raw[c][2 * e2], raw[c][2 * e2 + 1]);
+            else if constexpr (s0 < NSEG) w[e2] = (operand_pair<F16>(raw[c][2 * e2], 0u) & 0xFFFFu) | ((s1 <= NSEG + 1 ? kOne : 0u) << 16);
+            else w[e2] = ((s0 == NSEG || s0 == NSEG + 1) ? kOne : 0u) | (((s1 == NSEG || s1 == NSEG + 1) ? kOne : 0u) << 16);
         });
-        *reinterpret_cast<uint4 *>(sT + (size_t)item * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+        *reinterpret_cast<uint4 *>(sT + (size_t)(c * TC_TPX + x) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    });
 }
 
 // Barrier slots in shared memory.
 enum { B_W = 0, B_AFULL = 1, B_AEMPTY = 3, B_D0FULL = 5 /* [slot][sub-network] */, B_DFREE = 9, B_H0FULL = 11, B_D1FULL = 13,
-       B_H1FULL = 15, B_D2FULL = 17, B_D2FREE = 19, B_COUNT = 21 };
-
-// LLICTI_TC_DEBUG=1: cycles CTA 0 spends per phase (epilogue warp 0 of each sub-network, the MMA issuer), printed per launch.
-__device__ unsigned long long g_tc_dbg[24];
-#define TC_T(slot) do { if (dbg) { const long long now_ = clock64(); if (dbg_on) acc[slot] += (unsigned long long)(now_ - t_last); t_last = now_; } } while (0)
+       B_H1FULL = 15, B_D2FULL = 17, B_COUNT = 19 };
 
 template <int BAND, bool F16, int NP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__restrict__ packed, float *__restrict__ params, int dbg) {
+cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__restrict__ packed, float *__restrict__ params) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NCH = band_nchunk(BAND);
     const int tid = threadIdx.x;
@@ -407,16 +386,15 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     if (tid == 0) {
         mbar_init(bar(B_W), 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(B_AFULL + s), TC_PRODUCERS / 32);       // one arrival per warp (128 same-address arrivals serialise)
+            mbar_init(bar(B_AFULL + s), TC_PRODUCERS);
             mbar_init(bar(B_AEMPTY + s), 1);
             mbar_init(bar(B_D0FULL + 2 * s), 1);
             mbar_init(bar(B_D0FULL + 2 * s + 1), 1);
             mbar_init(bar(B_DFREE + s), 2 * TC_M);
-            mbar_init(bar(B_H0FULL + s), TC_M / 32);
+            mbar_init(bar(B_H0FULL + s), TC_M);
             mbar_init(bar(B_D1FULL + s), 1);
-            mbar_init(bar(B_H1FULL + s), TC_M / 32);
+            mbar_init(bar(B_H1FULL + s), TC_M);
             mbar_init(bar(B_D2FULL + s), 1);
-            mbar_init(bar(B_D2FREE + s), TC_M / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -428,53 +406,32 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     if (warp >= 8 && warp < 16) {
         // ================= producers: stage the receptive field of every tile, pixel-major =================
         const int pt = tid - 256;
-        uint32_t raw[TileItems<BAND>::kRounds][8];
+        const bool stager = pt < TC_TPX;
+        uint32_t raw[NCH][8];
         auto tile_coords = [&](int it, int &img, int &i, int &j0) {
             const int tile = tile0 + it * tile_stride;
             const int rowid = tile / tg.tpr, jb = tile - rowid * tg.tpr;       // (image, plane row), column block
             img = rowid / tg.nrows; i = tg.row0 + rowid - img * tg.nrows; j0 = jb * TC_M;
         };
-        if (my_tiles > 0) {
+        if (my_tiles > 0 && stager) {
             int img, i, j0;
             tile_coords(0, img, i, j0);
             load_items<BAND>(planes, tg, img, i, j0, pt, raw);
         }
-        // The producer warps also write the network outputs (layer 2 -> fp32 params): warp 8 + w reads the TMEM lane quadrant
-        // w % 4 of sub-network w / 4's D2 two tiles after staging -- ~170 instructions per tile that used to sit on the
-        // epilogue warps' serial chain (every instruction of a lone warp costs 5-6 cycles there).
-        const int og = (pt >> 5) >> 2, orow = ((pt >> 5) & 3) * 32 + lane;
-        const uint32_t d2_addr = tmem + ((uint32_t)(((pt >> 5) & 3) * 32) << 16) + (uint32_t)(5 * NP + og * 16);
-        auto store_params = [&](int k) {
-            const int tile = tile0 + k * tile_stride;
-            const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + orow;   // this thread's position: plane row, column
-            const int img = rowid / tg.nrows, p = (tg.row0 + rowid - img * tg.nrows) * tg.Ws + jcol;
-            float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + og) * 15) * tg.P + p;
-            mbar_wait(bar(B_D2FULL + og), k & 1);
-            tc_fence_after();
-            uint32_t r[16];
-            TMEM_LD_X16(d2_addr, r);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive_warp(bar(B_D2FREE + og), lane);        // layer 2 of the next tile may overwrite D2
-            if (jcol < tg.Ws) {
-#pragma unroll
-                for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
-            }
-        };
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
             mbar_wait(bar(B_AEMPTY + s), ((it >> 1) & 1) ^ 1);     // MMAs that read this stage are complete
-            store_items<BAND, F16>(sT + s * t_stage, pt, raw);
-            fence_async_smem();
-            mbar_arrive_warp(bar(B_AFULL + s), lane);
-            if (it + 1 < my_tiles) {                               // the next tile's samples travel while this one is multiplied
+            if (stager) {
+                store_items<BAND, F16>(sT + s * t_stage, pt, raw);
+                fence_async_smem();
+            }
+            mbar_arrive(bar(B_AFULL + s));
+            if (it + 1 < my_tiles && stager) {                     // the next tile's samples travel while this one is multiplied
                 int img, i, j0;
                 tile_coords(it + 1, img, i, j0);
                 load_items<BAND>(planes, tg, img, i, j0, pt, raw);
             }
-            if (it >= 2) store_params(it - 2);
         }
-        for (int k = max(my_tiles - 2, 0); k < my_tiles; ++k) store_params(k);
     } else if (warp == 16) {
         // ================= MMA issuer =================
         // The whole warp runs this code (so every address below is warp-uniform and lives in uniform registers); one elected
@@ -536,7 +493,6 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         auto l2_group = [&](int it, auto g_) {       // layer 2; A = H1_g in TMEM (over H0_g: the layer-1 MMAs that read it are complete)
             constexpr int g = decltype(g_)::value;
             mbar_wait(bar(B_H1FULL + g), it & 1);
-            if (it > 0) mbar_wait(bar(B_D2FREE + g), (it - 1) & 1);     // the output warps have read D2 of the previous tile
             tc_fence_after();
             if (leader) {
 #pragma unroll
@@ -549,56 +505,59 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         };
         constexpr std::integral_constant<int, 0> G0{};
         constexpr std::integral_constant<int, 1> G1{};
-        unsigned long long acc[8] = {};
-        long long t_last = 0;
-        const bool dbg_on = dbg && blockIdx.x == 0 && leader;
         if (my_tiles > 0) { l0_half(0, G0); l0_half(0, G1); }
         if (my_tiles > 1) l0_half(1, G0);
-        TC_T(7);
         for (int it = 0; it < my_tiles; ++it) {
-            l1_group(it, G0); TC_T(0);
+            l1_group(it, G0);
             if (it + 1 < my_tiles) l0_half(it + 1, G1);
-            TC_T(1);
-            l1_group(it, G1); TC_T(2);
-            l2_group(it, G0); TC_T(3);
+            l1_group(it, G1);
+            l2_group(it, G0);
             if (it + 2 < my_tiles) l0_half(it + 2, G0);
-            TC_T(4);
-            l2_group(it, G1); TC_T(5);
+            l2_group(it, G1);
         }
-        if (dbg_on) { for (int k = 0; k < 6; ++k) g_tc_dbg[16 + k] = acc[k]; g_tc_dbg[22] = (unsigned long long)my_tiles; }
     } else {
         // ================= epilogue warps: warps 0-3 sub-network 0, warps 4-7 sub-network 1 =================
         // (a warp reaches the TMEM lanes 32 * (warp % 4) .. +31, so each quadrant of rows has one warp per sub-network)
         const int row = tid & (TC_M - 1), g = tid >> 7;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t hcol = tmem + lane_base + (uint32_t)(4 * NP + g * (NP / 2));
-        unsigned long long acc[8] = {};
-        long long t_last = 0;
-        const bool dbg_on = dbg && blockIdx.x == 0 && (tid & 127) == 0;
-        TC_T(7);
+        // layer 2 of tile `it` -> params (fp32).  Runs one step late (after the NEXT tile's first epilogue), off the chain.
+        auto store_params = [&](int it) {
+            const int tile = tile0 + it * tile_stride;
+            const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + row;   // this thread's position: plane row, column
+            uint32_t r[16];
+            TMEM_LD_X16(tmem + lane_base + (uint32_t)(5 * NP + g * 16), r);
+            tmem_ld_wait();
+            if (jcol < tg.Ws) {
+                const int img = rowid / tg.nrows, p = (tg.row0 + rowid - img * tg.nrows) * tg.Ws + jcol;
+                float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + g) * 15) * tg.P + p;
+#pragma unroll
+                for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
+            }
+        };
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
             const uint32_t dbase = tmem + lane_base + (uint32_t)(s * 2 * NP);
             // ---- layer 0 -> H0.  The layer-2 MMAs of the previous tile read these TMEM columns: they must be complete. ----
             if (it > 0) mbar_wait(bar(B_D2FULL + g), (it - 1) & 1);
-            TC_T(0);
             mbar_wait(bar(B_D0FULL + 2 * s + g), (it >> 1) & 1);
-            TC_T(1);
             tc_fence_after();
             epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
-            mbar_arrive_warp(bar(B_H0FULL + g), lane);
-            TC_T(2);
+            mbar_arrive(bar(B_H0FULL + g));
+            if (it > 0) store_params(it - 1);       // (D2 of the previous tile: its MMAs completed before the wait above)
             // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
             mbar_wait(bar(B_D1FULL + g), it & 1);
-            TC_T(4);
             tc_fence_after();
             epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
-            mbar_arrive_warp(bar(B_H1FULL + g), lane);         // also: D1 of this slot has been read (the issuer's licence to overwrite it)
-            TC_T(5);
+            mbar_arrive(bar(B_H1FULL + g));         // also: D1 of this slot has been read (the issuer's licence to overwrite it)
         }
-        if (dbg_on) for (int k = 0; k < 7; ++k) g_tc_dbg[g * 8 + k] = acc[k];
+        if (my_tiles > 0) {
+            mbar_wait(bar(B_D2FULL + g), (my_tiles - 1) & 1);
+            tc_fence_after();
+            store_params(my_tiles - 1);
+        }
         tc_fence_before();
     }
 
@@ -719,18 +678,6 @@ int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w) {
     const bool f16 = tw->f16;
     auto cv = [f16](float v) { return f16 ? f2h(v) : f2bf(v); };
     auto back = [f16](uint16_t v) { return f16 ? h2f(v) : bf2f(v); };
-    {
-        uint8_t plane[3][40] = {};
-        int8_t dy[3][40] = {};
-        for (int band = 0; band < 3; ++band)
-            for (int slot = 0; slot < band_nseg(band); ++slot) {
-                const SegTc sg = band_seg(band, slot);
-                plane[band][slot] = (uint8_t)(sg.phase * 3 + sg.chan);
-                dy[band][slot] = (int8_t)sg.dy;
-            }
-        LLICTI_CUDA(cudaMemcpyToSymbol(c_slot_plane, plane, sizeof(plane)));
-        LLICTI_CUDA(cudaMemcpyToSymbol(c_slot_dy, dy, sizeof(dy)));
-    }
     for (int band = 0; band < 3; ++band) {
         const int K0 = band_k0(band), K0p = band_k0p(band), NSEG = band_nseg(band);
         LLICTI_REQUIRE(K0 == ctx->taps[band].K0, "tap tables disagree for band %d", band);
@@ -861,10 +808,9 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
     // persistent grid: one CTA per SM, an even number (one sub-network pair per CTA), no more than the work
     const int ctas = std::min(sm_count / 2 * 2, tg.ntiles * 2);
     LLICTI_REQUIRE(tg.NP == 96 || tg.NP == 64, "tcgen05 CNN is built for chs = 88 and 60");
-    static const int dbg = [] { const char *e = getenv("LLICTI_TC_DEBUG"); return e && *e ? atoi(e) : 0; }();
 #define LLICTI_TC_LAUNCH2(B, F) \
-    do { if (tg.NP == 96) cnn_tc_kernel<B, F, 96><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params, dbg); \
-         else cnn_tc_kernel<B, F, 64><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params, dbg); } while (0)
+    do { if (tg.NP == 96) cnn_tc_kernel<B, F, 96><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); \
+         else cnn_tc_kernel<B, F, 64><<<ctas, TC_THREADS, tb.smem_bytes, st>>>(planes, tg, tb.packed, params); } while (0)
 #define LLICTI_TC_LAUNCH(B) do { if (tw->f16) LLICTI_TC_LAUNCH2(B, true); else LLICTI_TC_LAUNCH2(B, false); } while (0)
     if (band == 0) LLICTI_TC_LAUNCH(0);
     else if (band == 1) LLICTI_TC_LAUNCH(1);
@@ -873,16 +819,6 @@ int launch_cnn_tc(llicti_ctx *ctx, int band, const int16_t *planes, int n, int H
 #undef LLICTI_TC_LAUNCH2
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
-    if (dbg) {
-        unsigned long long h[24];
-        LLICTI_CUDA(cudaStreamSynchronize(st));
-        LLICTI_CUDA(cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h)));
-        const double t = h[22] ? (double)h[22] : 1.0;
-        fprintf(stderr, "[tc] band %d n %d %dx%d tiles/CTA %.0f | epilogue g0: waitD2 %.0f waitD0 %.0f epi0 %.0f ldD2 %.0f store %.0f waitD1 %.0f epi1 %.0f | g1: %.0f %.0f %.0f %.0f %.0f %.0f %.0f | "
-                "issuer: L1g0 %.0f L0g1 %.0f L1g1 %.0f L2g0 %.0f L0g0 %.0f L2g1 %.0f cycles per tile\n", band, n, Hs, Ws, t,
-                h[0] / t, h[1] / t, h[2] / t, h[6] / t, h[3] / t, h[4] / t, h[5] / t, h[8] / t, h[9] / t, h[10] / t, h[14] / t, h[11] / t, h[12] / t, h[13] / t,
-                h[16] / t, h[17] / t, h[18] / t, h[19] / t, h[20] / t, h[21] / t);
-    }
     return LLICTI_OK;
 }
 
