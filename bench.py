@@ -23,8 +23,9 @@ Rank 0 prints ONE JSON line on stdout:
   cpu_baseline  the CPU oracle on a bounded sample, run in a fresh process (`bench.py --impl reference`); a failure
                 there is recorded in the JSON line and never discards the GPU measurement
 
-`--impl reference` times the CPU oracle alone (the reference is a Python script tree and cannot travel to the GPU
-box; oracle/llicti_oracle.py restates it with the same cost structure).
+`--impl reference` times the reference's CPU path alone: the UNMODIFIED reference sources from oracle/_ref (copied
+there by oracle/make_ref.py in the build container; the directory travels to the GPU box) when present, else
+oracle/llicti_oracle.py, which restates it with the same cost structure.
 """
 import argparse
 import json

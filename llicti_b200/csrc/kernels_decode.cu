@@ -1394,12 +1394,17 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
     // coefficients (Co: one set, Cg: two); staged parameter k sits at stage[.][k][thread]
     const float *p_sigma = pp + (size_t)(cl * kM) * P, *p_mu = pp + (size_t)((3 + cl) * kM) * P, *p_w = pp + (size_t)((6 + cl) * kM) * P;
     const float *p_cpl = pp + (size_t)((cl == 1 ? 9 : 10) * kM) * P;
+    // position of step t: i = j + t S -> (row, column) of the cropped band, advanced by (S / crop_w, S % crop_w) per step
+    // (two counters: the prefetch runs two steps ahead of the decode)
+    const int step_r = dg.S / dg.crop_w, step_c = dg.S - step_r * dg.crop_w;
+    int pf_r = j / dg.crop_w, pf_c = j - pf_r * dg.crop_w;
+    int dec_r = pf_r, dec_c = pf_c;
     auto prefetch = [&](int tau) {                            // parameters consumed in iteration tau (this lane's step tau - clr)
         const int t = tau - cl;
         if (t >= 0 && t < n_steps) {
-            const int i = j + t * dg.S;
-            const int r = i / dg.crop_w, c = i - r * dg.crop_w;
-            const size_t off = (size_t)r * dg.Ws + c;
+            const size_t off = (size_t)pf_r * dg.Ws + pf_c;
+            pf_c += step_c; pf_r += step_r;
+            if (pf_c >= dg.crop_w) { pf_c -= dg.crop_w; ++pf_r; }
             float *dst = &stage[tau % kLaneStages][0][threadIdx.x];
 #pragma unroll
             for (int m = 0; m < kM; ++m) {
@@ -1516,8 +1521,9 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
             if (t + 1 < n_steps) consume_closed_form(d, q_lo, q_hi);                // torchac does not update after the last symbol
             yv = s_lo + g.min_val;
             {                                                                       // the sample goes straight into the planes, with the replicate padding
-                const int i = j + t * dg.S;
-                const int r = i / dg.crop_w, c = i - r * dg.crop_w;
+                const int r = dec_r, c = dec_c;
+                dec_c += step_c; dec_r += step_r;
+                if (dec_c >= dg.crop_w) { dec_c -= dg.crop_w; ++dec_r; }
                 const int16_t v = (int16_t)yv;
                 int16_t *dst = yb + (size_t)r * dg.Ws + c;
                 dst[0] = v;
