@@ -269,7 +269,7 @@ class Workload:
         else:
             first, last = rank * total, (rank + 1) * total
         self.job_images, self.shard_images = (total if wl["shard"] else total * world), last - first
-        self.n = min(wl["batch"], self.shard_images)
+        self.n = min(args.batch or wl["batch"], self.shard_images)
         self.job_batches = -(-self.shard_images // self.n)                    # batches this rank would code for the whole job
         nb = max(1, min(self.job_batches, max_batches))
         t0 = time.perf_counter()
@@ -583,6 +583,7 @@ def main():
     ap.add_argument("--workload", default="", choices=[""] + sorted(WORKLOADS),
                     help="default: c2 on one GPU, c3 (sharded) on several")
     ap.add_argument("--images", type=int, default=0, help="override the job's images per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's images per batch (= per step)")
     ap.add_argument("--cnn", type=int, default=int(os.environ.get("LLICTI_CNN", "1")), help="0 fp32 CUDA cores, 1 tcgen05")
     ap.add_argument("--decode-impl", type=int, default=0, help="0 default schedules, 1 legacy one-warp-per-chain")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
