@@ -599,6 +599,32 @@ def test_lane_decoder_reads_every_edge_image(L, skew, sub_len, monkeypatch):
     codec.close()
 
 
+@pytest.mark.parametrize("n", [2, 5])
+def test_pipelined_host_entry_points_equal_the_plain_ones(L, n, monkeypatch):
+    """llicti_encode_host / llicti_decode_host code a large batch as two half batches whose copies overlap the other half's
+    kernels: the caller must see exactly what one batch gives -- the same bytes, the same global offsets, the same images."""
+    ocfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(ocfg)
+    imgs = np.stack([O.synthetic_image(97, 131, 70 + i) for i in range(n)])
+    imgs[-1] = np.random.default_rng(3).integers(0, 256, size=imgs[-1].shape, dtype=np.uint8)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LLICTI_HOST_PIPELINE", mode)
+        codec = make_codec(L, ocfg, sd, sub_len=300, cnn_impl=L.CNN_TCGEN05)
+        bsls = codec.compress_images(imgs)
+        out[mode] = bsls
+        assert np.array_equal(codec.decompress_images(bsls), imgs), mode
+        codec.close()
+    assert len(out["0"]) == len(out["1"]) == n
+    for a, b in zip(out["0"], out["1"]):
+        assert [[bytes(x) for x in row] for row in a] == [[bytes(x) for x in row] for row in b]
+    # streams made by one path decode through the other
+    monkeypatch.setenv("LLICTI_HOST_PIPELINE", "0")
+    codec = make_codec(L, ocfg, sd, sub_len=300, cnn_impl=L.CNN_TCGEN05)
+    assert np.array_equal(codec.decompress_images(out["1"]), imgs)
+    codec.close()
+
+
 def test_lane_group_and_window_decoders_read_the_same_streams(L, monkeypatch):
     ocfg = O.OracleConfig()
     sd = O.synthetic_state_dict(ocfg)
