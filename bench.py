@@ -8,7 +8,7 @@ Workloads are BASELINE.json's configs:
 
   c0  configs[0]  llicti_A, 24 x 768x512, torchac-compatible streams (the reference's own CPU-runnable case)
   c1  configs[1]  llicti_B, the same 24 images, torchac-compatible byte-exact mode
-  c2  configs[2]  llicti_A, 100 x 2040x1356 in 2 batches of 50, interleaved-substream coder      <- default at N = 1
+  c2  configs[2]  llicti_A, 100 x 2040x1356 as one batch per step, interleaved-substream coder   <- default at N = 1
   c3  configs[3]  llicti_A, 512 x 3840x2160 sharded over the N GPUs (512 / N distinct images per rank, batches of 32)
                                                                                                 <- default at N > 1
   c4  configs[4]  llicti_A, 50,000 x 512x512 sharded over the N GPUs (batches of 512)
@@ -50,8 +50,10 @@ WORKLOADS = {
                cfg="llicti_A.json", batch=24, H=512, W=768, sub_len=0, total=24, shard=False),
     "c1": dict(desc="configs[1]: llicti_B eval_model, 24 synthetic 768x512 RGB images, torchac-compatible byte-exact mode",
                cfg="llicti_B.json", batch=24, H=512, W=768, sub_len=0, total=24, shard=False),
-    "c2": dict(desc="configs[2]: llicti_A, 100 synthetic 2040x1356 images in 2 batches of 50, interleaved-substream coder",
-               cfg="llicti_A.json", batch=50, H=1356, W=2040, sub_len=2048, total=100, shard=False),
+    # (one batch = the config's 100 images: the decoder's chain-parallel kernels fill the machine better with 2 x 17.6 k chains
+    #  per launch than with one -- 1419 against 1333 MP/s in two batches of 50, profiles/r02/bench_c2_batch100.json)
+    "c2": dict(desc="configs[2]: llicti_A, 100 synthetic 2040x1356 images (one batch per step), interleaved-substream coder",
+               cfg="llicti_A.json", batch=100, H=1356, W=2040, sub_len=2048, total=100, shard=False),
     "c3": dict(desc="configs[3]: llicti_A, 512 synthetic 3840x2160 images sharded over the GPUs, batches of 32, "
                     "interleaved-substream coder",
                cfg="llicti_A.json", batch=32, H=2160, W=3840, sub_len=2048, total=512, shard=True),
