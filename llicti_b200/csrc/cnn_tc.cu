@@ -521,18 +521,32 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         const int row = tid & (TC_M - 1), g = tid >> 7;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t hcol = tmem + lane_base + (uint32_t)(4 * NP + g * (NP / 2));
-        // layer 2 of tile `it` -> params (fp32).  Runs one step late (after the NEXT tile's first epilogue), off the chain.
-        auto store_params = [&](int it) {
-            const int tile = tile0 + it * tile_stride;
-            const int rowid = tile / tg.tpr, jcol = (tile - rowid * tg.tpr) * TC_M + row;   // this thread's position: plane row, column
+        // layer 2 of a tile -> params (fp32).  Runs one step late (after the NEXT tile's first epilogue), off the chain; the
+        // tiles are visited in order, so the tile's (image, plane row, column block) is carried along instead of divided out
+        // (two integer divisions = ~50 dependent instructions of a warp that has 5 - 6 cycles per instruction here).
+        int o_jb, o_i, o_img;
+        {
+            const int rowid = tile0 / tg.tpr;
+            o_jb = tile0 - rowid * tg.tpr;
+            o_img = rowid / tg.nrows;
+            o_i = rowid - o_img * tg.nrows;
+        }
+        const int d_rows = tile_stride / tg.tpr, d_jb = tile_stride - d_rows * tg.tpr;
+        const size_t plane_bytes = (size_t)tg.P * sizeof(float);
+        auto store_params = [&]() {
             uint32_t r[16];
             TMEM_LD_X16(tmem + lane_base + (uint32_t)(5 * NP + g * 16), r);
+            const int jcol = o_jb * TC_M + row;                    // this thread's position: plane row tg.row0 + o_i of image o_img, column jcol
+            char *o = reinterpret_cast<char *>(params + (size_t)o_img * kParamCh * tg.P + (size_t)((2 * pair + g) * 15) * tg.P +
+                                               (size_t)(tg.row0 + o_i) * tg.Ws + jcol);
+            const bool in = jcol < tg.Ws;
+            o_jb += d_jb; o_i += d_rows;                           // the next tile of this CTA
+            if (o_jb >= tg.tpr) { o_jb -= tg.tpr; ++o_i; }
+            while (o_i >= tg.nrows) { o_i -= tg.nrows; ++o_img; }
             tmem_ld_wait();
-            if (jcol < tg.Ws) {
-                const int img = rowid / tg.nrows, p = (tg.row0 + rowid - img * tg.nrows) * tg.Ws + jcol;
-                float *o = params + (size_t)img * kParamCh * tg.P + (size_t)((2 * pair + g) * 15) * tg.P + p;
+            if (in) {
 #pragma unroll
-                for (int c = 0; c < 15; ++c) o[(size_t)c * tg.P] = __uint_as_float(r[c]);
+                for (int c = 0; c < 15; ++c) *reinterpret_cast<float *>(o + c * plane_bytes) = __uint_as_float(r[c]);
             }
         };
         for (int it = 0; it < my_tiles; ++it) {
@@ -545,7 +559,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             epilogue_hidden<NP, F16>(dbase + (uint32_t)(g * NP), hcol);
             tc_fence_before();
             mbar_arrive(bar(B_H0FULL + g));
-            if (it > 0) store_params(it - 1);       // (D2 of the previous tile: its MMAs completed before the wait above)
+            if (it > 0) store_params();       // (D2 of the previous tile: its MMAs completed before the wait above)
             // ---- layer 1 -> H1 (over H0: the layer-1 MMAs that read it are complete) ----
             mbar_wait(bar(B_D1FULL + g), it & 1);
             tc_fence_after();
@@ -556,7 +570,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         if (my_tiles > 0) {
             mbar_wait(bar(B_D2FULL + g), (my_tiles - 1) & 1);
             tc_fence_after();
-            store_params(my_tiles - 1);
+            store_params();
         }
         tc_fence_before();
     }

@@ -722,6 +722,26 @@ selftest_fdiv_kernel(uint64_t seed, int per_thread, NumericsProfile np, unsigned
         const float x = __fsub_rn(pt, c.mu[0]);
         const float a = fdiv_hoisted(x, c.sigma[0], c.rinv[0], 1), b = __fdiv_rn(x, c.sigma[0]);
         bad += __float_as_uint(a) != __float_as_uint(b);
+        // the weight normalisation of gmm_prepare: five weights in [1e-6, 2^9] with random mantissas (every 8th hard), against
+        // div.rn.f32 by the same denominator
+        {
+            const uint64_t r2 = splitmix64(s), r3 = splitmix64(s);
+            GmmChannel cw;
+            float wraw[kM];
+#pragma unroll
+            for (int m = 0; m < kM; ++m) {
+                const uint64_t rr = m < 3 ? (r2 >> (21 * m)) : (r3 >> (21 * (m - 3)));
+                const int ew = (int)(rr % 29) - 20;                                   // 2^-20 .. 2^8
+                uint32_t mw = (uint32_t)(rr >> 5) & 0x7FFFFFu;
+                if (((rr >> 3) & 7) == 0) mw = (rr & 4) ? 0x7FFFFFu - (uint32_t)(rr & 3) : (uint32_t)(rr & 3);
+                wraw[m] = fmaxf(__uint_as_float(((uint32_t)(ew + 127) << 23) | mw), 1e-6f);
+                cw.w[m] = wraw[m]; cw.sigma[m] = 0.01f; cw.mu[m] = 0.f;
+            }
+            const float den = __fadd_rn(sum5(wraw, np), 1e-9f);
+            gmm_prepare(cw, np);
+#pragma unroll
+            for (int m = 0; m < kM; ++m) bad += __float_as_uint(cw.w[m]) != __float_as_uint(__fdiv_rn(wraw[m], den));
+        }
     }
     if (bad) atomicAdd(mismatches, bad);
 }
