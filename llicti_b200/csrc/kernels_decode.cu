@@ -1459,12 +1459,23 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
             // ---- guess: floor of the root of q~(x) = target, by Newton steps kept inside a bracket [a, b) -------------
             int guess = 0;
             if (last >= 2) {
-                float mean = 0.f;
-#pragma unroll
-                for (int m = 0; m < kM; ++m) mean = fmaf(ch.w[m], ch.mu[m], mean);
                 // torchac's search key ((value - low + 1) 2^16 - 1) / span, in fp32 (a guess is all it feeds)
                 const float tf = __fdividef(((float)(value32 - low) + 1.0f) * 65536.0f, (float)sm1 + 1.0f);
-                int a = 0, b = last, k = __float2int_rn(mean * 255.0f) - g.min_val;
+                // first probe: the target's quantile of the Gaussian with the mixture's mean and variance, through the same
+                // logistic stand-in -- y = logit(u) / 2c, z from z + 0.044715 z^3 = y by one Newton step off z0 = y / (1 + 0.044715 y^2)
+                // (the mixture mean alone is the right start only for targets near one half: one iteration more on average)
+                float mean = 0.f, m2 = 0.f;
+#pragma unroll
+                for (int m = 0; m < kM; ++m) {
+                    mean = fmaf(ch.w[m], ch.mu[m], mean);
+                    m2 = fmaf(ch.w[m], fmaf(ch.sigma[m], ch.sigma[m], ch.mu[m] * ch.mu[m]), m2);
+                }
+                const float sd = sqrtf(fmaxf(fmaf(-mean, mean, m2), 1e-12f));
+                const float u = fminf(fmaxf(tf * (1.0f / 65536.0f), 1e-6f), 1.0f - 1e-6f);
+                const float y = (__log2f(u) - __log2f(1.0f - u)) * 0.43436f;                     // ln 2 / (2 c)
+                const float z0 = __fdividef(y, fmaf(0.044715f * y, y, 1.0f));
+                const float zq = z0 - __fdividef(fmaf(0.044715f * z0 * z0, z0, z0) - y, fmaf(0.134145f * z0, z0, 1.0f));
+                int a = 0, b = last, k = __float2int_rd(fmaf(zq, sd, mean) * 255.0f + 0.5f) - g.min_val;
 #pragma unroll 1
                 for (int it = 0;; ++it) {
                     if (b - a <= 1) { guess = a; break; }

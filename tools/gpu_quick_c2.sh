@@ -8,6 +8,6 @@ echo "bench rc=$?"; python - <<PY
 import json
 try:
     d=json.loads(open('gpurun_out/q_c2.json').read().strip().splitlines()[-1])
-    print('value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'enc', round(d['encode_mpps']), 'dec', round(d['decode_mpps']), {k:round(v,2) for k,v in d['kernel_ms_per_step'].items()}, 'cnn TF', round(d['cnn_tflops'],1))
+    print('value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'enc', round(d['encode_mpps']), 'dec', round(d['decode_mpps']), {k:round(v,2) for k,v in d['kernel_ms_per_step'].items()}, 'cnn TF', round(d['cnn_tflops'],1), 'newton', d['decode_stats_per_step']['consumer_polls'], 'extra', d['decode_stats_per_step']['slow_path_symbols'])
 except Exception as e: print('failed', e)
 PY
