@@ -50,7 +50,7 @@
 namespace llicti {
 
 constexpr int TC_M = 128;            // positions per tile = UMMA_M
-constexpr int TC_THREADS = 544;      // 8 epilogue warps (4 per sub-network), 8 im2col warps, 1 MMA warp
+constexpr int TC_THREADS = 448;      // 8 epilogue warps (4 per sub-network), 5 producer warps, 1 MMA warp: 4 warps per scheduler at most (128 registers)
 constexpr int TC_TMEM_COLS = 512;
 // TMEM columns: tile slot s holds D0/D1 of both sub-networks at [s * 2NP, (s + 1) * 2NP); hidden activations of sub-network g
 // at 4NP + g * NP/2 (bf16 pairs); D2 of sub-network g at 5NP + 16 g.
@@ -216,27 +216,16 @@ __device__ __forceinline__ uint32_t relu_pair(uint32_t lo, uint32_t hi) {
     else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
     return w;
 }
-// (The third load of NP = 96 is issued once the first 32 columns are converted: at most 80 accumulator / operand registers
-// are live, which keeps the kernel inside the 96 registers a 17-warp CTA leaves per thread.)
 template <int NP, bool F16>
 __device__ __forceinline__ void epilogue_hidden(uint32_t d_addr, uint32_t h_addr) {
-    uint32_t ra[32], rb[32], w[32];
-    TMEM_LD_X32(d_addr, ra);
-    TMEM_LD_X32(d_addr + 32u, rb);
+    uint32_t r[NP], w[NP / 2];
+#pragma unroll
+    for (int c = 0; c < NP / 32; ++c) TMEM_LD_X32(d_addr + (uint32_t)(c * 32), (r + c * 32));
     tmem_ld_wait();
 #pragma unroll
-    for (int e = 0; e < 16; ++e) w[e] = relu_pair<F16>(ra[2 * e], ra[2 * e + 1]);
-    if (NP == 96) TMEM_LD_X32(d_addr + 64u, ra);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) w[16 + e] = relu_pair<F16>(rb[2 * e], rb[2 * e + 1]);
+    for (int e = 0; e < NP / 2; ++e) w[e] = relu_pair<F16>(r[2 * e], r[2 * e + 1]);
     TMEM_ST_X32(h_addr, w);
-    if (NP == 96) {
-        tmem_ld_wait();
-        uint32_t w2[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) w2[e] = relu_pair<F16>(ra[2 * e], ra[2 * e + 1]);
-        TMEM_ST_X16(h_addr + 32u, w2);
-    }
+    if (NP == 96) TMEM_ST_X16(h_addr + 32u, (w + 32));
     tmem_st_wait();
 }
 
@@ -307,7 +296,7 @@ __device__ __forceinline__ uint32_t operand_pair(uint32_t u0, uint32_t u1) {
 // Producer thread x < TC_TPX owns staged pixel x of every chunk: 8 NCH two-byte loads with compile-time plane / row
 // offsets (three instructions each), conversion, NCH 16-byte stores.  The raw samples of the NEXT tile are fetched into
 // registers before this tile's are converted and stored, so the global-memory latency is off the tile-to-tile path.
-constexpr int TC_PRODUCERS = 256;      // producer threads (the first TC_TPX of them stage; all of them keep the barrier phases)
+constexpr int TC_PRODUCERS = 160;      // producer threads (the first TC_TPX of them stage; all of them keep the barrier phases)
 
 template <int BAND>
 __device__ __forceinline__ void load_items(const int16_t *__restrict__ planes, const TcGeom &tg, int img, int i, int j0, int x,
@@ -403,7 +392,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 8 && warp < 16) {
+    if (warp >= 8 && warp < 13) {
         // ================= producers: stage the receptive field of every tile, pixel-major =================
         const int pt = tid - 256;
         const bool stager = pt < TC_TPX;
@@ -432,7 +421,7 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
                 load_items<BAND>(planes, tg, img, i, j0, pt, raw);
             }
         }
-    } else if (warp == 16) {
+    } else if (warp == 13) {
         // ================= MMA issuer =================
         // The whole warp runs this code (so every address below is warp-uniform and lives in uniform registers); one elected
         // lane issues the TMA copy, the MMAs and the commits.  Descriptors are a 64-bit base plus a compile-time multiple of
