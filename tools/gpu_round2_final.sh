@@ -15,18 +15,18 @@ try:
 except Exception as e: print('failed', e)
 PY
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_arm.json 2> gpurun_out/bench_reference_arm.err; echo "reference arm rc=$?"; tail -c 600 gpurun_out/bench_reference_arm.json
-timeout 300 python bench.py --batch 100 --steps 3 --warmup 2 --no-cpu --no-per-config > gpurun_out/bench_c2_batch100.json 2> gpurun_out/bench_c2_batch100.err; echo "batch100 rc=$?"
+timeout 300 python bench.py --batch 50 --steps 3 --warmup 2 --no-cpu --no-per-config > gpurun_out/bench_c2_batch50.json 2> gpurun_out/bench_c2_batch50.err; echo "batch50 rc=$?"
 python - <<PY
 import json
 try:
-    d=json.loads(open('gpurun_out/bench_c2_batch100.json').read().strip().splitlines()[-1])
-    print('batch100 value', round(d['value'],1), 'enc', round(d['encode_mpps']), 'dec', round(d['decode_mpps']), {k:round(v,2) for k,v in d['kernel_ms_per_step'].items()})
+    d=json.loads(open('gpurun_out/bench_c2_batch50.json').read().strip().splitlines()[-1])
+    print('batch50 value', round(d['value'],1), 'enc', round(d['encode_mpps']), 'dec', round(d['decode_mpps']), {k:round(v,2) for k,v in d['kernel_ms_per_step'].items()})
 except Exception as e: print('failed', e)
 PY
 C2="python bench.py --workload c2 --images 8 --steps 1 --warmup 1 --no-cpu --no-per-config"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/${TAG}_launches_c2_8img.csv $C2 > gpurun_out/ncu_launches.log 2>&1; echo "launch list rc=$?"
 NCU="ncu --set full --clock-control none --import-source on"
 $NCU --kernel-name-base demangled -k "regex:cnn_tc_kernel<\(int\)2" -s 4 -c 1 -o gpurun_out/${TAG}_cnn_c2 $C2 > gpurun_out/ncu_a.log 2>&1; echo "ncu cnn rc=$?"
-$NCU -k regex:decode_band_lane -s 6 -c 1 -o gpurun_out/${TAG}_lane_c2 $C2 > gpurun_out/ncu_b.log 2>&1; echo "ncu lane rc=$?"
+$NCU -k regex:decode_band_lane -s 3 -c 1 -o gpurun_out/${TAG}_lane_c2 $C2 > gpurun_out/ncu_b.log 2>&1; echo "ncu lane rc=$?"
 $NCU -k regex:band_bounds -s 12 -c 1 -o gpurun_out/${TAG}_bounds_c2 $C2 > gpurun_out/ncu_c.log 2>&1; echo "ncu bounds rc=$?"
 ls -la gpurun_out/${TAG}_*
