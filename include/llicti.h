@@ -178,7 +178,10 @@ LLICTI_API int llicti_ac_decode_table(llicti_ctx *ctx, const int16_t *table_dev,
  * The header's remaining pieces (dims, pad word, raw x00) are functions of the input and
  * the geometry and are assembled by the host wrapper.  *_host copies in and out on
  * `stream` and returns after the stream is idle; *_dev takes device pointers and is
- * asynchronous (stream_off / minmax then are device pointers too). */
+ * asynchronous (stream_off / minmax then are device pointers too).
+ * llicti_encode_host codes a large batch of the substream container (>= 16 images, >= 64 MB of pixels) in two to four
+ * parts on two copy streams of its own, so that one part's host<->device copies run while another part is coded; the
+ * caller sees what one batch gives (contiguous bytes, global offsets).  LLICTI_HOST_PIPELINE=0 turns that off. */
 LLICTI_API int llicti_encode_host(llicti_ctx *ctx, const uint8_t *rgb, int n, int H, int W, uint8_t *out,
                        size_t out_cap, uint64_t *stream_off, int16_t *minmax, void *stream);
 LLICTI_API int llicti_encode_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, uint8_t *out_dev,

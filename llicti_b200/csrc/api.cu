@@ -343,7 +343,7 @@ int llicti_reserve(llicti_ctx *ctx, int max_images, int H, int W) {
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_sublen, n * (size_t)g.substreams * sizeof(uint32_t)));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_suboff, n * (size_t)g.substreams * sizeof(uint64_t)));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_stream_bytes, (n * p.n_streams + 1) * sizeof(uint64_t)));
-    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_stream_off, (n * p.n_streams + 2) * sizeof(uint64_t)));   // + 1: the two half batches of the pipelined host path each end with a total
+    LLICTI_CUDA(cudaMalloc((void **)&ctx->d_stream_off, (n * p.n_streams + 4) * sizeof(uint64_t)));   // + 3: every part of the pipelined host path ends with a total of its own
     ctx->blob_cap = n * (size_t)g.max_stream_bytes;
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_blob, ctx->blob_cap));
     LLICTI_CUDA(cudaMalloc((void **)&ctx->d_x00, n * 3 * (size_t)g.Hs[S - 1] * g.Ws[S - 1]));
@@ -554,49 +554,61 @@ static int encode_host_pipelined(llicti_ctx *ctx, const uint8_t *rgb, int n, int
     int rc = ensure_copy_streams(ctx);
     if (rc) return rc;
     cudaStream_t cin = (cudaStream_t)ctx->copy_in, cout = (cudaStream_t)ctx->copy_out;
-    cudaEvent_t e_start = (cudaEvent_t)ctx->ev_pipe[0], eh0 = (cudaEvent_t)ctx->ev_pipe[1], eh1 = (cudaEvent_t)ctx->ev_pipe[2],
-                ec0 = (cudaEvent_t)ctx->ev_pipe[3], ec1 = (cudaEvent_t)ctx->ev_pipe[4];
-    const int ns = ctx->plan.n_streams, n0 = (n + 1) / 2, n1 = n - n0;
-    const size_t img = (size_t)3 * H * W, cap0 = (size_t)n0 * (size_t)ctx->plan.g.max_stream_bytes;
-    uint64_t *off1_dev = ctx->d_stream_off + ((size_t)n0 * ns + 1);
+    constexpr int kMaxParts = 4;
+    cudaEvent_t e_start = (cudaEvent_t)ctx->ev_pipe[0];
+    cudaEvent_t eh[kMaxParts], ec[kMaxParts];
+    for (int k = 0; k < kMaxParts; ++k) { eh[k] = (cudaEvent_t)ctx->ev_pipe[1 + k]; ec[k] = (cudaEvent_t)ctx->ev_pipe[5 + k]; }
+    // parts of at least 16 images (the kernels of a part should still fill the machine), at most four
+    const int parts = n >= 64 ? 4 : n >= 48 ? 3 : 2;
+    const int ns = ctx->plan.n_streams;
+    const size_t img = (size_t)3 * H * W, cap_img = (size_t)ctx->plan.g.max_stream_bytes;
+    int first[kMaxParts + 1];
+    for (int k = 0; k <= parts; ++k) first[k] = (int)((long long)n * k / parts);
+    // part k's offsets live at d_stream_off + first[k] * ns + k (each part ends with its own total: one extra entry per part)
     LLICTI_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int32_t), st));
     LLICTI_CUDA(cudaEventRecord(e_start, st));                       // the copy streams start after whatever precedes on st
     LLICTI_CUDA(cudaStreamWaitEvent(cin, e_start, 0));
     LLICTI_CUDA(cudaStreamWaitEvent(cout, e_start, 0));
-    LLICTI_CUDA(cudaMemcpyAsync(ctx->d_rgb, rgb, n0 * img, cudaMemcpyHostToDevice, cin));
-    LLICTI_CUDA(cudaEventRecord(eh0, cin));
-    LLICTI_CUDA(cudaMemcpyAsync(ctx->d_rgb + n0 * img, rgb + n0 * img, n1 * img, cudaMemcpyHostToDevice, cin));
-    LLICTI_CUDA(cudaEventRecord(eh1, cin));
-    LLICTI_CUDA(cudaStreamWaitEvent(st, eh0, 0));
-    if ((rc = llicti_encode_dev(ctx, ctx->d_rgb, n0, H, W, ctx->d_blob, cap0, ctx->d_stream_off, ctx->d_minmax16, st))) return rc;
-    LLICTI_CUDA(cudaEventRecord(ec0, st));
-    LLICTI_CUDA(cudaStreamWaitEvent(cout, ec0, 0));
-    LLICTI_CUDA(cudaMemcpyAsync(stream_off, ctx->d_stream_off, ((size_t)n0 * ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, cout));
-    LLICTI_CUDA(cudaMemcpyAsync(minmax, ctx->d_minmax16, (size_t)n0 * 6 * sizeof(int16_t), cudaMemcpyDeviceToHost, cout));
-    LLICTI_CUDA(cudaStreamWaitEvent(st, eh1, 0));
-    if ((rc = llicti_encode_dev(ctx, ctx->d_rgb + n0 * img, n1, H, W, ctx->d_blob + cap0, ctx->blob_cap - cap0, off1_dev,
-                                ctx->d_minmax16 + (size_t)n0 * 6, st)))
-        return rc;
-    LLICTI_CUDA(cudaEventRecord(ec1, st));
-    LLICTI_CUDA(cudaStreamSynchronize(cout));                        // the first half's offsets are here: its bytes can leave
-    const uint64_t total0 = stream_off[(size_t)n0 * ns];
-    const bool fits0 = total0 <= out_cap;
-    if (fits0) LLICTI_CUDA(cudaMemcpyAsync(out, ctx->d_blob, total0, cudaMemcpyDeviceToHost, cout));
-    LLICTI_CUDA(cudaStreamWaitEvent(cout, ec1, 0));
-    // the second half's offsets start at 0 again: its first entry is dropped (it coincides with total0), the rest is rebased below
-    LLICTI_CUDA(cudaMemcpyAsync(stream_off + (size_t)n0 * ns + 1, off1_dev + 1, (size_t)n1 * ns * sizeof(uint64_t), cudaMemcpyDeviceToHost, cout));
-    LLICTI_CUDA(cudaMemcpyAsync(minmax + (size_t)n0 * 6, ctx->d_minmax16 + (size_t)n0 * 6, (size_t)n1 * 6 * sizeof(int16_t), cudaMemcpyDeviceToHost, cout));
+    for (int k = 0; k < parts; ++k) {
+        LLICTI_CUDA(cudaMemcpyAsync(ctx->d_rgb + first[k] * img, rgb + first[k] * img, (size_t)(first[k + 1] - first[k]) * img,
+                                    cudaMemcpyHostToDevice, cin));
+        LLICTI_CUDA(cudaEventRecord(eh[k], cin));
+    }
+    uint64_t total = 0;                                              // bytes of the parts whose offsets have arrived
+    bool fits = true;
+    for (int k = 0; k <= parts; ++k) {
+        if (k < parts) {                                             // code part k (its input has arrived) ...
+            const int n_k = first[k + 1] - first[k];
+            LLICTI_CUDA(cudaStreamWaitEvent(st, eh[k], 0));
+            if ((rc = llicti_encode_dev(ctx, ctx->d_rgb + first[k] * img, n_k, H, W, ctx->d_blob + first[k] * cap_img, n_k * cap_img,
+                                        ctx->d_stream_off + ((size_t)first[k] * ns + k), ctx->d_minmax16 + (size_t)first[k] * 6, st)))
+                return rc;
+            LLICTI_CUDA(cudaEventRecord(ec[k], st));
+        }
+        if (k > 0) {                                                 // ... while part k - 1 leaves: offsets first (the host needs its total)
+            const int j = k - 1, n_j = first[j + 1] - first[j];
+            uint64_t *dst = stream_off + (size_t)first[j] * ns;      // global offsets: part j's entry 0 coincides with the total so far
+            LLICTI_CUDA(cudaStreamWaitEvent(cout, ec[j], 0));
+            LLICTI_CUDA(cudaMemcpyAsync(dst + 1, ctx->d_stream_off + ((size_t)first[j] * ns + j) + 1, (size_t)n_j * ns * sizeof(uint64_t),
+                                        cudaMemcpyDeviceToHost, cout));
+            LLICTI_CUDA(cudaMemcpyAsync(minmax + (size_t)first[j] * 6, ctx->d_minmax16 + (size_t)first[j] * 6, (size_t)n_j * 6 * sizeof(int16_t),
+                                        cudaMemcpyDeviceToHost, cout));
+            LLICTI_CUDA(cudaStreamSynchronize(cout));
+            dst[0] = total;
+            const uint64_t total_j = dst[(size_t)n_j * ns];
+            for (size_t i = 1; i <= (size_t)n_j * ns; ++i) dst[i] += total;
+            fits = fits && total + total_j <= out_cap;
+            if (fits) LLICTI_CUDA(cudaMemcpyAsync(out + total, ctx->d_blob + first[j] * cap_img, total_j, cudaMemcpyDeviceToHost, cout));
+            total += total_j;
+        }
+    }
     rc = read_status(ctx, st);
     LLICTI_CUDA(cudaStreamSynchronize(cout));
     if (rc) return rc;
-    const uint64_t total1 = stream_off[(size_t)n * ns];
-    for (size_t i = (size_t)n0 * ns + 1; i <= (size_t)n * ns; ++i) stream_off[i] += total0;
-    if (!fits0 || total0 + total1 > out_cap) {
-        set_error("output needs %llu bytes, capacity is %llu", (unsigned long long)(total0 + total1), (unsigned long long)out_cap);
+    if (!fits) {
+        set_error("output needs %llu bytes, capacity is %llu", (unsigned long long)total, (unsigned long long)out_cap);
         return LLICTI_E_NOMEM;
     }
-    LLICTI_CUDA(cudaMemcpyAsync(out + total0, ctx->d_blob + cap0, total1, cudaMemcpyDeviceToHost, cout));
-    LLICTI_CUDA(cudaStreamSynchronize(cout));
     return LLICTI_OK;
 }
 
@@ -613,7 +625,7 @@ static int decode_host_pipelined(llicti_ctx *ctx, const uint8_t *blob, const uin
     if (rc) return rc;
     cudaStream_t cin = (cudaStream_t)ctx->copy_in, cout = (cudaStream_t)ctx->copy_out;
     cudaEvent_t e_start = (cudaEvent_t)ctx->ev_pipe[0], eh0 = (cudaEvent_t)ctx->ev_pipe[1], eh1 = (cudaEvent_t)ctx->ev_pipe[2],
-                ec0 = (cudaEvent_t)ctx->ev_pipe[3], ec1 = (cudaEvent_t)ctx->ev_pipe[4];
+                ec0 = (cudaEvent_t)ctx->ev_pipe[5], ec1 = (cudaEvent_t)ctx->ev_pipe[6];
     std::vector<uint64_t> off1((size_t)n1 * ns + 1);                 // the second half's offsets, relative to its own bytes
     for (size_t i = 0; i < off1.size(); ++i) off1[i] = stream_off[(size_t)n0 * ns + i] - total0;
     uint64_t *off1_dev = ctx->d_stream_off + ((size_t)n0 * ns + 1);

@@ -125,7 +125,7 @@ struct llicti_ctx {
     int64_t sym_cap = 0;
     void *d_chain_state_raw = nullptr;
     void *side_stream = nullptr, *ev_fork = nullptr, *ev_join = nullptr;   // second stream of the wavefront decode (consumer kernel)
-    void *copy_in = nullptr, *copy_out = nullptr, *ev_pipe[5] = {};        // host-buffer entry points: copies of one half batch overlap the other half's kernels (api.cu)
+    void *copy_in = nullptr, *copy_out = nullptr, *ev_pipe[9] = {};        // host-buffer entry points: copies of one part of a batch overlap the other parts' kernels (api.cu)
     bool no_coresidency = false;       // a decode gave up waiting (LLICTI_E_TIMEOUT): only schedules without kernel-to-kernel hand-overs from now on
     bool concurrent_kernels = false;   // two kernels on two streams really overlap (false under kernel-serialising profilers)
     bool wave_ws = false;              // workspace holds three bands' worth of decode buffers (wavefront schedule)

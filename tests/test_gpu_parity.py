@@ -599,13 +599,15 @@ def test_lane_decoder_reads_every_edge_image(L, skew, sub_len, monkeypatch):
     codec.close()
 
 
-@pytest.mark.parametrize("n", [2, 5])
+@pytest.mark.parametrize("n", [2, 5, 50, 67])
 def test_pipelined_host_entry_points_equal_the_plain_ones(L, n, monkeypatch):
-    """llicti_encode_host / llicti_decode_host code a large batch as two half batches whose copies overlap the other half's
-    kernels: the caller must see exactly what one batch gives -- the same bytes, the same global offsets, the same images."""
+    """llicti_encode_host codes a large batch in two to four parts whose copies overlap the other parts' kernels (and
+    llicti_decode_host, when forced, in two halves): the caller must see exactly what one batch gives -- the same bytes,
+    the same global offsets, the same images."""
     ocfg = O.OracleConfig()
     sd = O.synthetic_state_dict(ocfg)
-    imgs = np.stack([O.synthetic_image(97, 131, 70 + i) for i in range(n)])
+    H, W = (97, 131) if n < 16 else (41, 56)
+    imgs = np.stack([O.synthetic_image(H, W, 70 + i) for i in range(n)])
     imgs[-1] = np.random.default_rng(3).integers(0, 256, size=imgs[-1].shape, dtype=np.uint8)
     out = {}
     for mode in ("0", "1"):
