@@ -212,7 +212,20 @@ def cpu_baseline_leg(workload, steps=4):
 BOUND = {"cnn": "tensor"}
 
 
-def algorithmic_work(geom, chs, n, blob_bytes):
+def windowed_bands(geom, n, sub_len):
+    """Which (scale, band) pairs decode through the windowed schedules (window rows through HBM, then the chain kernel): all
+    of them for torchac-compatible streams; for the substream container the bands with too few chains for the lane decoder
+    (the library's rule, kernels_decode.cu: ceil(n * S / 10) warps of chains >= LLICTI_LANE_MIN_WARPS, default 148)."""
+    S = geom.num_scales
+    if sub_len <= 0:
+        return {(s, b) for s in range(S) for b in range(3)}
+    min_warps = int(os.environ.get("LLICTI_LANE_MIN_WARPS", "148"))
+    lanes = os.environ.get("LLICTI_DECODE_LANES", "1") != "0"
+    return {(s, b) for s in range(S) for b in range(3)
+            if lanes and -(-n * geom.num_sub[s][b] // 10) < min_warps}
+
+
+def algorithmic_work(geom, chs, n, blob_bytes, sub_len):
     """Per-step ALGORITHMIC bytes / flops of each kernel class for n images:
     what the stage has to read and write by definition, not what a particular schedule moves internally."""
     S = geom.num_scales
@@ -220,26 +233,29 @@ def algorithmic_work(geom, chs, n, blob_bytes):
     sym_band = [[geom.crop_h[s][b] * geom.crop_w[s][b] for b in range(3)] for s in range(S)]
     macs = sum(pos[s] * sum(MAC_PER_POS[chs]) for s in range(S))
     coded_pos = sum(sum(sym_band[s]) for s in range(S))
+    win = windowed_bands(geom, n, sub_len)
+    win_pos = sum(sym_band[s][b] for (s, b) in win)
     return {
         "split": n * (3 * geom.H * geom.W + 2 * 12 * sum(pos)),                 # u8 in, int16 planes out
         "cnn_flops": 2 * n * 2.0 * macs,                                        # the CNN runs in both directions
         "cnn": 2 * n * sum(pos[s] * (2 * 3 * (b + 1) + 240) for s in range(S) for b in range(3)),
         "bounds": n * coded_pos * (240 + 6 + 12),                               # 258 B per (position, band)
         "encode": n * geom.symbols * 4 + blob_bytes,                            # 4 B bounds in + bytes out
-        "window": n * coded_pos * (240 + 6),                                    # params + symbols in (the rows it writes are internal)
-        "decode": n * coded_pos * (240 + 6) + blob_bytes,                       # params + stream bytes in, symbols out
+        # decode side, 246 B per (position, band) = params + symbols, plus the stream bytes: the windowed bands' share belongs
+        # to the window kernel (the rows it writes and the chain kernel reads back are internal), the rest to the class that
+        # decodes straight from the params (lane / group decoder)
+        # (torchac-compatible streams: the wavefront / piped schedules produce and consume inside ONE kernel class, "decode")
+        "window": n * win_pos * (240 + 6),
+        "decode": n * (coded_pos if sub_len <= 0 else coded_pos - win_pos) * (240 + 6) + blob_bytes,
         "merge": n * (2 * 12 * sum(pos) + 3 * geom.H * geom.W),
     }
 
 
-def internal_traffic(geom, n, prof):
+def internal_traffic(geom, n, sub_len):
     """Bytes the windowed decode schedules move through HBM on top of the algorithmic ones: 3 x 64 B of window rows per
     (position, band) written by the producers and read back by the chains."""
-    S = geom.num_scales
-    coded_pos = sum(geom.crop_h[s][b] * geom.crop_w[s][b] for s in range(S) for b in range(3))
-    windows = prof.get("window", (0.0, 0))[1] > 0 or prof.get("decode", (0.0, 0))[1] > 0
-    return {"window_rows_written": n * coded_pos * 3 * 64 if windows else 0,
-            "window_rows_read": n * coded_pos * 3 * 64 if windows else 0}
+    win_pos = sum(geom.crop_h[s][b] * geom.crop_w[s][b] for (s, b) in windowed_bands(geom, n, sub_len))
+    return {"window_rows_written": n * win_pos * 3 * 64, "window_rows_read": n * win_pos * 3 * 64}
 
 
 class Workload:
@@ -459,7 +475,7 @@ def rooflines(w, dev_r, args, steps):
         peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops_sustained": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
                  "src": "measured (MEASURED_PEAKS.json; sustained bf16 figure: the kernels are timed inside a long step)"}
     prof, K = dev_r["prof"], steps
-    work_step = algorithmic_work(w.geom, w.ccfg.chs, w.n, dev_r["blob_bytes"])
+    work_step = algorithmic_work(w.geom, w.ccfg.chs, w.n, dev_r["blob_bytes"], w.wl["sub_len"])
     kernel_ms = {k: v[0] / K for k, v in prof.items()}
     step_ms = (dev_r["p_enc"] + dev_r["p_dec"]) / K
     traffic_db = {}
@@ -494,7 +510,7 @@ def rooflines(w, dev_r, args, steps):
     allr = {c: {k: v for k, v in r.items() if k in ("bound", "achieved", "peak", "unit", "frac", "share_of_step")}
             for c in kernel_ms if kernel_ms[c] > 0 for r in [roofline_of(c)] if r}
     cnn_tflops = work_step["cnn_flops"] / (max(kernel_ms["cnn"], 1e-9) * 1e-3) / 1e12
-    return roof, allr, kernel_ms, cnn_tflops, internal_traffic(w.geom, w.n, prof)
+    return roof, allr, kernel_ms, cnn_tflops, internal_traffic(w.geom, w.n, w.wl["sub_len"])
 
 
 def run_b200(args, rank, world, local_rank):
