@@ -62,7 +62,9 @@ class BaseAgent:
                 self.eval_model()
             elif mode == "model_size":
                 self.model_size_estimation(print_params=True)
-            elif mode in ("train", "debug", "validate", "test", "flops_est"):
+            elif mode == "validate":
+                self.validate()
+            elif mode in ("train", "debug", "test", "flops_est"):
                 raise NotImplementedError(f"mode '{mode}' is outside the B200 compress/decompress path")
             else:
                 raise NameError("'" + mode + "' is not a valid training mode.")
@@ -122,6 +124,30 @@ class LLICTIAgent(BaseAgent):
             "{}{}={}".format(k, "[tcgen05]" if k == "cnn" and cc.cnn_impl == 1 else "", int(v[1])) for k, v in prof.items() if v[1]))
         if self.test_logger.rate:
             self.test_logger.display(lr=0.0, typ="te")
+
+    @torch.no_grad()
+    def validate(self):
+        """The reference's validate() (agents/llicti_agent.py:85-103) without its learning-rate scheduler: the rate
+        estimate of forward() (`llicti_forward_dev`) over the validation crops, logged as the 'va' table."""
+        import torch.nn.functional as F
+        from .image_dl import ValidImageLoader
+        from .rate import TrainRLossList
+        self.model.eval()
+        valid_data = getattr(self.config, "valid_data", None) or self.config.test_data      # (the shipped configs carry no training keys)
+        loader = ValidImageLoader(valid_data, getattr(self.config, "val_patch_size", 0), getattr(self.config, "val_batch_size", 1))
+        train_loss, valid_logger = TrainRLossList(), RateLogger()
+        B = 2 ** (max(self.config.dwtlevels) + 1)
+        for x in loader:
+            x = x.to(self.device)
+            h, w = x.size(2), x.size(3)
+            x = F.pad(x, (0, (w + B - 1) // B * B - w, 0, (h + B - 1) // B * B - h), mode="replicate")   # _pad_img (:105-113)
+            _, rate1_list = train_loss.forward(torch.numel(x), self.model(x))
+            valid_logger(rate1_list)
+        if not valid_logger.rate:
+            self.logger.info(" validate: no images in {}".format(valid_data))
+            return None
+        valid_rate_loss, valid_rate2_loss = valid_logger.display(lr=0.0, typ="va")
+        return valid_rate_loss + valid_rate2_loss
 
     def model_size_estimation(self, print_params=False):
         psz = sum(p.nelement() * p.element_size() for p in self.model.parameters())

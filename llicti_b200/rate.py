@@ -20,6 +20,22 @@ class CompressionRLossList:
     __call__ = forward
 
 
+class TrainRLossList:
+    """Rate estimate from the self-informations of forward() (graphs/losses/rate_dist.py:97-104): per scale the nine
+    sums over (batch, rows, columns) / numel * 3 bits per pixel, and their total.  Inference only (validate())."""
+
+    def __init__(self):
+        self.rate1 = 0.0
+        self.rate1list = []
+
+    def forward(self, numel_x, sinfoslist):
+        self.rate1list = [[float(v) / numel_x * 3 for v in s.double().sum(dim=(0, 2, 3)).tolist()] for s in sinfoslist]
+        self.rate1 = float(sum(sum(r) for r in self.rate1list))
+        return self.rate1, self.rate1list
+
+    __call__ = forward
+
+
 class RateLogger:
     """Accumulates per-image rate tables and prints their mean (header row + one row per
     scale, nine columns each = 3 bands x (Y, Co, Cg))."""

@@ -48,6 +48,44 @@ def test_main_eval_model(tmp_path, cfg_name, ocfg):
     assert (ckdir / "checkpoint.pth.tar").exists()
 
 
+def test_main_validate_mode(tmp_path):
+    """`mode: validate` (the reference's validate(): forward() rate estimate over centre crops of the validation images) runs
+    through the entry point and logs the 'va' table; its total is the oracle's rate estimate of the same crops."""
+    from PIL import Image
+    ocfg = O.OracleConfig()
+    cfg = json.load(open(os.path.join(ROOT, "configs", "llicti_A.json")))
+    data = tmp_path / "valid"
+    data.mkdir()
+    imgs = [O.synthetic_image(80, 112, 20 + i) for i in range(3)]
+    for i, im in enumerate(imgs):
+        Image.fromarray(im.transpose(1, 2, 0)).save(data / f"v{i}.png")
+    cfg.update({"mode": "validate", "valid_data": str(data), "val_patch_size": 64, "val_batch_size": 2, "test_data": str(data)})
+    cfg_path = tmp_path / "cfg.json"
+    cfg_path.write_text(json.dumps(cfg))
+    exp = os.path.join("experiments", cfg["multi_exp_name"], "exp_0")
+    ckdir = tmp_path / exp / "checkpoints"
+    ckdir.mkdir(parents=True)
+    sd_np = O.synthetic_state_dict(ocfg)
+    torch.save({"epoch": 1, "iteration": 2, "best_valid_loss": np.float64(1.0),
+                "state_dict": {k: torch.from_numpy(v) for k, v in sd_np.items()}}, ckdir / "model_best.pth.tar")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), str(cfg_path)], cwd=tmp_path, env=dict(os.environ, PYTHONPATH=ROOT),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    log = (tmp_path / exp / "logs" / "exp_debug.log").read_text()
+    assert "Valid Epoch:" in log and "Rates: scl0->" in log, log[-2000:]
+    import re
+    total = float(re.findall(r"\(\(([0-9.]+)\)\)", log)[-1])
+    # the oracle's forward() on the same centre crops (64 x 64: a multiple of the 32 the agent pads to)
+    want, net = [], O.OracleNet(ocfg, sd_np)
+    for im in imgs:
+        crop = np.ascontiguousarray(im[:, 8:72, 24:88])
+        sinfo = O.forward_self_informations(ocfg, net, crop)
+        want.append(sum(float(s.sum()) for s in sinfo) / crop.size * 3)
+    # batches of (2, 1) images: the table averages the per-batch rates
+    per_batch = [(want[0] + want[1]) / 2, want[2]]
+    assert abs(total - sum(per_batch) / 2) < 0.02 * total, (total, want)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("sub_len", [0, 512])
 def test_cli_encode_decode_files(tmp_path, sub_len):
