@@ -534,6 +534,7 @@ def run_b200(args, rank, world, local_rank):
     wl = w.wl
     cfg_entry = {"workload": wl["desc"], "model_config": wl["cfg"], "images_per_step_per_gpu": w.n, "height": w.H, "width": w.W,
                  "sub_len": wl["sub_len"], "cnn_impl": "tcgen05" if args.cnn == 1 else "fp32-cuda-core",
+                 "cnn_operands": {0: "fp32", 1: "bf16 (fp32 accumulate)", 2: "fp16 (fp32 accumulate)"}.get(int(w.codec.cnn_operands), "?"),
                  "decode_impl": "default" if args.decode_impl == 0 else "legacy-warp",
                  "distinct_batches_resident_per_gpu": len(w.batches),
                  "weights": "llicti_b200.synth.synthetic_state_dict(seed=1337) (shipped checkpoint absent)",
