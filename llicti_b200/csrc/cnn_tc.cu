@@ -443,14 +443,15 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         // Issue order.  What bounds the tile rate is the serial chain of a tile and sub-network g -- D0 -> epilogue -> layer 1 ->
         // epilogue -> layer 2, TMEM holding the hidden activations of ONE tile per sub-network -- so the long layer 0 of the tiles
         // ahead is cut in its two sub-network halves and slotted between the chain's short MMA groups, software-pipelined:
-        //     L1 g0 (t) | L0 g1 (t+1) | L1 g1 (t) | L2 g0 (t) | L0 g0 (t+2) | L2 g1 (t)
-        // A chain group never queues behind more than half a layer 0 on the in-order tensor pipe, and every accumulator slot
+        //     L1 g0 (t) | L0 g1 a (t+1) | L1 g1 (t) | L0 g1 b (t+1) | L2 g0 (t) | L0 g0 a (t+2) | L2 g1 (t) | L0 g0 b (t+2)
+        // (a, b = the two halves of the sub-network's K steps)
+        // A chain group never queues behind more than a quarter of a layer 0 on the in-order tensor pipe, and every accumulator slot
         // is provably free when its layer 0 is issued: L0 g (t+2) overwrites D1 g (t), whose epilogue finished before the
         // H1FULL g (t) this warp has already waited for (no extra barrier).
-        auto l0_half = [&](int it, auto g_) {
-            constexpr int g = decltype(g_)::value;
+        auto l0_part = [&](int it, auto g_, auto q_) {                     // K steps [q NCH, (q + 1) NCH) of sub-network g's layer 0
+            constexpr int g = decltype(g_)::value, q = decltype(q_)::value;
             const int s = it & 1;
-            if (g == 0) mbar_wait(bar(B_AFULL + s), (it >> 1) & 1);        // the producers have staged tile `it`
+            if (g == 0 && q == 0) mbar_wait(bar(B_AFULL + s), (it >> 1) & 1);   // the producers have staged tile `it`
             tc_fence_after();
             const uint32_t d0 = tmem + (uint32_t)(s * 2 * NP + g * NP);
             const uint64_t a0 = a_desc0 + (uint64_t)((uint32_t)s * (t_stage >> 4));
@@ -458,11 +459,13 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
             // chunk, rows (positions) are 16 bytes apart, the two taps of the step one pixel (16 bytes) apart.
             if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < 2 * NCH; ++ks)
+                for (int ks = q * NCH; ks < (q + 1) * NCH; ++ks)
                     umma_bf16(d0, a0 + (uint64_t)(((ks >> 1) * TC_CHUNK_BYTES + (ks & 1) * 32) >> 4),
                               w0_desc0 + (uint64_t)((ks * 2 * w0_lbo + (uint32_t)(g * NP) * 16) >> 4), idesc1, ks > 0);
-                umma_commit(bar(B_D0FULL + 2 * s + g));
-                if (g == 1) umma_commit(bar(B_AEMPTY + s));               // both halves have read the staged tile
+                if (q == 1) {
+                    umma_commit(bar(B_D0FULL + 2 * s + g));
+                    if (g == 1) umma_commit(bar(B_AEMPTY + s));           // both sub-networks have read the staged tile
+                }
             }
             __syncwarp();
         };
@@ -494,15 +497,17 @@ cnn_tc_kernel(const int16_t *__restrict__ planes, TcGeom tg, const uint8_t *__re
         };
         constexpr std::integral_constant<int, 0> G0{};
         constexpr std::integral_constant<int, 1> G1{};
-        if (my_tiles > 0) { l0_half(0, G0); l0_half(0, G1); }
-        if (my_tiles > 1) l0_half(1, G0);
+        if (my_tiles > 0) { l0_part(0, G0, G0); l0_part(0, G0, G1); l0_part(0, G1, G0); l0_part(0, G1, G1); }
+        if (my_tiles > 1) { l0_part(1, G0, G0); l0_part(1, G0, G1); }
         for (int it = 0; it < my_tiles; ++it) {
             l1_group(it, G0);
-            if (it + 1 < my_tiles) l0_half(it + 1, G1);
+            if (it + 1 < my_tiles) l0_part(it + 1, G1, G0);
             l1_group(it, G1);
+            if (it + 1 < my_tiles) l0_part(it + 1, G1, G1);
             l2_group(it, G0);
-            if (it + 2 < my_tiles) l0_half(it + 2, G0);
+            if (it + 2 < my_tiles) l0_part(it + 2, G0, G0);
             l2_group(it, G1);
+            if (it + 2 < my_tiles) l0_part(it + 2, G0, G1);
         }
     } else {
         // ================= epilogue warps: warps 0-3 sub-network 0, warps 4-7 sub-network 1 =================
