@@ -627,6 +627,26 @@ def test_pipelined_host_entry_points_equal_the_plain_ones(L, n, monkeypatch):
     codec.close()
 
 
+def test_lane_decoder_with_trained_weights(L, monkeypatch):
+    """Trained weights drive spreads down to the 0.11-level clamp: the mixture CDF is nearly a staircase there, the worst
+    case for the Newton search on the stand-in (flat stretches, steps of the whole range).  The lane decoder must still
+    decode every stream (bracketing, bisection and the exact pair test take over), and to the same bytes' images as the
+    windowed schedule."""
+    ocfg = O.OracleConfig()
+    sd = trained_state_dict()
+    imgs = np.stack([O.synthetic_image(181, 250, 400 + i, noise=0.7 if i % 2 else 0.0) for i in range(4)])
+    imgs[3] = np.stack([np.full((181, 250), v, np.uint8) for v in (12, 200, 90)])          # constant image: one-symbol chroma alphabets
+    monkeypatch.setenv("LLICTI_LANE_MIN_WARPS", "1")
+    enc = make_codec(L, ocfg, sd, sub_len=512, cnn_impl=L.CNN_TCGEN05)
+    bsls = enc.compress_images(imgs)
+    assert np.array_equal(enc.decompress_images(bsls), imgs)
+    enc.close()
+    monkeypatch.setenv("LLICTI_LANE_MIN_WARPS", "1000000")
+    dec = make_codec(L, ocfg, sd, sub_len=512, cnn_impl=L.CNN_TCGEN05)
+    assert np.array_equal(dec.decompress_images(bsls), imgs)
+    dec.close()
+
+
 def test_lane_group_and_window_decoders_read_the_same_streams(L, monkeypatch):
     ocfg = O.OracleConfig()
     sd = O.synthetic_state_dict(ocfg)
