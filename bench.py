@@ -278,6 +278,9 @@ class Workload:
         self.ccfg = CodecConfig.from_json_dict(self.cfg, sub_len=wl["sub_len"], numerics=L.NUM_TORCH_CUDA, cnn_impl=args.cnn,
                                                device=local_rank, decode_impl=args.decode_impl)
         self.sd = synth.synthetic_state_dict(self.ccfg.chs, self.ccfg.num_mixtures, int(self.cfg["Evens"][0]), int(self.cfg["Odds"][0]))
+        if args.weights_npz:                      # e.g. tests/golden/ckpt_A_trained.npz: weights short-trained by the reference's own code
+            with np.load(args.weights_npz) as z:
+                self.sd = {k: z[k] for k in z.files}
         self.codec = Codec(self.ccfg, self.sd)
         H, W = wl["H"], wl["W"]
         self.H, self.W = H, W
@@ -546,7 +549,7 @@ def run_b200(args, rank, world, local_rank):
                  "cnn_operands": {0: "fp32", 1: "bf16 (fp32 accumulate)", 2: "fp16 (fp32 accumulate)"}.get(int(w.codec.cnn_operands), "?"),
                  "decode_impl": "default" if args.decode_impl == 0 else "legacy-warp",
                  "distinct_batches_resident_per_gpu": len(w.batches),
-                 "weights": "llicti_b200.synth.synthetic_state_dict(seed=1337) (shipped checkpoint absent)",
+                 "weights": (args.weights_npz or "llicti_b200.synth.synthetic_state_dict(seed=1337) (shipped checkpoint absent)"),
                  "images": f"llicti_b200.synth.synthetic_batch_torch, image k of the job seeded by 1000 + k; generated in {w.gen_s:.1f} s",
                  "l2": "256 MiB buffer written before every timed encode and decode (L2 flushed)",
                  "parallelism": (f"{w.job_images} images sharded over {world} GPU(s): {w.shard_images} distinct images per rank"
@@ -611,6 +614,7 @@ def main():
     ap.add_argument("--workload", default="", choices=[""] + sorted(WORKLOADS),
                     help="default: c2 on one GPU, c3 (sharded) on several")
     ap.add_argument("--images", type=int, default=0, help="override the job's images per GPU")
+    ap.add_argument("--weights-npz", default="", help="state_dict as .npz instead of the synthetic stand-in weights (llicti_A shapes)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's images per batch (= per step)")
     ap.add_argument("--cnn", type=int, default=int(os.environ.get("LLICTI_CNN", "1")), help="0 fp32 CUDA cores, 1 tcgen05")
     ap.add_argument("--decode-impl", type=int, default=0, help="0 default schedules, 1 legacy one-warp-per-chain")

@@ -1342,25 +1342,30 @@ constexpr int kLaneParams = 5 * kM;     // 15 mixture parameters + up to 10 coup
 #endif
 constexpr float kLaneMargin = LLICTI_LANE_MARGIN;
 
-// Stand-in table entry q~(k) and its slope per index step (see approx_q), 1 <= k <= Lp - 2.
-__device__ __forceinline__ void approx_q_slope(const GmmChannel &c, const CdfGrid &g, int k, float &q, float &dq) {
+// Stand-in table entry q~(k), its slope and its curvature per index step, 1 <= k <= Lp - 2.  The normal CDF through
+// Abramowitz & Stegun 7.1.26, erfc(x) = (a1 t + ... + a5 t^5) exp(-x^2), t = 1 / (1 + p x), |error| < 1.5e-7 -- MUFU.RCP +
+// MUFU.EX2 + five FMAs per mixture, a third of libdevice's erfcf -- and the same exponential is the density (the slope) and,
+// times -z / sigma, its derivative (the curvature).  Still a GUESS: the exact entries decide.
+__device__ __forceinline__ void approx_q_slope(const GmmChannel &c, const CdfGrid &g, int k, float &q, float &dq, float &ddq) {
     const float p = ((float)(g.min_val + k) - 0.5f) * (1.0f / 255.0f);
-    float acc = 0.f, dacc = 0.f;
+    float acc = 0.f, dacc = 0.f, cacc = 0.f;
 #pragma unroll
     for (int m = 0; m < kM; ++m) {
         const float z = (p - c.mu[m]) * c.rinv[m];
-        const float z2 = z * z;
-        const float y = z * fmaf(z2, 0.044715f, 1.0f);
-        float e, r;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * -2.3022082f));
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-        acc = fmaf(c.w[m], r, acc);
-        // d/dz 1 / (1 + exp(-2 c (z + a z^3))) = r (1 - r) 2 c (1 + 3 a z^2)
-        const float s = fmaf(-r, r, r) * fmaf(z2, 0.21406557f, 1.5957691f);
-        dacc = fmaf(c.w[m] * c.rinv[m], s, dacc);
+        const float x = fabsf(z) * 0.70710678f;
+        float e, t;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -1.4426950f));              // exp(-x^2) = exp(-z^2 / 2)
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
+        const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+        const float h = 0.5f * poly * e;                                                     // 0.5 erfc(|z| / sqrt 2)
+        acc = fmaf(c.w[m], z >= 0.f ? 1.0f - h : h, acc);
+        const float wd = c.w[m] * c.rinv[m] * e;                                             // density / 0.39894228
+        dacc += wd;
+        cacc = fmaf(wd * c.rinv[m], -z, cacc);                                               // its derivative: -z / sigma times it
     }
     q = fmaf(acc, g.scale, (float)k);
-    dq = fmaf(dacc, g.scale * (1.0f / 255.0f), 1.0f);
+    dq = fmaf(dacc, g.scale * (0.39894228f / 255.0f), 1.0f);
+    ddq = cacc * (g.scale * (0.39894228f / (255.0f * 255.0f)));
 }
 
 __global__ void __launch_bounds__(128, 3)
@@ -1471,6 +1476,10 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
                     m2 = fmaf(ch.w[m], fmaf(ch.sigma[m], ch.sigma[m], ch.mu[m] * ch.mu[m]), m2);
                 }
                 const float sd = sqrtf(fmaxf(fmaf(-mean, mean, m2), 1e-12f));
+                float smin = 1.0f;                                                               // over the components that carry weight
+#pragma unroll
+                for (int m = 0; m < kM; ++m) smin = fminf(smin, ch.w[m] >= 0.004f ? ch.sigma[m] : 1.0f);
+                const bool smooth = smin >= 0.75f / 255.0f;                                       // every such component at least 3/4 of a level wide
                 const float u = fminf(fmaxf(tf * (1.0f / 65536.0f), 1e-6f), 1.0f - 1e-6f);
                 const float y = (__log2f(u) - __log2f(1.0f - u)) * 0.43436f;                     // ln 2 / (2 c)
                 const float z0 = __fdividef(y, fmaf(0.044715f * y, y, 1.0f));
@@ -1480,21 +1489,40 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
                 for (int it = 0;; ++it) {
                     if (b - a <= 1) { guess = a; break; }
                     k = min(max(k, a + 1), b - 1);
-                    float q, dq;
-                    approx_q_slope(ch, g, k, q, dq);
-                    const float res = tf - q, dx = __fdividef(res, dq);
+                    float q, dq, ddq;
+                    approx_q_slope(ch, g, k, q, dq, ddq);
+                    // Halley step: the Newton step corrected by the curvature (res = dq dx + ddq dx^2 / 2).  In the tails of a
+                    // peaky mixture the CDF bends so much within one symbol that the plain Newton step -- accepted when it
+                    // lands inside the neighbouring symbol -- was one symbol short in 1.5 % of the cases with trained weights.
+                    const float res = tf - q, dxn = __fdividef(res, dq);
+                    const float dx = __fdividef(res, fmaxf(fmaf(0.5f * ddq, dxn, dq), 0.3f * dq));
                     ++newton_its;
                     // The estimated root k + dx decides as long as it is not within kLaneMargin of the bound the bracket has not
-                    // confirmed; otherwise the neighbouring entry is evaluated too (1.8 % of the guesses were one off without this).
+                    // confirmed; otherwise the neighbouring entry is evaluated too.  Only for smooth mixtures: with a component
+                    // near the spread clamp the CDF is a staircase, a local slope says nothing about the next entry, and the
+                    // bracket alone decides.
                     if (res >= 0.f) {
                         a = k;
-                        if (dx < 1.0f - kLaneMargin || b == k + 1) { guess = k; break; }          // root in [k, k + 1)
+                        if (b == k + 1 || (smooth && dx < 1.0f - kLaneMargin)) { guess = k; break; }          // root in [k, k + 1)
                     } else {
                         b = k;
-                        if (dx >= -1.0f + kLaneMargin || a == k - 1) { guess = k - 1; break; }    // root in (k - 1, k)
+                        if (a == k - 1 || (smooth && dx >= -1.0f + kLaneMargin)) { guess = k - 1; break; }    // root in (k - 1, k)
                     }
-                    const int kn = k + (int)floorf(fminf(fmaxf(res >= 0.f ? dx + kLaneMargin : dx, -70000.f), 70000.f));
-                    k = (kn <= a || kn >= b || it >= 6) ? (a + b) >> 1 : kn;
+                    int kn = k + (int)floorf(fminf(fmaxf(res >= 0.f ? dx + kLaneMargin : dx, -70000.f), 70000.f));
+                    // A long step means a flat stretch of the staircase: the CDF only rises around the components' means, so
+                    // the next probe is the nearest mean on the root's side (not the far end of the bracket, which bisection
+                    // would then halve eight times).
+                    if (!smooth && fabsf(dx) > 3.0f) {
+                        int best = res >= 0.f ? b : a;
+#pragma unroll
+                        for (int m = 0; m < kM; ++m) {
+                            const int km = __float2int_rd(fmaf(ch.mu[m], 255.0f, 0.5f)) - g.min_val + (res >= 0.f ? 0 : 1);
+                            if (res >= 0.f) { if (km > k && km < best) best = km; }
+                            else if (km < k && km > best) best = km;
+                        }
+                        if (best > a && best < b) kn = best;
+                    }
+                    k = (kn <= a || kn >= b || it >= 8) ? (a + b) >> 1 : kn;
                 }
             }
             if (guess_skew) guess = min(max(guess + (int)((unsigned)(tau * 7 + lane) % (unsigned)(2 * guess_skew + 1)) - guess_skew, 0), last - 1);   // tests: wrong guesses
@@ -1503,23 +1531,31 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
             // q(s_lo) has been evaluated.
             int s_lo = 0, s_hi = last, ka = guess, kb = guess + 1, round = 0, dir = 0;
             uint32_t q_lo = 0u, q_hi = 0x10000u;
-            bool lo_known = false;
+            bool lo_known = false, single = false;     // single: this round evaluates entry ka only
 #pragma unroll 1
             for (;;) {
                 const uint32_t qa = cdf_q(ch, g, ka, np);
-                const uint32_t qb = kb < last ? cdf_q(ch, g, kb, np) : 0x10000u;
+                const uint32_t qb = !single && kb < last ? cdf_q(ch, g, kb, np) : 0x10000u;
                 // candidate test low + ((span * q) >> 16) <= value in 32 bits: the high word of span * (q << 16); the full
                 // range (span = 2^32, seen as 0) gives q << 16 itself
                 const uint32_t qa16 = qa << 16, qb16 = qb << 16;
                 const bool va = ka == 0 || low + (span == 0u ? qa16 : __umulhi(span, qa16)) <= value32;
-                const bool vb = kb < last && low + (span == 0u ? qb16 : __umulhi(span, qb16)) <= value32;
+                const bool vb = !single && kb < last && low + (span == 0u ? qb16 : __umulhi(span, qb16)) <= value32;
                 if (!va) { s_hi = ka; q_hi = qa; dir = -1; }
+                else if (single) { s_lo = ka; q_lo = qa; lo_known = true; }
                 else if (!vb) { s_lo = ka; q_lo = qa; lo_known = true; s_hi = kb; q_hi = qb; }
                 else { s_lo = kb; q_lo = qb; lo_known = true; dir = 1; }
                 ++round;
                 if (s_hi - s_lo == 1 && lo_known) break;
+                // A guess that was one off -- the usual miss -- needs ONE more entry (the other bound is already exact): the
+                // second round evaluates just the neighbour; later rounds probe pairs four apart, then thirds of what is left.
+                single = round == 1;
+                if (single) {
+                    ka = dir < 0 ? max(s_hi - 1, 0) : s_lo + 1;
+                    continue;
+                }
                 const int lo_min = lo_known ? s_lo + 1 : s_lo, hi_max = s_hi - 1;     // entries still worth evaluating (lo_min <= hi_max)
-                const int step = round == 1 ? 1 : round == 2 ? 4 : max((s_hi - s_lo) / 3, 1);
+                const int step = round == 2 ? 4 : max((s_hi - s_lo) / 3, 1);
                 if (dir < 0) { kb = max(s_hi - step, lo_min); ka = max(kb - step, lo_min); }
                 else { ka = min(s_lo + step, hi_max); kb = min(ka + step, hi_max); }
                 if (ka == kb) {
