@@ -1509,18 +1509,15 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
                         if (a == k - 1 || (smooth && dx >= -1.0f + kLaneMargin)) { guess = k - 1; break; }    // root in (k - 1, k)
                     }
                     int kn = k + (int)floorf(fminf(fmaxf(res >= 0.f ? dx + kLaneMargin : dx, -70000.f), 70000.f));
-                    // A long step means a flat stretch of the staircase: the CDF only rises around the components' means, so
-                    // the next probe is the nearest mean on the root's side (not the far end of the bracket, which bisection
-                    // would then halve eight times).
-                    if (!smooth && fabsf(dx) > 3.0f) {
-                        int best = res >= 0.f ? b : a;
-#pragma unroll
-                        for (int m = 0; m < kM; ++m) {
-                            const int km = __float2int_rd(fmaf(ch.mu[m], 255.0f, 0.5f)) - g.min_val + (res >= 0.f ? 0 : 1);
-                            if (res >= 0.f) { if (km > k && km < best) best = km; }
-                            else if (km < k && km > best) best = km;
-                        }
-                        if (best > a && best < b) kn = best;
+                    // Peaky mixtures (trained weights: one component of 3/4 of the weight a level wide, narrow ones at the spread
+                    // clamp, a broad one of a few percent) bend so hard that a step taken from the flank overshoots into the
+                    // flat tail by a hundred symbols, and bisection then needs seven evaluations to come back: the step is
+                    // limited to 2, 4, 8, ... symbols, and moves at least one (tools/search_sim.py: the slowest of a warp's 30
+                    // lanes needs 3.9 evaluations instead of 7.1).
+                    if (!smooth) {
+                        const int lim = 2 << min(it, 8);
+                        kn = min(max(kn, k - lim), k + lim);
+                        if (kn == k) kn = res >= 0.f ? k + 1 : k - 1;
                     }
                     k = (kn <= a || kn >= b || it >= 8) ? (a + b) >> 1 : kn;
                 }
