@@ -103,7 +103,7 @@ def search(sig, mu, w, tf, variant, last=256, min_val=-127, margin=0.2):
                     kn = k + 1
                 if variant == "dom2" and kn == k and res < 0:
                     kn = k - 1
-        if "clamp" in variant and not smooth:
+        if "clamp" in variant and not smooth and not ("dq" in variant and dq <= float(variant.split("dq")[1] or 4)):
             lim = 2 * (it + 1) if "lin" in variant else (1 << it) if "one" in variant else (3 << it) if "three" in variant else 2 << it
             kn = min(max(kn, k - lim), k + lim)
             if kn == k:
