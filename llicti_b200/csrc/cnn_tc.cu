@@ -120,7 +120,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a barrier that never completes (a programming error) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 22)) __trap();
+        if (spins > (1u << 24)) __trap();
 }
 __device__ __forceinline__ bool elect_one() {      // one lane of the (converged) warp
     uint32_t pred;
