@@ -1368,12 +1368,19 @@ __device__ __forceinline__ void approx_q_slope(const GmmChannel &c, const CdfGri
     ddq = cacc * (g.scale * (0.39894228f / (255.0f * 255.0f)));
 }
 
-__global__ void __launch_bounds__(128, 3)
+// kOcc = CTAs per SM the register allocation aims at.  A band of the finest scale of a c2 / c3 batch is ~ 24 warps of chains
+// per SM: with kOcc = 6 (80 registers, 4 bytes of spill) ALL of them are resident in one wave -- six warps per scheduler hide
+// the dependent-issue latency that bounds the kernel -- where 4 CTAs per SM at 118 registers ran a full wave and a half-empty
+// one.  The staging buffer holds the 30 working lanes of a warp only (36,000 B: six CTAs fit the SM's shared memory).
+constexpr int kLaneSlots = 4 * 3 * kLaneChains;   // working lanes of a CTA
+template <int kOcc>
+__global__ void __launch_bounds__(128, kOcc)
 decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ planes, const int32_t *__restrict__ minmax,
                         DecodeGeom dg, NumericsProfile np, const uint8_t *__restrict__ blob,
                         const uint64_t *__restrict__ suboff, const uint32_t *__restrict__ sublen, int total_sub, int n, int guess_skew) {
-    __shared__ float stage[kLaneStages][kLaneParams][128];
+    __shared__ float stage[kLaneStages][kLaneParams][kLaneSlots];
     const int lane = threadIdx.x & 31;
+    const int slot = min((int)(threadIdx.x >> 5) * 3 * kLaneChains + lane, kLaneSlots - 1);   // (idle lanes 30, 31 never stage)
     const int clr = lane / kLaneChains;                       // 3: idle lane
     const long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long gid = wg * kLaneChains + (lane - clr * kLaneChains);
@@ -1410,20 +1417,20 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
             const size_t off = (size_t)pf_r * dg.Ws + pf_c;
             pf_c += step_c; pf_r += step_r;
             if (pf_c >= dg.crop_w) { pf_c -= dg.crop_w; ++pf_r; }
-            float *dst = &stage[tau % kLaneStages][0][threadIdx.x];
+            float *dst = &stage[tau % kLaneStages][0][slot];
 #pragma unroll
             for (int m = 0; m < kM; ++m) {
-                cp_async_f32(dst + m * 128, p_sigma + off + (size_t)m * P);
-                cp_async_f32(dst + (kM + m) * 128, p_mu + off + (size_t)m * P);
-                cp_async_f32(dst + (2 * kM + m) * 128, p_w + off + (size_t)m * P);
+                cp_async_f32(dst + m * kLaneSlots, p_sigma + off + (size_t)m * P);
+                cp_async_f32(dst + (kM + m) * kLaneSlots, p_mu + off + (size_t)m * P);
+                cp_async_f32(dst + (2 * kM + m) * kLaneSlots, p_w + off + (size_t)m * P);
             }
             if (cl >= 1) {
 #pragma unroll
-                for (int m = 0; m < kM; ++m) cp_async_f32(dst + (3 * kM + m) * 128, p_cpl + off + (size_t)m * P);
+                for (int m = 0; m < kM; ++m) cp_async_f32(dst + (3 * kM + m) * kLaneSlots, p_cpl + off + (size_t)m * P);
             }
             if (cl == 2) {
 #pragma unroll
-                for (int m = 0; m < kM; ++m) cp_async_f32(dst + (4 * kM + m) * 128, p_cpl + off + (size_t)(kM + m) * P);
+                for (int m = 0; m < kM; ++m) cp_async_f32(dst + (4 * kM + m) * kLaneSlots, p_cpl + off + (size_t)(kM + m) * P);
             }
         }
         cp_async_commit();
@@ -1441,23 +1448,23 @@ decode_band_lane_kernel(const float *__restrict__ params, int16_t *__restrict__ 
         const bool live = t >= 0 && t < n_steps;
         int yv = 0;
         if (live) {
-            const float *sp = &stage[tau % kLaneStages][0][threadIdx.x];
+            const float *sp = &stage[tau % kLaneStages][0][slot];
             GmmChannel ch;
 #pragma unroll
             for (int m = 0; m < kM; ++m) {
-                ch.sigma[m] = sp[m * 128];
-                ch.mu[m] = sp[(kM + m) * 128];
-                ch.w[m] = sp[(2 * kM + m) * 128];
+                ch.sigma[m] = sp[m * kLaneSlots];
+                ch.mu[m] = sp[(kM + m) * kLaneSlots];
+                ch.w[m] = sp[(2 * kM + m) * kLaneSlots];
             }
             if (cl == 1) {                                    // mean coupling (LLICTI_nets.py:385-392), as staged_channel
                 const float f0 = div255((float)in0, np);
 #pragma unroll
-                for (int m = 0; m < kM; ++m) ch.mu[m] = __fadd_rn(ch.mu[m], __fmul_rn(sp[(3 * kM + m) * 128], f0));
+                for (int m = 0; m < kM; ++m) ch.mu[m] = __fadd_rn(ch.mu[m], __fmul_rn(sp[(3 * kM + m) * kLaneSlots], f0));
             } else if (cl == 2) {
                 const float f0 = div255((float)in0, np), f1 = div255((float)in1, np);
 #pragma unroll
                 for (int m = 0; m < kM; ++m)
-                    ch.mu[m] = __fadd_rn(ch.mu[m], __fadd_rn(__fmul_rn(sp[(3 * kM + m) * 128], f0), __fmul_rn(sp[(4 * kM + m) * 128], f1)));
+                    ch.mu[m] = __fadd_rn(ch.mu[m], __fadd_rn(__fmul_rn(sp[(3 * kM + m) * kLaneSlots], f0), __fmul_rn(sp[(4 * kM + m) * kLaneSlots], f1)));
             }
             gmm_prepare(ch, np);
             const uint32_t low = d.low, sm1 = d.high - d.low, span = sm1 + 1u, value32 = d.value;
@@ -1708,8 +1715,16 @@ int launch_decode_band(llicti_ctx *ctx, const Plan &p, int scale, int band, cons
         ProfScope prof_(ctx, KC_DECODE, st);
         const long long warps = ((long long)n * dg.S + kLaneChains - 1) / kLaneChains;
         const int blocks = (int)((warps + 3) / 4);
-        decode_band_lane_kernel<<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n,
-                                                        env_int("LLICTI_TEST_GUESS_SKEW", 0));
+        const int skew = env_int("LLICTI_TEST_GUESS_SKEW", 0);
+        static const int occ = env_int("LLICTI_LANE_OCC", 6);      // A/B: 4 = the 118-register build
+        // (the carve-out is a per-device attribute of the function: set at every launch, a host-side call of about a microsecond)
+#define LLICTI_LANE_LAUNCH(OCC) do { \
+            LLICTI_CUDA(cudaFuncSetAttribute(decode_band_lane_kernel<OCC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+            decode_band_lane_kernel<OCC><<<blocks, 128, 0, st>>>(params, planes, minmax, dg, ctx->num, blob, suboff, sublen, total_sub, n, skew); } while (0)
+        if (occ >= 6) LLICTI_LANE_LAUNCH(6);
+        else if (occ == 5) LLICTI_LANE_LAUNCH(5);
+        else LLICTI_LANE_LAUNCH(4);
+#undef LLICTI_LANE_LAUNCH
         ctx->launches += 1;
         LLICTI_CUDA(cudaGetLastError());
         return LLICTI_OK;
