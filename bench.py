@@ -446,6 +446,54 @@ class Workload:
                         "tables and flush bytes counted"}
 
 
+def train_step_pass(local_rank, steps, warmup, batch=32, patch=160):
+    """One training step = llicti_set_weights_dev + llicti_forward_dev + llicti_backward_dev on a batch resident in HBM
+    (the optimizer is torch's and outside the timed region, as it is outside the library)."""
+    from llicti_b200 import _lib as L
+    from llicti_b200.codec import Codec, CodecConfig, PREFIX
+    from llicti_b200 import synth
+    sd = synth.synthetic_state_dict()
+    codec = Codec(CodecConfig(cnn_impl=L.CNN_FP32, device=local_rank), sd)
+    dev = codec.device
+    wts = {k: torch.from_numpy(v).to(dev) for k, v in sd.items() if k.startswith(PREFIX) and "conditional_prob_model" not in k}
+    names = list(wts)
+    rgbs = [synth.synthetic_batch_torch(batch, patch, patch, 4000 + 64 * k, dev) for k in range(2)]
+    numel = batch * 3 * patch * patch
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ms, loss = [], None
+    for k in range(warmup + steps):
+        if k == warmup:
+            codec.profile(True)
+        rgb = rgbs[k % 2]
+        torch.cuda.synchronize(dev)
+        ev[0].record()
+        codec.set_weights_dev(wts)
+        sinfo = codec.forward_dev(rgb)
+        gs = [torch.full_like(t, 3.0 / numel) for t in sinfo]
+        grads = codec.backward_dev(rgb, gs, names)
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        if k >= warmup:
+            ms.append(ev[0].elapsed_time(ev[1]))
+        loss = sum(float(t.double().sum()) for t in sinfo) / numel * 3
+        assert all(bool(torch.isfinite(g).all()) for g in grads.values())
+    prof = codec.profile_read()
+    codec.profile(False)
+    codec.close()
+    t = float(np.mean(ms))
+    G = 88
+    pos = sum(batch * (patch >> (s + 1)) ** 2 for s in range(5))
+    fwd = sum(2 * 4 * (k0 * G + G * G + 15 * G) for k0 in (48, 72, 120))                      # FLOP per position, three bands
+    bwd = sum(2 * 4 * (2 * k0 * G + 3 * G * G + 30 * G) for k0 in (48, 72, 120))              # recompute of two layers + five products
+    return {"workload": f"training step, llicti_A, {batch} patches of {patch}x{patch} (the reference's batch_size / patch_size), fp32",
+            "ms_per_step": t, "patches_per_s": batch / t * 1e3, "value": batch * patch * patch / t / 1e3, "unit": "MP/s",
+            "steps": steps, "warmup": warmup, "loss_bpp": loss,
+            "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items() if v[1]},
+            "cnn_class_tflops": pos * (2 * fwd + bwd) / (prof["cnn"][0] / steps * 1e-3) / 1e12 if prof.get("cnn", (0, 0))[0] else None,
+            "note": "cnn class = fp32 forward (twice: forward() and the backward's recompute of the parameters) + cnn_backward_kernel; "
+                    "bounds class = self_info_kernel + self_info_grad_kernel"}
+
+
 def reduce_workload(w, dev_r, host_r, steps):
     """Max over ranks of the times, sum over ranks of the work; every rank returns the same dict."""
     from llicti_b200.shard import reduce_stats
@@ -596,6 +644,13 @@ def run_b200(args, rank, world, local_rank):
             o.close()
         except Exception as e:       # noqa: BLE001
             per_config[primary + "_trained_weights"] = {"error": f"{type(e).__name__}: {e}"}
+    # the training step on the reference's training batch (configs/llicti_A.json of the reference: 32 patches
+    # of 160 x 160): forward() + backward through the library, fp32; never fatal
+    if world == 1 and not args.no_per_config:
+        try:
+            per_config["train_step"] = train_step_pass(local_rank, min(K, 5), min(Wm, 3))
+        except Exception as e:       # noqa: BLE001
+            per_config["train_step"] = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         return
 

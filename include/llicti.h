@@ -219,6 +219,23 @@ LLICTI_API int llicti_decode_batch_host(llicti_ctx *ctx, const llicti_decode_ite
 LLICTI_API int llicti_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W,
                        float *const *fplanes_dev, float *const *sinfo_dev, void *stream);
 
+/* The device half of the reference's training step (agents/llicti_agent.py:48-83: `self.model(x)`, TrainRLossList,
+ * `.backward()`).  The optimizer, gradient clipping and the checkpoint stay with the caller, as in the
+ * reference's agent.  Both calls need a context created with cnn_impl = LLICTI_CNN_FP32 (the reference trains in fp32).
+ *
+ * llicti_set_weights_dev: replace the context's weights by the ones at these DEVICE pointers (PyTorch layouts, the
+ *   shapes of llicti_weights) -- the parameters after an optimizer step.
+ * llicti_backward_dev: gradients of a loss L over forward()'s outputs with respect to every weight.
+ *   fplanes_dev[s]  float [n][12][Hs][Ws]  scratch, as in llicti_forward_dev
+ *   gsinfo_dev[s]   float [n][9][Hs][Ws]   dL / d self-information (what autograd hands the backward of forward())
+ *   grads_dev       DEVICE pointers, layouts and order of llicti_weights; overwritten with dL / d weight (each of a
+ *                   band's branch biases receives the gradient of their sum)
+ * compressai's LowerBound gradient rule (pass where x >= bound or where the step would raise x) applies to the spreads,
+ * the mixture weights and the likelihood (entropy_layer_nets.py:135, 176, 181). */
+LLICTI_API int llicti_set_weights_dev(llicti_ctx *ctx, const llicti_weights *w_dev, void *stream);
+LLICTI_API int llicti_backward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, float *const *fplanes_dev,
+                        const float *const *gsinfo_dev, const llicti_weights *grads_dev, void *stream);
+
 /* LLICTI.decompres for a batch (LLICTI_nets.py:161-179, 415-509).
  *   blob / stream_off  as produced by encode
  *   minmax             int16 [n][6]

@@ -1,9 +1,11 @@
-"""Agent layer of the `main.py <config.json>` entry point for `mode: eval_model`
-(mirrors agents/base.py:13-150 and agents/llicti_agent.py:14-164 of the reference: device
-selection, checkpoint loading by the reference's file layout and key names, the per-image
-compress -> rate table -> decompres -> lossless check loop and its log lines).
+"""Agent layer of the `main.py <config.json>` entry point (mirrors agents/base.py:13-150 and
+agents/llicti_agent.py:14-164 of the reference: device selection, checkpoint loading and saving by the reference's
+file layout and key names, `mode: eval_model` -- the per-image compress -> rate table -> decompres -> lossless check
+loop and its log lines --, `mode: validate` and `mode: train`).
 
-Training / validation modes are outside the B200 hot path and raise NotImplementedError.
+`mode: train` is the reference's loop (llicti_agent.py:48-83, base.py:132-146) around the library's training step:
+`self.model(x)` and `.backward()` run in libllicti_b200 (`llicti_forward_dev` / `llicti_backward_dev`, fp32); Adam,
+gradient clipping, ReduceLROnPlateau and the checkpoint are torch's, as in the reference.
 """
 import logging
 import shutil
@@ -42,6 +44,10 @@ class BaseAgent:
             self.current_iteration = ckpt.get("iteration", 0)
             self.best_valid_loss = ckpt.get("best_valid_loss", self.best_valid_loss)
             self.model.load_state_dict(ckpt["state_dict"])
+            if getattr(self.config, "resume_training", False) and self.config.mode == "train":          # base.py:61-75
+                for key in ("optimizer", "scheduler", "train_logger", "trnit_logger", "valid_logger"):
+                    if key in ckpt and getattr(self, key, None) is not None:
+                        getattr(self, key).load_state_dict(ckpt[key])
             self.logger.info("Checkpoint loaded successfully from '{}' at (epoch {}) at (iteration {})".format(
                 self.config.checkpoint_dir, self.current_epoch, self.current_iteration))
         except OSError:
@@ -51,6 +57,10 @@ class BaseAgent:
     def save_checkpoint(self, filename="checkpoint.pth.tar", is_best=0):
         state = {"epoch": self.current_epoch, "iteration": self.current_iteration,
                  "best_valid_loss": self.best_valid_loss, "state_dict": self.model.state_dict()}
+        for key in ("optimizer", "scheduler", "train_logger", "trnit_logger", "valid_logger"):   # base.py:88-92 (training runs)
+            obj = getattr(self, key, None)
+            if obj is not None:
+                state[key] = obj.state_dict()
         torch.save(state, self.config.checkpoint_dir + filename)
         if is_best:
             shutil.copyfile(self.config.checkpoint_dir + filename, self.config.checkpoint_dir + "model_best.pth.tar")
@@ -64,12 +74,28 @@ class BaseAgent:
                 self.model_size_estimation(print_params=True)
             elif mode == "validate":
                 self.validate()
-            elif mode in ("train", "debug", "test", "flops_est"):
-                raise NotImplementedError(f"mode '{mode}' is outside the B200 compress/decompress path")
+            elif mode == "train":
+                self.train()
+            elif mode in ("debug", "test", "flops_est"):
+                raise NotImplementedError(f"mode '{mode}' is outside the B200 path")
             else:
                 raise NameError("'" + mode + "' is not a valid training mode.")
         except KeyboardInterrupt:
             self.logger.info("You have entered CTRL+C.. Wait to finalize")
+
+    def train(self):
+        """base.py:132-146."""
+        for epoch in range(self.current_epoch, self.config.max_epoch):
+            self.current_epoch = epoch
+            self.train_one_epoch()
+            if not (self.current_epoch + 1) % getattr(self.config, "validate_every", 1):
+                valid_loss = self.validate()
+                if valid_loss is not None:
+                    is_best = valid_loss < self.best_valid_loss
+                    if is_best:
+                        self.best_valid_loss = valid_loss
+                    self.save_checkpoint(is_best=is_best)
+            self.current_epoch += 1
 
     def finalize(self):
         self.logger.info("Please wait while finalizing the operation.. Thank you")
@@ -84,9 +110,54 @@ class LLICTIAgent(BaseAgent):
         self.compr_loss = CompressionRLossList()
         self.test_logger = RateLogger()
         self.test_loader = TestImageLoader(config.test_data)
+        self.optimizer = self.scheduler = self.train_logger = self.trnit_logger = self.valid_logger = None
+        if config.mode == "train":                                   # llicti_agent.py:19-37
+            from .image_dl import TrainImageLoader
+            from .rate import TrainRLossList
+            dirs = [getattr(config, "train_data_%d" % i) for i in range(1, int(getattr(config, "num_train_dirs", 1)) + 1)]
+            self.train_loader = TrainImageLoader(dirs, config.patch_size, config.batch_size,
+                                                 getattr(config, "patches_per_img", 1), seed=config.seed)
+            self.train_loss = TrainRLossList()
+            self.train_logger, self.trnit_logger, self.valid_logger = RateLogger(), RateLogger(), RateLogger()
+            self.lr = config.learning_rate
+            self.optimizer = torch.optim.Adam([{"params": self.model.parameters(), "lr": self.lr}])
+            self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, factor=0.5, patience=16, threshold=0.0001,
+                                                                        threshold_mode="rel", cooldown=15, min_lr=2.5e-05, eps=1e-08)
+            self.grad_acc_iters = int(getattr(config, "grad_acc_iters", 1))
         if config.mode in ("test", "validate", "debug", "eval_model"):
             self.load_checkpoint("model_best.pth.tar")
+        elif getattr(config, "resume_training", False):
+            self.load_checkpoint(getattr(config, "checkpoint_file", "checkpoint.pth.tar"))
         self.model_size_estimation()
+
+    def train_one_epoch(self):
+        """llicti_agent.py:48-83, line for line; `self.model(x)` and `.backward()` are the library's training step."""
+        self.model.train()
+        for batch_idx, x in enumerate(self.train_loader):
+            x = x.to(self.device)
+            if x.dim() == 5:
+                x = x.view(-1, x.shape[2], x.shape[3], x.shape[4])
+            self_infos_y_list = self.model(x)
+            r_loss, rate1_list = self.train_loss.forward(torch.numel(x), self_infos_y_list)
+            (r_loss / self.grad_acc_iters).backward()
+            if (self.current_iteration + 1) % self.grad_acc_iters == 0:
+                torch.nn.utils.clip_grad_value_(self.model.parameters(), clip_value=5.0)
+                self.optimizer.step()
+                self.optimizer.zero_grad()
+            self.current_iteration += 1
+            self.train_logger(rate1_list)
+            self.trnit_logger(rate1_list)
+            if not (self.current_iteration + 1) % getattr(self.config, "loss_prnt_iters", 2000):
+                self.trnit_logger.display(lr=self.optimizer.param_groups[0]["lr"], typ="it")
+                valid_loss = self.validate()
+                self.model.train()
+                if valid_loss is not None:
+                    is_best = valid_loss < self.best_valid_loss
+                    if is_best:
+                        self.best_valid_loss = valid_loss
+                    self.save_checkpoint(is_best=is_best)
+        if self.train_logger.rate:
+            self.train_logger.display(lr=self.optimizer.param_groups[0]["lr"], typ="tr")
 
     @torch.no_grad()
     def eval_model(self):
@@ -127,15 +198,16 @@ class LLICTIAgent(BaseAgent):
 
     @torch.no_grad()
     def validate(self):
-        """The reference's validate() (agents/llicti_agent.py:85-103) without its learning-rate scheduler: the rate
-        estimate of forward() (`llicti_forward_dev`) over the validation crops, logged as the 'va' table."""
+        """The reference's validate() (agents/llicti_agent.py:85-103): the rate estimate of forward()
+        (`llicti_forward_dev`) over the validation crops, logged as the 'va' table; during training the result steps the
+        learning-rate scheduler (:101)."""
         import torch.nn.functional as F
         from .image_dl import ValidImageLoader
         from .rate import TrainRLossList
         self.model.eval()
         valid_data = getattr(self.config, "valid_data", None) or self.config.test_data      # (the shipped configs carry no training keys)
         loader = ValidImageLoader(valid_data, getattr(self.config, "val_patch_size", 0), getattr(self.config, "val_batch_size", 1))
-        train_loss, valid_logger = TrainRLossList(), RateLogger()
+        train_loss, valid_logger = TrainRLossList(), (self.valid_logger or RateLogger())
         B = 2 ** (max(self.config.dwtlevels) + 1)
         for x in loader:
             x = x.to(self.device)
@@ -147,6 +219,8 @@ class LLICTIAgent(BaseAgent):
             self.logger.info(" validate: no images in {}".format(valid_data))
             return None
         valid_rate_loss, valid_rate2_loss = valid_logger.display(lr=0.0, typ="va")
+        if self.scheduler is not None:
+            self.scheduler.step(valid_rate_loss + valid_rate2_loss)
         return valid_rate_loss + valid_rate2_loss
 
     def model_size_estimation(self, print_params=False):

@@ -287,6 +287,71 @@ class Codec:
         L.check(self.lib.llicti_forward_dev(self._ctx, rgb.data_ptr(), n, H, W, fp, op, self._stream()))
         return out
 
+    # -- training step (agents/llicti_agent.py:48-83): weights in from the optimizer, gradients out ------------
+    def _weights_struct(self, tensors: Dict[str, torch.Tensor]):
+        """llicti_weights holding the DEVICE pointers of fp32 CUDA tensors under the reference's state_dict names."""
+        g, w, keep = self.cfg.chs, L.Weights(), []
+
+        def ptr(name, shape):
+            t = tensors[name]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == self.device):
+                raise ValueError(f"{name}: expected a contiguous float32 tensor on {self.device}")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{name}: unexpected shape {tuple(t.shape)}, expected {shape}")
+            keep.append(t)
+            return t.data_ptr()
+
+        for i, (band, name) in enumerate(L0_NAMES):
+            kh, kw = L0_SHAPES[name]
+            w.l0_w[i] = ptr(f"{PREFIX}{band}.{name}.weight", (4 * g, 3, kh, kw))
+            w.l0_b[i] = ptr(f"{PREFIX}{band}.{name}.bias", (4 * g,))
+        for band in range(3):
+            w.l1_w[band] = ptr(f"{PREFIX}{band}.layers1toL.0.weight", (4 * g, g, 1, 1))
+            w.l1_b[band] = ptr(f"{PREFIX}{band}.layers1toL.0.bias", (4 * g,))
+            w.l2_w[band] = ptr(f"{PREFIX}{band}.layers1toL.2.weight", (12 * self.cfg.num_mixtures, g, 1, 1))
+            w.l2_b[band] = ptr(f"{PREFIX}{band}.layers1toL.2.bias", (12 * self.cfg.num_mixtures,))
+        return w, keep
+
+    def set_weights_dev(self, tensors: Dict[str, torch.Tensor]):
+        """Replace the context's weights by these CUDA tensors (the parameters after an optimizer step).  fp32-CNN
+        contexts only; the stream fingerprint of this codec no longer describes its weights afterwards."""
+        w, keep = self._weights_struct(tensors)
+        L.check(self.lib.llicti_set_weights_dev(self._ctx, C.byref(w), self._stream()))
+        self.fingerprint = None
+        del keep
+
+    def backward_dev(self, rgb: torch.Tensor, gsinfo: Sequence[torch.Tensor], names: Sequence[str]) -> Dict[str, torch.Tensor]:
+        """Gradients of a loss with respect to every weight, given dL / d self-information per scale (float32
+        [n,9,Hs,Ws], the shapes forward_dev returns).  `names`: the state_dict keys wanted (all 24 weight tensors)."""
+        assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
+        n, _, H, W = rgb.shape
+        self.reserve(n, H, W)
+        g = self.geometry(H, W)
+        S, G, M = self.cfg.num_scales, self.cfg.chs, self.cfg.num_mixtures
+        gs = []
+        for s in range(S):
+            t = gsinfo[s].to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != (n, 9, g.Hs[s], g.Ws[s]):
+                raise ValueError(f"gradient of scale {s}: shape {tuple(t.shape)}, expected {(n, 9, g.Hs[s], g.Ws[s])}")
+            gs.append(t)
+        fpl = [torch.empty((n, 12, g.Hs[s], g.Ws[s]), dtype=torch.float32, device=self.device) for s in range(S)]
+        grads = {}
+        for band, name in L0_NAMES:
+            kh, kw = L0_SHAPES[name]
+            grads[f"{PREFIX}{band}.{name}.weight"] = torch.empty((4 * G, 3, kh, kw), dtype=torch.float32, device=self.device)
+            grads[f"{PREFIX}{band}.{name}.bias"] = torch.empty((4 * G,), dtype=torch.float32, device=self.device)
+        for band in range(3):
+            grads[f"{PREFIX}{band}.layers1toL.0.weight"] = torch.empty((4 * G, G, 1, 1), dtype=torch.float32, device=self.device)
+            grads[f"{PREFIX}{band}.layers1toL.0.bias"] = torch.empty((4 * G,), dtype=torch.float32, device=self.device)
+            grads[f"{PREFIX}{band}.layers1toL.2.weight"] = torch.empty((12 * M, G, 1, 1), dtype=torch.float32, device=self.device)
+            grads[f"{PREFIX}{band}.layers1toL.2.bias"] = torch.empty((12 * M,), dtype=torch.float32, device=self.device)
+        w, keep = self._weights_struct(grads)
+        fp = (C.c_void_p * S)(*[t.data_ptr() for t in fpl])
+        gp = (C.c_void_p * S)(*[t.data_ptr() for t in gs])
+        L.check(self.lib.llicti_backward_dev(self._ctx, rgb.data_ptr(), n, H, W, fp, gp, C.byref(w), self._stream()))
+        del keep
+        return {k: grads[k] for k in names}
+
     # -- bytestream_list assembly (LLICTI_nets.py:346-354, 409-411) ----------------------------
     def to_bytestream_lists(self, rgb: np.ndarray, blob: np.ndarray, off: np.ndarray, mm: np.ndarray):
         S = self.cfg.num_scales

@@ -307,6 +307,7 @@ void llicti_destroy(llicti_ctx *ctx) {
     free_workspace(ctx);
     for (auto &b : ctx->wf32) { cudaFree(b.w0); cudaFree(b.b0); cudaFree(b.w1); cudaFree(b.b1); cudaFree(b.w2); cudaFree(b.b2); }
     tc_free_weights(ctx);
+    train_free(ctx);
     if (ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
     if (ctx->side_stream) cudaStreamDestroy((cudaStream_t)ctx->side_stream);
@@ -519,10 +520,54 @@ int llicti_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, in
     if ((rc = launch_color_split_float(ctx, p, rgb_dev, n, fplanes_dev, ctx->d_planes, st))) return rc;
     for (int s = 0; s < g.num_scales; ++s)
         for (int b = 0; b < 3; ++b) {
-            if ((rc = cnn(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st))) return rc;
+            // fp32 contexts feed the CNN the float lifting's own values (what the reference's convolutions see); the tcgen05
+            // CNN reads the int16 planes (value * 255, the same numbers up to an ulp of the quotient)
+            if (ctx->cfg.cnn_impl == LLICTI_CNN_FP32) rc = launch_cnn_fp32(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st, fplanes_dev[s]);
+            else rc = cnn(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st);
+            if (rc) return rc;
             if ((rc = launch_self_info(ctx, ctx->d_params, fplanes_dev[s], b, n, g.Hs[s] * g.Ws[s], sinfo_dev[s], st))) return rc;
         }
     return LLICTI_OK;
+}
+
+// ---- training step ------------------------------------------------------------------
+// New fp32 weights from device memory (the optimizer's parameters): repacked in place by three small kernels per band.
+// Only for contexts of the fp32 CNN: the tcgen05 operand pack, the fp16-range proof and the stream fingerprint belong to
+// the weights given at creation.
+int llicti_set_weights_dev(llicti_ctx *ctx, const llicti_weights *w_dev, void *stream) {
+    LLICTI_REQUIRE(ctx && w_dev, "null argument");
+    LLICTI_REQUIRE(ctx->cfg.cnn_impl == LLICTI_CNN_FP32,
+                   "llicti_set_weights_dev needs a context created with cnn_impl = LLICTI_CNN_FP32 (the training context); "
+                   "create a new context to code with the trained weights");
+    ctx->weights_from_device = true;
+    return launch_train_layouts(ctx, *w_dev, true, (cudaStream_t)stream);
+}
+
+// d loss / d weights for a loss whose gradient with respect to forward()'s self-informations is gsinfo_dev: the colour
+// split and the fp32 CNN are re-run per band (nothing but the self-informations was kept from the forward pass), the
+// likelihood is differentiated in place over the parameters, the CNN backward accumulates packed weight gradients, which
+// are written to grads_dev in PyTorch's layouts at the end.
+int llicti_backward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, float *const *fplanes_dev,
+                        const float *const *gsinfo_dev, const llicti_weights *grads_dev, void *stream) {
+    int rc = check_batch(ctx, n, H, W);
+    if (rc) return rc;
+    LLICTI_REQUIRE(rgb_dev && fplanes_dev && gsinfo_dev && grads_dev, "null argument");
+    LLICTI_REQUIRE(ctx->cfg.cnn_impl == LLICTI_CNN_FP32, "llicti_backward_dev needs a context created with cnn_impl = LLICTI_CNN_FP32");
+    const Plan &p = ctx->plan;
+    const llicti_geom &g = p.g;
+    LLICTI_REQUIRE(H % (1 << g.num_scales) == 0 && W % (1 << g.num_scales) == 0,
+                   "backward() needs H and W to be multiples of 2^num_scales = %d, as forward()", 1 << g.num_scales);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s = 0; s < g.num_scales; ++s) LLICTI_REQUIRE(fplanes_dev[s] && gsinfo_dev[s], "null plane pointer");
+    if ((rc = launch_train_zero_grads(ctx, st))) return rc;
+    if ((rc = launch_color_split_float(ctx, p, rgb_dev, n, fplanes_dev, ctx->d_planes, st))) return rc;
+    for (int s = 0; s < g.num_scales; ++s)
+        for (int b = 0; b < 3; ++b) {
+            if ((rc = launch_cnn_fp32(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st, fplanes_dev[s]))) return rc;
+            if ((rc = launch_self_info_grad(ctx, ctx->d_params, fplanes_dev[s], gsinfo_dev[s], b, n, g.Hs[s] * g.Ws[s], st))) return rc;
+            if ((rc = launch_cnn_backward(ctx, b, fplanes_dev[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st))) return rc;
+        }
+    return launch_train_layouts(ctx, *grads_dev, false, st);
 }
 
 // ---- host-buffer entry points, pipelined ----------------------------------------------------------

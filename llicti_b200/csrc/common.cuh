@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -146,6 +147,8 @@ struct llicti_ctx {
     int pipe_resident = 0;             // one-warp CTAs of decode_band_pipe_kernel per SM
     int prod_resident = 0, cons_regs = 0, prod_regs = 0;   // wavefront kernels
     size_t tc_attr_smem = 0;           // dynamic shared memory opted in for the tcgen05 CNN kernels
+    void *train_state = nullptr;       // packed gradient accumulators of the training step (kernels_train.cu), on first use
+    bool weights_from_device = false;  // llicti_set_weights_dev replaced the fp32 weights given at creation
 };
 
 namespace llicti {
@@ -191,7 +194,15 @@ int launch_minmax32(llicti_ctx *ctx, const int16_t *minmax16, int32_t *minmax, i
 
 // kernels_cnn_fp32.cu
 int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
-                    cudaStream_t st);
+                    cudaStream_t st, const float *fplanes = nullptr);
+
+// kernels_train.cu
+int launch_self_info_grad(llicti_ctx *ctx, float *params, const float *fplanes, const float *gsinfo, int band, int n, int P,
+                          cudaStream_t st);
+int launch_cnn_backward(llicti_ctx *ctx, int band, const float *fplanes, int n, int Hs, int Ws, const float *dparams, cudaStream_t st);
+int launch_train_zero_grads(llicti_ctx *ctx, cudaStream_t st);
+int launch_train_layouts(llicti_ctx *ctx, const llicti_weights &tw, bool to_packed, cudaStream_t st);
+void train_free(llicti_ctx *ctx);
 
 // cnn_tc.cu
 int tc_pack_weights(llicti_ctx *ctx, const llicti_weights &w);

@@ -1,4 +1,4 @@
-"""Image loading for eval_model and validate (mirrors dataloaders/image_dl.py:40-51, 60-78, 106-111: every *.png / *.jpg of
+"""Image loading for eval_model, validate and train (mirrors dataloaders/image_dl.py:40-51, 60-78, 106-111: every *.png / *.jpg of
 `config.test_data` as float32 [1,3,H,W] in [0,1], batch 1; `config.valid_data` centre-cropped to `val_patch_size` in
 batches of `val_batch_size`)."""
 import os
@@ -61,3 +61,47 @@ class ValidImageLoader:
             return
         for k in range(0, len(self.files), self.batch_size):
             yield torch.stack([self._load(p) for p in self.files[k:k + self.batch_size]])
+
+
+class TrainImageLoader:
+    """The reference's train_loader (image_dl.py:18-39, 54-104): every epoch visits the images of the training
+    directories in a new random order; each yields `patches_per_img` random crops of `size` x `size`, flipped left-right
+    with probability 1/2; images smaller than the crop are resized to fit it (ImageOps.fit); batches of `batch_size`
+    images (so [B, 3, size, size], or [B, patches_per_img, 3, size, size] like the reference, which the training loop
+    flattens).  The random stream is a numpy Generator seeded by the caller (the reference relies on torch's global
+    seed and the DataLoader workers' own)."""
+
+    def __init__(self, roots, size, batch_size, patches_per_img=1, seed=0):
+        roots = [roots] if isinstance(roots, str) else list(roots)
+        self.files = [f for r in roots for f in list_images(r)]
+        self.size, self.batch_size, self.patches = int(size), max(int(batch_size), 1), max(int(patches_per_img), 1)
+        if self.size <= 0:
+            raise ValueError("training needs patch_size > 0")
+        self.rng = np.random.default_rng(seed)
+
+    def __len__(self):
+        return -(-len(self.files) // self.batch_size)
+
+    def _patches(self, path):
+        from PIL import Image, ImageOps
+        with open(path, "rb") as f:
+            img = Image.open(f).convert("RGB")
+        w, h = img.size
+        if w < self.size or h < self.size:
+            img = ImageOps.fit(img, (max(w, self.size) if w >= self.size else self.size,
+                                     max(h, self.size) if h >= self.size else self.size))
+        a = np.asarray(img)
+        out = []
+        for _ in range(self.patches):
+            top = int(self.rng.integers(0, a.shape[0] - self.size + 1))
+            left = int(self.rng.integers(0, a.shape[1] - self.size + 1))
+            p = a[top:top + self.size, left:left + self.size]
+            if self.rng.random() < 0.5:
+                p = p[:, ::-1]
+            out.append(torch.from_numpy(np.ascontiguousarray(p.transpose(2, 0, 1))).to(torch.float32) / 255)
+        return out[0] if self.patches == 1 else torch.stack(out)
+
+    def __iter__(self):
+        order = self.rng.permutation(len(self.files))
+        for k in range(0, len(order), self.batch_size):
+            yield torch.stack([self._patches(self.files[i]) for i in order[k:k + self.batch_size]])

@@ -96,6 +96,31 @@ class LLICTIEntropyLayer(nn.Module):
         self.entmdls_scale_band = nn.ModuleList([bands])
 
 
+class _SelfInformations(torch.autograd.Function):
+    """forward() with an autograd edge: the reference's training step calls `self.model(x)`, sums the result into a
+    loss and calls `.backward()` (agents/llicti_agent.py:56-61).  Both directions run in libllicti_b200
+    (`llicti_forward_dev`, `llicti_backward_dev`); nothing but the input batch is kept between them."""
+
+    @staticmethod
+    def forward(ctx, model, rgb, names, *params):
+        codec = model._train_codec()
+        codec.set_weights_dev(dict(zip(names, [p.detach() for p in params])))
+        ctx.model, ctx.rgb, ctx.names = model, rgb, names
+        return tuple(codec.forward_dev(rgb))
+
+    @staticmethod
+    def backward(ctx, *gsinfo):
+        codec = ctx.model._train_codec()
+        shapes = None
+        if any(g is None for g in gsinfo):                           # a scale the loss did not touch
+            n, _, H, W = ctx.rgb.shape
+            geo = codec.geometry(H, W)
+            shapes = [(n, 9, geo.Hs[s], geo.Ws[s]) for s in range(len(gsinfo))]
+        gs = [g if g is not None else torch.zeros(shapes[s], dtype=torch.float32, device=codec.device) for s, g in enumerate(gsinfo)]
+        grads = codec.backward_dev(ctx.rgb, gs, ctx.names)
+        return (None, None, None) + tuple(grads[k] for k in ctx.names)
+
+
 class LLICTI(nn.Module):
     """Drop-in for the reference's LLICTI on the eval_model path."""
 
@@ -112,6 +137,7 @@ class LLICTI(nn.Module):
         self.ycocg = True
         self.entropymodel = LLICTIEntropyLayer(self.codec_config.chs, self.codec_config.num_mixtures, self)
         self.__dict__["_codec_obj"] = None
+        self.__dict__["_train_codec_obj"] = None
 
     # -- parameter plumbing -------------------------------------------------------------------
     def _invalidate(self):
@@ -119,6 +145,10 @@ class LLICTI(nn.Module):
         if c is not None:
             c.close()
         self.__dict__["_codec_obj"] = None
+        t = self.__dict__.get("_train_codec_obj")
+        if t is not None:
+            t.close()
+        self.__dict__["_train_codec_obj"] = None
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         own = set(self.state_dict().keys())
@@ -148,16 +178,45 @@ class LLICTI(nn.Module):
             self.__dict__["_codec_obj"] = c
         return c
 
+    def _train_codec(self) -> Codec:
+        """The training context: fp32 CNN (the reference trains in fp32), weights pushed from the parameters before every
+        forward pass (`llicti_set_weights_dev`)."""
+        c = self.__dict__.get("_train_codec_obj")
+        if c is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("llicti_b200.LLICTI needs a CUDA device; there is no CPU fallback")
+            p = next(self.parameters())
+            if not p.is_cuda:
+                raise RuntimeError("training needs the model on a CUDA device: model.to('cuda')")
+            cfg = CodecConfig(**{**self.codec_config.__dict__, "cnn_impl": L.CNN_FP32, "device": int(p.device.index or 0)})
+            c = Codec(cfg, self.state_dict())
+            self.__dict__["_train_codec_obj"] = c
+        return c
+
     # -- reference interface ----------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, x):
         """x float32 [B,3,H,W] in [0,1] (uint8/255), H and W multiples of 2^num_scales -> list[num_scales] of
-        float32 [B,9,Hs,Ws] self-informations (reference :101-123): the rate-estimation path of validate().  Inference
-        only: the values carry no autograd graph (training is outside the B200 path)."""
+        float32 [B,9,Hs,Ws] self-informations (reference :101-123): the rate-estimation path of validate() and the
+        forward half of the training step.  In training mode (`model.train()`, the reference's agent sets it before every
+        epoch), with gradients enabled and parameters that require them, the result carries an autograd edge whose backward is `llicti_backward_dev` (fp32 CNN), so the reference's
+        `loss.backward(); optimizer.step()` works on it unchanged; otherwise it is inference only."""
         assert x.dim() == 4 and x.shape[1] == 3, "expected [B,3,H,W]"
-        codec = self._codec()
-        rgb = torch.round(x.to(codec.device) * 255).to(torch.uint8).contiguous()
-        return codec.forward_dev(rgb)
+        named = [(k, p) for k, p in self.named_parameters() if p.requires_grad]
+        if self.training and torch.is_grad_enabled() and named:
+            dev = named[0][1].device
+            rgb = torch.round(x.detach().to(dev) * 255).to(torch.uint8).contiguous()
+            c = self.__dict__.get("_codec_obj")
+            if c is not None:                      # the coding context holds weights that are about to change
+                c.close()
+                self.__dict__["_codec_obj"] = None
+            names = tuple(k for k, _ in named)
+            if len(names) != 24:
+                raise RuntimeError("training needs all 24 weight tensors to require gradients")
+            return list(_SelfInformations.apply(self, rgb, names, *[p for _, p in named]))
+        with torch.no_grad():
+            codec = self._codec()
+            rgb = torch.round(x.to(codec.device) * 255).to(torch.uint8).contiguous()
+            return codec.forward_dev(rgb)
 
     @torch.no_grad()
     def compress(self, x: torch.Tensor):

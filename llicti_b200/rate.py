@@ -22,13 +22,23 @@ class CompressionRLossList:
 
 class TrainRLossList:
     """Rate estimate from the self-informations of forward() (graphs/losses/rate_dist.py:97-104): per scale the nine
-    sums over (batch, rows, columns) / numel * 3 bits per pixel, and their total.  Inference only (validate())."""
+    sums over (batch, rows, columns) / numel * 3 bits per pixel, and their total.  When the self-informations carry an
+    autograd edge (the training step) the total is a tensor to call `.backward()` on, as in the reference; otherwise a
+    float summed in double precision (validate())."""
 
     def __init__(self):
         self.rate1 = 0.0
         self.rate1list = []
 
     def forward(self, numel_x, sinfoslist):
+        if any(getattr(s, "requires_grad", False) for s in sinfoslist):
+            import torch
+            self.rate1, self.rate1list = 0, []
+            for s in sinfoslist:
+                per = torch.sum(s, dim=(0, 2, 3)) / numel_x * 3
+                self.rate1list.append(per.tolist())
+                self.rate1 = self.rate1 + torch.sum(per)
+            return self.rate1, self.rate1list
         self.rate1list = [[float(v) / numel_x * 3 for v in s.double().sum(dim=(0, 2, 3)).tolist()] for s in sinfoslist]
         self.rate1 = float(sum(sum(r) for r in self.rate1list))
         return self.rate1, self.rate1list

@@ -246,6 +246,16 @@ def synthetic_state_dict(cfg: OracleConfig, seed: int = 1337) -> Dict[str, np.nd
     return sd
 
 
+def jittered_state_dict(cfg: OracleConfig, seed: int = 1337, jitter: float = 2e-3) -> Dict[str, np.ndarray]:
+    """synthetic_state_dict with every weight moved by N(0, jitter^2).  The hand-wired interpolation path (taps of exactly
+    +-0.25 over integer / 255 samples, zero weights elsewhere) puts pre-activations EXACTLY on the ReLU's kink wherever
+    four neighbours cancel; there the gradient depends on rounding noise (the reference's float lifting leaves +-1e-9
+    where integers would cancel).  Gradient parity is tested with these generic weights, as trained ones are."""
+    rng = np.random.default_rng(seed + 977)
+    sd = synthetic_state_dict(cfg, seed)
+    return {k: (sd[k] + jitter * rng.standard_normal(sd[k].shape)).astype(np.float32) for k in sorted(sd)}
+
+
 # --------------------------------------------------------------------------
 # a2: integer YCoCg-R  (LLICTI_nets.py:62-74, 77-88, 571-582)
 # --------------------------------------------------------------------------
@@ -649,13 +659,34 @@ def float_ycocg_r(x: torch.Tensor) -> torch.Tensor:
     return torch.cat((Y, Co, Cg), dim=1)
 
 
-def forward_self_informations(cfg: OracleConfig, net: "OracleNet", rgb: np.ndarray) -> List[np.ndarray]:
-    """rgb uint8 [3,H,W], H and W multiples of 2^S (the un-padded lazyDWT needs equal phase sizes; the reference
-    trains on such patches and pads validation images, agents/llicti_agent.py:105-116) -> per scale fp32
-    [9,Hs,Ws]: -log2 p of band b, channel clr at index 3 b + clr."""
+class _LowerBoundFn(torch.autograd.Function):
+    """compressai.ops.LowerBound as the reference's entropy layer uses it (entropy_layer_nets.py:9, 135, 158, 176):
+    max(x, bound) whose gradient passes where x >= bound or where the step would raise x."""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        ctx.save_for_backward(x, bound)
+        return torch.max(x, bound)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, bound = ctx.saved_tensors
+        return ((x >= bound) | (grad_output < 0)) * grad_output, None
+
+
+def _lower_bound(x: torch.Tensor, bound: float) -> torch.Tensor:
+    b = torch.tensor([bound])
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _LowerBoundFn.apply(x, b)
+    return torch.max(x, b)
+
+
+def self_informations_torch(cfg: OracleConfig, net: "OracleNet", x: torch.Tensor) -> List[torch.Tensor]:
+    """LLICTI.forward (LLICTI_nets.py:101-123, 318-342, 827-935) on x float32 [B,3,H,W] = uint8 / 255, H and W multiples of
+    2^S: per scale fp32 [B,9,Hs,Ws], -log2 p of band b, channel clr at index 3 b + clr.  Differentiable with respect to the
+    tensors of `net.sd` when they require grad (the training step differentiates exactly this graph)."""
     S, M = len(cfg.dwtlevels), cfg.num_mixtures
-    assert rgb.shape[1] % 2 ** S == 0 and rgb.shape[2] % 2 ** S == 0
-    x = torch.from_numpy(rgb.astype(np.float32) / np.float32(255.0))[None]          # ToTensor()
+    assert x.shape[2] % 2 ** S == 0 and x.shape[3] % 2 ** S == 0
     x = float_ycocg_r(x)
     x[:, 0] = x[:, 0] - (2 ** 7 - 1) / (2 ** 8 - 1)                                  # :110, mean_y_ycocg :26
     out = []
@@ -674,19 +705,44 @@ def forward_self_informations(cfg: OracleConfig, net: "OracleNet", rgb: np.ndarr
             mean[:, 2 * M:3 * M] = mean[:, 2 * M:3 * M] + bb * yt[:, 0:1] + d * yt[:, 1:2]
             # GaussianConditionalLosslessGMM.forward: channels-last, inputs repeated per mixture
             inp = yt.permute(0, 2, 3, 1).repeat_interleave(M, dim=3)
-            sc = torch.max(stdev.permute(0, 2, 3, 1), torch.tensor([SCALE_BOUND]))
+            sc = _lower_bound(stdev.permute(0, 2, 3, 1), SCALE_BOUND)
             values = torch.abs(inp - mean.permute(0, 2, 3, 1))
             const = float(-(2 ** -0.5))
             upper = 0.5 * torch.erfc(const * ((half - values) / sc))
             lower = 0.5 * torch.erfc(const * ((-half - values) / sc))
             lik_m = (upper - lower).view(B_, H, W, 3, M)
-            w = torch.max(wts.permute(0, 2, 3, 1).view(B_, H, W, 3, M), torch.tensor([WEIGHT_BOUND]))
+            w = _lower_bound(wts.permute(0, 2, 3, 1).view(B_, H, W, 3, M), WEIGHT_BOUND)
             w = w / torch.sum(w, dim=4, keepdim=True)
             lik = torch.sum(w * lik_m, dim=4).permute(0, 3, 1, 2)
-            lik = torch.max(lik, torch.tensor([LIKELIHOOD_BOUND]))
+            lik = _lower_bound(lik, LIKELIHOOD_BOUND)
             infos.append(-torch.log2(lik))
-        out.append(torch.cat(infos, dim=1)[0].numpy())
+        out.append(torch.cat(infos, dim=1))
     return out
+
+
+def forward_self_informations(cfg: OracleConfig, net: "OracleNet", rgb: np.ndarray) -> List[np.ndarray]:
+    """rgb uint8 [3,H,W], H and W multiples of 2^S (the un-padded lazyDWT needs equal phase sizes; the reference
+    trains on such patches and pads validation images, agents/llicti_agent.py:105-116) -> per scale fp32
+    [9,Hs,Ws]: -log2 p of band b, channel clr at index 3 b + clr."""
+    x = torch.from_numpy(rgb.astype(np.float32) / np.float32(255.0))[None]          # ToTensor()
+    with torch.no_grad():
+        return [t[0].numpy() for t in self_informations_torch(cfg, net, x)]
+
+
+def train_loss_and_grads(cfg: OracleConfig, state_dict, rgb: np.ndarray, grad_acc_iters: int = 1):
+    """One backward pass of the reference's training step (agents/llicti_agent.py:52-61) on a batch rgb uint8 [B,3,H,W]:
+    self-informations -> TrainRLossList (graphs/losses/rate_dist.py:97-104: sum over scales of sum(sinfo) / numel(x) * 3) ->
+    (loss / grad_acc_iters).backward().  Returns (loss, {state_dict key: gradient as fp32 array})."""
+    net = OracleNet(cfg, state_dict)
+    for t in net.sd.values():
+        t.requires_grad_(True)
+    x = torch.from_numpy(rgb.astype(np.float32) / np.float32(255.0))
+    sinfos = self_informations_torch(cfg, net, x)
+    loss = 0
+    for t in sinfos:
+        loss = loss + torch.sum(torch.sum(t, dim=(0, 2, 3)) / x.numel() * 3)
+    (loss / grad_acc_iters).backward()
+    return float(loss.item()), {k: t.grad.numpy().copy() for k, t in net.sd.items()}
 
 
 def diagnose_round_trip(codec: "OracleCodec", rgb: np.ndarray) -> str:

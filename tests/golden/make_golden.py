@@ -221,6 +221,46 @@ def run_forward_case(name, cfg_name, kind, H, W, idx):
     print(f"{name}: {H}x{W} {cfg_name} estimated {bits / (H * W):.3f} bpp -> OK (reference forward == oracle)")
 
 
+TRAIN_CASES = [
+    # name, config, B, H, W, first image index: one backward pass of the reference's training step
+    ("train_a_2x32x32", "llicti_A.json", 2, 32, 32, 30),
+    ("train_b_3x24x40", "llicti_B.json", 3, 24, 40, 33),
+]
+
+
+def run_train_case(name, cfg_name, B, H, W, idx):
+    """The backward pass of the unmodified reference's training step (agents/llicti_agent.py:52-61): model.train(),
+    self_infos = model(x), TrainRLossList, loss.backward().  Stored: the batch, the loss and every parameter's gradient;
+    checked against the oracle's restatement (oracle.train_loss_and_grads)."""
+    from graphs.losses.rate_dist import TrainRLossList
+    cfg = ref_config(cfg_name)
+    ocfg = O.OracleConfig.from_dict(cfg)
+    sd = O.jittered_state_dict(ocfg, seed=1337)       # generic weights: no pre-activation sits exactly on a ReLU kink
+    torch.manual_seed(0)
+    model = LLICTI(cfg).train()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    rgb = np.stack([make_image("photo" if i % 2 == 0 else "noise", H, W, idx + i) for i in range(B)])
+    x = torch.from_numpy(rgb.astype(np.float32) / np.float32(255.0))
+    sinfos = model(x.clone())
+    loss, rate1_list = TrainRLossList().forward(torch.numel(x), sinfos)
+    loss.backward()
+    ref = {k: p.grad.numpy() for k, p in model.named_parameters() if p.grad is not None}
+    o_loss, mine = O.train_loss_and_grads(ocfg, sd, rgb)
+    assert set(ref) == set(mine), (set(ref) ^ set(mine))
+    worst = 0.0
+    for k in ref:
+        err = float(np.abs(ref[k] - mine[k]).max()) / (float(np.abs(ref[k]).max()) + 1e-30)
+        worst = max(worst, err)
+        assert err < 1e-5, f"{name}: gradient of {k} differs between reference and oracle ({err:.3e})"
+    assert abs(o_loss - float(loss.item())) < 1e-6 * abs(o_loss)
+    out = {"rgb": rgb, "config": np.array(cfg_name), "loss": np.array(float(loss.item()))}
+    for k, v in ref.items():
+        out["grad/" + k] = v.astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {B}x{H}x{W} {cfg_name} loss {float(loss.item()):.4f} bpp, {len(ref)} gradients, "
+          f"worst relative difference reference vs oracle {worst:.2e} -> OK")
+
+
 def canary():
     """Bit patterns of the two host-dependent float primitives (vector erfc, reduction
     order); tests skip the bit-exact float checks when the running host disagrees."""
@@ -236,6 +276,10 @@ def canary():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     canary()
+    if "--only-train-step" in sys.argv:
+        for c in TRAIN_CASES:
+            run_train_case(*c)
+        sys.exit(0)
     if "--only-forward" not in sys.argv and "--only-trained" not in sys.argv:
         for i, c in enumerate(CASES):
             run_case(*c, idx=i)
@@ -246,5 +290,7 @@ if __name__ == "__main__":
         sys.exit(0)
     for c in FORWARD_CASES:
         run_forward_case(*c)
+    for c in TRAIN_CASES:
+        run_train_case(*c)
     sz = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print("fixtures total bytes:", sz)

@@ -784,7 +784,7 @@ def test_forward_through_the_model_interface(L):
     from llicti_b200 import LLICTI
     from llicti_b200._lib import LlictiError
     cfg = json.load(open(os.path.join(ROOT, "configs", "llicti_A.json")))
-    model = LLICTI(cfg, cnn_impl=0, numerics=L.NUM_TORCH_CPU).to("cuda")
+    model = LLICTI(cfg, cnn_impl=0, numerics=L.NUM_TORCH_CPU).to("cuda").eval()
     ocfg = O.OracleConfig()
     sd = O.synthetic_state_dict(ocfg)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
