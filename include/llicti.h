@@ -225,16 +225,22 @@ LLICTI_API int llicti_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n
  *
  * llicti_set_weights_dev: replace the context's weights by the ones at these DEVICE pointers (PyTorch layouts, the
  *   shapes of llicti_weights) -- the parameters after an optimizer step.
+ * llicti_train_forward_dev: llicti_forward_dev that keeps every band's 60 network outputs for the backward pass.
+ *   params_keep_dev float [180 * n * sum_s Hs*Ws]  (blocks [n][60][Hs*Ws] in (scale, band) order; llicti_geom.positions = sum_s Hs*Ws)
  * llicti_backward_dev: gradients of a loss L over forward()'s outputs with respect to every weight.
- *   fplanes_dev[s]  float [n][12][Hs][Ws]  scratch, as in llicti_forward_dev
+ *   fplanes_dev[s]  float [n][12][Hs][Ws]  the planes llicti_train_forward_dev wrote (scratch when params_kept_dev is NULL)
  *   gsinfo_dev[s]   float [n][9][Hs][Ws]   dL / d self-information (what autograd hands the backward of forward())
+ *   params_kept_dev the buffer llicti_train_forward_dev filled for this batch (consumed: overwritten with the gradients
+ *                   of the network outputs), or NULL: colour split and CNN are run again
  *   grads_dev       DEVICE pointers, layouts and order of llicti_weights; overwritten with dL / d weight (each of a
  *                   band's branch biases receives the gradient of their sum)
  * compressai's LowerBound gradient rule (pass where x >= bound or where the step would raise x) applies to the spreads,
  * the mixture weights and the likelihood (entropy_layer_nets.py:135, 176, 181). */
 LLICTI_API int llicti_set_weights_dev(llicti_ctx *ctx, const llicti_weights *w_dev, void *stream);
+LLICTI_API int llicti_train_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, float *const *fplanes_dev,
+                             float *const *sinfo_dev, float *params_keep_dev, void *stream);
 LLICTI_API int llicti_backward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, float *const *fplanes_dev,
-                        const float *const *gsinfo_dev, const llicti_weights *grads_dev, void *stream);
+                        const float *const *gsinfo_dev, float *params_kept_dev, const llicti_weights *grads_dev, void *stream);
 
 /* LLICTI.decompres for a batch (LLICTI_nets.py:161-179, 415-509).
  *   blob / stream_off  as produced by encode

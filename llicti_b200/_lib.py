@@ -88,8 +88,10 @@ _PROTOS = {
     "llicti_forward_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.c_void_p]),
     "llicti_set_weights_dev": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
+    "llicti_train_forward_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "llicti_backward_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
-                                      C.POINTER(C.c_void_p), C.POINTER(Weights), C.c_void_p]),
+                                      C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "llicti_cnn_operands": (C.c_int, [C.c_void_p]),
     "llicti_encode_batch_host": (C.c_int, [C.c_void_p, C.POINTER(EncodeItem), C.c_int, C.c_void_p]),
     "llicti_decode_batch_host": (C.c_int, [C.c_void_p, C.POINTER(DecodeItem), C.c_int, C.c_void_p]),

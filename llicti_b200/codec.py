@@ -320,9 +320,26 @@ class Codec:
         self.fingerprint = None
         del keep
 
-    def backward_dev(self, rgb: torch.Tensor, gsinfo: Sequence[torch.Tensor], names: Sequence[str]) -> Dict[str, torch.Tensor]:
+    def train_forward_dev(self, rgb: torch.Tensor):
+        """forward_dev for a training step: returns (self-informations per scale, kept) where `kept` = (fp32 planes,
+        network outputs of every band) is what backward_dev needs to skip the colour split and the CNN."""
+        assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
+        n, _, H, W = rgb.shape
+        self.reserve(n, H, W)
+        g = self.geometry(H, W)
+        S = self.cfg.num_scales
+        fpl = [torch.empty((n, 12, g.Hs[s], g.Ws[s]), dtype=torch.float32, device=self.device) for s in range(S)]
+        out = [torch.empty((n, 9, g.Hs[s], g.Ws[s]), dtype=torch.float32, device=self.device) for s in range(S)]
+        keep = torch.empty((180 * n * int(g.positions),), dtype=torch.float32, device=self.device)
+        fp = (C.c_void_p * S)(*[t.data_ptr() for t in fpl])
+        op = (C.c_void_p * S)(*[t.data_ptr() for t in out])
+        L.check(self.lib.llicti_train_forward_dev(self._ctx, rgb.data_ptr(), n, H, W, fp, op, keep.data_ptr(), self._stream()))
+        return out, (fpl, keep)
+
+    def backward_dev(self, rgb: torch.Tensor, gsinfo: Sequence[torch.Tensor], names: Sequence[str], kept=None) -> Dict[str, torch.Tensor]:
         """Gradients of a loss with respect to every weight, given dL / d self-information per scale (float32
-        [n,9,Hs,Ws], the shapes forward_dev returns).  `names`: the state_dict keys wanted (all 24 weight tensors)."""
+        [n,9,Hs,Ws], the shapes forward_dev returns).  `names`: the state_dict keys wanted (all 24 weight tensors);
+        `kept`: the second result of train_forward_dev for this batch (consumed), or None to recompute."""
         assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
         n, _, H, W = rgb.shape
         self.reserve(n, H, W)
@@ -334,7 +351,12 @@ class Codec:
             if tuple(t.shape) != (n, 9, g.Hs[s], g.Ws[s]):
                 raise ValueError(f"gradient of scale {s}: shape {tuple(t.shape)}, expected {(n, 9, g.Hs[s], g.Ws[s])}")
             gs.append(t)
-        fpl = [torch.empty((n, 12, g.Hs[s], g.Ws[s]), dtype=torch.float32, device=self.device) for s in range(S)]
+        if kept is not None:
+            fpl, keep_params = kept
+            assert keep_params.numel() == 180 * n * int(g.positions) and len(fpl) == S
+        else:
+            fpl = [torch.empty((n, 12, g.Hs[s], g.Ws[s]), dtype=torch.float32, device=self.device) for s in range(S)]
+            keep_params = None
         grads = {}
         for band, name in L0_NAMES:
             kh, kw = L0_SHAPES[name]
@@ -348,7 +370,8 @@ class Codec:
         w, keep = self._weights_struct(grads)
         fp = (C.c_void_p * S)(*[t.data_ptr() for t in fpl])
         gp = (C.c_void_p * S)(*[t.data_ptr() for t in gs])
-        L.check(self.lib.llicti_backward_dev(self._ctx, rgb.data_ptr(), n, H, W, fp, gp, C.byref(w), self._stream()))
+        L.check(self.lib.llicti_backward_dev(self._ctx, rgb.data_ptr(), n, H, W, fp, gp,
+                                             keep_params.data_ptr() if keep_params is not None else None, C.byref(w), self._stream()))
         del keep
         return {k: grads[k] for k in names}
 

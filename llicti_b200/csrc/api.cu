@@ -543,12 +543,44 @@ int llicti_set_weights_dev(llicti_ctx *ctx, const llicti_weights *w_dev, void *s
     return launch_train_layouts(ctx, *w_dev, true, (cudaStream_t)stream);
 }
 
-// d loss / d weights for a loss whose gradient with respect to forward()'s self-informations is gsinfo_dev: the colour
-// split and the fp32 CNN are re-run per band (nothing but the self-informations was kept from the forward pass), the
-// likelihood is differentiated in place over the parameters, the CNN backward accumulates packed weight gradients, which
-// are written to grads_dev in PyTorch's layouts at the end.
+// Offset (in floats) of band b of scale s in the kept-parameter buffer of a training step: blocks [n][60][P_s] in
+// (scale, band) order.
+static size_t kept_offset(const llicti_geom &g, int n, int s, int b) {
+    size_t pos = 0;
+    for (int t = 0; t < s; ++t) pos += (size_t)3 * g.Hs[t] * g.Ws[t];
+    return (size_t)kParamCh * n * (pos + (size_t)b * g.Hs[s] * g.Ws[s]);
+}
+
+// forward() of a training step: as llicti_forward_dev on an fp32 context, but every band's 60 network outputs stay in
+// params_keep_dev (180 * n * sum_s Hs*Ws floats) for the backward pass, which then neither repeats the colour split nor the CNN.
+int llicti_train_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, float *const *fplanes_dev,
+                             float *const *sinfo_dev, float *params_keep_dev, void *stream) {
+    int rc = check_batch(ctx, n, H, W);
+    if (rc) return rc;
+    LLICTI_REQUIRE(rgb_dev && fplanes_dev && sinfo_dev && params_keep_dev, "null argument");
+    LLICTI_REQUIRE(ctx->cfg.cnn_impl == LLICTI_CNN_FP32, "llicti_train_forward_dev needs a context created with cnn_impl = LLICTI_CNN_FP32");
+    const Plan &p = ctx->plan;
+    const llicti_geom &g = p.g;
+    LLICTI_REQUIRE(H % (1 << g.num_scales) == 0 && W % (1 << g.num_scales) == 0,
+                   "forward() needs H and W to be multiples of 2^num_scales = %d", 1 << g.num_scales);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s = 0; s < g.num_scales; ++s) LLICTI_REQUIRE(fplanes_dev[s] && sinfo_dev[s], "null plane pointer");
+    if ((rc = launch_color_split_float(ctx, p, rgb_dev, n, fplanes_dev, ctx->d_planes, st))) return rc;
+    for (int s = 0; s < g.num_scales; ++s)
+        for (int b = 0; b < 3; ++b) {
+            float *params = params_keep_dev + kept_offset(g, n, s, b);
+            if ((rc = launch_cnn_fp32(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], params, st, fplanes_dev[s]))) return rc;
+            if ((rc = launch_self_info(ctx, params, fplanes_dev[s], b, n, g.Hs[s] * g.Ws[s], sinfo_dev[s], st))) return rc;
+        }
+    return LLICTI_OK;
+}
+
+// d loss / d weights for a loss whose gradient with respect to forward()'s self-informations is gsinfo_dev.  Per band:
+// the network outputs (kept by llicti_train_forward_dev, or -- params_kept_dev == NULL -- recomputed: colour split and fp32
+// CNN again), the likelihood differentiated in place over them, the CNN backward accumulating packed weight gradients,
+// which are written to grads_dev in PyTorch's layouts at the end.
 int llicti_backward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, int W, float *const *fplanes_dev,
-                        const float *const *gsinfo_dev, const llicti_weights *grads_dev, void *stream) {
+                        const float *const *gsinfo_dev, float *params_kept_dev, const llicti_weights *grads_dev, void *stream) {
     int rc = check_batch(ctx, n, H, W);
     if (rc) return rc;
     LLICTI_REQUIRE(rgb_dev && fplanes_dev && gsinfo_dev && grads_dev, "null argument");
@@ -560,12 +592,13 @@ int llicti_backward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, i
     cudaStream_t st = (cudaStream_t)stream;
     for (int s = 0; s < g.num_scales; ++s) LLICTI_REQUIRE(fplanes_dev[s] && gsinfo_dev[s], "null plane pointer");
     if ((rc = launch_train_zero_grads(ctx, st))) return rc;
-    if ((rc = launch_color_split_float(ctx, p, rgb_dev, n, fplanes_dev, ctx->d_planes, st))) return rc;
+    if (!params_kept_dev && (rc = launch_color_split_float(ctx, p, rgb_dev, n, fplanes_dev, ctx->d_planes, st))) return rc;
     for (int s = 0; s < g.num_scales; ++s)
         for (int b = 0; b < 3; ++b) {
-            if ((rc = launch_cnn_fp32(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st, fplanes_dev[s]))) return rc;
-            if ((rc = launch_self_info_grad(ctx, ctx->d_params, fplanes_dev[s], gsinfo_dev[s], b, n, g.Hs[s] * g.Ws[s], st))) return rc;
-            if ((rc = launch_cnn_backward(ctx, b, fplanes_dev[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st))) return rc;
+            float *params = params_kept_dev ? params_kept_dev + kept_offset(g, n, s, b) : ctx->d_params;
+            if (!params_kept_dev && (rc = launch_cnn_fp32(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], params, st, fplanes_dev[s]))) return rc;
+            if ((rc = launch_self_info_grad(ctx, params, fplanes_dev[s], gsinfo_dev[s], b, n, g.Hs[s] * g.Ws[s], st))) return rc;
+            if ((rc = launch_cnn_backward(ctx, b, fplanes_dev[s], n, g.Hs[s], g.Ws[s], params, st))) return rc;
         }
     return launch_train_layouts(ctx, *grads_dev, false, st);
 }

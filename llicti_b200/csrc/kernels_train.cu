@@ -132,16 +132,26 @@ __device__ __forceinline__ void layer_forward(const float *X, int K, const float
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[c][q] = bv;
     }
-    const float *wp = Wt + cg * CPT;
+    const float *wp = Wt + cg * CPT;       // 8-byte (CPT = 6, GP = 96) / 16-byte (CPT = 4, GP = 68) aligned in every row
+#pragma unroll 2
     for (int k = 0; k < K; ++k) {
         const float4 a = *reinterpret_cast<const float4 *>(X + k * BLD + pg * 4);
+        float wv[CPT];                     // (columns G .. GP-1 of the packed rows are zero padding)
+        if constexpr (CPT == 6) {
+            const float2 w01 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP));
+            const float2 w23 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP + 2));
+            const float2 w45 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP + 4));
+            wv[0] = w01.x; wv[1] = w01.y; wv[2] = w23.x; wv[3] = w23.y; wv[4] = w45.x; wv[5] = w45.y;
+        } else {
+            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wp + (size_t)k * GP));
+            wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+        }
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
-            const float wv = __ldg(wp + (size_t)k * GP + c);       // (columns G .. GP-1 of the packed rows are zero padding)
-            acc[c][0] = fmaf(a.x, wv, acc[c][0]);
-            acc[c][1] = fmaf(a.y, wv, acc[c][1]);
-            acc[c][2] = fmaf(a.z, wv, acc[c][2]);
-            acc[c][3] = fmaf(a.w, wv, acc[c][3]);
+            acc[c][0] = fmaf(a.x, wv[c], acc[c][0]);
+            acc[c][1] = fmaf(a.y, wv[c], acc[c][1]);
+            acc[c][2] = fmaf(a.z, wv[c], acc[c][2]);
+            acc[c][3] = fmaf(a.w, wv[c], acc[c][3]);
         }
     }
 #pragma unroll
@@ -165,16 +175,19 @@ __device__ __forceinline__ void layer_backward_data(const float *X, const float 
     for (int c = 0; c < CPT; ++c)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[c][q] = 0.f;
-    for (int o = 0; o < No; ++o) {
-        const float4 d = *reinterpret_cast<const float4 *>(dY + o * BLD + pg * 4);
+    for (int o = 0; o < No; o += 4) {       // No % 4 == 0; rows of Wt are 16-byte aligned at multiples of four columns
+        const float4 d0 = *reinterpret_cast<const float4 *>(dY + (o + 0) * BLD + pg * 4);
+        const float4 d1 = *reinterpret_cast<const float4 *>(dY + (o + 1) * BLD + pg * 4);
+        const float4 d2 = *reinterpret_cast<const float4 *>(dY + (o + 2) * BLD + pg * 4);
+        const float4 d3 = *reinterpret_cast<const float4 *>(dY + (o + 3) * BLD + pg * 4);
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int k = min(cg * CPT + c, G - 1);
-            const float wv = __ldg(Wt + (size_t)k * wstride + o);
-            acc[c][0] = fmaf(d.x, wv, acc[c][0]);
-            acc[c][1] = fmaf(d.y, wv, acc[c][1]);
-            acc[c][2] = fmaf(d.z, wv, acc[c][2]);
-            acc[c][3] = fmaf(d.w, wv, acc[c][3]);
+            const float4 wv = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)k * wstride + o));
+            acc[c][0] = fmaf(d3.x, wv.w, fmaf(d2.x, wv.z, fmaf(d1.x, wv.y, fmaf(d0.x, wv.x, acc[c][0]))));
+            acc[c][1] = fmaf(d3.y, wv.w, fmaf(d2.y, wv.z, fmaf(d1.y, wv.y, fmaf(d0.y, wv.x, acc[c][1]))));
+            acc[c][2] = fmaf(d3.z, wv.w, fmaf(d2.z, wv.z, fmaf(d1.z, wv.y, fmaf(d0.z, wv.x, acc[c][2]))));
+            acc[c][3] = fmaf(d3.w, wv.w, fmaf(d2.w, wv.z, fmaf(d1.w, wv.y, fmaf(d0.w, wv.x, acc[c][3]))));
         }
     }
 #pragma unroll
@@ -275,17 +288,20 @@ cnn_backward_kernel(const float *__restrict__ fplanes, int Hs, int Ws, int K0, T
         const int p0 = (int)(t - (long long)img * tiles_per_img) * BT;
         const float *pl = fplanes + (size_t)img * 12 * P;     // the float lifting's values, as the reference's graph sees them
         __syncthreads();                 // the previous tile's products have read A0 / H2 / D2 / DO
-        for (int e = tid; e < K0 * BT; e += BNT) {
-            const int k = e / BT, q = e - k * BT;
+        {   // a thread stages ONE position's column: its row / column once, then every fourth tap and output row
+            const int q = tid & (BT - 1), k4 = tid >> 6;
             const int p = min(p0 + q, P - 1);
             const int i = p / Ws, j = p - i * Ws;
-            const int rr = min(max(i + taps.dy[k], 0), Hs - 1);
-            const int cc = min(max(j + taps.dx[k], 0), Ws - 1);
-            A0[k * BLD + q] = pl[(size_t)(taps.phase[k] * 3 + taps.chan[k]) * P + (size_t)rr * Ws + cc];
-        }
-        for (int e = tid; e < 15 * BT; e += BNT) {
-            const int o = e / BT, q = e - o * BT;
-            DO[o * BLD + q] = (p0 + q < P) ? dparams[((size_t)img * kParamCh + g * 15 + o) * P + p0 + q] : 0.f;   // positions past the end: no gradient
+#pragma unroll 4
+            for (int k = k4; k < K0; k += BNT / BT) {
+                const int rr = min(max(i + taps.dy[k], 0), Hs - 1);
+                const int cc = min(max(j + taps.dx[k], 0), Ws - 1);
+                A0[k * BLD + q] = pl[(size_t)(taps.phase[k] * 3 + taps.chan[k]) * P + (size_t)rr * Ws + cc];
+            }
+            const bool inside = p0 + q < P;                      // positions past the end: no gradient
+            const float *dp = dparams + ((size_t)img * kParamCh + g * 15) * P + p;
+#pragma unroll
+            for (int o = k4; o < 15; o += BNT / BT) DO[o * BLD + q] = inside ? dp[(size_t)o * P] : 0.f;
         }
         __syncthreads();
         layer_forward<G>(A0, K0, w0, b0, H1, tid);
@@ -295,7 +311,7 @@ cnn_backward_kernel(const float *__restrict__ fplanes, int Hs, int Ws, int K0, T
         // layer 2: d W2 = H2 dO^T, d b2, d H2 = relu'(H2) * (W2 dO)
         weight_grad(H2, G, DO, 16, GW2, 16, tid);
         bias_grad(DO, 16, GB2, tid);
-        layer_backward_data<G>(H2, w2, 16, DO, 15, D2, tid);
+        layer_backward_data<G>(H2, w2, 16, DO, 16, D2, tid);      // (column 15 of the packed W2 and row 15 of dO are zero)
         __syncthreads();
         // layer 1: d W1 = H1 dH2^T, d b1, d H1 = relu'(H1) * (W1 dH2) -> H2's buffer
         weight_grad(H1, G, D2, G, GW1, G, tid);

@@ -99,14 +99,16 @@ class LLICTIEntropyLayer(nn.Module):
 class _SelfInformations(torch.autograd.Function):
     """forward() with an autograd edge: the reference's training step calls `self.model(x)`, sums the result into a
     loss and calls `.backward()` (agents/llicti_agent.py:56-61).  Both directions run in libllicti_b200
-    (`llicti_forward_dev`, `llicti_backward_dev`); nothing but the input batch is kept between them."""
+    (`llicti_train_forward_dev`, `llicti_backward_dev`); the fp32 planes and the network outputs (240 B per position and
+    band) are kept between them, no hidden activation is."""
 
     @staticmethod
     def forward(ctx, model, rgb, names, *params):
         codec = model._train_codec()
         codec.set_weights_dev(dict(zip(names, [p.detach() for p in params])))
-        ctx.model, ctx.rgb, ctx.names = model, rgb, names
-        return tuple(codec.forward_dev(rgb))
+        outs, kept = codec.train_forward_dev(rgb)
+        ctx.model, ctx.rgb, ctx.names, ctx.kept = model, rgb, names, kept
+        return tuple(outs)
 
     @staticmethod
     def backward(ctx, *gsinfo):
@@ -117,7 +119,8 @@ class _SelfInformations(torch.autograd.Function):
             geo = codec.geometry(H, W)
             shapes = [(n, 9, geo.Hs[s], geo.Ws[s]) for s in range(len(gsinfo))]
         gs = [g if g is not None else torch.zeros(shapes[s], dtype=torch.float32, device=codec.device) for s, g in enumerate(gsinfo)]
-        grads = codec.backward_dev(ctx.rgb, gs, ctx.names)
+        kept, ctx.kept = ctx.kept, None                                # consumed: a second backward recomputes
+        grads = codec.backward_dev(ctx.rgb, gs, ctx.names, kept=kept)
         return (None, None, None) + tuple(grads[k] for k in ctx.names)
 
 

@@ -54,8 +54,12 @@ def test_backward_equals_the_reference_gradients(L, name):
     assert abs(loss - float(g["loss"])) <= 1e-4 * abs(loss), (loss, float(g["loss"]))
     gs = [torch.full_like(s, 3.0 / rgb.numel()) for s in sinfo]
     names = [k[5:] for k in g.files if k.startswith("grad/")]
-    grads = codec.backward_dev(rgb, gs, names)
+    grads = codec.backward_dev(rgb, gs, names)                      # colour split and CNN recomputed
     _compare(grads, {k: g["grad/" + k] for k in names})
+    sinfo2, kept = codec.train_forward_dev(rgb)                    # planes and network outputs kept from the forward pass
+    assert all(torch.equal(a, b) for a, b in zip(sinfo, sinfo2))
+    grads2 = codec.backward_dev(rgb, gs, names, kept=kept)
+    _compare(grads2, {k: g["grad/" + k] for k in names})
     codec.close()
 
 
