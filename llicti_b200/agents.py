@@ -16,6 +16,7 @@ import torch
 from .image_dl import TestImageLoader
 from .model import LLICTI
 from .rate import CompressionRLossList, RateLogger
+from .shard import average_gradients
 
 
 class BaseAgent:
@@ -29,6 +30,13 @@ class BaseAgent:
         if not (torch.cuda.is_available() and config.cuda):
             raise RuntimeError("the B200 path needs `cuda: true` and a CUDA device; there is no CPU fallback")
         self.cuda = True
+        # one process per GPU under torchrun (data-parallel training): the rank's own device, NCCL for the gradient average
+        import os
+        self.world, self.rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+        if self.world > 1:
+            config.gpu_device = int(os.environ.get("LOCAL_RANK", "0"))
+            if not torch.distributed.is_initialized():
+                torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", int(config.gpu_device)))
         self.device = torch.device("cuda", int(config.gpu_device))
         torch.cuda.set_device(self.device)
         torch.cuda.manual_seed(self.manual_seed)
@@ -55,6 +63,8 @@ class BaseAgent:
                 self.config.checkpoint_dir))
 
     def save_checkpoint(self, filename="checkpoint.pth.tar", is_best=0):
+        if getattr(self, "rank", 0) != 0:            # data-parallel training: the ranks hold the same weights, rank 0 writes
+            return
         state = {"epoch": self.current_epoch, "iteration": self.current_iteration,
                  "best_valid_loss": self.best_valid_loss, "state_dict": self.model.state_dict()}
         for key in ("optimizer", "scheduler", "train_logger", "trnit_logger", "valid_logger"):   # base.py:88-92 (training runs)
@@ -100,6 +110,13 @@ class BaseAgent:
     def finalize(self):
         self.logger.info("Please wait while finalizing the operation.. Thank you")
         self.save_checkpoint()
+        import os
+        dump = os.environ.get("LLICTI_TEST_DUMP_WEIGHTS")          # tests: every rank's final weights ("{rank}" in the path)
+        if dump:
+            torch.save({k: v.detach().cpu() for k, v in self.model.state_dict().items()}, dump.format(rank=getattr(self, "rank", 0)))
+        if getattr(self, "world", 1) > 1 and torch.distributed.is_initialized():
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
 
 
 class LLICTIAgent(BaseAgent):
@@ -116,7 +133,7 @@ class LLICTIAgent(BaseAgent):
             from .rate import TrainRLossList
             dirs = [getattr(config, "train_data_%d" % i) for i in range(1, int(getattr(config, "num_train_dirs", 1)) + 1)]
             self.train_loader = TrainImageLoader(dirs, config.patch_size, config.batch_size,
-                                                 getattr(config, "patches_per_img", 1), seed=config.seed)
+                                                 getattr(config, "patches_per_img", 1), seed=config.seed, rank=self.rank, world=self.world)
             self.train_loss = TrainRLossList()
             self.train_logger, self.trnit_logger, self.valid_logger = RateLogger(), RateLogger(), RateLogger()
             self.lr = config.learning_rate
@@ -141,6 +158,7 @@ class LLICTIAgent(BaseAgent):
             r_loss, rate1_list = self.train_loss.forward(torch.numel(x), self_infos_y_list)
             (r_loss / self.grad_acc_iters).backward()
             if (self.current_iteration + 1) % self.grad_acc_iters == 0:
+                average_gradients(list(self.model.parameters()))      # identity on one GPU; the mean over the ranks under torchrun
                 torch.nn.utils.clip_grad_value_(self.model.parameters(), clip_value=5.0)
                 self.optimizer.step()
                 self.optimizer.zero_grad()

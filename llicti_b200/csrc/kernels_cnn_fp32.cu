@@ -45,18 +45,21 @@ cnn_fp32_kernel(const int16_t *__restrict__ planes, const float *__restrict__ fp
     const int tid = threadIdx.x;
 
     // ---- im2col with replicate padding (clamped indices) --------------------------------
-    for (int e = tid; e < K0 * TM; e += NT) {
-        const int k = e / TM, q = e - k * TM;
+    {   // a thread stages one position's column: its row / column once, then every second tap
+        const int q = tid & (TM - 1);
         const int p = min(p0 + q, P - 1);
         const int i = p / Ws, j = p - i * Ws;
-        const int rr = min(max(i + taps.dy[k], 0), Hs - 1);
-        const int cc = min(max(j + taps.dx[k], 0), Ws - 1);
-        const size_t src = (size_t)(taps.phase[k] * 3 + taps.chan[k]) * P + (size_t)rr * Ws + cc;
-        if (kFloatIn) {
-            A0[k * TM + q] = fpl[src];
-        } else {
-            const float v = (float)pl[src];
-            A0[k * TM + q] = div255_recip ? __fmul_rn(v, 1.0f / 255.0f) : __fdiv_rn(v, 255.0f);
+#pragma unroll 4
+        for (int k = tid / TM; k < K0; k += NT / TM) {
+            const int rr = min(max(i + taps.dy[k], 0), Hs - 1);
+            const int cc = min(max(j + taps.dx[k], 0), Ws - 1);
+            const size_t src = (size_t)(taps.phase[k] * 3 + taps.chan[k]) * P + (size_t)rr * Ws + cc;
+            if (kFloatIn) {
+                A0[k * TM + q] = fpl[src];
+            } else {
+                const float v = (float)pl[src];
+                A0[k * TM + q] = div255_recip ? __fmul_rn(v, 1.0f / 255.0f) : __fdiv_rn(v, 255.0f);
+            }
         }
     }
     __syncthreads();
@@ -81,11 +84,20 @@ cnn_fp32_kernel(const int16_t *__restrict__ planes, const float *__restrict__ fp
                 const float4 a0 = *reinterpret_cast<const float4 *>(A0 + k * TM + pg * PPT);
                 const float4 a1 = *reinterpret_cast<const float4 *>(A0 + k * TM + pg * PPT + 4);
                 const float av[PPT] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float wv[CPT];             // one row segment of the packed weights: 8-byte (CPT = 6) / 16-byte (CPT = 4) aligned
+                if constexpr (CPT == 6) {
+                    const float2 w01 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP));
+                    const float2 w23 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP + 2));
+                    const float2 w45 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP + 4));
+                    wv[0] = w01.x; wv[1] = w01.y; wv[2] = w23.x; wv[3] = w23.y; wv[4] = w45.x; wv[5] = w45.y;
+                } else {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wp + (size_t)k * GP));
+                    wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+                }
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
-                    const float wv = __ldg(wp + (size_t)k * GP + c);
 #pragma unroll
-                    for (int q = 0; q < PPT; ++q) acc[c][q] = fmaf(av[q], wv, acc[c][q]);
+                    for (int q = 0; q < PPT; ++q) acc[c][q] = fmaf(av[q], wv[c], acc[c][q]);
                 }
             }
 #pragma unroll
@@ -113,11 +125,20 @@ cnn_fp32_kernel(const int16_t *__restrict__ planes, const float *__restrict__ fp
                 const float4 a0 = *reinterpret_cast<const float4 *>(H1 + k * TM + pg * PPT);
                 const float4 a1 = *reinterpret_cast<const float4 *>(H1 + k * TM + pg * PPT + 4);
                 const float av[PPT] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float wv[CPT];             // one row segment of the packed weights: 8-byte (CPT = 6) / 16-byte (CPT = 4) aligned
+                if constexpr (CPT == 6) {
+                    const float2 w01 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP));
+                    const float2 w23 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP + 2));
+                    const float2 w45 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP + 4));
+                    wv[0] = w01.x; wv[1] = w01.y; wv[2] = w23.x; wv[3] = w23.y; wv[4] = w45.x; wv[5] = w45.y;
+                } else {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wp + (size_t)k * GP));
+                    wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+                }
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
-                    const float wv = __ldg(wp + (size_t)k * GP + c);
 #pragma unroll
-                    for (int q = 0; q < PPT; ++q) acc[c][q] = fmaf(av[q], wv, acc[c][q]);
+                    for (int q = 0; q < PPT; ++q) acc[c][q] = fmaf(av[q], wv[c], acc[c][q]);
                 }
             }
 #pragma unroll

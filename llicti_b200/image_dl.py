@@ -69,18 +69,22 @@ class TrainImageLoader:
     with probability 1/2; images smaller than the crop are resized to fit it (ImageOps.fit); batches of `batch_size`
     images (so [B, 3, size, size], or [B, patches_per_img, 3, size, size] like the reference, which the training loop
     flattens).  The random stream is a numpy Generator seeded by the caller (the reference relies on torch's global
-    seed and the DataLoader workers' own)."""
+    seed and the DataLoader workers' own).  With `world` > 1 (data-parallel training under torchrun) a rank visits every
+    world-th image of the epoch's shared order, `batch_size` of them per step: the global batch is world x batch_size."""
 
-    def __init__(self, roots, size, batch_size, patches_per_img=1, seed=0):
+    def __init__(self, roots, size, batch_size, patches_per_img=1, seed=0, rank=0, world=1):
         roots = [roots] if isinstance(roots, str) else list(roots)
+        self.rank, self.world = int(rank), max(int(world), 1)
         self.files = [f for r in roots for f in list_images(r)]
         self.size, self.batch_size, self.patches = int(size), max(int(batch_size), 1), max(int(patches_per_img), 1)
         if self.size <= 0:
             raise ValueError("training needs patch_size > 0")
-        self.rng = np.random.default_rng(seed)
+        self.order_rng = np.random.default_rng(seed)                 # the epoch's order: the same stream on every rank
+        self.rng = np.random.default_rng([seed, self.rank])          # crops and flips: a stream per rank
 
     def __len__(self):
-        return -(-len(self.files) // self.batch_size)
+        from .shard import rank_share
+        return -(-len(rank_share(range(len(self.files)), self.rank, self.world)) // self.batch_size)
 
     def _patches(self, path):
         from PIL import Image, ImageOps
@@ -102,6 +106,7 @@ class TrainImageLoader:
         return out[0] if self.patches == 1 else torch.stack(out)
 
     def __iter__(self):
-        order = self.rng.permutation(len(self.files))
+        from .shard import rank_share
+        order = rank_share(self.order_rng.permutation(len(self.files)), self.rank, self.world)
         for k in range(0, len(order), self.batch_size):
             yield torch.stack([self._patches(self.files[i]) for i in order[k:k + self.batch_size]])

@@ -4,6 +4,11 @@ Every image (or 4K image treated as one unit) is coded independently -- own head
 own streams (reference: the eval loop of agents/llicti_agent.py:129-149 walks images with batch
 size 1) -- so the hot path needs no collective.  The only exchange is the reduction of the
 (pixels, bytes, launches, ...) sums and of the per-rank device times (max) at the end.
+
+The training step is the one place with a real exchange: under `torchrun` every rank takes its share of each
+batch and the weight gradients are averaged (one all-reduce of the 24 tensors as one flat buffer, NCCL over NVLink)
+before clipping and the optimizer step -- the loss is a mean over the batch, so the average of the ranks' gradients is
+the gradient of the global batch.
 """
 from __future__ import annotations
 
@@ -31,3 +36,33 @@ def reduce_stats(sums: Sequence[float], maxs: Sequence[float], device=None):
         torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
         torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.MAX)
     return s.tolist(), m.tolist()
+
+
+def average_gradients(params) -> int:
+    """All-reduce (mean) of the `.grad` of `params` over the ranks as ONE flat buffer; identity without an initialised
+    process group.  Returns the number of elements exchanged (0 when nothing was)."""
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return off
+
+
+def rank_share(order: Sequence[int], rank: int, world: int):
+    """This rank's items of one epoch's (shared) random order: every world-th item, the same count on every rank (the
+    remainder of an order that does not divide is dropped for the epoch, so that all ranks take the same number of
+    optimizer steps); a set smaller than the world is left whole on every rank."""
+    order = list(order)
+    if world <= 1 or len(order) < world:
+        return order
+    per = len(order) // world
+    return order[rank:per * world:world]

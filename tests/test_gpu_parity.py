@@ -86,6 +86,30 @@ def test_color_split_bit_exact(L, name):
     assert np.array_equal(rec[0].cpu().numpy(), img)
 
 
+@pytest.mark.parametrize("H,W,n", [(1356, 2040, 2), (2160, 3840, 1), (1355, 2039, 1), (512, 768, 3)],
+                         ids=["div2k", "4k", "div2k-odd", "kodak"])
+def test_color_split_bit_exact_at_full_size(L, H, W, n):
+    """The integer stages at BASELINE's full image sizes (the vectorised kernels run here; the edge images above take the
+    scalar ones): every plane of every scale, the min/max words and the pad flags against the oracle, and the inverse."""
+    ocfg = O.OracleConfig()
+    codec = make_codec(L, ocfg, O.synthetic_state_dict(ocfg))
+    rng = np.random.default_rng(H + W)
+    imgs = np.stack([O.synthetic_image(H, W, 400 + i, noise=6.0) for i in range(n)])
+    imgs[0, :, :3, :] = rng.integers(0, 256, size=(3, 3, W), dtype=np.uint8)        # full-range noise on the first rows
+    planes, mm = codec.color_split(torch.from_numpy(imgs).cuda())
+    for i in range(n):
+        ycc = O.rgb_to_ycocg_r(imgs[i])
+        cen = ycc.copy()
+        cen[0] -= 127
+        o_planes, flags, pad_int = O.pyramid_split(cen, ocfg.dwtlevels)
+        for s in range(5):
+            assert np.array_equal(planes[s][i].cpu().numpy(), o_planes[s]), f"image {i} scale {s}"
+        assert mm[i].tolist() == [int(ycc[1].min()), int(ycc[2].min()), int(ycc[1].max()), int(ycc[2].max())]
+        assert codec.geometry(H, W).pad_int == pad_int
+    rec = codec.merge_color(planes[0], H, W)
+    assert np.array_equal(rec.cpu().numpy(), imgs)
+
+
 # ---------------------------------------------------------------------------- stage K4-K6 (b)
 CNN_ATOL = 2e-5   # fp32 accumulation-order noise on outputs of magnitude ~1e-2..1 (params are value/255 scaled)
 CNN_RTOL = 2e-4

@@ -171,3 +171,41 @@ def test_main_train_mode(tmp_path):
     ck = torch.load(tmp_path / exp / "checkpoints" / "checkpoint.pth.tar", map_location="cpu", weights_only=False)
     assert {"epoch", "iteration", "best_valid_loss", "state_dict", "optimizer", "scheduler", "train_logger", "valid_logger"} <= set(ck)
     assert ck["iteration"] == 9 and (tmp_path / exp / "checkpoints" / "model_best.pth.tar").exists()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_main_train_mode_two_ranks(tmp_path):
+    """`mode: train` under torchrun: one process per GPU, each a share of every epoch, gradients averaged over NCCL; both
+    ranks end with the same weights (rank 0's checkpoint, rank 1's dumped by the test hook)."""
+    import socket
+    from PIL import Image
+    cfg = json.load(open(os.path.join(ROOT, "configs", "llicti_B.json")))
+    tr, va = tmp_path / "train", tmp_path / "valid"
+    tr.mkdir(), va.mkdir()
+    for i in range(16):
+        Image.fromarray(O.synthetic_image(72, 88, 500 + i).transpose(1, 2, 0)).save(tr / f"t{i}.png")
+    for i in range(2):
+        Image.fromarray(O.synthetic_image(64, 64, 600 + i).transpose(1, 2, 0)).save(va / f"v{i}.png")
+    cfg.update({"mode": "train", "num_train_dirs": 1, "train_data_1": str(tr), "valid_data": str(va), "test_data": str(va),
+                "patch_size": 64, "batch_size": 4, "patches_per_img": 1, "grad_acc_iters": 1, "loss_prnt_iters": 1000,
+                "val_patch_size": 64, "val_batch_size": 2, "learning_rate": 1e-3, "max_epoch": 2, "validate_every": 1,
+                "resume_training": False, "seed": 7})
+    cfg_path = tmp_path / "cfg.json"
+    cfg_path.write_text(json.dumps(cfg))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PYTHONPATH=ROOT, LLICTI_TEST_DUMP_WEIGHTS=str(tmp_path / "rank{rank}.pt"))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "main.py"), str(cfg_path)], cwd=tmp_path, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    exp = os.path.join("experiments", cfg["multi_exp_name"], "exp_0")
+    ck = torch.load(tmp_path / exp / "checkpoints" / "checkpoint.pth.tar", map_location="cpu", weights_only=False)
+    assert ck["iteration"] == 4                      # 16 images / 2 ranks / batch 4 = 2 steps per epoch, 2 epochs
+    w0 = torch.load(tmp_path / "rank0.pt", map_location="cpu")
+    w1 = torch.load(tmp_path / "rank1.pt", map_location="cpu")
+    assert set(w0) == set(w1) == set(ck["state_dict"])
+    for k in w0:
+        assert torch.equal(w0[k], w1[k]), k          # the same averaged gradients, the same Adam: identical weights
+        assert torch.equal(w0[k], ck["state_dict"][k]), k
