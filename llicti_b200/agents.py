@@ -145,6 +145,10 @@ class LLICTIAgent(BaseAgent):
             self.load_checkpoint("model_best.pth.tar")
         elif getattr(config, "resume_training", False):
             self.load_checkpoint(getattr(config, "checkpoint_file", "checkpoint.pth.tar"))
+        if self.world > 1 and config.mode == "train":                # every rank starts from rank 0's weights (fresh initialisations differ)
+            with torch.no_grad():
+                for p in self.model.parameters():
+                    torch.distributed.broadcast(p.data, 0)
         self.model_size_estimation()
 
     def train_one_epoch(self):
