@@ -117,9 +117,9 @@ struct BwdShape {
     static_assert(15 * CPT >= G && G % 4 == 0, "channel groups must cover the sub-network width");
 };
 
-// Y[ch][q] = relu(b[ch] + sum_k X[k][q] * Wt[k][ch])   (X: [K][BLD] in shared memory, Wt: packed [K][GP] in global memory)
+// Y[ch][q] = relu(b[ch] + sum_k X[k][q] * Wt[k][ch])   (X: [K][BLD], Wt: packed [K][GP], both in shared memory)
 template <int G>
-__device__ __forceinline__ void layer_forward(const float *X, int K, const float *__restrict__ Wt, const float *__restrict__ b,
+__device__ __forceinline__ void layer_forward(const float *X, int K, const float *Wt, const float *__restrict__ b,
                                               float *Y, int tid) {
     constexpr int CPT = BwdShape<G>::CPT, GP = BwdShape<G>::GP;
     const int pg = tid & 15, cg = tid >> 4;
@@ -138,12 +138,12 @@ __device__ __forceinline__ void layer_forward(const float *X, int K, const float
         const float4 a = *reinterpret_cast<const float4 *>(X + k * BLD + pg * 4);
         float wv[CPT];                     // (columns G .. GP-1 of the packed rows are zero padding)
         if constexpr (CPT == 6) {
-            const float2 w01 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP));
-            const float2 w23 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP + 2));
-            const float2 w45 = __ldg(reinterpret_cast<const float2 *>(wp + (size_t)k * GP + 4));
+            const float2 w01 = *reinterpret_cast<const float2 *>(wp + k * GP);
+            const float2 w23 = *reinterpret_cast<const float2 *>(wp + k * GP + 2);
+            const float2 w45 = *reinterpret_cast<const float2 *>(wp + k * GP + 4);
             wv[0] = w01.x; wv[1] = w01.y; wv[2] = w23.x; wv[3] = w23.y; wv[4] = w45.x; wv[5] = w45.y;
         } else {
-            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wp + (size_t)k * GP));
+            const float4 w4 = *reinterpret_cast<const float4 *>(wp + k * GP);
             wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
         }
 #pragma unroll
@@ -165,7 +165,7 @@ __device__ __forceinline__ void layer_forward(const float *X, int K, const float
 
 // dX[k][q] = (X[k][q] > 0) * sum_o Wt[k][o] * dY[o][q]   for k < G; o < No.  OUT may alias neither X nor dY.
 template <int G>
-__device__ __forceinline__ void layer_backward_data(const float *X, const float *__restrict__ Wt, int wstride, const float *dY, int No,
+__device__ __forceinline__ void layer_backward_data(const float *X, const float *Wt, int wstride, const float *dY, int No,
                                                     float *OUT, int tid) {
     constexpr int CPT = BwdShape<G>::CPT;
     const int pg = tid & 15, cg = tid >> 4;
@@ -183,7 +183,7 @@ __device__ __forceinline__ void layer_backward_data(const float *X, const float 
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int k = min(cg * CPT + c, G - 1);
-            const float4 wv = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)k * wstride + o));
+            const float4 wv = *reinterpret_cast<const float4 *>(Wt + k * wstride + o);
             acc[c][0] = fmaf(d3.x, wv.w, fmaf(d2.x, wv.z, fmaf(d1.x, wv.y, fmaf(d0.x, wv.x, acc[c][0]))));
             acc[c][1] = fmaf(d3.y, wv.w, fmaf(d2.y, wv.z, fmaf(d1.y, wv.y, fmaf(d0.y, wv.x, acc[c][1]))));
             acc[c][2] = fmaf(d3.z, wv.w, fmaf(d2.z, wv.z, fmaf(d1.z, wv.y, fmaf(d0.z, wv.x, acc[c][2]))));
@@ -202,37 +202,59 @@ __device__ __forceinline__ void layer_backward_data(const float *X, const float 
     }
 }
 
-// ACC[i][j] += sum_q A[i][q] * B[j][q]  (i < Ra, j < Rb; both multiples of 4).  A thread owns 4 x 4 outputs whose rows are
-// nbA / nbB apart, so that the lanes of a warp read CONSECUTIVE rows of B (four banks apart: conflict-free 16-byte loads) and
-// mostly the same rows of A (broadcast).
-__device__ __forceinline__ void weight_grad(const float *A, int Ra, const float *B, int Rb, float *ACC, int acc_stride, int tid) {
-    const int nbA = Ra >> 2, nbB = Rb >> 2;
-    for (int blk = tid; blk < nbA * nbB; blk += BNT) {
-        const int ib = blk / nbB, jb = blk - ib * nbB;
-        float acc[4][4];
+// acc[i][j] += sum_q A[i][q] * B[j][q]  (i < RA, j < RB; both multiples of 4).  A thread owns NB blocks of 4 x 4 outputs IN
+// REGISTERS for the whole kernel (block tid + i * BNT); a block's rows are nbA / nbB apart, so that the lanes of a warp read
+// CONSECUTIVE rows of B (four banks apart: conflict-free 16-byte loads) and mostly the same rows of A (broadcast).
+template <int RA, int RB>
+struct WGrad {
+    static constexpr int nbA = RA / 4, nbB = RB / 4, NB = (nbA * nbB + BNT - 1) / BNT;
+    static_assert(RA % 4 == 0 && RB % 4 == 0, "4 x 4 blocks");
+
+    static __device__ __forceinline__ void zero(float (&acc)[NB][4][4]) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-#pragma unroll 2
-        for (int q = 0; q < BT; q += 4) {
-            float4 a[4], b[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4 *>(A + (ib + r * nbA) * BLD + q);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4 *>(B + (jb + c * nbB) * BLD + q);
+        for (int i = 0; i < NB; ++i)
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    acc[r][c] = fmaf(a[r].x, b[c].x, fmaf(a[r].y, b[c].y, fmaf(a[r].z, b[c].z, fmaf(a[r].w, b[c].w, acc[r][c]))));
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) ACC[(ib + r * nbA) * acc_stride + jb + c * nbB] += acc[r][c];
+                for (int c = 0; c < 4; ++c) acc[i][r][c] = 0.f;
     }
-}
+
+    static __device__ __forceinline__ void accumulate(const float *A, const float *B, float (&acc)[NB][4][4], int tid) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int blk = tid + i * BNT;
+            if (blk >= nbA * nbB) break;
+            const int ib = blk / nbB, jb = blk - ib * nbB;
+#pragma unroll 2
+            for (int q = 0; q < BT; q += 4) {
+                float4 a[4], b[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4 *>(A + (ib + r * nbA) * BLD + q);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4 *>(B + (jb + c * nbB) * BLD + q);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        acc[i][r][c] = fmaf(a[r].x, b[c].x, fmaf(a[r].y, b[c].y, fmaf(a[r].z, b[c].z, fmaf(a[r].w, b[c].w, acc[i][r][c]))));
+            }
+        }
+    }
+
+    // one atomicAdd per element into the packed global accumulator (row stride dst_stride)
+    static __device__ __forceinline__ void flush(const float (&acc)[NB][4][4], float *dst, int dst_stride, int tid) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int blk = tid + i * BNT;
+            if (blk >= nbA * nbB) break;
+            const int ib = blk / nbB, jb = blk - ib * nbB;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) atomicAdd(dst + (size_t)(ib + r * nbA) * dst_stride + jb + c * nbB, acc[i][r][c]);
+        }
+    }
+};
 
 // ACC[j] += sum_q B[j][q]
 __device__ __forceinline__ void bias_grad(const float *B, int Rb, float *ACC, int tid) {
@@ -251,9 +273,9 @@ struct BandGradsF32 {      // packed like BandWeightsF32
     float *w0, *b0, *w1, *b1, *w2, *b2;
 };
 
-template <int G>
+template <int G, int K0>
 __global__ void __launch_bounds__(BNT, 1)
-cnn_backward_kernel(const float *__restrict__ fplanes, int Hs, int Ws, int K0, TapTable taps, BandWeightsF32 w,
+cnn_backward_kernel(const float *__restrict__ fplanes, int Hs, int Ws, TapTable taps, BandWeightsF32 w,
                     const float *__restrict__ dparams, int n, BandGradsF32 gr) {
     constexpr int GP = BwdShape<G>::GP;
     extern __shared__ __align__(16) float smem[];
@@ -262,32 +284,45 @@ cnn_backward_kernel(const float *__restrict__ fplanes, int Hs, int Ws, int K0, T
     float *H2 = H1 + G * BLD;            // [G][BLD]   later d H1
     float *D2 = H2 + G * BLD;            // [G][BLD]   d H2
     float *DO = D2 + G * BLD;            // [16][BLD]  d outputs of this sub-network (row 15: zero)
-    float *GW0 = DO + 16 * BLD;          // [K0][G]
-    float *GW1 = GW0 + K0 * G;           // [G][G]
-    float *GW2 = GW1 + G * G;            // [G][16]
-    float *GB0 = GW2 + G * 16;           // [G]
+    float *W0 = DO + 16 * BLD;           // [K0][GP]   this sub-network's packed weights, resident for the whole kernel
+    float *W1 = W0 + K0 * GP;            // [G][GP]
+    float *W2 = W1 + G * GP;             // [G][16]
+    float *GB0 = W2 + G * 16;            // [G]        bias gradients
     float *GB1 = GB0 + G;                // [G]
     float *GB2 = GB1 + G;                // [16]
-    const int n_acc = K0 * G + G * G + G * 16 + 2 * G + 16;
 
     const int tid = threadIdx.x;
     const int g = blockIdx.y;
     const int P = Hs * Ws;
     const int tiles_per_img = (P + BT - 1) / BT;
     const long long tiles = (long long)tiles_per_img * n;
+    if (tiles <= (long long)blockIdx.x) return;            // (whole CTA) no tile: nothing to add
 
-    for (int e = tid; e < n_acc; e += BNT) GW0[e] = 0.f;
+    {   // weights in (16-byte copies: all three packed blocks are multiples of four floats and 16-byte aligned)
+        const float4 *s0 = reinterpret_cast<const float4 *>(w.w0 + (size_t)g * K0 * GP);
+        const float4 *s1 = reinterpret_cast<const float4 *>(w.w1 + (size_t)g * G * GP);
+        const float4 *s2 = reinterpret_cast<const float4 *>(w.w2 + (size_t)g * G * 16);
+        for (int e = tid; e < K0 * GP / 4; e += BNT) reinterpret_cast<float4 *>(W0)[e] = __ldg(s0 + e);
+        for (int e = tid; e < G * GP / 4; e += BNT) reinterpret_cast<float4 *>(W1)[e] = __ldg(s1 + e);
+        for (int e = tid; e < G * 16 / 4; e += BNT) reinterpret_cast<float4 *>(W2)[e] = __ldg(s2 + e);
+    }
+    for (int e = tid; e < 2 * G + 16; e += BNT) GB0[e] = 0.f;
     for (int e = tid; e < BLD; e += BNT) DO[15 * BLD + e] = 0.f;
+    const float *b0 = w.b0 + g * G, *b1 = w.b1 + g * G;
 
-    const float *w0 = w.w0 + (size_t)g * K0 * GP, *b0 = w.b0 + g * G;
-    const float *w1 = w.w1 + (size_t)g * G * GP, *b1 = w.b1 + g * G;
-    const float *w2 = w.w2 + (size_t)g * G * 16;
+    using WG2 = WGrad<G, 16>;
+    using WG1 = WGrad<G, G>;
+    using WG0 = WGrad<K0, G>;
+    float gw2[WG2::NB][4][4], gw1[WG1::NB][4][4], gw0[WG0::NB][4][4];      // the CTA's weight gradients: registers
+    WG2::zero(gw2);
+    WG1::zero(gw1);
+    WG0::zero(gw0);
 
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int img = (int)(t / tiles_per_img);
         const int p0 = (int)(t - (long long)img * tiles_per_img) * BT;
         const float *pl = fplanes + (size_t)img * 12 * P;     // the float lifting's values, as the reference's graph sees them
-        __syncthreads();                 // the previous tile's products have read A0 / H2 / D2 / DO
+        __syncthreads();                 // the previous tile's products have read A0 / H2 / D2 / DO (first tile: weights are in)
         {   // a thread stages ONE position's column: its row / column once, then every fourth tap and output row
             const int q = tid & (BT - 1), k4 = tid >> 6;
             const int p = min(p0 + q, P - 1);
@@ -304,29 +339,28 @@ cnn_backward_kernel(const float *__restrict__ fplanes, int Hs, int Ws, int K0, T
             for (int o = k4; o < 15; o += BNT / BT) DO[o * BLD + q] = inside ? dp[(size_t)o * P] : 0.f;
         }
         __syncthreads();
-        layer_forward<G>(A0, K0, w0, b0, H1, tid);
+        layer_forward<G>(A0, K0, W0, b0, H1, tid);
         __syncthreads();
-        layer_forward<G>(H1, G, w1, b1, H2, tid);
+        layer_forward<G>(H1, G, W1, b1, H2, tid);
         __syncthreads();
         // layer 2: d W2 = H2 dO^T, d b2, d H2 = relu'(H2) * (W2 dO)
-        weight_grad(H2, G, DO, 16, GW2, 16, tid);
+        WG2::accumulate(H2, DO, gw2, tid);
         bias_grad(DO, 16, GB2, tid);
-        layer_backward_data<G>(H2, w2, 16, DO, 16, D2, tid);      // (column 15 of the packed W2 and row 15 of dO are zero)
+        layer_backward_data<G>(H2, W2, 16, DO, 16, D2, tid);      // (column 15 of the packed W2 and row 15 of dO are zero)
         __syncthreads();
         // layer 1: d W1 = H1 dH2^T, d b1, d H1 = relu'(H1) * (W1 dH2) -> H2's buffer
-        weight_grad(H1, G, D2, G, GW1, G, tid);
+        WG1::accumulate(H1, D2, gw1, tid);
         bias_grad(D2, G, GB1, tid);
-        layer_backward_data<G>(H1, w1, GP, D2, G, H2, tid);
+        layer_backward_data<G>(H1, W1, GP, D2, G, H2, tid);
         __syncthreads();
         // layer 0: d W0 = A0 dH1^T, d b0
-        weight_grad(A0, K0, H2, G, GW0, G, tid);
+        WG0::accumulate(A0, H2, gw0, tid);
         bias_grad(H2, G, GB0, tid);
     }
+    WG0::flush(gw0, gr.w0 + (size_t)g * K0 * GP, GP, tid);
+    WG1::flush(gw1, gr.w1 + (size_t)g * G * GP, GP, tid);
+    WG2::flush(gw2, gr.w2 + (size_t)g * G * 16, 16, tid);
     __syncthreads();
-    if (tiles <= (long long)blockIdx.x) return;            // this CTA had no tile: nothing to add
-    for (int e = tid; e < K0 * G; e += BNT) atomicAdd(gr.w0 + ((size_t)g * K0 + e / G) * GP + e % G, GW0[e]);
-    for (int e = tid; e < G * G; e += BNT) atomicAdd(gr.w1 + ((size_t)g * G + e / G) * GP + e % G, GW1[e]);
-    for (int e = tid; e < G * 16; e += BNT) atomicAdd(gr.w2 + (size_t)g * G * 16 + e, GW2[e]);
     for (int e = tid; e < G; e += BNT) {
         atomicAdd(gr.b0 + g * G + e, GB0[e]);
         atomicAdd(gr.b1 + g * G + e, GB1[e]);
@@ -382,13 +416,13 @@ int launch_train_zero_grads(llicti_ctx *ctx, cudaStream_t st) {
     return LLICTI_OK;
 }
 
-template <int G>
+template <int G, int K0>
 static int launch_backward_t(llicti_ctx *ctx, TrainState *ts, int band, const float *fplanes, int n, int Hs, int Ws, const float *dparams,
                              cudaStream_t st) {
     const TapTable &t = ctx->taps[band];
-    const int K0 = t.K0;
-    const size_t smem = (size_t)(K0 * BLD + 3 * G * BLD + 16 * BLD + K0 * G + G * G + G * 16 + 2 * G + 16) * sizeof(float);
-    LLICTI_CUDA(cudaFuncSetAttribute(cnn_backward_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int GP = BwdShape<G>::GP;
+    const size_t smem = (size_t)(K0 * BLD + 3 * G * BLD + 16 * BLD + K0 * GP + G * GP + G * 16 + 2 * G + 16) * sizeof(float);
+    LLICTI_CUDA(cudaFuncSetAttribute(cnn_backward_kernel<G, K0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!ctx->sm_count) {
         int dev = 0;
         LLICTI_CUDA(cudaGetDevice(&dev));
@@ -398,10 +432,22 @@ static int launch_backward_t(llicti_ctx *ctx, TrainState *ts, int band, const fl
     // one CTA per SM (shared memory); the four sub-networks share the SMs: a quarter of them each, at least one CTA
     const int per_net = (int)std::max(1LL, std::min(tiles, (long long)ctx->sm_count / 4));
     dim3 grid(per_net, 4);
-    cnn_backward_kernel<G><<<grid, BNT, smem, st>>>(fplanes, Hs, Ws, K0, t, ctx->wf32[band], dparams, n, ts->g[band]);
+    cnn_backward_kernel<G, K0><<<grid, BNT, smem, st>>>(fplanes, Hs, Ws, t, ctx->wf32[band], dparams, n, ts->g[band]);
     ctx->launches += 1;
     LLICTI_CUDA(cudaGetLastError());
     return LLICTI_OK;
+}
+
+template <int G>
+static int launch_backward_g(llicti_ctx *ctx, TrainState *ts, int band, const float *fplanes, int n, int Hs, int Ws, const float *dparams,
+                             cudaStream_t st) {
+    switch (ctx->taps[band].K0) {                  // 3 x (4x4 | 3x4 + 4x3 | 4x3 + 3x4 + 4x4) taps: compile-time loop bounds
+        case 48: return launch_backward_t<G, 48>(ctx, ts, band, fplanes, n, Hs, Ws, dparams, st);
+        case 72: return launch_backward_t<G, 72>(ctx, ts, band, fplanes, n, Hs, Ws, dparams, st);
+        case 120: return launch_backward_t<G, 120>(ctx, ts, band, fplanes, n, Hs, Ws, dparams, st);
+    }
+    set_error("cnn backward: unexpected layer-0 depth %d", ctx->taps[band].K0);
+    return LLICTI_E_ARG;
 }
 
 int launch_cnn_backward(llicti_ctx *ctx, int band, const float *fplanes, int n, int Hs, int Ws, const float *dparams, cudaStream_t st) {
@@ -409,8 +455,8 @@ int launch_cnn_backward(llicti_ctx *ctx, int band, const float *fplanes, int n, 
     TrainState *ts;
     int rc = train_state(ctx, &ts);
     if (rc) return rc;
-    if (ctx->cfg.chs == 88) return launch_backward_t<88>(ctx, ts, band, fplanes, n, Hs, Ws, dparams, st);
-    if (ctx->cfg.chs == 60) return launch_backward_t<60>(ctx, ts, band, fplanes, n, Hs, Ws, dparams, st);
+    if (ctx->cfg.chs == 88) return launch_backward_g<88>(ctx, ts, band, fplanes, n, Hs, Ws, dparams, st);
+    if (ctx->cfg.chs == 60) return launch_backward_g<60>(ctx, ts, band, fplanes, n, Hs, Ws, dparams, st);
     set_error("cnn backward: unsupported sub-network width %d (88 or 60)", ctx->cfg.chs);
     return LLICTI_E_ARG;
 }
