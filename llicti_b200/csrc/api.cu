@@ -569,7 +569,7 @@ int llicti_train_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int
     for (int s = 0; s < g.num_scales; ++s)
         for (int b = 0; b < 3; ++b) {
             float *params = params_keep_dev + kept_offset(g, n, s, b);
-            if ((rc = launch_cnn_fp32(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], params, st, fplanes_dev[s]))) return rc;
+            if ((rc = launch_cnn_forward_train(ctx, b, fplanes_dev[s], n, g.Hs[s], g.Ws[s], params, st))) return rc;
             if ((rc = launch_self_info(ctx, params, fplanes_dev[s], b, n, g.Hs[s] * g.Ws[s], sinfo_dev[s], st))) return rc;
         }
     return LLICTI_OK;

@@ -200,6 +200,7 @@ int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int
 int launch_self_info_grad(llicti_ctx *ctx, float *params, const float *fplanes, const float *gsinfo, int band, int n, int P,
                           cudaStream_t st);
 int launch_cnn_backward(llicti_ctx *ctx, int band, const float *fplanes, int n, int Hs, int Ws, const float *dparams, cudaStream_t st);
+int launch_cnn_forward_train(llicti_ctx *ctx, int band, const float *fplanes, int n, int Hs, int Ws, float *params, cudaStream_t st);
 int launch_train_zero_grads(llicti_ctx *ctx, cudaStream_t st);
 int launch_train_layouts(llicti_ctx *ctx, const llicti_weights &tw, bool to_packed, cudaStream_t st);
 void train_free(llicti_ctx *ctx);

@@ -368,6 +368,79 @@ cnn_backward_kernel(const float *__restrict__ fplanes, int Hs, int Ws, TapTable 
     for (int e = tid; e < 15; e += BNT) atomicAdd(gr.b2 + g * 15 + e, GB2[e]);
 }
 
+// The forward half of a training step with the same organisation: persistent CTAs, one sub-network each, its packed weights
+// resident in shared memory; a tile's two hidden layers and its 15 outputs.  Every output is the same fmaf chain (bias
+// first, k ascending) as in cnn_fp32_kernel: the two kernels agree bit for bit.
+template <int G, int K0>
+__global__ void __launch_bounds__(BNT, 1)
+cnn_forward_train_kernel(const float *__restrict__ fplanes, int Hs, int Ws, TapTable taps, BandWeightsF32 w, int n,
+                         float *__restrict__ params) {
+    constexpr int GP = BwdShape<G>::GP;
+    extern __shared__ __align__(16) float smem[];
+    float *A0 = smem;                    // [K0][BLD]
+    float *H1 = A0 + K0 * BLD;           // [G][BLD]
+    float *H2 = H1 + G * BLD;            // [G][BLD]
+    float *W0 = H2 + G * BLD;            // [K0][GP]
+    float *W1 = W0 + K0 * GP;            // [G][GP]
+    float *W2 = W1 + G * GP;             // [G][16]
+    const int tid = threadIdx.x;
+    const int g = blockIdx.y;
+    const int P = Hs * Ws;
+    const int tiles_per_img = (P + BT - 1) / BT;
+    const long long tiles = (long long)tiles_per_img * n;
+    if (tiles <= (long long)blockIdx.x) return;
+    {
+        const float4 *s0 = reinterpret_cast<const float4 *>(w.w0 + (size_t)g * K0 * GP);
+        const float4 *s1 = reinterpret_cast<const float4 *>(w.w1 + (size_t)g * G * GP);
+        const float4 *s2 = reinterpret_cast<const float4 *>(w.w2 + (size_t)g * G * 16);
+        for (int e = tid; e < K0 * GP / 4; e += BNT) reinterpret_cast<float4 *>(W0)[e] = __ldg(s0 + e);
+        for (int e = tid; e < G * GP / 4; e += BNT) reinterpret_cast<float4 *>(W1)[e] = __ldg(s1 + e);
+        for (int e = tid; e < G * 16 / 4; e += BNT) reinterpret_cast<float4 *>(W2)[e] = __ldg(s2 + e);
+    }
+    const float *b0 = w.b0 + g * G, *b1 = w.b1 + g * G;
+    const int pg = tid & 15, og = tid >> 4;             // layer 2: four positions x one output per thread (og < 15)
+    const float b2 = og < 15 ? __ldg(w.b2 + g * 15 + og) : 0.f;
+
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int img = (int)(t / tiles_per_img);
+        const int p0 = (int)(t - (long long)img * tiles_per_img) * BT;
+        const float *pl = fplanes + (size_t)img * 12 * P;
+        __syncthreads();                 // the previous tile's layers have read A0 / H1 / H2 (first tile: weights are in)
+        {
+            const int q = tid & (BT - 1), k4 = tid >> 6;
+            const int p = min(p0 + q, P - 1);
+            const int i = p / Ws, j = p - i * Ws;
+#pragma unroll 4
+            for (int k = k4; k < K0; k += BNT / BT) {
+                const int rr = min(max(i + taps.dy[k], 0), Hs - 1);
+                const int cc = min(max(j + taps.dx[k], 0), Ws - 1);
+                A0[k * BLD + q] = pl[(size_t)(taps.phase[k] * 3 + taps.chan[k]) * P + (size_t)rr * Ws + cc];
+            }
+        }
+        __syncthreads();
+        layer_forward<G>(A0, K0, W0, b0, H1, tid);
+        __syncthreads();
+        layer_forward<G>(H1, G, W1, b1, H2, tid);
+        __syncthreads();
+        if (og < 15) {
+            float acc[4] = {b2, b2, b2, b2};
+#pragma unroll 4
+            for (int k = 0; k < G; ++k) {
+                const float4 a = *reinterpret_cast<const float4 *>(H2 + k * BLD + pg * 4);
+                const float wv = W2[k * 16 + og];
+                acc[0] = fmaf(a.x, wv, acc[0]);
+                acc[1] = fmaf(a.y, wv, acc[1]);
+                acc[2] = fmaf(a.z, wv, acc[2]);
+                acc[3] = fmaf(a.w, wv, acc[3]);
+            }
+            float *o = params + ((size_t)img * kParamCh + g * 15 + og) * P + p0 + pg * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (p0 + pg * 4 + q < P) o[q] = acc[q];
+        }
+    }
+}
+
 // Packed gradient accumulators of the three bands: one allocation, laid out like the packed weights.
 struct TrainState {
     float *base = nullptr;
@@ -447,6 +520,45 @@ static int launch_backward_g(llicti_ctx *ctx, TrainState *ts, int band, const fl
         case 120: return launch_backward_t<G, 120>(ctx, ts, band, fplanes, n, Hs, Ws, dparams, st);
     }
     set_error("cnn backward: unexpected layer-0 depth %d", ctx->taps[band].K0);
+    return LLICTI_E_ARG;
+}
+
+template <int G, int K0>
+static int launch_forward_t(llicti_ctx *ctx, int band, const float *fplanes, int n, int Hs, int Ws, float *params, cudaStream_t st) {
+    const TapTable &t = ctx->taps[band];
+    constexpr int GP = BwdShape<G>::GP;
+    const size_t smem = (size_t)(K0 * BLD + 2 * G * BLD + K0 * GP + G * GP + G * 16) * sizeof(float);
+    LLICTI_CUDA(cudaFuncSetAttribute(cnn_forward_train_kernel<G, K0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!ctx->sm_count) {
+        int dev = 0;
+        LLICTI_CUDA(cudaGetDevice(&dev));
+        LLICTI_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long tiles = (long long)((Hs * Ws + BT - 1) / BT) * n;
+    const int per_net = (int)std::max(1LL, std::min(tiles, (long long)ctx->sm_count / 4));
+    cnn_forward_train_kernel<G, K0><<<dim3(per_net, 4), BNT, smem, st>>>(fplanes, Hs, Ws, t, ctx->wf32[band], n, params);
+    ctx->launches += 1;
+    LLICTI_CUDA(cudaGetLastError());
+    return LLICTI_OK;
+}
+
+template <int G>
+static int launch_forward_g(llicti_ctx *ctx, int band, const float *fplanes, int n, int Hs, int Ws, float *params, cudaStream_t st) {
+    switch (ctx->taps[band].K0) {
+        case 48: return launch_forward_t<G, 48>(ctx, band, fplanes, n, Hs, Ws, params, st);
+        case 72: return launch_forward_t<G, 72>(ctx, band, fplanes, n, Hs, Ws, params, st);
+        case 120: return launch_forward_t<G, 120>(ctx, band, fplanes, n, Hs, Ws, params, st);
+    }
+    set_error("cnn forward (training): unexpected layer-0 depth %d", ctx->taps[band].K0);
+    return LLICTI_E_ARG;
+}
+
+// fp32 CNN of one band from the fp32 planes, for batches of many tiles (training): bit-identical to launch_cnn_fp32(..., fplanes)
+int launch_cnn_forward_train(llicti_ctx *ctx, int band, const float *fplanes, int n, int Hs, int Ws, float *params, cudaStream_t st) {
+    ProfScope prof_(ctx, KC_CNN, st);
+    if (ctx->cfg.chs == 88) return launch_forward_g<88>(ctx, band, fplanes, n, Hs, Ws, params, st);
+    if (ctx->cfg.chs == 60) return launch_forward_g<60>(ctx, band, fplanes, n, Hs, Ws, params, st);
+    set_error("cnn forward (training): unsupported sub-network width %d (88 or 60)", ctx->cfg.chs);
     return LLICTI_E_ARG;
 }
 
