@@ -188,6 +188,53 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def cpu_train_pass(batch=4, patch=160, steps=3):
+    """The reference's training step on the host cores (bounded sample: `batch` patches per step): the UNMODIFIED
+    reference from oracle/_ref -- model.train(); model(x); TrainRLossList; loss.backward() as agents/llicti_agent.py:52-61 --
+    else the oracle's autograd restatement (kind "port").  Prints one JSON line."""
+    from oracle import llicti_oracle as O
+    from oracle import make_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg = O.OracleConfig()
+    sd = O.synthetic_state_dict(ocfg)
+    model = None if os.environ.get("LLICTI_BENCH_PORT") else make_ref.load_reference_model("llicti_A.json", sd)
+    kind = "reference" if model is not None else "port"
+    if model is not None:
+        from graphs.losses.rate_dist import TrainRLossList         # the reference's (oracle/_ref is on sys.path now)
+        model.train()
+        loss_fn = TrainRLossList()
+    times = []
+    for it in range(1 + steps):
+        rgb = np.stack([O.synthetic_image(patch, patch, 4000 + batch * it + i) for i in range(batch)])
+        t0 = time.perf_counter()
+        if model is not None:
+            x = torch.from_numpy(rgb.astype(np.float32) / np.float32(255.0))
+            model.zero_grad()
+            loss, _ = loss_fn.forward(torch.numel(x), model(x))
+            loss.backward()
+        else:
+            O.train_loss_and_grads(ocfg, sd, rgb)
+        if it >= 1:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    print(json.dumps({"value": batch / t, "unit": "patches/s", "ms_per_step": 1e3 * t, "cores": torch.get_num_threads(), "kind": kind,
+                      "sample": f"{steps} step(s) of {batch} synthetic {patch}x{patch} patches, forward + backward, llicti_A, "
+                                f"{torch.get_num_threads()} torch threads"}), flush=True)
+
+
+def cpu_train_leg():
+    """cpu_train_pass in a fresh process without CUDA; never fatal."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-train-leg"], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        line = next((ln for ln in reversed(r.stdout.splitlines()) if ln.startswith("{")), None)
+        if r.returncode != 0 or line is None:
+            return {"error": f"cpu training process exited {r.returncode}: {r.stderr.strip().splitlines()[-1:] or ''}"}
+        return json.loads(line)
+    except Exception as e:       # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def cpu_baseline_leg(workload, steps=4):
     """The CPU oracle on a bounded sample, in a FRESH process (the state the reference arm runs in): whatever this
     process has loaded (CUDA, NCCL, the codec library, pinned allocations) cannot disturb it, and a failure becomes
@@ -651,6 +698,8 @@ def run_b200(args, rank, world, local_rank):
             per_config["train_step"] = train_step_pass(local_rank, min(K, 5), min(Wm, 3))
         except Exception as e:       # noqa: BLE001
             per_config["train_step"] = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and not args.no_cpu:
+            per_config["train_step"]["cpu_baseline"] = cpu_train_leg()     # a few seconds of host work
     if rank != 0:
         return
 
@@ -692,11 +741,15 @@ def main():
     ap.add_argument("--cnn", type=int, default=int(os.environ.get("LLICTI_CNN", "1")), help="0 fp32 CUDA cores, 1 tcgen05")
     ap.add_argument("--decode-impl", type=int, default=0, help="0 default schedules, 1 legacy one-warp-per-chain")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-train-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-per-config", action="store_true", help="skip the short passes over the other configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.cpu_train_leg:
+        cpu_train_pass()
+        return
     if args.impl == "reference":
         if not args.workload:
             args.workload = "c2" if world == 1 else "c3"

@@ -171,6 +171,18 @@ def test_main_train_mode(tmp_path):
     ck = torch.load(tmp_path / exp / "checkpoints" / "checkpoint.pth.tar", map_location="cpu", weights_only=False)
     assert {"epoch", "iteration", "best_valid_loss", "state_dict", "optimizer", "scheduler", "train_logger", "valid_logger"} <= set(ck)
     assert ck["iteration"] == 9 and (tmp_path / exp / "checkpoints" / "model_best.pth.tar").exists()
+    # resume (base.py:51-81 with resume_training): one more epoch from checkpoint.pth.tar, Adam's moments and the loggers restored
+    cfg.update({"resume_training": True, "checkpoint_file": "checkpoint.pth.tar", "max_epoch": 4})
+    cfg_path.write_text(json.dumps(cfg))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), str(cfg_path)], cwd=tmp_path, env=dict(os.environ, PYTHONPATH=ROOT),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ck2 = torch.load(tmp_path / exp / "checkpoints" / "checkpoint.pth.tar", map_location="cpu", weights_only=False)
+    assert ck2["iteration"] == 12 and ck2["epoch"] == 4
+    step = ck2["optimizer"]["state"][0]["step"]
+    assert int(step) == 12, step                         # Adam continued from the restored state (9 steps) instead of restarting
+    log = (tmp_path / exp / "logs" / "exp_debug.log").read_text()
+    assert log.count("Train Epoch:") == 4 and "Checkpoint loaded successfully" in log
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
