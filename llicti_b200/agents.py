@@ -1,7 +1,7 @@
 """Agent layer of the `main.py <config.json>` entry point (mirrors agents/base.py:13-150 and
 agents/llicti_agent.py:14-164 of the reference: device selection, checkpoint loading and saving by the reference's
 file layout and key names, `mode: eval_model` -- the per-image compress -> rate table -> decompres -> lossless check
-loop and its log lines --, `mode: validate` and `mode: train`).
+loop and its log lines --, `mode: validate`, `mode: train` / `debug`, `model_size`, `flops_est`, `test`).
 
 `mode: train` is the reference's loop (llicti_agent.py:48-83, base.py:132-146) around the library's training step:
 `self.model(x)` and `.backward()` run in libllicti_b200 (`llicti_forward_dev` / `llicti_backward_dev`, fp32); Adam,
@@ -84,10 +84,12 @@ class BaseAgent:
                 self.model_size_estimation(print_params=True)
             elif mode == "validate":
                 self.validate()
-            elif mode == "train":
-                self.train()
-            elif mode in ("debug", "test", "flops_est"):
-                raise NotImplementedError(f"mode '{mode}' is outside the B200 path")
+            elif mode in ("train", "debug"):      # debug: the reference wraps train() in autograd's anomaly detection (base.py:113-115),
+                self.train()                      # which has nothing to inspect in a backward pass that is one library call
+            elif mode == "test":
+                self.test()
+            elif mode == "flops_est":
+                self.flops_estimation()
             else:
                 raise NameError("'" + mode + "' is not a valid training mode.")
         except KeyboardInterrupt:
@@ -244,6 +246,28 @@ class LLICTIAgent(BaseAgent):
         if self.scheduler is not None:
             self.scheduler.step(valid_rate_loss + valid_rate2_loss)
         return valid_rate_loss + valid_rate2_loss
+
+    @torch.no_grad()
+    def test(self):
+        """The reference's test() is an empty stub (agents/llicti_agent.py:114-119, "test should be modified to have actual
+        entropy coding"): eval_model is the mode that codes."""
+        self.model.eval()
+
+    def flops_estimation(self):
+        """The reference asks ptflops for the multiply-accumulates of one forward() of a 3 x 512 x 512 image
+        (agents/llicti_agent.py:194-200).  The count is closed-form here: per position of a scale, band b runs four
+        sub-networks of (taps_b x chs + chs x chs + chs x 15) MACs, taps = 3 channels x kernel positions of the band's
+        branches (LLICTI_nets.py:650-675), and scale s has (512 / 2^(s+1))^2 positions."""
+        G, S = self.model.codec_config.chs, self.model.num_scales
+        taps = (3 * 16, 3 * (12 + 12), 3 * (12 + 12 + 16))
+        per_pos = [4 * (t * G + G * G + G * 15) for t in taps]
+        positions = sum((512 >> (s + 1)) ** 2 for s in range(S))
+        macs = positions * sum(per_pos)
+        params = sum(p.nelement() for p in self.model.parameters())
+        self.logger.info("{:<30}  {:.3f} GMac  (per position: {} + {} + {} MACs for the three bands; {} positions over {} scales)".format(
+            "Computational complexity: ", macs / 1e9, *per_pos, positions, S))
+        self.logger.info("{:<30}  {:.3f} M".format("Number of parameters: ", params / 1e6))
+        return macs, params
 
     def model_size_estimation(self, print_params=False):
         psz = sum(p.nelement() * p.element_size() for p in self.model.parameters())

@@ -99,3 +99,28 @@ def test_cli_encode_decode_files(tmp_path, sub_len):
     assert cli.main(["encode", str(src), str(mid), "--config", cfg, "--sub-len", str(sub_len)]) == 0
     assert cli.main(["decode", str(mid), str(dst), "--config", cfg]) == 0
     assert np.array_equal(np.asarray(Image.open(dst)).transpose(2, 0, 1), img)
+
+
+@pytest.mark.parametrize("mode,needle", [("flops_est", "Computational complexity:"), ("model_size", "model param+buffer=total size"),
+                                         ("test", "Checkpoint loaded successfully")])
+def test_main_auxiliary_modes(tmp_path, mode, needle):
+    """The reference's remaining agent modes run through the entry point (flops_est: closed-form MACs of one 512 x 512
+    forward, cfg A: 64 + 16 + 4 + 1 + 0.25 thousand positions x 193,248 MACs)."""
+    cfg = json.load(open(os.path.join(ROOT, "configs", "llicti_A.json")))
+    data = tmp_path / "data"
+    data.mkdir()
+    cfg.update({"mode": mode, "test_data": str(data), "valid_data": str(data)})
+    cfg_path = tmp_path / "cfg.json"
+    cfg_path.write_text(json.dumps(cfg))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), str(cfg_path)], cwd=tmp_path, env=dict(os.environ, PYTHONPATH=ROOT),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    exp = os.path.join("experiments", cfg["multi_exp_name"], "exp_0")
+    log = (tmp_path / exp / "logs" / "exp_debug.log").read_text()
+    if mode == "test":
+        assert "No checkpoint exists" in log or needle in log
+        return
+    assert needle in log, log[-1500:]
+    if mode == "flops_est":
+        positions = sum((512 >> (s + 1)) ** 2 for s in range(5))
+        assert "{:.3f} GMac".format(positions * 193248 / 1e9) in log, log[-1500:]
