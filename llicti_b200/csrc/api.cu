@@ -522,7 +522,7 @@ int llicti_forward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, in
         for (int b = 0; b < 3; ++b) {
             // fp32 contexts feed the CNN the float lifting's own values (what the reference's convolutions see); the tcgen05
             // CNN reads the int16 planes (value * 255, the same numbers up to an ulp of the quotient)
-            if (ctx->cfg.cnn_impl == LLICTI_CNN_FP32) rc = launch_cnn_fp32(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st, fplanes_dev[s]);
+            if (ctx->cfg.cnn_impl == LLICTI_CNN_FP32) rc = launch_cnn_forward_train(ctx, b, fplanes_dev[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st);
             else rc = cnn(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], ctx->d_params, st);
             if (rc) return rc;
             if ((rc = launch_self_info(ctx, ctx->d_params, fplanes_dev[s], b, n, g.Hs[s] * g.Ws[s], sinfo_dev[s], st))) return rc;
@@ -596,7 +596,7 @@ int llicti_backward_dev(llicti_ctx *ctx, const uint8_t *rgb_dev, int n, int H, i
     for (int s = 0; s < g.num_scales; ++s)
         for (int b = 0; b < 3; ++b) {
             float *params = params_kept_dev ? params_kept_dev + kept_offset(g, n, s, b) : ctx->d_params;
-            if (!params_kept_dev && (rc = launch_cnn_fp32(ctx, b, ctx->d_planes[s], n, g.Hs[s], g.Ws[s], params, st, fplanes_dev[s]))) return rc;
+            if (!params_kept_dev && (rc = launch_cnn_forward_train(ctx, b, fplanes_dev[s], n, g.Hs[s], g.Ws[s], params, st))) return rc;
             if ((rc = launch_self_info_grad(ctx, params, fplanes_dev[s], gsinfo_dev[s], b, n, g.Hs[s] * g.Ws[s], st))) return rc;
             if ((rc = launch_cnn_backward(ctx, b, fplanes_dev[s], n, g.Hs[s], g.Ws[s], params, st))) return rc;
         }

@@ -194,7 +194,7 @@ int launch_minmax32(llicti_ctx *ctx, const int16_t *minmax16, int32_t *minmax, i
 
 // kernels_cnn_fp32.cu
 int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
-                    cudaStream_t st, const float *fplanes = nullptr);
+                    cudaStream_t st);
 
 // kernels_train.cu
 int launch_self_info_grad(llicti_ctx *ctx, float *params, const float *fplanes, const float *gsinfo, int band, int n, int P,

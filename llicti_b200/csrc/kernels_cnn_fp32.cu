@@ -24,12 +24,10 @@ struct CnnShape {
     static_assert(15 * CPT >= G, "channel groups must cover the sub-network width");
 };
 
-// kFloatIn: the receptive fields come from fp32 planes (LLICTI.forward's float lifting: the values the reference's
-// training / validation graph feeds its convolutions, an ulp away from integer / 255) instead of the coder's int16 planes.
-template <int G, bool kFloatIn>
+template <int G>
 __global__ void __launch_bounds__(NT)
-cnn_fp32_kernel(const int16_t *__restrict__ planes, const float *__restrict__ fplanes, int Hs, int Ws, int K0, TapTable taps,
-                BandWeightsF32 w, int div255_recip, float *__restrict__ params) {
+cnn_fp32_kernel(const int16_t *__restrict__ planes, int Hs, int Ws, int K0, TapTable taps, BandWeightsF32 w,
+                int div255_recip, float *__restrict__ params) {
     using S = CnnShape<G>;
     constexpr int CPT = S::CPT, GP = S::GP;
     extern __shared__ float smem[];
@@ -41,7 +39,6 @@ cnn_fp32_kernel(const int16_t *__restrict__ planes, const float *__restrict__ fp
     const int img = blockIdx.y;
     const int p0 = blockIdx.x * TM;
     const int16_t *pl = planes + (size_t)img * 12 * P;
-    const float *fpl = fplanes + (size_t)img * 12 * P;
     const int tid = threadIdx.x;
 
     // ---- im2col with replicate padding (clamped indices) --------------------------------
@@ -53,13 +50,8 @@ cnn_fp32_kernel(const int16_t *__restrict__ planes, const float *__restrict__ fp
         for (int k = tid / TM; k < K0; k += NT / TM) {
             const int rr = min(max(i + taps.dy[k], 0), Hs - 1);
             const int cc = min(max(j + taps.dx[k], 0), Ws - 1);
-            const size_t src = (size_t)(taps.phase[k] * 3 + taps.chan[k]) * P + (size_t)rr * Ws + cc;
-            if (kFloatIn) {
-                A0[k * TM + q] = fpl[src];
-            } else {
-                const float v = (float)pl[src];
-                A0[k * TM + q] = div255_recip ? __fmul_rn(v, 1.0f / 255.0f) : __fdiv_rn(v, 255.0f);
-            }
+            const float v = (float)pl[(size_t)(taps.phase[k] * 3 + taps.chan[k]) * P + (size_t)rr * Ws + cc];
+            A0[k * TM + q] = div255_recip ? __fmul_rn(v, 1.0f / 255.0f) : __fdiv_rn(v, 255.0f);
         }
     }
     __syncthreads();
@@ -175,17 +167,17 @@ cnn_fp32_kernel(const int16_t *__restrict__ planes, const float *__restrict__ fp
     }
 }
 
-template <int G, bool kFloatIn>
-static int launch_cnn_fp32_t(llicti_ctx *ctx, const TapTable &t, int band, const int16_t *planes, const float *fplanes, dim3 grid, size_t smem,
-                             int Hs, int Ws, float *params, cudaStream_t st) {
+template <int G>
+static int launch_cnn_fp32_t(llicti_ctx *ctx, const TapTable &t, int band, const int16_t *planes, dim3 grid, size_t smem, int Hs, int Ws,
+                             float *params, cudaStream_t st) {
     // (the opt-in is a per-device attribute of the function: set at every launch, a host-side call of about a microsecond)
-    LLICTI_CUDA(cudaFuncSetAttribute(cnn_fp32_kernel<G, kFloatIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cnn_fp32_kernel<G, kFloatIn><<<grid, NT, smem, st>>>(planes, fplanes, Hs, Ws, t.K0, t, ctx->wf32[band], ctx->num.div255_recip, params);
+    LLICTI_CUDA(cudaFuncSetAttribute(cnn_fp32_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cnn_fp32_kernel<G><<<grid, NT, smem, st>>>(planes, Hs, Ws, t.K0, t, ctx->wf32[band], ctx->num.div255_recip, params);
     return LLICTI_OK;
 }
 
 int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int Hs, int Ws, float *params,
-                    cudaStream_t st, const float *fplanes) {
+                    cudaStream_t st) {
     ProfScope prof_(ctx, KC_CNN, st);
     const int G = ctx->cfg.chs;
     const int P = Hs * Ws;
@@ -194,11 +186,9 @@ int launch_cnn_fp32(llicti_ctx *ctx, int band, const int16_t *planes, int n, int
     dim3 grid((P + TM - 1) / TM, n);
     int rc;
     if (G == 88) {
-        rc = fplanes ? launch_cnn_fp32_t<88, true>(ctx, t, band, planes, fplanes, grid, smem, Hs, Ws, params, st)
-                     : launch_cnn_fp32_t<88, false>(ctx, t, band, planes, fplanes, grid, smem, Hs, Ws, params, st);
+        rc = launch_cnn_fp32_t<88>(ctx, t, band, planes, grid, smem, Hs, Ws, params, st);
     } else if (G == 60) {
-        rc = fplanes ? launch_cnn_fp32_t<60, true>(ctx, t, band, planes, fplanes, grid, smem, Hs, Ws, params, st)
-                     : launch_cnn_fp32_t<60, false>(ctx, t, band, planes, fplanes, grid, smem, Hs, Ws, params, st);
+        rc = launch_cnn_fp32_t<60>(ctx, t, band, planes, grid, smem, Hs, Ws, params, st);
     } else {
         set_error("cnn: unsupported sub-network width %d (88 or 60)", G);
         return LLICTI_E_ARG;

@@ -368,9 +368,11 @@ cnn_backward_kernel(const float *__restrict__ fplanes, int Hs, int Ws, TapTable 
     for (int e = tid; e < 15; e += BNT) atomicAdd(gr.b2 + g * 15 + e, GB2[e]);
 }
 
-// The forward half of a training step with the same organisation: persistent CTAs, one sub-network each, its packed weights
-// resident in shared memory; a tile's two hidden layers and its 15 outputs.  Every output is the same fmaf chain (bias
-// first, k ascending) as in cnn_fp32_kernel: the two kernels agree bit for bit.
+// The fp32 CNN over the FLOAT planes (LLICTI.forward's float lifting: the values the reference's training / validation graph
+// feeds its convolutions, an ulp away from integer / 255) with the backward kernel's organisation: persistent CTAs, one
+// sub-network each, its packed weights resident in shared memory; a tile's two hidden layers and its 15 outputs.  Every
+// output is the same fmaf chain (bias first, k ascending) as in cnn_fp32_kernel.  Serves forward() and the training step of
+// fp32 contexts.
 template <int G, int K0>
 __global__ void __launch_bounds__(BNT, 1)
 cnn_forward_train_kernel(const float *__restrict__ fplanes, int Hs, int Ws, TapTable taps, BandWeightsF32 w, int n,
@@ -553,7 +555,7 @@ static int launch_forward_g(llicti_ctx *ctx, int band, const float *fplanes, int
     return LLICTI_E_ARG;
 }
 
-// fp32 CNN of one band from the fp32 planes, for batches of many tiles (training): bit-identical to launch_cnn_fp32(..., fplanes)
+// fp32 CNN of one band from the fp32 planes (forward() / training step of fp32 contexts)
 int launch_cnn_forward_train(llicti_ctx *ctx, int band, const float *fplanes, int n, int Hs, int Ws, float *params, cudaStream_t st) {
     ProfScope prof_(ctx, KC_CNN, st);
     if (ctx->cfg.chs == 88) return launch_forward_g<88>(ctx, band, fplanes, n, Hs, Ws, params, st);
