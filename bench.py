@@ -493,6 +493,24 @@ class Workload:
                         "tables and flush bytes counted"}
 
 
+def _fp32_roofline(flop_per_step, cnn_ms_per_step, dev):
+    """The training kernels are fp32 CUDA-core kernels: their ceiling is the FMA pipe (SMs x 128 lanes x 2 FLOP x the
+    maximum SM clock), not the tensor pipe and not HBM."""
+    if not cnn_ms_per_step:
+        return None
+    p = torch.cuda.get_device_properties(dev)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        mhz = pynvml.nvmlDeviceGetMaxClockInfo(pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0), pynvml.NVML_CLOCK_SM)
+    except Exception:       # noqa: BLE001
+        mhz = p.clock_rate / 1e3 if getattr(p, "clock_rate", 0) else 1965.0
+    peak = p.multi_processor_count * 128 * 2 * mhz * 1e6 / 1e12
+    ach = flop_per_step / (cnn_ms_per_step * 1e-3) / 1e12
+    return {"bound": "fp32 FMA pipe", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "kernels": "cnn_forward_train_kernel + cnn_backward_kernel (algorithmic FLOP: one forward, the recompute of two layers, five backward products)"}
+
+
 def train_step_pass(local_rank, steps, warmup, batch=32, patch=160):
     """One training step = llicti_set_weights_dev + llicti_train_forward_dev + llicti_backward_dev on a batch resident in HBM
     (the optimizer is torch's and outside the timed region, as it is outside the library)."""
@@ -537,6 +555,7 @@ def train_step_pass(local_rank, steps, warmup, batch=32, patch=160):
             "steps": steps, "warmup": warmup, "loss_bpp": loss,
             "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items() if v[1]},
             "cnn_class_tflops": pos * (fwd + bwd) / (prof["cnn"][0] / steps * 1e-3) / 1e12 if prof.get("cnn", (0, 0))[0] else None,
+            "roofline": _fp32_roofline(pos * (fwd + bwd), prof.get("cnn", (0, 0))[0] / steps, dev),
             "note": "cnn class = fp32 forward + cnn_backward_kernel (which recomputes the two hidden layers); "
                     "bounds class = self_info_kernel + self_info_grad_kernel"}
 
