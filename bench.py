@@ -226,7 +226,7 @@ def cpu_train_leg():
     """cpu_train_pass in a fresh process without CUDA; never fatal."""
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-train-leg"], capture_output=True, text=True, timeout=300,
-                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), preexec_fn=_unbound)
         line = next((ln for ln in reversed(r.stdout.splitlines()) if ln.startswith("{")), None)
         if r.returncode != 0 or line is None:
             return {"error": f"cpu training process exited {r.returncode}: {r.stderr.strip().splitlines()[-1:] or ''}"}
@@ -242,7 +242,7 @@ def cpu_baseline_leg(workload, steps=4):
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", str(steps),
            "--warmup", "0"]
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), preexec_fn=_unbound)
         line = next((ln for ln in reversed(r.stdout.splitlines()) if ln.startswith("{")), None)
         if r.returncode != 0 or line is None:
             return {"error": f"cpu oracle process exited {r.returncode}: {r.stderr.strip().splitlines()[-1:] or ''}", "kind": "port"}
@@ -639,8 +639,20 @@ def rooflines(w, dev_r, args, steps):
     return roof, allr, kernel_ms, cnn_tflops, internal_traffic(w.geom, w.n, w.wl["sub_len"])
 
 
+ALL_CPUS = set(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None
+
+
+def _unbound():
+    """preexec_fn of the CPU legs: they run on every host core this process started with, not on the GPU's NUMA node."""
+    if ALL_CPUS:
+        os.sched_setaffinity(0, ALL_CPUS)
+
+
 def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
+    from llicti_b200.shard import bind_host_to_gpu
+    bound = bind_host_to_gpu(local_rank)          # before any pinned allocation: staging buffers local to the GPU's PCIe root
+    log(f"[rank {rank}] host threads bound to {len(bound)} CPUs local to GPU {local_rank}" if bound else f"[rank {rank}] no CPU binding")
     primary = args.workload or ("c2" if world == 1 else "c3")
     K, Wm = args.steps, args.warmup
 
@@ -666,6 +678,8 @@ def run_b200(args, rank, world, local_rank):
                  "weights": (args.weights_npz or "llicti_b200.synth.synthetic_state_dict(seed=1337) (shipped checkpoint absent)"),
                  "images": f"llicti_b200.synth.synthetic_batch_torch, image k of the job seeded by 1000 + k; generated in {w.gen_s:.1f} s",
                  "l2": "256 MiB buffer written before every timed encode and decode (L2 flushed)",
+                 "host_cpus_bound": (f"{len(bound)} CPUs local to the GPU (NVML affinity), set before the pinned buffers were allocated" if bound
+                                     else "none (all of the process's CPUs are local to the GPU, or NVML gave no affinity)"),
                  "parallelism": (f"{w.job_images} images sharded over {world} GPU(s): {w.shard_images} distinct images per rank"
                                  if wl["shard"] else f"{w.shard_images} distinct images per rank on {world} GPU(s)") +
                                 ", no data-path collective; NCCL only reduces the statistics"}

@@ -66,3 +66,32 @@ def rank_share(order: Sequence[int], rank: int, world: int):
         return order
     per = len(order) // world
     return order[rank:per * world:world]
+
+
+def bind_host_to_gpu(device_index: int):
+    """Restrict this process's host threads to the CPUs NVML reports as local to CUDA device `device_index` (the GPU's NUMA
+    node), so that pinned staging buffers allocated afterwards are local to the GPU's PCIe root: with one process per GPU
+    on a two-socket box, host<->device copies of half the ranks otherwise cross the socket interconnect.  Returns the CPU
+    list bound to, or None when nothing was changed (no NVML, no affinity API, an empty intersection with the CPUs this
+    process may use, or LLICTI_NUMA_BIND=0)."""
+    import os
+    if os.environ.get("LLICTI_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:       # noqa: BLE001 -- older bindings want bytes
+            h = pynvml.nvmlDeviceGetHandleByUUID((("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid).encode())
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed | {os.cpu_count() or 1}) // 64) + 1)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus = sorted(local & allowed)
+        if not cpus or set(cpus) == set(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:           # noqa: BLE001 -- an optimisation, never a requirement
+        return None
