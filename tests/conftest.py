@@ -27,7 +27,7 @@ GOLDEN_CASES = ["a_photo_33x47", "a_photo_53x77", "a_photo_64x96", "a_const_40x7
 
 
 TRAINED_CASES = ["t_photo_64x96", "t_photo_53x77"]     # weights trained by the reference's own mode: train (ckpt_A_trained.npz)
-TRAIN_CASES = ["train_a_2x32x32", "train_b_3x24x40"]     # one backward pass of the reference's training step (make_golden.py)
+TRAIN_CASES = ["train_a_2x32x32", "train_b_3x24x40", "train_t_2x64x32"]     # one backward pass of the reference's training step (make_golden.py)
 FORWARD_CASES = ["fwd_a_photo_64x96", "fwd_a_noise_32x64", "fwd_a_checker_32x32", "fwd_b_photo_64x96", "fwd_b_photo_36x52"]
 
 
@@ -38,7 +38,7 @@ def load_golden(name):
 
 def oracle_config_for(name):
     from oracle import llicti_oracle as O
-    return O.OracleConfig() if name.startswith(("a_", "fwd_a_", "t_", "train_a_")) else O.OracleConfig(dwtlevels=(0, 1), chs=60)
+    return O.OracleConfig() if name.startswith(("a_", "fwd_a_", "t_", "train_a_", "train_t_")) else O.OracleConfig(dwtlevels=(0, 1), chs=60)
 
 
 def trained_state_dict():
@@ -47,3 +47,11 @@ def trained_state_dict():
     import numpy as np
     with np.load(os.path.join(GOLDEN, "ckpt_A_trained.npz")) as z:
         return {k: z[k] for k in z.files}
+
+
+def train_state_dict(name):
+    """Weights of a training-step fixture: the reference-trained checkpoint for train_t_*, else generic (jittered) ones."""
+    from oracle import llicti_oracle as O
+    if name.startswith("train_t_"):
+        return trained_state_dict()
+    return O.jittered_state_dict(oracle_config_for(name), seed=1337)

