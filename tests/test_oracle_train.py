@@ -62,3 +62,28 @@ def test_train_loss_list_is_differentiable():
     assert abs(float(loss) - ref) < 1e-5
     f, _ = TrainRLossList().forward(2 * 3 * 8 * 8, [t.detach() for t in s])
     assert isinstance(f, float) and abs(f - ref) < 1e-5
+
+
+def test_checkpoint_trained_on_the_b200_path_works_in_the_reference_model():
+    """tests/golden/ckpt_A_b200_trained.npz: llicti_A trained from a fresh initialisation by THIS repo's `mode: train`
+    (tools/train_b200_ckpt.py --epochs 14 on a B200: 672 steps of llicti_backward_dev + Adam, 19 s).  In the reference's own
+    forward (the oracle's bit-exact restatement, CPU) its rate on the recipe's eight validation images is the 11.99 bpp
+    the GPU's validate() logged at the end of that training; the checkpoint the unmodified reference trained on the same
+    recipe (six epochs on the CPU) gives 11.76."""
+    import os
+    from conftest import GOLDEN
+    from llicti_b200.synth import synthetic_image
+    ocfg = O.OracleConfig()
+    torch.set_num_threads(4)
+
+    def rate(npz):
+        with np.load(os.path.join(GOLDEN, npz)) as z:
+            net = O.OracleNet(ocfg, {k: z[k] for k in z.files})
+        tot = []
+        for i in range(8):                                      # the validation set of tools/train_*_ckpt.py
+            img = synthetic_image(160, 160, 5000 + 384 + 1 + i, noise=(0.7, 1.5, 2.5, 4.0)[i % 4])
+            tot.append(sum(float(t.sum(dtype=np.float64)) for t in O.forward_self_informations(ocfg, net, img)) / img.size * 3)
+        return float(np.mean(tot))
+
+    assert abs(rate("ckpt_A_b200_trained.npz") - 11.990) < 0.02
+    assert abs(rate("ckpt_A_trained.npz") - 11.755) < 0.02
