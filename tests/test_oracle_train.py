@@ -69,7 +69,7 @@ def test_checkpoint_trained_on_the_b200_path_works_in_the_reference_model():
     (tools/train_b200_ckpt.py --epochs 14 on a B200: 672 steps of llicti_backward_dev + Adam, 19 s).  In the reference's own
     forward (the oracle's bit-exact restatement, CPU) its rate on the recipe's eight validation images is the 11.99 bpp
     the GPU's validate() logged at the end of that training; the checkpoint the unmodified reference trained on the same
-    recipe (six epochs on the CPU) gives 11.76."""
+    images (tests/golden/ckpt_A_trained.npz, a longer run) gives 11.76."""
     import os
     from conftest import GOLDEN
     from llicti_b200.synth import synthetic_image
