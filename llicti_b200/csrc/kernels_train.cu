@@ -4,13 +4,14 @@
 // differentiates is LLICTI_nets.py:101-123, 827-935 and entropy_layer_nets.py:121-139, 160-183, with
 // compressai's LowerBound on the spreads, the mixture weights and the likelihood).
 //
-// Two kernels per (scale, band), after the fp32 CNN of kernels_cnn_fp32.cu has written the band's parameters:
-//   self_info_grad_kernel   one thread per position: d loss / d (60 network outputs), in place over the parameters
-//   cnn_backward_kernel<G>  persistent CTAs, one of the four sub-networks each (blockIdx.y): a tile of 64 positions is
-//                           re-staged (im2col), the two hidden layers are recomputed in shared memory (nothing but the
-//                           60 outputs ever went to HBM), and the five products of the backward pass run on the tile;
-//                           weight gradients accumulate in shared memory over all tiles of the CTA and leave with one
-//                           atomicAdd per element at the end.
+// Three kernels per (scale, band):
+//   cnn_forward_train_kernel<G, K0>  (forward pass) the band's 60 network outputs from the fp32 planes, kept for the backward pass
+//   self_info_grad_kernel            one thread per position: d loss / d (60 network outputs), in place over the outputs
+//   cnn_backward_kernel<G, K0>       persistent CTAs, one of the four sub-networks each (blockIdx.y), its packed weights
+//                                    resident in shared memory: a tile of 64 positions is re-staged (im2col), the two hidden
+//                                    layers are recomputed in shared memory (nothing but the 60 outputs ever went to HBM),
+//                                    and the five products of the backward pass run on the tile; the CTA's weight gradients
+//                                    accumulate in REGISTERS over all its tiles and leave with one atomicAdd per element.
 // fp32 throughout (the reference trains in fp32).  Results equal torch.autograd's up to summation order.
 #include "common.cuh"
 #include "gmm.cuh"
