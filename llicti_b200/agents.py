@@ -193,7 +193,14 @@ class LLICTIAgent(BaseAgent):
             cc.sub_len, "interleaved substreams" if cc.sub_len > 0 else "torchac-compatible streams",
             codec.fingerprint.hex()))
         codec.profile(True)          # per-kernel-class launch groups of this run, logged below
+        first = 0
+        if self.world > 1:           # one process per GPU (torchrun): a contiguous block of the test images per rank, no exchange
+            from .shard import shard_range
+            files = self.test_loader.files
+            first, stop = shard_range(len(files), self.rank, self.world)
+            self.test_loader.files = files[first:stop]
         for batch_idx, x in enumerate(self.test_loader):
+            batch_idx += first
             x = x.to(self.device)
             text = "{:3d} {:3d}x{:3d} ".format(batch_idx, x.shape[2], x.shape[3])
             t0 = time.time()
@@ -217,6 +224,14 @@ class LLICTIAgent(BaseAgent):
         codec.profile(False)
         self.logger.info(" B200 kernel classes launched: " + ", ".join(
             "{}{}={}".format(k, "[tcgen05]" if k == "cnn" and cc.cnn_impl == 1 else "", int(v[1])) for k, v in prof.items() if v[1]))
+        if self.world > 1:           # the table is the mean over ALL images: sums and counts reduced over the ranks, rank 0 prints
+            import numpy as np
+            from .shard import reduce_stats
+            rows = self.model.num_scales + 1
+            local = np.asarray(self.test_logger.rate, dtype=np.float64).reshape(-1, rows, 9)
+            sums, _ = reduce_stats(local.sum(axis=0).reshape(-1).tolist() + [float(local.shape[0])], [0.0], device=self.device)
+            n_all = sums[-1]
+            self.test_logger.rate = [np.asarray(sums[:-1]).reshape(rows, 9) / n_all] if (n_all and self.rank == 0) else []
         if self.test_logger.rate:
             self.test_logger.display(lr=0.0, typ="te")
 

@@ -124,3 +124,42 @@ def test_main_auxiliary_modes(tmp_path, mode, needle):
     if mode == "flops_est":
         positions = sum((512 >> (s + 1)) ** 2 for s in range(5))
         assert "{:.3f} GMac".format(positions * 193248 / 1e9) in log, log[-1500:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_main_eval_model_two_ranks(tmp_path):
+    """eval_model under torchrun: the test images are sharded over the ranks (contiguous blocks), every image is coded and
+    checked once, and the rate table -- the mean over all images, reduced over NCCL -- is the single-process table."""
+    import re
+    import socket
+    from PIL import Image
+    ocfg = O.OracleConfig()
+    cfg = json.load(open(os.path.join(ROOT, "configs", "llicti_A.json")))
+    data = tmp_path / "data"
+    data.mkdir()
+    for i, (h, w) in enumerate([(64, 96), (53, 77), (80, 64), (33, 47), (96, 96)]):
+        Image.fromarray(O.synthetic_image(h, w, 40 + i).transpose(1, 2, 0)).save(data / f"img{i}.png")
+    cfg["test_data"] = str(data)
+    cfg_path = tmp_path / "cfg.json"
+    cfg_path.write_text(json.dumps(cfg))
+    exp = os.path.join("experiments", cfg["multi_exp_name"], "exp_0")
+    sd = {k: torch.from_numpy(v) for k, v in O.synthetic_state_dict(ocfg).items()}
+    totals = []
+    for world in (1, 2):
+        run = tmp_path / f"w{world}"
+        (run / exp / "checkpoints").mkdir(parents=True)
+        torch.save({"epoch": 1, "iteration": 2, "best_valid_loss": np.float64(1.0), "state_dict": sd}, run / exp / "checkpoints" / "model_best.pth.tar")
+        cmd = [sys.executable, os.path.join(ROOT, "main.py"), str(cfg_path)]
+        if world > 1:
+            with socket.socket() as s:
+                s.bind(("127.0.0.1", 0))
+                port = s.getsockname()[1]
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                   "--master-port", str(port), os.path.join(ROOT, "main.py"), str(cfg_path)]
+        r = subprocess.run(cmd, cwd=run, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        log = (run / exp / "logs" / "exp_debug.log").read_text()
+        assert log.count("(Check: Decoded img matches original)") == 5, log[-3000:]
+        assert log.count("Test Epoch:") == 1, log[-3000:]
+        totals.append(re.findall(r"\(\(([0-9.]+)\)\)", log)[-1])
+    assert totals[0] == totals[1], totals
