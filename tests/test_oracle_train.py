@@ -87,3 +87,24 @@ def test_checkpoint_trained_on_the_b200_path_works_in_the_reference_model():
 
     assert abs(rate("ckpt_A_b200_trained.npz") - 11.990) < 0.02
     assert abs(rate("ckpt_A_trained.npz") - 11.755) < 0.02
+
+
+def test_hand_wired_weights_sit_on_relu_kinks_generic_weights_do_not(monkeypatch):
+    """Why gradient parity is tested with jittered weights: the stand-in weights' interpolation path (taps of exactly
+    +-0.25) gives pre-activations that are mathematically ZERO wherever four neighbours cancel, so whether a ReLU passes the
+    gradient there is decided by rounding noise of the inputs -- the float lifting's fl(fl(r/255) - fl(b/255)) against the
+    same sample snapped to integer / 255 (an ulp apart).  With generic weights the two inputs give the same gradients."""
+    ocfg = O.OracleConfig(dwtlevels=(0, 1), chs=60)
+    rgb = np.stack([O.synthetic_image(24, 40, 33 + i, noise=3.0) for i in range(2)])
+    torch.set_num_threads(4)
+    orig = O.float_ycocg_r
+
+    def worst(sd):
+        _, g_float = O.train_loss_and_grads(ocfg, sd, rgb)
+        monkeypatch.setattr(O, "float_ycocg_r", lambda x: torch.round(orig(x) * 255) / 255)
+        _, g_snap = O.train_loss_and_grads(ocfg, sd, rgb)
+        monkeypatch.setattr(O, "float_ycocg_r", orig)
+        return max(float(np.abs(g_float[k] - g_snap[k]).max()) / (float(np.abs(g_float[k]).max()) + 1e-30) for k in g_float)
+
+    assert worst(O.jittered_state_dict(ocfg, seed=1337)) < 1e-4
+    assert worst(O.synthetic_state_dict(ocfg, seed=1337)) > 1e-3
